@@ -1,0 +1,221 @@
+/*
+ * km_b200.h -- C-ABI of libkm_b200.so, the B200 (sm_100a) registration engine that sits
+ * underneath the Python surface of alanqrwang/keymorph.
+ *
+ * The reference has no FFI layer of its own: its "plugin boundary" is the
+ * set of torch call sites listed below.  Every entry point here replaces one of those call sites
+ * and is what a ctypes / pybind stub on the reference side binds.
+ *
+ * Conventions
+ *   - plain pointers + explicit sizes, no torch types; all pointers are DEVICE pointers unless
+ *     the parameter name ends in _host;
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant,
+ *     and never allocates: the caller owns outputs and workspaces (sizes from *_workspace_bytes);
+ *   - return value 0 = success, negative = KM_E*; km_last_error() returns a thread-local message;
+ *   - volumes are (N, C, D, H, W) fp32 contiguous ("NCDHW") at the API surface, activations
+ *     inside the backbone are (N, D, H, W, C) bf16 ("NDHWC");
+ *   - points are (N, K, 3) fp32 in the reference's 'ij' order (z, y, x), normalised to [-1, 1];
+ *     flow fields are (N, D, H, W, 3) fp32 in grid_sample's (x, y, z) order.
+ */
+#ifndef KM_B200_H
+#define KM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KM_OK 0
+#define KM_EINVAL (-1)   /* bad argument (shape, alignment, unsupported size) */
+#define KM_ECUDA (-2)    /* CUDA runtime / driver error, text in km_last_error() */
+#define KM_ENOSUPPORT (-3)
+
+typedef void* km_stream_t; /* cudaStream_t */
+
+int km_version(void);
+const char* km_last_error(void);
+/* number of SMs of the current device (grid sizing for the persistent kernels) */
+int km_sm_count(void);
+/* runtime options: key KM_OPT_TPS_FAST (default 1): evaluate the TPS radial basis of the dense
+ * flow field with lg2.approx / rsqrt.approx instead of logf / sqrtf. */
+#define KM_OPT_TPS_FAST 1
+int km_set_option(int key, int value);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Warp: keymorph/utils.py:14-21  align_img -> F.grid_sample(mode, padding_mode="border",
+ * align_corners=False)
+ * ------------------------------------------------------------------------------------------ */
+#define KM_INTERP_BILINEAR 0
+#define KM_INTERP_NEAREST 1
+
+/* out[n,c,d,h,w] = sample(x[n,c], grid[n,d,h,w,:]);  x: (N,C,Di,Hi,Wi), grid: (N,Do,Ho,Wo,3) */
+int km_grid_sample3d(const float* x, const float* grid, float* out, int N, int C, int Di, int Hi,
+                     int Wi, int Do, int Ho, int Wo, int mode, km_stream_t stream);
+
+/* keymorph/transformations.py:37-79,98-114 (AffineTransform.get_flow_field) with
+ * keymorph/utils.py:387-398 (uniform_norm_grid) generated in-register.
+ * mat: (N,3,4) row-major, rows/cols in (z,y,x) order = inverse_transform_matrix[:, :3, :].
+ * grid: (N,D,H,W,3) in (x,y,z) order (the reference's .flip(-1)). */
+int km_flow_field_affine(const float* mat, float* grid, int N, int D, int H, int W,
+                         km_stream_t stream);
+
+/* keymorph/keypoint_aligners.py:365-449 (TPS.get_flow_field / transform_points).
+ * ctrl: (N,K,3) control points (points_f), theta: (N,K+4,3) from km_tps_fit. */
+int km_flow_field_tps(const float* ctrl, const float* theta, float* grid, int N, int K, int D,
+                      int H, int W, km_stream_t stream);
+
+/* keymorph/transformations.py:81-114: out[n,p,:] = mat[n] (3x4) * [pts[n,p,:]; 1] */
+int km_points_transform_affine(const float* mat, const float* pts, float* out, int N, int P,
+                               km_stream_t stream);
+/* keymorph/keypoint_aligners.py:399-433 (TPS.transform_points) on arbitrary points */
+int km_points_transform_tps(const float* ctrl, const float* theta, const float* pts, float* out,
+                            int N, int K, int P, km_stream_t stream);
+
+/* Fused warp + loss: coordinates are generated from the affine matrix (or the
+ * TPS parameters, or read from `grid`), the moving volume is gathered (trilinear, border), the
+ * warped volume is optionally stored (out may be NULL) and the loss partial sums are reduced
+ * deterministically in two stages.
+ *   sums layout per (n, c): [sum (a-f)^2, sum a*f, sum a*a, sum f*f]  (fp64, 4 doubles)
+ * `fixed` may be NULL (then only the warp is performed and sums are untouched).
+ * workspace: km_warp_loss_workspace_bytes(N, C). */
+#define KM_COORD_AFFINE 0
+#define KM_COORD_TPS 1
+#define KM_COORD_GRID 2
+size_t km_warp_loss_workspace_bytes(int N, int C);
+int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const float* theta, int K,
+                 const float* grid, const float* moving, const float* fixed, float* out,
+                 double* sums, void* workspace, int N, int C, int D, int H, int W, int mode,
+                 km_stream_t stream);
+
+/* keymorph/loss_ops.py:9-13 and :16-63.  Elementwise-pair statistics of two (N,C,M) fp32 tensors:
+ * sums[n,c,:] = [sum (p-t)^2, sum p*t, sum p*p, sum t*t] (fp64).  With hard != 0 pred is replaced
+ * by one_hot(argmax_c pred) (first maximum wins, like torch.argmax) before the products.
+ * workspace: km_pair_stats_workspace_bytes(N, C, M, hard) (hard Dice keeps the int32 label map
+ * behind the partial sums). */
+size_t km_pair_stats_workspace_bytes(int N, int C, long long M, int hard);
+int km_pair_stats(const float* pred, const float* target, double* sums, void* workspace, int N,
+                  int C, long long M, int hard, km_stream_t stream);
+/* hard-Dice labels: labels[n,m] = argmax_c pred[n,c,m] (int32, first max wins) */
+int km_argmax_channels(const float* pred, int32_t* labels, int N, int C, long long M,
+                       km_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Keypoint layer: keymorph/layers.py:92-134 CenterOfMass3d (+ keymorph/model.py:95-109 power)
+ * heat: (N,K,D,H,W) fp32.  points: (N,K,3) in 'ij' (z,y,x) order when ij != 0 else (x,y,z).
+ * mass (optional, may be NULL): (N,K) = sum relu(heat).
+ * ------------------------------------------------------------------------------------------ */
+size_t km_com3d_workspace_bytes(int N, int K);
+int km_com3d(const float* heat, float* points, float* mass, void* workspace, int N, int K, int D,
+             int H, int W, int ij, km_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Closed-form aligners: keymorph/keypoint_aligners.py:76-114 (affine), :151-213 (rigid),
+ * keymorph/transformations.py:10-35 (square + inverse).
+ * x, y: (N,K,3); w: (N,K) or NULL.  Fits y ~ A [x;1].
+ * A44: (N,4,4) = square(A); A44_inv: (N,4,4) = inverse(square(A)); status: (N) int32, nonzero
+ * when the normal matrix (affine) or A (inverse) is singular (the reference raises LinAlgError).
+ * ------------------------------------------------------------------------------------------ */
+int km_fit_affine(const float* x, const float* y, const float* w, float* A44, float* A44_inv,
+                  int32_t* status, int N, int K, km_stream_t stream);
+int km_fit_rigid(const float* x, const float* y, const float* w, float* A44, float* A44_inv,
+                 int32_t* status, int N, int K, km_stream_t stream);
+/* inverse of N 4x4 matrices (keymorph/transformations.py:25,28) */
+int km_inverse44(const float* m, float* inv, int32_t* status, int N, km_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * TPS fit: keymorph/keypoint_aligners.py:276-363 (fit / fit_dim / d / u).
+ * c_src, c_dst: (N,K,3); lmbda: (N); w: (N,K) or NULL; theta: (N,K+4,3) fp32.
+ * Assembles [[U + lmbda*I, P],[P^T, 0]] and solves for the three right-hand sides at once with a
+ * partially pivoted LU held in `workspace` (km_tps_fit_workspace_bytes(N, K)).
+ * ------------------------------------------------------------------------------------------ */
+size_t km_tps_fit_workspace_bytes(int N, int K);
+int km_tps_fit(const float* c_src, const float* c_dst, const float* lmbda, const float* w,
+               float* theta, int32_t* status, void* workspace, int N, int K, km_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Backbone (keymorph/unet3d/buildingblocks.py:39-132, keymorph/layers.py:137-187,
+ * keymorph/net.py:7-36).  bf16 NDHWC activations, fp32 accumulation.
+ * ------------------------------------------------------------------------------------------ */
+/* fp32 (Cout,Cin,3,3,3) [or (Cout,Cin,1,1,1) with taps=1] -> bf16 [tap][Cout][Cin];
+ * in_scale (Cin) optional per-input-channel multiplier (NULL = 1). */
+int km_pack_weights(const float* w, void* packed_bf16, int Cout, int Cin, int taps,
+                    km_stream_t stream);
+
+/* per-(n,c) sum / sum-of-squares partials -> GroupNorm / InstanceNorm scale+shift.
+ * stats layouts: (nparts, N, C, 2) fp32 partials written by the producing kernel. */
+/* y = a*x + b with a = gamma*rstd, b = beta - mean*rstd*gamma per (n, c).
+ * Two sources (for the decoder concat): channels [0,C0) come from stats0 with count0 elements per
+ * channel, channels [C0,C0+C1) from stats1 with count1 elements, each weighted by rep (x8 for the
+ * nearest-upsampled source: rep1 = 8).  groups: number of GroupNorm groups over C0+C1 channels
+ * (groups == C0+C1 -> InstanceNorm).  gamma/beta may be NULL (no affine). */
+int km_norm_finalize(const float* stats0, int nparts0, int C0, double count0,
+                     const float* stats1, int nparts1, int C1, double count1, double rep1,
+                     const float* gamma, const float* beta, int groups, float eps, float* scale,
+                     float* shift, int N, km_stream_t stream);
+
+/* per-(n,c) sum / sumsq partials of a bf16 NDHWC tensor: stats (nparts,N,C,2),
+ * nparts = km_pool_nparts() (used when the decoder's upsample is not an exact x2). */
+int km_channel_stats(const void* x, float* stats, int N, int C, long long nvox,
+                     km_stream_t stream);
+
+/* out[n,v,c] = act(scale[n,c]*src[n,v',c] + shift[n,c]) in bf16 NDHWC.
+ * Source 0 (C0 channels) is sampled at the output resolution; source 1 (C1 channels, may be NULL /
+ * C1 = 0) is nearest-upsampled from (D1,H1,W1) (keymorph/unet3d/buildingblocks.py:464-475,580-582)
+ * and concatenated after source 0.  relu != 0 applies max(.,0). pool != 0 applies MaxPool3d(2)
+ * on source 0 after the activation (output dims are then D/2,H/2,W/2; keymorph/layers.py:176-187). */
+int km_norm_apply(const void* src0, int C0, const void* src1, int C1, int D1, int H1, int W1,
+                  const float* scale, const float* shift, void* out, int N, int D, int H, int W,
+                  int relu, int pool, km_stream_t stream);
+
+/* MaxPool3d(2) (keymorph/unet3d/buildingblocks.py:363,387) on bf16 NDHWC + per-(n,c) stats of the
+ * pooled tensor.  stats: (nparts,N,C,2) with nparts = km_pool_nparts(). */
+int km_pool_nparts(void);
+int km_maxpool2_stats(const void* src, void* out, float* stats, int N, int C, int D, int H, int W,
+                      km_stream_t stream);
+
+/* sum / sumsq of an fp32 volume per sample (GroupNorm of the 1-channel input image).
+ * stats: (nparts,N,1,2), nparts = km_pool_nparts(). */
+int km_volume_stats(const float* x, float* stats, int N, long long M, km_stream_t stream);
+
+/* stem: 3x3x3 conv of the 1-channel fp32 volume with on-the-fly GroupNorm(1 group) of the input
+ * (zero padding of the NORMALISED volume), + optional bias, optional ReLU -> bf16 NDHWC,
+ * + per-(n,c) stats of the output.  w: fp32 (Cout,1,3,3,3), Cout in {16,32}.
+ * stats: (nparts,N,Cout,2), nparts = km_stem_nparts(N,D,H,W). */
+int km_stem_nparts(int N, int D, int H, int W);
+int km_conv3d_stem(const float* x, const float* w, const float* bias, const float* in_scale,
+                   const float* in_shift, void* out, float* stats, int N, int Cout, int D, int H,
+                   int W, int relu, km_stream_t stream);
+
+/* tcgen05 implicit-GEMM convolution, kernel 3x3x3 pad 1 (taps = 27) or 1x1x1 (taps = 1).
+ *   x: bf16 NDHWC (N,D,H,W,Cin), Cin % 16 == 0;  wp: bf16 [tap][Cout][Cin] from km_pack_weights;
+ *   out: bf16 NDHWC (N,D,H,W,Cout), Cout % 16 == 0 (may be NULL with KM_CONV_COM);
+ *   bias: fp32 (Cout) or NULL;  flags: KM_CONV_RELU | KM_CONV_STATS | KM_CONV_COM.
+ *   stats: (nparts,N,Cout,2) fp32 partial sum/sumsq of the stored values (KM_CONV_STATS);
+ *   com:   (nparts,N,Cout,4) fp32 partial [sum h, sum h*lz, sum h*ly, sum h*lx] of h = relu(out)
+ *          (KM_CONV_COM; the heat map is not written when out == NULL);
+ *   nparts = km_conv_nparts() (one partial per persistent CTA). */
+#define KM_CONV_RELU 1
+#define KM_CONV_STATS 2
+#define KM_CONV_COM 4
+int km_conv_nparts(void);
+int km_conv3d_tc(const void* x, const void* wp, const float* bias, void* out, float* stats,
+                 float* com, int N, int Cin, int Cout, int D, int H, int W, int taps, int flags,
+                 km_stream_t stream);
+
+/* com partials -> keypoints (N,K,3) 'ij' order + optional mass (N,K)
+ * (keymorph/layers.py:121-134: c = sum(lin*m)/(M+1e-8), *2-1). */
+int km_com_finalize(const float* com, int nparts, float* points, float* mass, int N, int K,
+                    km_stream_t stream);
+
+/* bf16 NDHWC (N,D,H,W,C) -> fp32 NCDHW (N,C,D,H,W) and back (feature export / tests) */
+int km_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int N, int C, int D, int H, int W,
+                               km_stream_t stream);
+int km_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int N, int C, int D, int H, int W,
+                               km_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KM_B200_H */

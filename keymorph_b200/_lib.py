@@ -1,0 +1,99 @@
+"""ctypes binding of libkm_b200.so (C ABI declared in include/km_b200.h).
+
+There is no CPU path behind this module: if the shared library is missing or a CUDA device is not
+present the calls fail loudly.  Nothing under oracle/ is ever imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libkm_b200.so")
+
+_p = C.c_void_p
+_i = C.c_int
+_ll = C.c_longlong
+_f = C.c_float
+_d = C.c_double
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/km_b200.h one to one
+SIGNATURES = {
+    "km_version": (_i, []),
+    "km_last_error": (C.c_char_p, []),
+    "km_sm_count": (_i, []),
+    "km_set_option": (_i, [_i, _i]),
+    "km_grid_sample3d": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "km_flow_field_affine": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "km_flow_field_tps": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "km_points_transform_affine": (_i, [_p, _p, _p, _i, _i, _p]),
+    "km_points_transform_tps": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "km_warp_loss_workspace_bytes": (_sz, [_i, _i]),
+    "km_warp_loss": (_i, [_i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "km_pair_stats_workspace_bytes": (_sz, [_i, _i, _ll, _i]),
+    "km_pair_stats": (_i, [_p, _p, _p, _p, _i, _i, _ll, _i, _p]),
+    "km_argmax_channels": (_i, [_p, _p, _i, _i, _ll, _p]),
+    "km_com3d_workspace_bytes": (_sz, [_i, _i]),
+    "km_com3d": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "km_fit_affine": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "km_fit_rigid": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "km_inverse44": (_i, [_p, _p, _p, _i, _p]),
+    "km_tps_fit_workspace_bytes": (_sz, [_i, _i]),
+    "km_tps_fit": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "km_pack_weights": (_i, [_p, _p, _i, _i, _i, _p]),
+    "km_norm_finalize": (_i, [_p, _i, _i, _d, _p, _i, _i, _d, _d, _p, _p, _i, _f, _p, _p, _i, _p]),
+    "km_channel_stats": (_i, [_p, _p, _i, _i, _ll, _p]),
+    "km_norm_apply": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "km_pool_nparts": (_i, []),
+    "km_maxpool2_stats": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "km_volume_stats": (_i, [_p, _p, _i, _ll, _p]),
+    "km_stem_nparts": (_i, [_i, _i, _i, _i]),
+    "km_conv3d_stem": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "km_conv_nparts": (_i, []),
+    "km_conv3d_tc": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "km_com_finalize": (_i, [_p, _i, _p, _p, _i, _i, _p]),
+    "km_ndhwc_bf16_to_ncdhw_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "km_ncdhw_f32_to_ndhwc_bf16": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+}
+
+KM_CONV_RELU, KM_CONV_STATS, KM_CONV_COM = 1, 2, 4
+KM_INTERP_BILINEAR, KM_INTERP_NEAREST = 0, 1
+KM_COORD_AFFINE, KM_COORD_TPS, KM_COORD_GRID = 0, 1, 2
+KM_OPT_TPS_FAST = 1
+
+_lib = None
+
+
+class KMError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libkm_b200.so (built by keymorph_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KMError(
+            f"{LIB_PATH} is missing: run `python -m keymorph_b200.build` (there is no CPU fallback)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point and raise KMError with km_last_error() on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise KMError(f"{name} failed ({rc}): {lib.km_last_error().decode()}")
+
+
+def query(name: str, *args):
+    return getattr(load(), name)(*args)

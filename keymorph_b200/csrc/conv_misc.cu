@@ -1,0 +1,570 @@
+// HBM-bound companions of the tcgen05 convolution: the 1-channel stem stencil, GroupNorm /
+// InstanceNorm statistics + application (with the decoder's nearest-upsample + concat folded in),
+// MaxPool3d(2) and layout converters.  All reductions are two-stage and deterministic: every block
+// writes one partial slot, the finalize kernel adds the slots in a fixed order in fp64.
+//
+// Reference call sites: keymorph/unet3d/buildingblocks.py:39-132 (GroupNorm -> Conv3d -> ReLU),
+// :360-389 (MaxPool3d before the encoder's DoubleConv), :464-475,580-582 (nearest upsample + cat),
+// keymorph/layers.py:137-187 (Conv3d -> InstanceNorm3d -> ReLU -> MaxPool3d).
+#include "km_common.cuh"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// sum / sumsq of an fp32 volume, grid (KM_RED_BLOCKS, N)
+__global__ void __launch_bounds__(KM_RED_THREADS)
+volume_stats_kernel(const float* __restrict__ x, float* __restrict__ stats, long long M, int N) {
+  const int n = blockIdx.y;
+  const float* xn = x + (size_t)n * M;
+  float s = 0.f, ss = 0.f;
+  const long long M4 = (((uintptr_t)xn & 15) == 0) ? (M / 4) : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(xn);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x4 + i);
+    s += (v.x + v.y) + (v.z + v.w);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  for (long long i = M4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = xn[i];
+    s += v;
+    ss += v * v;
+  }
+  __shared__ float red[2][KM_RED_THREADS / 32];
+  s = km_warp_sum(s);
+  ss = km_warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < KM_RED_THREADS / 32; ++w) {
+      a += red[0][w];
+      b += red[1][w];
+    }
+    float* d = stats + ((size_t)blockIdx.x * N + n) * 2;
+    d[0] = a;
+    d[1] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic per-channel stats of a bf16 NDHWC tensor, grid (KM_RED_BLOCKS, N)
+__global__ void __launch_bounds__(KM_RED_THREADS)
+channel_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, long long nvox, int C,
+                     int N) {
+  extern __shared__ float sacc[];  // [C][2]
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cg = C / 8;
+  const long long total = nvox * cg;
+  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)n * nvox * C);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    float f[8];
+    unpack8(__ldg(src + i), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&sacc[(g * 8 + k) * 2 + 0], f[k]);
+      atomicAdd(&sacc[(g * 8 + k) * 2 + 1], f[k] * f[k]);
+    }
+  }
+  __syncthreads();
+  float* d = stats + ((size_t)blockIdx.x * N + n) * C * 2;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) d[i] = sacc[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm / InstanceNorm finalize: one block per sample
+__global__ void norm_finalize_kernel(const float* __restrict__ stats0, int nparts0, int C0,
+                                     double count0, const float* __restrict__ stats1, int nparts1,
+                                     int C1, double count1, double rep1,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     int groups, float eps, float* __restrict__ scale,
+                                     float* __restrict__ shift, int N) {
+  extern __shared__ double sd[];  // [C][2] then [groups][2]
+  const int n = blockIdx.x;
+  const int C = C0 + C1;
+  double* csum = sd;
+  double* gstat = sd + 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s = 0.0, ss = 0.0;
+    if (c < C0) {
+      for (int p = 0; p < nparts0; ++p) {
+        const float* q = stats0 + (((size_t)p * N + n) * C0 + c) * 2;
+        s += (double)q[0];
+        ss += (double)q[1];
+      }
+    } else {
+      const int c1 = c - C0;
+      for (int p = 0; p < nparts1; ++p) {
+        const float* q = stats1 + (((size_t)p * N + n) * C1 + c1) * 2;
+        s += (double)q[0];
+        ss += (double)q[1];
+      }
+      s *= rep1;
+      ss *= rep1;
+    }
+    csum[2 * c] = s;
+    csum[2 * c + 1] = ss;
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double s = 0.0, ss = 0.0, cnt = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      s += csum[2 * c];
+      ss += csum[2 * c + 1];
+      cnt += (c < C0) ? count0 : count1 * rep1;
+    }
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;  // biased variance (torch group_norm / instance_norm)
+    if (var < 0.0) var = 0.0;
+    gstat[2 * g] = mean;
+    gstat[2 * g + 1] = 1.0 / sqrt(var + (double)eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double mean = gstat[2 * g], rstd = gstat[2 * g + 1];
+    const double ga = gamma ? (double)gamma[c] : 1.0;
+    const double be = beta ? (double)beta[c] : 0.0;
+    scale[(size_t)n * C + c] = (float)(ga * rstd);
+    shift[(size_t)n * C + c] = (float)(be - mean * rstd * ga);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// out = act(scale*src + shift) with optional second (nearest-upsampled) source and optional pool
+__global__ void __launch_bounds__(256)
+norm_apply_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict__ src1, int C1,
+                  int D1, int H1, int W1, const float* __restrict__ scale,
+                  const float* __restrict__ shift, bf16* __restrict__ out, int N, int D, int H,
+                  int W, int relu) {
+  const int C = C0 + C1;
+  const int cg = C / 8, cg0 = C0 / 8;
+  const long long nvox = (long long)D * H * W;
+  const long long total = (long long)N * nvox * cg;
+  // ATen upsample_nearest3d: src = min(floor(dst * (in / out)), in - 1) with a float scale
+  const float sz = (float)D1 / (float)D, sy = (float)H1 / (float)H, sx = (float)W1 / (float)W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long v = i / cg;
+    const int n = (int)(v / nvox);
+    uint4 raw;
+    if (g < cg0) {
+      raw = __ldg(reinterpret_cast<const uint4*>(src0 + (size_t)v * C0) + g);
+    } else {
+      const long long r = v % nvox;
+      const int x = (int)(r % W), y = (int)((r / W) % H), z = (int)(r / ((long long)W * H));
+      const int x1 = min((int)floorf(x * sx), W1 - 1);
+      const int y1 = min((int)floorf(y * sy), H1 - 1);
+      const int z1 = min((int)floorf(z * sz), D1 - 1);
+      const size_t v1 = (((size_t)n * D1 + z1) * H1 + y1) * W1 + x1;
+      raw = __ldg(reinterpret_cast<const uint4*>(src1 + v1 * C1) + (g - cg0));
+    }
+    float f[8];
+    unpack8(raw, f);
+    const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)n * C + g * 8);
+    const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)n * C + g * 8);
+    const float4 a0 = __ldg(sc), a1 = __ldg(sc + 1), b0 = __ldg(sh), b1 = __ldg(sh + 1);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      f[k] = fmaf(a[k], f[k], b[k]);
+      if (relu) f[k] = fmaxf(f[k], 0.f);
+    }
+    reinterpret_cast<uint4*>(out)[i] = pack8(f);
+  }
+}
+
+// normalise + activation + MaxPool3d(2) in one pass (ConvNet blocks 2/4/6/8)
+__global__ void __launch_bounds__(256)
+norm_apply_pool_kernel(const bf16* __restrict__ src, int C, const float* __restrict__ scale,
+                       const float* __restrict__ shift, bf16* __restrict__ out, int N, int D, int H,
+                       int W, int relu) {
+  const int cg = C / 8;
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long nvo = (long long)Do * Ho * Wo;
+  const long long total = (long long)N * nvo * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long v = i / cg;
+    const int n = (int)(v / nvo);
+    const long long r = v % nvo;
+    const int x = (int)(r % Wo), y = (int)((r / Wo) % Ho), z = (int)(r / ((long long)Wo * Ho));
+    const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)n * C + g * 8);
+    const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)n * C + g * 8);
+    const float4 a0 = __ldg(sc), a1 = __ldg(sc + 1), b0 = __ldg(sh), b1 = __ldg(sh + 1);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t vi = (((size_t)n * D + (2 * z + dz)) * H + (2 * y + dy)) * W + (2 * x + dx);
+          float f[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(src + vi * C) + g), f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], fmaf(a[k], f[k], b[k]));
+        }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], 0.f);
+    }
+    reinterpret_cast<uint4*>(out)[i] = pack8(m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MaxPool3d(2) + per-channel stats of the pooled tensor, grid (KM_RED_BLOCKS, N), 256 threads.
+// Requires (gridDim.x * 256) % (C/8) == 0 and 256 % (C/8) == 0 so that a thread keeps one channel
+// group for its whole grid-stride loop (checked on the host).
+__global__ void __launch_bounds__(256)
+maxpool2_stats_kernel(const bf16* __restrict__ src, bf16* __restrict__ out,
+                      float* __restrict__ stats, int N, int C, int D, int H, int W) {
+  __shared__ float red[256][17];
+  const int n = blockIdx.y;
+  const int cg = C / 8;
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long nvo = (long long)Do * Ho * Wo;
+  const long long total = nvo * cg;
+  const bf16* sn = src + (size_t)n * D * H * W * C;
+  uint4* on = reinterpret_cast<uint4*>(out + (size_t)n * nvo * C);
+  float s[8], ss[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = ss[k] = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long r = i / cg;
+    const int x = (int)(r % Wo), y = (int)((r / Wo) % Ho), z = (int)(r / ((long long)Wo * Ho));
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t vi = ((size_t)(2 * z + dz) * H + (2 * y + dy)) * W + (2 * x + dx);
+          float f[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(sn + vi * C) + g), f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+        }
+    on[i] = pack8(m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s[k] += m[k];
+      ss[k] = fmaf(m[k], m[k], ss[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[threadIdx.x][k] = s[k];
+    red[threadIdx.x][8 + k] = ss[k];
+  }
+  __syncthreads();
+  // channel c = g*8 + k is owned by the threads t with t % cg == g
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / 8, k = c % 8;
+    float a = 0.f, b = 0.f;
+    for (int t = g; t < 256; t += cg) {
+      a += red[t][k];
+      b += red[t][8 + k];
+    }
+    float* d = stats + (((size_t)blockIdx.x * N + n) * C + c) * 2;
+    d[0] = a;
+    d[1] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stem: 1-channel fp32 volume -> COUT bf16 channels, 3x3x3, pad 1.
+// Block tile 32(x) x 4(y) x 2(z) outputs, halo tile staged in smem already normalised
+// (zero outside the volume = padding of the normalised tensor).  grid (KM_RED_BLOCKS, N).
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv_stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                 const float* __restrict__ bias, const float* __restrict__ in_scale,
+                 const float* __restrict__ in_shift, bf16* __restrict__ out,
+                 float* __restrict__ stats, int N, int D, int H, int W, int relu) {
+  constexpr int TX = 32, TY = 4, TZ = 2;
+  constexpr int HX = TX + 2, HY = TY + 2, HZ = TZ + 2;
+  __shared__ float tile[HZ][HY][HX];
+  __shared__ __align__(16) float sw[27][COUT];
+  __shared__ float sbias[COUT];
+  __shared__ float red[8][2 * COUT];
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < 27 * COUT; i += 256) {
+    const int co = i % COUT, tap = i / COUT;
+    sw[tap][co] = w[co * 27 + tap];
+  }
+  for (int i = threadIdx.x; i < COUT; i += 256) sbias[i] = bias ? bias[i] : 0.f;
+  const float a_in = in_scale ? in_scale[n] : 1.f;
+  const float b_in = in_shift ? in_shift[n] : 0.f;
+  const float* xn = x + (size_t)n * D * H * W;
+  bf16* on = out + (size_t)n * D * H * W * COUT;
+
+  const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY, tiles_z = (D + TZ - 1) / TZ;
+  const long long ntiles = (long long)tiles_x * tiles_y * tiles_z;
+  const int lx = threadIdx.x % TX, ly = (threadIdx.x / TX) % TY, lz = threadIdx.x / (TX * TY);
+
+  float s[COUT], ss[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) s[c] = ss[c] = 0.f;
+
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int x0 = (int)(t % tiles_x) * TX;
+    const int y0 = (int)((t / tiles_x) % tiles_y) * TY;
+    const int z0 = (int)(t / ((long long)tiles_x * tiles_y)) * TZ;
+    __syncthreads();  // previous tile fully consumed (also orders the weight staging)
+    for (int i = threadIdx.x; i < HZ * HY * HX; i += 256) {
+      const int hx = i % HX, hy = (i / HX) % HY, hz = i / (HX * HY);
+      const int gx = x0 + hx - 1, gy = y0 + hy - 1, gz = z0 + hz - 1;
+      float v = 0.f;
+      if (gx >= 0 && gx < W && gy >= 0 && gy < H && gz >= 0 && gz < D)
+        v = fmaf(a_in, __ldg(xn + ((size_t)gz * H + gy) * W + gx), b_in);
+      tile[hz][hy][hx] = v;
+    }
+    __syncthreads();
+    const int gx = x0 + lx, gy = y0 + ly, gz = z0 + lz;
+    if (gx < W && gy < H && gz < D) {
+      float acc[COUT];
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc[c] = sbias[c];
+#pragma unroll
+      for (int tap = 0; tap < 27; ++tap) {
+        const float v = tile[lz + tap / 9][ly + (tap / 3) % 3][lx + tap % 3];
+        const float4* wr = reinterpret_cast<const float4*>(&sw[tap][0]);
+#pragma unroll
+        for (int c4 = 0; c4 < COUT / 4; ++c4) {
+          const float4 wv = wr[c4];
+          acc[4 * c4 + 0] = fmaf(v, wv.x, acc[4 * c4 + 0]);
+          acc[4 * c4 + 1] = fmaf(v, wv.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(v, wv.z, acc[4 * c4 + 2]);
+          acc[4 * c4 + 3] = fmaf(v, wv.w, acc[4 * c4 + 3]);
+        }
+      }
+      uint4* dst = reinterpret_cast<uint4*>(on + (((size_t)gz * H + gy) * W + gx) * COUT);
+#pragma unroll
+      for (int c8 = 0; c8 < COUT / 8; ++c8) {
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float v = acc[8 * c8 + k];
+          if (relu) v = fmaxf(v, 0.f);
+          // statistics are taken over the values actually stored (bf16-rounded)
+          v = __bfloat162float(__float2bfloat16_rn(v));
+          f[k] = v;
+          s[8 * c8 + k] += v;
+          ss[8 * c8 + k] = fmaf(v, v, ss[8 * c8 + k]);
+        }
+        dst[c8] = pack8(f);
+      }
+    }
+  }
+  // deterministic block reduction of the per-thread accumulators
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) {
+    s[c] = km_warp_sum(s[c]);
+    ss[c] = km_warp_sum(ss[c]);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+      red[threadIdx.x >> 5][2 * c] = s[c];
+      red[threadIdx.x >> 5][2 * c + 1] = ss[c];
+    }
+  }
+  __syncthreads();
+  if (stats) {
+    for (int i = threadIdx.x; i < 2 * COUT; i += 256) {
+      float a = 0.f;
+      for (int wv = 0; wv < 8; ++wv) a += red[wv][i];
+      stats[((size_t)blockIdx.x * N + n) * COUT * 2 + i] = a;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int N,
+                                      int C, long long nvox) {
+  const long long total = (long long)N * C * nvox;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i % nvox;
+    const int c = (int)((i / nvox) % C);
+    const int n = (int)(i / (nvox * C));
+    dst[i] = __bfloat162float(src[((size_t)n * nvox + v) * C + c]);
+  }
+}
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N,
+                                      int C, long long nvox) {
+  const long long total = (long long)N * C * nvox;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long v = (i / C) % nvox;
+    const int n = (int)(i / (nvox * C));
+    dst[i] = __float2bfloat16_rn(src[((size_t)n * C + c) * nvox + v]);
+  }
+}
+
+inline int blocks_for(long long work_items, int threads) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = 148ll * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+extern "C" int km_pool_nparts(void) { return KM_RED_BLOCKS; }
+extern "C" int km_stem_nparts(int, int, int, int) { return KM_RED_BLOCKS; }
+
+extern "C" int km_volume_stats(const float* x, float* stats, int N, long long M,
+                               km_stream_t stream) {
+  KM_CHECK_ARG(x && stats && N > 0 && M > 0, "km_volume_stats: bad arguments");
+  volume_stats_kernel<<<dim3(KM_RED_BLOCKS, N), KM_RED_THREADS, 0, km_cs(stream)>>>(x, stats, M, N);
+  KM_LAUNCH_OK("volume_stats_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_channel_stats(const void* x, float* stats, int N, int C, long long nvox,
+                                km_stream_t stream) {
+  KM_CHECK_ARG(x && stats && N > 0 && C % 8 == 0 && nvox > 0, "km_channel_stats: bad arguments");
+  channel_stats_kernel<<<dim3(KM_RED_BLOCKS, N), KM_RED_THREADS, 2 * C * sizeof(float),
+                         km_cs(stream)>>>(reinterpret_cast<const bf16*>(x), stats, nvox, C, N);
+  KM_LAUNCH_OK("channel_stats_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_norm_finalize(const float* stats0, int nparts0, int C0, double count0,
+                                const float* stats1, int nparts1, int C1, double count1,
+                                double rep1, const float* gamma, const float* beta, int groups,
+                                float eps, float* scale, float* shift, int N, km_stream_t stream) {
+  KM_CHECK_ARG(stats0 && C0 > 0 && nparts0 > 0 && scale && shift && N > 0,
+               "km_norm_finalize: bad arguments");
+  KM_CHECK_ARG(C1 == 0 || (stats1 && nparts1 > 0), "km_norm_finalize: second source missing");
+  const int C = C0 + C1;
+  KM_CHECK_ARG(groups > 0 && C % groups == 0, "km_norm_finalize: %d channels not divisible by %d groups",
+               C, groups);
+  const size_t smem = (size_t)(2 * C + 2 * groups) * sizeof(double);
+  norm_finalize_kernel<<<N, 256, smem, km_cs(stream)>>>(stats0, nparts0, C0, count0, stats1, nparts1,
+                                                       C1, count1, rep1, gamma, beta, groups, eps,
+                                                       scale, shift, N);
+  KM_LAUNCH_OK("norm_finalize_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_norm_apply(const void* src0, int C0, const void* src1, int C1, int D1, int H1,
+                             int W1, const float* scale, const float* shift, void* out, int N,
+                             int D, int H, int W, int relu, int pool, km_stream_t stream) {
+  KM_CHECK_ARG(src0 && scale && shift && out && N > 0 && D > 0 && H > 0 && W > 0,
+               "km_norm_apply: bad arguments");
+  KM_CHECK_ARG(C0 % 8 == 0 && C1 % 8 == 0 && C0 > 0, "km_norm_apply: channels must be multiples of 8");
+  KM_CHECK_ARG(C1 == 0 || src1, "km_norm_apply: second source missing");
+  if (pool) {
+    KM_CHECK_ARG(C1 == 0, "km_norm_apply: pool is only supported for a single source");
+    KM_CHECK_ARG(D >= 2 && H >= 2 && W >= 2, "km_norm_apply: volume too small to pool");
+    const long long total = (long long)N * (D / 2) * (H / 2) * (W / 2) * (C0 / 8);
+    norm_apply_pool_kernel<<<blocks_for(total, 256), 256, 0, km_cs(stream)>>>(
+        reinterpret_cast<const bf16*>(src0), C0, scale, shift, reinterpret_cast<bf16*>(out), N, D, H,
+        W, relu);
+    KM_LAUNCH_OK("norm_apply_pool_kernel");
+    return KM_OK;
+  }
+  const long long total = (long long)N * D * H * W * ((C0 + C1) / 8);
+  norm_apply_kernel<<<blocks_for(total, 256), 256, 0, km_cs(stream)>>>(
+      reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1,
+      C1 ? D1 : 1, C1 ? H1 : 1, C1 ? W1 : 1, scale, shift, reinterpret_cast<bf16*>(out), N, D, H, W,
+      relu);
+  KM_LAUNCH_OK("norm_apply_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_maxpool2_stats(const void* src, void* out, float* stats, int N, int C, int D,
+                                 int H, int W, km_stream_t stream) {
+  KM_CHECK_ARG(src && out && stats && N > 0, "km_maxpool2_stats: bad arguments");
+  KM_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0,
+               "km_maxpool2_stats: C/8 must divide 256 (C=%d)", C);
+  KM_CHECK_ARG(D >= 2 && H >= 2 && W >= 2, "km_maxpool2_stats: volume too small");
+  maxpool2_stats_kernel<<<dim3(KM_RED_BLOCKS, N), 256, 0, km_cs(stream)>>>(
+      reinterpret_cast<const bf16*>(src), reinterpret_cast<bf16*>(out), stats, N, C, D, H, W);
+  KM_LAUNCH_OK("maxpool2_stats_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_conv3d_stem(const float* x, const float* w, const float* bias,
+                              const float* in_scale, const float* in_shift, void* out, float* stats,
+                              int N, int Cout, int D, int H, int W, int relu, km_stream_t stream) {
+  KM_CHECK_ARG(x && w && out && N > 0 && D > 0 && H > 0 && W > 0, "km_conv3d_stem: bad arguments");
+  KM_CHECK_ARG(Cout == 16 || Cout == 32, "km_conv3d_stem: Cout must be 16 or 32 (got %d)", Cout);
+  const dim3 grid(KM_RED_BLOCKS, N);
+  if (Cout == 16)
+    conv_stem_kernel<16><<<grid, 256, 0, km_cs(stream)>>>(x, w, bias, in_scale, in_shift,
+                                                         reinterpret_cast<bf16*>(out), stats, N, D,
+                                                         H, W, relu);
+  else
+    conv_stem_kernel<32><<<grid, 256, 0, km_cs(stream)>>>(x, w, bias, in_scale, in_shift,
+                                                         reinterpret_cast<bf16*>(out), stats, N, D,
+                                                         H, W, relu);
+  KM_LAUNCH_OK("conv_stem_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int N, int C, int D, int H,
+                                          int W, km_stream_t stream) {
+  KM_CHECK_ARG(src && dst && N > 0 && C > 0, "km_ndhwc_bf16_to_ncdhw_f32: bad arguments");
+  const long long nvox = (long long)D * H * W;
+  ndhwc_to_ncdhw_kernel<<<blocks_for((long long)N * C * nvox, 256), 256, 0, km_cs(stream)>>>(
+      reinterpret_cast<const bf16*>(src), dst, N, C, nvox);
+  KM_LAUNCH_OK("ndhwc_to_ncdhw_kernel");
+  return KM_OK;
+}
+extern "C" int km_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int N, int C, int D, int H,
+                                          int W, km_stream_t stream) {
+  KM_CHECK_ARG(src && dst && N > 0 && C > 0, "km_ncdhw_f32_to_ndhwc_bf16: bad arguments");
+  const long long nvox = (long long)D * H * W;
+  ncdhw_to_ndhwc_kernel<<<blocks_for((long long)N * C * nvox, 256), 256, 0, km_cs(stream)>>>(
+      src, reinterpret_cast<bf16*>(dst), N, C, nvox);
+  KM_LAUNCH_OK("ncdhw_to_ndhwc_kernel");
+  return KM_OK;
+}

@@ -1,0 +1,586 @@
+// tcgen05 implicit-GEMM 3-D convolution for the keypoint backbones.
+//
+// Replaces the cuDNN call sites keymorph/unet3d/buildingblocks.py:50-52 (Conv3d k3 p1, no bias),
+// keymorph/layers.py:173-175 (Conv3d k3 p1 + bias) and keymorph/unet3d/model.py:99,389 (final
+// 1x1x1 conv), the latter fused with keymorph/layers.py:92-134 (ReLU + centre of mass) so that the
+// heat map never has to reach HBM.
+//
+// GEMM view:  D[128 voxels x BN] += A[128 voxels x kc] * B[BN x kc]^T  for every (tap, Cin chunk)
+//   A = activation brick (TW x TH x TD = 128 voxels) shifted by the tap offset, fetched by ONE TMA
+//       box copy from the bf16 NDHWC tensor (out-of-bounds rows are zero-filled = conv padding);
+//   B = weights [tap][Cout][Cin], K-major, fetched by TMA;
+//   D = fp32 accumulator in TMEM, double buffered so the epilogue of tile i overlaps tile i+1.
+// Roles (192 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU -> bf16 staging in smem -> coalesced stores,
+// per-channel sum / sum-of-squares for the next GroupNorm, or centre-of-mass partials).
+#include "km_common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace kmtc;
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kFstagePitch = 33;  // floats, conflict-free transposed access
+
+struct ConvGeom {
+  int N, D, H, W, Cin, Cout;
+  int taps;
+  int kc, chunks;      // Cin chunk per k-iteration, number of chunks
+  int TW, TH, TD;      // output brick, TW*TH*TD == 128
+  int tiles_x, tiles_y, tiles_z;
+  int BN, n_blocks;    // output-channel block
+  int stages;
+  int flags;
+  int has_out;
+  uint32_t a_bytes, b_bytes, b_stride;  // per stage
+  uint32_t off_staging, off_fstage, off_rowinfo, off_stats, off_com, off_scratch, off_bars;
+  uint32_t staging_pitch;               // bytes per staged row (BN*2 + 16)
+  uint32_t tmem_cols;
+  uint32_t idesc;
+  uint32_t sbo, layout;
+  long long total_tiles;
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct TileCoord {
+  int nb, n, x0, y0, z0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, long long t) {
+  TileCoord c;
+  c.nb = (int)(t % g.n_blocks);
+  t /= g.n_blocks;
+  c.x0 = (int)(t % g.tiles_x) * g.TW;
+  t /= g.tiles_x;
+  c.y0 = (int)(t % g.tiles_y) * g.TH;
+  t /= g.tiles_y;
+  c.z0 = (int)(t % g.tiles_z) * g.TD;
+  t /= g.tiles_z;
+  c.n = (int)t;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const ConvGeom g, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+               float* __restrict__ stats, float* __restrict__ com) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_u32);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = g.stages;
+  const uint32_t stage_stride = g.a_bytes + g.b_stride;
+
+  const uint32_t bars = base + g.off_bars;  // full[stages], empty[stages], tfull[2], tempty[2]
+  auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(stages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * stages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * stages + 2 + a); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + g.off_bars + 8u * (2 * stages + 4));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kEpiThreads);
+    }
+    fence_mbar_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), g.tmem_cols);
+    tmem_relinquish();
+  }
+  // zero the per-CTA accumulators
+  {
+    float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);
+    float* s_com = reinterpret_cast<float*>(sm + g.off_com);
+    if (g.flags & KM_CONV_STATS)
+      for (int i = threadIdx.x; i < g.N * g.Cout * 2; i += kThreads) s_stats[i] = 0.f;
+    if (g.flags & KM_CONV_COM)
+      for (int i = threadIdx.x; i < g.N * g.Cout * 4; i += kThreads) s_com[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int kiters = g.taps * g.chunks;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      long long it = 0;
+      for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(g, tile);
+        for (int tap = 0; tap < g.taps; ++tap) {
+          int dz = 0, dy = 0, dx = 0;
+          if (g.taps == 27) {
+            dz = tap / 9 - 1;
+            dy = (tap / 3) % 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          for (int ch = 0; ch < g.chunks; ++ch, ++it) {
+            const int s = (int)(it % stages);
+            const uint32_t ph = (uint32_t)((it / stages) & 1);
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            mbar_arrive_expect_tx(full_bar(s), g.a_bytes + g.b_bytes);
+            const uint32_t a_dst = base + (uint32_t)s * stage_stride;
+            const uint32_t b_dst = a_dst + g.a_bytes;
+            tma_load_5d(a_dst, &tmA, full_bar(s), ch * g.kc, tc.x0 + dx, tc.y0 + dy, tc.z0 + dz,
+                        tc.n);
+            tma_load_3d(b_dst, &tmB, full_bar(s), ch * g.kc, tc.nb * g.BN, tap);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      long long it = 0;
+      long long tcount = 0;
+      const int ksteps = g.kc / 16;
+      for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tcount) {
+        const int acc = (int)(tcount & 1);
+        const uint32_t acc_ph = (uint32_t)((tcount >> 1) & 1);
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.BN);
+        for (int ki = 0; ki < kiters; ++ki, ++it) {
+          const int s = (int)(it % stages);
+          const uint32_t ph = (uint32_t)((it / stages) & 1);
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_addr = base + (uint32_t)s * stage_stride;
+          const uint32_t b_addr = a_addr + g.a_bytes;
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t adesc = umma_smem_desc(a_addr + 32u * kk, g.sbo, g.layout);
+            const uint64_t bdesc = umma_smem_desc(b_addr + 32u * kk, g.sbo, g.layout);
+            umma_bf16(d_tmem, adesc, bdesc, g.idesc, (ki > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // frees the smem stage when these MMAs have read it
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // =============================== epilogue ====================================
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;   // accumulator row == voxel within the brick
+    const int et = row;              // epilogue thread id 0..127
+    uint8_t* staging = sm + g.off_staging;
+    float* fstage = reinterpret_cast<float*>(sm + g.off_fstage);
+    float* rowlin = reinterpret_cast<float*>(sm + g.off_rowinfo);          // [3][128] lz, ly, lx
+    uint8_t* rowvalid = sm + g.off_rowinfo + 3 * kTileM * sizeof(float);   // [128]
+    float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);
+    float* s_com = reinterpret_cast<float*>(sm + g.off_com);
+    float* scratch = reinterpret_cast<float*>(sm + g.off_scratch);         // [2][4][32][4]
+    const bool do_relu = (g.flags & KM_CONV_RELU) != 0;
+    const bool do_stats = (g.flags & KM_CONV_STATS) != 0;
+    const bool do_com = (g.flags & KM_CONV_COM) != 0;
+    const bool has_out = g.has_out != 0;
+    const int BN = g.BN;
+    const uint32_t pitch = g.staging_pitch;
+    const int cpr = BN / 8;  // 16-byte chunks per staged row
+
+    long long tcount = 0;
+    for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tcount) {
+      const TileCoord tc = decode_tile(g, tile);
+      const int acc = (int)(tcount & 1);
+      const uint32_t acc_ph = (uint32_t)((tcount >> 1) & 1);
+      const int n0 = tc.nb * BN;
+
+      // voxel of this row
+      const int tx = row % g.TW;
+      const int ty = (row / g.TW) % g.TH;
+      const int tz = row / (g.TW * g.TH);
+      const int vx = tc.x0 + tx, vy = tc.y0 + ty, vz = tc.z0 + tz;
+      const bool valid = (vx < g.W) && (vy < g.H) && (vz < g.D);
+      rowvalid[row] = valid ? 1 : 0;
+      if (do_com) {
+        rowlin[0 * kTileM + row] = km_linspace(0.f, 1.f, g.D, vz);
+        rowlin[1 * kTileM + row] = km_linspace(0.f, 1.f, g.H, vy);
+        rowlin[2 * kTileM + row] = km_linspace(0.f, 1.f, g.W, vx);
+      }
+
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+
+      if (!do_com) {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + (uint32_t)c0, r);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a = __uint_as_float(r[2 * j]);
+            float b = __uint_as_float(r[2 * j + 1]);
+            if (bias) {
+              a += __ldg(bias + n0 + c0 + 2 * j);
+              b += __ldg(bias + n0 + c0 + 2 * j + 1);
+            }
+            if (do_relu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            }
+            pk[j] = pack_bf16(a, b);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(staging + (size_t)row * pitch + (size_t)c0 * 2);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        epi_bar();
+      } else {
+        // final conv + centre of mass: 32-column chunks, transposed through fp32 smem
+        const int nchunks = BN / 32;
+        for (int cc = 0; cc < nchunks; ++cc) {
+          const int c0 = cc * 32;
+          float* fs = fstage + (size_t)(cc & 1) * kTileM * kFstagePitch;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t)(c0 + 16 * h), r);
+            tmem_ld_wait();
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float v = __uint_as_float(r[j]);
+              if (bias) v += __ldg(bias + n0 + c0 + 16 * h + j);
+              r[j] = __float_as_uint(v);
+              fs[row * kFstagePitch + 16 * h + j] = valid ? fmaxf(v, 0.f) : 0.f;
+            }
+            if (has_out) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                pk[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+              uint4* dst = reinterpret_cast<uint4*>(staging + (size_t)row * pitch +
+                                                    (size_t)(c0 + 16 * h) * 2);
+              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+          if (cc == nchunks - 1) {
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+          }
+          epi_bar();
+          // combine the previous chunk's quarter partials (written before this barrier)
+          if (cc > 0 && et < 32) {
+            const float* sc = scratch + (size_t)((cc - 1) & 1) * 4 * 32 * 4;
+            float* dstc = s_com + ((size_t)tc.n * g.Cout + n0 + (cc - 1) * 32 + et) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              dstc[k] += ((sc[(0 * 32 + et) * 4 + k] + sc[(1 * 32 + et) * 4 + k]) +
+                          sc[(2 * 32 + et) * 4 + k]) + sc[(3 * 32 + et) * 4 + k];
+          }
+          // this thread: column (et & 31), rows [32*(et>>5), +32)
+          {
+            const int col = et & 31, rq = et >> 5;
+            float s0 = 0.f, sz = 0.f, sy = 0.f, sx = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              const int r2 = rq * 32 + rr;
+              const float hv = fs[r2 * kFstagePitch + col];
+              s0 += hv;
+              sz = fmaf(hv, rowlin[0 * kTileM + r2], sz);
+              sy = fmaf(hv, rowlin[1 * kTileM + r2], sy);
+              sx = fmaf(hv, rowlin[2 * kTileM + r2], sx);
+            }
+            float* sc = scratch + (size_t)(cc & 1) * 4 * 32 * 4 + (size_t)(rq * 32 + col) * 4;
+            sc[0] = s0;
+            sc[1] = sz;
+            sc[2] = sy;
+            sc[3] = sx;
+          }
+        }
+        epi_bar();
+        if (et < 32) {
+          const int cc = nchunks - 1;
+          const float* sc = scratch + (size_t)(cc & 1) * 4 * 32 * 4;
+          float* dstc = s_com + ((size_t)tc.n * g.Cout + n0 + cc * 32 + et) * 4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            dstc[k] += ((sc[(0 * 32 + et) * 4 + k] + sc[(1 * 32 + et) * 4 + k]) +
+                        sc[(2 * 32 + et) * 4 + k]) + sc[(3 * 32 + et) * 4 + k];
+        }
+      }
+
+      // ---- staged bf16 tile -> global (coalesced 16-byte chunks) + per-channel stats ----
+      if (has_out) {
+        const int total_chunks = kTileM * cpr;
+        for (int id = et; id < total_chunks; id += kEpiThreads) {
+          const int r2 = id / cpr, j = id % cpr;
+          if (!rowvalid[r2]) continue;
+          const int x2 = tc.x0 + r2 % g.TW;
+          const int y2 = tc.y0 + (r2 / g.TW) % g.TH;
+          const int z2 = tc.z0 + r2 / (g.TW * g.TH);
+          const size_t vox = (((size_t)tc.n * g.D + z2) * g.H + y2) * g.W + x2;
+          const uint4 v = *reinterpret_cast<const uint4*>(staging + (size_t)r2 * pitch + j * 16);
+          *reinterpret_cast<uint4*>(out + vox * g.Cout + n0 + j * 8) = v;
+        }
+      }
+      if (do_stats) {
+        for (int col = et; col < BN; col += kEpiThreads) {
+          float s = 0.f, ss = 0.f;
+          for (int r2 = 0; r2 < kTileM; ++r2) {
+            if (!rowvalid[r2]) continue;
+            const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
+                staging + (size_t)r2 * pitch + (size_t)col * 2));
+            s += v;
+            ss = fmaf(v, v, ss);
+          }
+          float* d = s_stats + ((size_t)tc.n * g.Cout + n0 + col) * 2;
+          d[0] += s;
+          d[1] += ss;
+        }
+      }
+      epi_bar();  // staging / rowinfo may be overwritten by the next tile
+    }
+
+    // ---- per-CTA partials -> global ----
+    epi_bar();
+    if (do_stats) {
+      float* dst = stats + (size_t)blockIdx.x * g.N * g.Cout * 2;
+      for (int i = et; i < g.N * g.Cout * 2; i += kEpiThreads) dst[i] = s_stats[i];
+    }
+    if (do_com) {
+      float* dst = com + (size_t)blockIdx.x * g.N * g.Cout * 4;
+      for (int i = et; i < g.N * g.Cout * 4; i += kEpiThreads) dst[i] = s_com[i];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, g.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight repack: fp32 (Cout, Cin, taps) -> bf16 [tap][Cout][Cin]
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p,
+                                    int Cout, int Cin, int taps) {
+  const long long total = (long long)taps * Cout * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int co = (int)((i / Cin) % Cout);
+    const int tap = (int)(i / ((long long)Cin * Cout));
+    p[i] = __float2bfloat16_rn(w[((long long)co * Cin + ci) * taps + tap]);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+int g_sm_count = 0;
+int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" int km_sm_count(void) { return sm_count(); }
+extern "C" int km_conv_nparts(void) { return sm_count(); }
+
+extern "C" int km_pack_weights(const float* w, void* packed, int Cout, int Cin, int taps,
+                               km_stream_t stream) {
+  KM_CHECK_ARG(w && packed && Cout > 0 && Cin > 0 && (taps == 27 || taps == 1),
+               "km_pack_weights: bad arguments");
+  const long long total = (long long)taps * Cout * Cin;
+  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  pack_weights_kernel<<<blocks, 256, 0, km_cs(stream)>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin, taps);
+  KM_LAUNCH_OK("pack_weights_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, void* out,
+                            float* stats, float* com, int N, int Cin, int Cout, int D, int H,
+                            int W, int taps, int flags, km_stream_t stream) {
+  KM_CHECK_ARG(x && wp, "km_conv3d_tc: null input");
+  KM_CHECK_ARG(taps == 27 || taps == 1, "km_conv3d_tc: taps must be 27 or 1");
+  KM_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0, "km_conv3d_tc: bad shape");
+  KM_CHECK_ARG(Cin % 16 == 0 && Cin >= 16, "km_conv3d_tc: Cin must be a multiple of 16 (got %d)",
+               Cin);
+  KM_CHECK_ARG(Cout % 16 == 0 && Cout >= 16, "km_conv3d_tc: Cout must be a multiple of 16 (got %d)",
+               Cout);
+  KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "km_conv3d_tc: KM_CONV_STATS needs stats");
+  KM_CHECK_ARG(!(flags & KM_CONV_COM) || com, "km_conv3d_tc: KM_CONV_COM needs com");
+  KM_CHECK_ARG(out || (flags & KM_CONV_COM), "km_conv3d_tc: out may only be NULL with KM_CONV_COM");
+  KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)out & 15) == 0,
+               "km_conv3d_tc: pointers must be 16-byte aligned");
+
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = N; g.D = D; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
+  g.taps = taps;
+  g.flags = flags;
+  g.has_out = out ? 1 : 0;
+  g.kc = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
+  g.chunks = Cin / g.kc;
+  // output brick: as long a W-run as possible, then H, then D (power-of-two factors of 128)
+  auto pow2_le = [](int v, int cap) { int p = 1; while (p * 2 <= v && p * 2 <= cap) p *= 2; return p; };
+  g.TW = pow2_le(W, 128);
+  g.TH = pow2_le(H, 128 / g.TW);
+  g.TD = 128 / (g.TW * g.TH);
+  KM_CHECK_ARG(g.TD <= D, "km_conv3d_tc: volume %dx%dx%d has fewer than 128 voxels per brick", D, H, W);
+  g.tiles_x = (W + g.TW - 1) / g.TW;
+  g.tiles_y = (H + g.TH - 1) / g.TH;
+  g.tiles_z = (D + g.TD - 1) / g.TD;
+  // output-channel block: largest divisor of Cout that is <= 256 and a multiple of 16 (32 for CoM)
+  const int gran = (flags & KM_CONV_COM) ? 32 : 16;
+  KM_CHECK_ARG(Cout % gran == 0, "km_conv3d_tc: Cout must be a multiple of %d in this mode", gran);
+  g.BN = 0;
+  for (int bn = 256; bn >= gran; bn -= gran)
+    if (Cout % bn == 0) { g.BN = bn; break; }
+  KM_CHECK_ARG(g.BN > 0, "km_conv3d_tc: no channel block for Cout=%d", Cout);
+  g.n_blocks = Cout / g.BN;
+  g.total_tiles = (long long)N * g.tiles_z * g.tiles_y * g.tiles_x * g.n_blocks;
+
+  const int row_bytes = g.kc * 2;
+  g.layout = umma_layout_for_row_bytes(row_bytes);
+  g.sbo = 8u * (uint32_t)row_bytes;
+  g.idesc = umma_idesc_bf16(kTileM, g.BN);
+  g.a_bytes = (uint32_t)kTileM * row_bytes;
+  g.b_bytes = (uint32_t)g.BN * row_bytes;
+  g.b_stride = round_up(g.b_bytes, 1024);
+  uint32_t cols = 32;
+  while (cols < 2u * (uint32_t)g.BN) cols *= 2;
+  g.tmem_cols = cols;
+  KM_CHECK_ARG(cols <= 512, "km_conv3d_tc: TMEM overflow");
+
+  // shared-memory carve-up (offsets relative to the 1024-aligned base)
+  const uint32_t kSmemMax = 232448 - 1024;  // 227 KB minus alignment slack
+  g.staging_pitch = (uint32_t)g.BN * 2 + 16;
+  uint32_t fixed = 0;
+  const uint32_t staging_bytes = g.has_out ? round_up(kTileM * g.staging_pitch, 16) : 0;
+  const uint32_t fstage_bytes = (flags & KM_CONV_COM) ? 2u * kTileM * kFstagePitch * 4u : 0;
+  const uint32_t rowinfo_bytes = 3u * kTileM * 4u + kTileM;
+  const uint32_t stats_bytes = (flags & KM_CONV_STATS) ? (uint32_t)N * Cout * 2u * 4u : 0;
+  const uint32_t com_bytes = (flags & KM_CONV_COM) ? (uint32_t)N * Cout * 4u * 4u : 0;
+  const uint32_t scratch_bytes = (flags & KM_CONV_COM) ? 2u * 4u * 32u * 4u * 4u : 0;
+  const uint32_t bars_bytes = 8u * (2u * 8u + 4u) + 16u;
+  fixed = staging_bytes + fstage_bytes + rowinfo_bytes + stats_bytes + com_bytes + scratch_bytes +
+          bars_bytes + 64;
+  const uint32_t stage_stride = g.a_bytes + g.b_stride;
+  KM_CHECK_ARG(fixed + 2 * stage_stride <= kSmemMax,
+               "km_conv3d_tc: shared memory budget exceeded (N*Cout too large: N=%d Cout=%d)", N, Cout);
+  int stages = (int)((kSmemMax - fixed) / stage_stride);
+  if (stages > 8) stages = 8;
+  const int kiters = taps * g.chunks;
+  (void)kiters;
+  g.stages = stages;
+  uint32_t off = (uint32_t)stages * stage_stride;
+  g.off_staging = off; off += staging_bytes;
+  g.off_fstage = off; off += fstage_bytes;
+  g.off_rowinfo = off; off += round_up(rowinfo_bytes, 16);
+  g.off_stats = off; off += stats_bytes;
+  g.off_com = off; off += com_bytes;
+  g.off_scratch = off; off += scratch_bytes;
+  off = round_up(off, 8);
+  g.off_bars = off; off += bars_bytes;
+  const uint32_t smem_bytes = off + 1024;
+  KM_CHECK_ARG(smem_bytes <= 232448, "km_conv3d_tc: shared memory overflow (%u)", smem_bytes);
+
+  PFN_encodeTiled encode = get_encode_fn();
+  if (!encode) {
+    km_set_error("km_conv3d_tc: cuTensorMapEncodeTiled unavailable");
+    return KM_ECUDA;
+  }
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                   : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2,
+                             (cuuint64_t)H * W * Cin * 2, (cuuint64_t)D * H * W * Cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)g.kc, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TD, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      km_set_error("km_conv3d_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+      return KM_ECUDA;
+    }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)g.kc, (cuuint32_t)g.BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wp), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      km_set_error("km_conv3d_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+      return KM_ECUDA;
+    }
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    232448));
+    attr_set = true;
+  }
+  const int nsm = sm_count();
+  const int grid = (int)(g.total_tiles < nsm ? g.total_tiles : nsm);
+  // partial slots of CTAs that are not launched must still be defined
+  if (grid < nsm) {
+    if (flags & KM_CONV_STATS)
+      KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * Cout * 2 * sizeof(float), km_cs(stream)));
+    if (flags & KM_CONV_COM)
+      KM_CUDA_OK(cudaMemsetAsync(com, 0, (size_t)nsm * N * Cout * 4 * sizeof(float), km_cs(stream)));
+  }
+  conv_tc_kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(
+      tmA, tmB, g, bias, reinterpret_cast<__nv_bfloat16*>(out), stats, com);
+  KM_LAUNCH_OK("conv_tc_kernel");
+  return KM_OK;
+}

@@ -1,0 +1,626 @@
+// Dense 3-D warp (grid_sample), flow-field generation and the fused warp + loss kernels.
+//
+// Reference call sites:
+//   keymorph/utils.py:14-21            align_img = F.grid_sample(x, grid, mode, "border", align_corners=False)
+//   keymorph/utils.py:387-398          uniform_norm_grid (linspace(-1,1,S)^3, 'ij' order)
+//   keymorph/transformations.py:37-114 AffineTransform.get_flow_field / transformed points
+//   keymorph/keypoint_aligners.py:365-449 TPS.get_flow_field / transform_points
+//   keymorph/loss_ops.py:9-63          MSELoss / DiceLoss
+// All kernels are HBM-bound streaming kernels: 4 consecutive x-voxels per thread, 16-byte loads
+// and stores on the contiguous streams (grid, fixed, out), gathers through the read-only path.
+#include "km_common.cuh"
+
+namespace {
+
+int g_tps_fast = 1;
+
+// ---- ATen grid_sampler_3d source-index arithmetic (align_corners=False, padding "border"),
+// written without FMA contraction so that it rounds like the scalar CPU reference.
+__device__ __forceinline__ float src_index(float g, int size) {
+  float v = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)size), 1.f), 0.5f);
+  v = fminf((float)(size - 1), fmaxf(v, 0.f));
+  return v;
+}
+
+struct Tri {
+  int x0, y0, z0;
+  float ix, iy, iz;
+};
+
+__device__ __forceinline__ Tri make_tri(float gx, float gy, float gz, int D, int H, int W) {
+  Tri t;
+  t.ix = src_index(gx, W);
+  t.iy = src_index(gy, H);
+  t.iz = src_index(gz, D);
+  t.x0 = (int)floorf(t.ix);
+  t.y0 = (int)floorf(t.iy);
+  t.z0 = (int)floorf(t.iz);
+  return t;
+}
+
+// trilinear gather; corners outside the volume are skipped exactly like ATen does
+__device__ __forceinline__ float tri_sample(const float* __restrict__ vol, const Tri& t, int D,
+                                            int H, int W) {
+  const float x0f = (float)t.x0, y0f = (float)t.y0, z0f = (float)t.z0;
+  const float wx1 = __fsub_rn(t.ix, x0f), wx0 = __fsub_rn(x0f + 1.f, t.ix);
+  const float wy1 = __fsub_rn(t.iy, y0f), wy0 = __fsub_rn(y0f + 1.f, t.iy);
+  const float wz1 = __fsub_rn(t.iz, z0f), wz0 = __fsub_rn(z0f + 1.f, t.iz);
+  const bool x1ok = t.x0 + 1 < W, y1ok = t.y0 + 1 < H, z1ok = t.z0 + 1 < D;
+  const size_t HW = (size_t)H * W;
+  const float* p = vol + (size_t)t.z0 * HW + (size_t)t.y0 * W + t.x0;
+  float acc = 0.f;
+  // order: tnw, tne, tsw, tse, bnw, bne, bsw, bse (t = z0, n = y0, w = x0)
+  acc = __fadd_rn(acc, __fmul_rn(__ldg(p), __fmul_rn(__fmul_rn(wx0, wy0), wz0)));
+  if (x1ok) acc = __fadd_rn(acc, __fmul_rn(__ldg(p + 1), __fmul_rn(__fmul_rn(wx1, wy0), wz0)));
+  if (y1ok) acc = __fadd_rn(acc, __fmul_rn(__ldg(p + W), __fmul_rn(__fmul_rn(wx0, wy1), wz0)));
+  if (x1ok && y1ok)
+    acc = __fadd_rn(acc, __fmul_rn(__ldg(p + W + 1), __fmul_rn(__fmul_rn(wx1, wy1), wz0)));
+  if (z1ok) {
+    const float* q = p + HW;
+    acc = __fadd_rn(acc, __fmul_rn(__ldg(q), __fmul_rn(__fmul_rn(wx0, wy0), wz1)));
+    if (x1ok) acc = __fadd_rn(acc, __fmul_rn(__ldg(q + 1), __fmul_rn(__fmul_rn(wx1, wy0), wz1)));
+    if (y1ok) acc = __fadd_rn(acc, __fmul_rn(__ldg(q + W), __fmul_rn(__fmul_rn(wx0, wy1), wz1)));
+    if (x1ok && y1ok)
+      acc = __fadd_rn(acc, __fmul_rn(__ldg(q + W + 1), __fmul_rn(__fmul_rn(wx1, wy1), wz1)));
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float nearest_sample(const float* __restrict__ vol, const Tri& t, int H,
+                                                int W) {
+  // std::nearbyint: round half to even
+  const int x = (int)rintf(t.ix), y = (int)rintf(t.iy), z = (int)rintf(t.iz);
+  return __ldg(vol + ((size_t)z * H + y) * W + x);
+}
+
+// ---- coordinate generators: (z,y,x) voxel -> grid_sample (gx,gy,gz) ----------------------
+struct AffineCoord {
+  float m[12];  // rows in (z,y,x) order
+  __device__ __forceinline__ void operator()(float pz, float py, float px, float& gx, float& gy,
+                                             float& gz) const {
+    gz = fmaf(m[0], pz, fmaf(m[1], py, fmaf(m[2], px, m[3])));
+    gy = fmaf(m[4], pz, fmaf(m[5], py, fmaf(m[6], px, m[7])));
+    gx = fmaf(m[8], pz, fmaf(m[9], py, fmaf(m[10], px, m[11])));
+  }
+};
+
+// TPS radial basis, keymorph/keypoint_aligners.py:322-339:
+//   r = sqrt(|a-b|^2 + 1e-6);  U = r^2 * log(r + 1e-6)
+template <bool FAST>
+__device__ __forceinline__ float tps_u(float d2) {
+  const float s = d2 + 1e-6f;
+  if (FAST) {
+    // log(r + e) = 0.5*log(s) + log1p(e/r) ~= 0.5*ln2*lg2(s) + e*rsqrt(s)   (e/r <= 1e-3)
+    const float l = fmaf(0.34657359028f, __log2f(s), 1e-6f * rsqrtf(s));
+    return s * l;
+  } else {
+    const float r = sqrtf(s);
+    return (r * r) * logf(r + 1e-6f);
+  }
+}
+
+// smem layout for TPS: c4[t] = (cz, cy, cx, 0), w4[t] = (wz, wy, wx, 0); aff[12] = rows 1,z,y,x
+template <bool FAST>
+__device__ __forceinline__ void tps_eval(const float4* __restrict__ c4, const float4* __restrict__ w4,
+                                         const float* __restrict__ aff, int K, float pz, float py,
+                                         float px, float& oz, float& oy, float& ox) {
+  float az = 0.f, ay = 0.f, ax = 0.f;
+#pragma unroll 4
+  for (int t = 0; t < K; ++t) {
+    const float4 c = c4[t];
+    const float4 w = w4[t];
+    const float dz = pz - c.x, dy = py - c.y, dx = px - c.z;
+    const float u = tps_u<FAST>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    az = fmaf(u, w.x, az);
+    ay = fmaf(u, w.y, ay);
+    ax = fmaf(u, w.z, ax);
+  }
+  // z = [1, p] . affine  (keymorph/keypoint_aligners.py:427-433), out = z + b
+  oz = (aff[0] + aff[3] * pz + aff[6] * py + aff[9] * px) + az;
+  oy = (aff[1] + aff[4] * pz + aff[7] * py + aff[10] * px) + ay;
+  ox = (aff[2] + aff[5] * pz + aff[8] * py + aff[11] * px) + ax;
+}
+
+__device__ __forceinline__ void load_tps_smem(const float* __restrict__ ctrl,
+                                              const float* __restrict__ theta, int K, float4* c4,
+                                              float4* w4, float* aff) {
+  for (int t = threadIdx.x; t < K; t += blockDim.x) {
+    c4[t] = make_float4(ctrl[t * 3 + 0], ctrl[t * 3 + 1], ctrl[t * 3 + 2], 0.f);
+    w4[t] = make_float4(theta[t * 3 + 0], theta[t * 3 + 1], theta[t * 3 + 2], 0.f);
+  }
+  for (int i = threadIdx.x; i < 12; i += blockDim.x) aff[i] = theta[K * 3 + i];
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// flow fields
+__global__ void __launch_bounds__(256)
+flow_affine_kernel(const float* __restrict__ mat, float* __restrict__ grid, int D, int H, int W) {
+  const int n = blockIdx.y;
+  AffineCoord ac;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) ac.m[i] = __ldg(mat + n * 12 + i);
+  const long long nvox = (long long)D * H * W;
+  float* gn = grid + (size_t)n * nvox * 3;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvox;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(v % W), y = (int)((v / W) % H), z = (int)(v / ((long long)W * H));
+    float gx, gy, gz;
+    ac(km_linspace(-1.f, 1.f, D, z), km_linspace(-1.f, 1.f, H, y), km_linspace(-1.f, 1.f, W, x), gx,
+       gy, gz);
+    gn[v * 3 + 0] = gx;
+    gn[v * 3 + 1] = gy;
+    gn[v * 3 + 2] = gz;
+  }
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(256)
+flow_tps_kernel(const float* __restrict__ ctrl, const float* __restrict__ theta,
+                float* __restrict__ grid, int K, int D, int H, int W) {
+  extern __shared__ float4 s4[];
+  float4* c4 = s4;
+  float4* w4 = s4 + K;
+  float* aff = reinterpret_cast<float*>(s4 + 2 * K);
+  const int n = blockIdx.y;
+  load_tps_smem(ctrl + (size_t)n * K * 3, theta + (size_t)n * (K + 4) * 3, K, c4, w4, aff);
+  const long long nvox = (long long)D * H * W;
+  float* gn = grid + (size_t)n * nvox * 3;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvox;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(v % W), y = (int)((v / W) % H), z = (int)(v / ((long long)W * H));
+    float oz, oy, ox;
+    tps_eval<FAST>(c4, w4, aff, K, km_linspace(-1.f, 1.f, D, z), km_linspace(-1.f, 1.f, H, y),
+                   km_linspace(-1.f, 1.f, W, x), oz, oy, ox);
+    gn[v * 3 + 0] = ox;
+    gn[v * 3 + 1] = oy;
+    gn[v * 3 + 2] = oz;
+  }
+}
+
+__global__ void points_affine_kernel(const float* __restrict__ mat, const float* __restrict__ pts,
+                                     float* __restrict__ out, int P) {
+  const int n = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float* m = mat + n * 12;
+  const float* q = pts + ((size_t)n * P + p) * 3;
+  float* o = out + ((size_t)n * P + p) * 3;
+  const float a = q[0], b = q[1], c = q[2];
+  o[0] = fmaf(m[0], a, fmaf(m[1], b, fmaf(m[2], c, m[3])));
+  o[1] = fmaf(m[4], a, fmaf(m[5], b, fmaf(m[6], c, m[7])));
+  o[2] = fmaf(m[8], a, fmaf(m[9], b, fmaf(m[10], c, m[11])));
+}
+
+__global__ void __launch_bounds__(128)
+points_tps_kernel(const float* __restrict__ ctrl, const float* __restrict__ theta,
+                  const float* __restrict__ pts, float* __restrict__ out, int K, int P) {
+  extern __shared__ float4 s4[];
+  float4* c4 = s4;
+  float4* w4 = s4 + K;
+  float* aff = reinterpret_cast<float*>(s4 + 2 * K);
+  const int n = blockIdx.y;
+  load_tps_smem(ctrl + (size_t)n * K * 3, theta + (size_t)n * (K + 4) * 3, K, c4, w4, aff);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float* q = pts + ((size_t)n * P + p) * 3;
+  float oz, oy, ox;
+  tps_eval<false>(c4, w4, aff, K, q[0], q[1], q[2], oz, oy, ox);
+  float* o = out + ((size_t)n * P + p) * 3;
+  o[0] = oz;
+  o[1] = oy;
+  o[2] = ox;
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone grid_sample: 4 output voxels per thread along W (V = 4) or 1 (V = 1)
+template <int V>
+__global__ void __launch_bounds__(256)
+grid_sample_kernel(const float* __restrict__ x, const float* __restrict__ grid,
+                   float* __restrict__ out, int C, int Di, int Hi, int Wi, long long nvo,
+                   int mode) {
+  const int n = blockIdx.y;
+  const long long ngroups = nvo / V;
+  const size_t in_vol = (size_t)Di * Hi * Wi;
+  const float* gn = grid + (size_t)n * nvo * 3;
+  for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < ngroups;
+       gidx += (long long)gridDim.x * blockDim.x) {
+    float g[3 * V];
+    if (V == 4) {
+      const float4* g4 = reinterpret_cast<const float4*>(gn + gidx * 12);
+      const float4 a = __ldg(g4), b = __ldg(g4 + 1), c = __ldg(g4 + 2);
+      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
+      g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+      g[8] = c.x; g[9] = c.y; g[10] = c.z; g[11] = c.w;
+    } else {
+      g[0] = __ldg(gn + gidx * 3);
+      g[1] = __ldg(gn + gidx * 3 + 1);
+      g[2] = __ldg(gn + gidx * 3 + 2);
+    }
+    Tri t[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) t[k] = make_tri(g[3 * k], g[3 * k + 1], g[3 * k + 2], Di, Hi, Wi);
+    for (int c = 0; c < C; ++c) {
+      const float* vol = x + ((size_t)n * C + c) * in_vol;
+      float r[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k)
+        r[k] = (mode == KM_INTERP_NEAREST) ? nearest_sample(vol, t[k], Hi, Wi)
+                                           : tri_sample(vol, t[k], Di, Hi, Wi);
+      float* o = out + ((size_t)n * C + c) * nvo + gidx * V;
+      if (V == 4)
+        *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+      else
+        o[0] = r[0];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused warp (+ store) (+ loss partials).  grid (KM_RED_BLOCKS, N), 256 threads.
+// partials: [gridDim.x][N][C][4] floats = sum (a-f)^2, sum a*f, sum a*a, sum f*f
+template <int COORD, int CCH, bool FAST>
+__global__ void __launch_bounds__(256)
+warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict__ theta, int K,
+                 const float* __restrict__ grid, const float* __restrict__ moving,
+                 const float* __restrict__ fixed, float* __restrict__ out,
+                 float* __restrict__ partials, int N, int C, int D, int H, int W, int mode) {
+  extern __shared__ float4 s4[];
+  __shared__ float red[8][CCH * 4];
+  const int n = blockIdx.y;
+  const long long nvox = (long long)D * H * W;
+  AffineCoord ac;
+  float4* c4 = s4;
+  float4* w4 = s4 + K;
+  float* aff = reinterpret_cast<float*>(s4 + 2 * K);
+  if (COORD == KM_COORD_AFFINE) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) ac.m[i] = __ldg(mat_or_ctrl + n * 12 + i);
+  } else if (COORD == KM_COORD_TPS) {
+    load_tps_smem(mat_or_ctrl + (size_t)n * K * 3, theta + (size_t)n * (K + 4) * 3, K, c4, w4, aff);
+  }
+  const float* gn = (COORD == KM_COORD_GRID) ? grid + (size_t)n * nvox * 3 : nullptr;
+  const long long ngroups = nvox / 4;  // W % 4 == 0 is checked on the host
+  const int W4 = W / 4;
+
+  for (int cbase = 0; cbase < C; cbase += CCH) {
+    const int cn = min(CCH, C - cbase);
+    float acc[CCH][4];
+#pragma unroll
+    for (int c = 0; c < CCH; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+
+    for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < ngroups;
+         gidx += (long long)gridDim.x * blockDim.x) {
+      Tri t[4];
+      if (COORD == KM_COORD_GRID) {
+        const float4* g4 = reinterpret_cast<const float4*>(gn + gidx * 12);
+        const float4 a = __ldg(g4), b = __ldg(g4 + 1), c = __ldg(g4 + 2);
+        t[0] = make_tri(a.x, a.y, a.z, D, H, W);
+        t[1] = make_tri(a.w, b.x, b.y, D, H, W);
+        t[2] = make_tri(b.z, b.w, c.x, D, H, W);
+        t[3] = make_tri(c.y, c.z, c.w, D, H, W);
+      } else {
+        const int xg = (int)(gidx % W4) * 4;
+        const int y = (int)((gidx / W4) % H);
+        const int z = (int)(gidx / ((long long)W4 * H));
+        const float pz = km_linspace(-1.f, 1.f, D, z), py = km_linspace(-1.f, 1.f, H, y);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float px = km_linspace(-1.f, 1.f, W, xg + k);
+          float gx, gy, gz;
+          if (COORD == KM_COORD_AFFINE) {
+            ac(pz, py, px, gx, gy, gz);
+          } else {
+            tps_eval<FAST>(c4, w4, aff, K, pz, py, px, gz, gy, gx);
+          }
+          t[k] = make_tri(gx, gy, gz, D, H, W);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CCH; ++c) {
+        if (c < cn) {
+          const size_t ch = (size_t)n * C + cbase + c;
+          const float* vol = moving + ch * nvox;
+          float r[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            r[k] = (mode == KM_INTERP_NEAREST) ? nearest_sample(vol, t[k], H, W)
+                                               : tri_sample(vol, t[k], D, H, W);
+          if (out)
+            *reinterpret_cast<float4*>(out + ch * nvox + gidx * 4) =
+                make_float4(r[0], r[1], r[2], r[3]);
+          if (fixed) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(fixed + ch * nvox) + gidx);
+            const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float d = r[k] - fv[k];
+              acc[c][0] = fmaf(d, d, acc[c][0]);
+              acc[c][1] = fmaf(r[k], fv[k], acc[c][1]);
+              acc[c][2] = fmaf(r[k], r[k], acc[c][2]);
+              acc[c][3] = fmaf(fv[k], fv[k], acc[c][3]);
+            }
+          }
+        }
+      }
+    }
+    if (fixed) {
+#pragma unroll
+      for (int c = 0; c < CCH; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[c][k] = km_warp_sum(acc[c][k]);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int c = 0; c < CCH; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) red[threadIdx.x >> 5][c * 4 + k] = acc[c][k];
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < cn * 4; i += blockDim.x) {
+        float a = 0.f;
+        for (int wv = 0; wv < 8; ++wv) a += red[wv][i];
+        partials[(((size_t)blockIdx.x * N + n) * C + cbase) * 4 + i] = a;
+      }
+    }
+  }
+}
+
+// partials [nparts][NC][4] -> sums[NC][4] (fp64)
+__global__ void sum_partials4_kernel(const float* __restrict__ partials, int nparts, int NC4,
+                                     double* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC4) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)partials[(size_t)p * NC4 + i];
+  sums[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// pair statistics (MSE / Dice), grid (KM_RED_BLOCKS, C, N): one channel per blockIdx.y
+__global__ void __launch_bounds__(KM_RED_THREADS)
+pair_stats_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                  const int32_t* __restrict__ labels, float* __restrict__ partials, int N, int C,
+                  long long M) {
+  const int c = blockIdx.y, n = blockIdx.z;
+  const float* p = pred + ((size_t)n * C + c) * M;
+  const float* t = target + ((size_t)n * C + c) * M;
+  const int32_t* lab = labels ? labels + (size_t)n * M : nullptr;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float tv = __ldg(t + i);
+    const float pv = lab ? ((__ldg(lab + i) == c) ? 1.f : 0.f) : __ldg(p + i);
+    const float d = pv - tv;
+    a0 = fmaf(d, d, a0);
+    a1 = fmaf(pv, tv, a1);
+    a2 = fmaf(pv, pv, a2);
+    a3 = fmaf(tv, tv, a3);
+  }
+  __shared__ float red[KM_RED_THREADS / 32][4];
+  a0 = km_warp_sum(a0);
+  a1 = km_warp_sum(a1);
+  a2 = km_warp_sum(a2);
+  a3 = km_warp_sum(a3);
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5][0] = a0;
+    red[threadIdx.x >> 5][1] = a1;
+    red[threadIdx.x >> 5][2] = a2;
+    red[threadIdx.x >> 5][3] = a3;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float a = 0.f;
+    for (int wv = 0; wv < KM_RED_THREADS / 32; ++wv) a += red[wv][threadIdx.x];
+    partials[(((size_t)blockIdx.x * N + n) * C + c) * 4 + threadIdx.x] = a;
+  }
+}
+
+// torch.argmax over the channel dim: first maximal value wins, NaN counts as maximal
+__global__ void __launch_bounds__(256)
+argmax_channels_kernel(const float* __restrict__ pred, int32_t* __restrict__ labels, int C,
+                       long long M) {
+  const int n = blockIdx.y;
+  const float* p = pred + (size_t)n * C * M;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M;
+       i += (long long)gridDim.x * blockDim.x) {
+    float best = __ldg(p + i);
+    int bi = 0;
+    for (int c = 1; c < C; ++c) {
+      const float v = __ldg(p + (size_t)c * M + i);
+      if (!(best != best) && (v > best || v != v)) {
+        best = v;
+        bi = c;
+      }
+    }
+    labels[(size_t)n * M + i] = bi;
+  }
+}
+
+inline int blocks_for(long long items, int threads, int cap) {
+  long long b = (items + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+extern "C" int km_set_option(int key, int value) {
+  if (key == KM_OPT_TPS_FAST) {
+    g_tps_fast = value ? 1 : 0;
+    return KM_OK;
+  }
+  km_set_error("km_set_option: unknown key %d", key);
+  return KM_EINVAL;
+}
+
+extern "C" int km_grid_sample3d(const float* x, const float* grid, float* out, int N, int C, int Di,
+                                int Hi, int Wi, int Do, int Ho, int Wo, int mode,
+                                km_stream_t stream) {
+  KM_CHECK_ARG(x && grid && out, "km_grid_sample3d: null pointer");
+  KM_CHECK_ARG(N > 0 && C > 0 && Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0,
+               "km_grid_sample3d: bad shape");
+  KM_CHECK_ARG(mode == KM_INTERP_BILINEAR || mode == KM_INTERP_NEAREST, "km_grid_sample3d: bad mode");
+  const long long nvo = (long long)Do * Ho * Wo;
+  const bool vec = (nvo % 4 == 0) && (((uintptr_t)grid & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  if (vec) {
+    const dim3 g(blocks_for(nvo / 4, 256, 148 * 16), N);
+    grid_sample_kernel<4><<<g, 256, 0, km_cs(stream)>>>(x, grid, out, C, Di, Hi, Wi, nvo, mode);
+  } else {
+    const dim3 g(blocks_for(nvo, 256, 148 * 16), N);
+    grid_sample_kernel<1><<<g, 256, 0, km_cs(stream)>>>(x, grid, out, C, Di, Hi, Wi, nvo, mode);
+  }
+  KM_LAUNCH_OK("grid_sample_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_flow_field_affine(const float* mat, float* grid, int N, int D, int H, int W,
+                                    km_stream_t stream) {
+  KM_CHECK_ARG(mat && grid && N > 0 && D > 0 && H > 0 && W > 0, "km_flow_field_affine: bad arguments");
+  const dim3 g(blocks_for((long long)D * H * W, 256, 148 * 8), N);
+  flow_affine_kernel<<<g, 256, 0, km_cs(stream)>>>(mat, grid, D, H, W);
+  KM_LAUNCH_OK("flow_affine_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_flow_field_tps(const float* ctrl, const float* theta, float* grid, int N, int K,
+                                 int D, int H, int W, km_stream_t stream) {
+  KM_CHECK_ARG(ctrl && theta && grid && N > 0 && K > 0 && D > 0 && H > 0 && W > 0,
+               "km_flow_field_tps: bad arguments");
+  const size_t smem = (size_t)(2 * K + 3) * sizeof(float4);
+  KM_CHECK_ARG(smem <= 48 * 1024, "km_flow_field_tps: K=%d too large", K);
+  const dim3 g(blocks_for((long long)D * H * W, 256, 148 * 8), N);
+  if (g_tps_fast)
+    flow_tps_kernel<true><<<g, 256, smem, km_cs(stream)>>>(ctrl, theta, grid, K, D, H, W);
+  else
+    flow_tps_kernel<false><<<g, 256, smem, km_cs(stream)>>>(ctrl, theta, grid, K, D, H, W);
+  KM_LAUNCH_OK("flow_tps_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_points_transform_affine(const float* mat, const float* pts, float* out, int N,
+                                          int P, km_stream_t stream) {
+  KM_CHECK_ARG(mat && pts && out && N > 0 && P > 0, "km_points_transform_affine: bad arguments");
+  points_affine_kernel<<<dim3((P + 127) / 128, N), 128, 0, km_cs(stream)>>>(mat, pts, out, P);
+  KM_LAUNCH_OK("points_affine_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_points_transform_tps(const float* ctrl, const float* theta, const float* pts,
+                                       float* out, int N, int K, int P, km_stream_t stream) {
+  KM_CHECK_ARG(ctrl && theta && pts && out && N > 0 && K > 0 && P > 0,
+               "km_points_transform_tps: bad arguments");
+  const size_t smem = (size_t)(2 * K + 3) * sizeof(float4);
+  KM_CHECK_ARG(smem <= 48 * 1024, "km_points_transform_tps: K=%d too large", K);
+  points_tps_kernel<<<dim3((P + 127) / 128, N), 128, smem, km_cs(stream)>>>(ctrl, theta, pts, out, K,
+                                                                           P);
+  KM_LAUNCH_OK("points_tps_kernel");
+  return KM_OK;
+}
+
+extern "C" size_t km_warp_loss_workspace_bytes(int N, int C) {
+  return (size_t)KM_RED_BLOCKS * N * C * 4 * sizeof(float);
+}
+static size_t pair_partials_bytes(int N, int C) {
+  return (size_t)KM_RED_BLOCKS * N * C * 4 * sizeof(float);
+}
+extern "C" size_t km_pair_stats_workspace_bytes(int N, int C, long long M, int hard) {
+  return pair_partials_bytes(N, C) + (hard ? (size_t)N * (size_t)M * sizeof(int32_t) : 0);
+}
+
+template <int COORD, int CCH>
+static void launch_warp_loss(bool fast, dim3 grid, size_t smem, cudaStream_t st, const float* a,
+                             const float* theta, int K, const float* g, const float* mov,
+                             const float* fix, float* out, float* part, int N, int C, int D, int H,
+                             int W, int mode) {
+  if (fast)
+    warp_loss_kernel<COORD, CCH, true><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, part,
+                                                                N, C, D, H, W, mode);
+  else
+    warp_loss_kernel<COORD, CCH, false><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, part,
+                                                                 N, C, D, H, W, mode);
+}
+
+extern "C" int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const float* theta, int K,
+                            const float* grid, const float* moving, const float* fixed, float* out,
+                            double* sums, void* workspace, int N, int C, int D, int H, int W,
+                            int mode, km_stream_t stream) {
+  KM_CHECK_ARG(moving && N > 0 && C > 0 && D > 0 && H > 0 && W > 0, "km_warp_loss: bad arguments");
+  KM_CHECK_ARG(W % 4 == 0, "km_warp_loss: W must be a multiple of 4 (got %d)", W);
+  KM_CHECK_ARG(mode == KM_INTERP_BILINEAR || mode == KM_INTERP_NEAREST, "km_warp_loss: bad mode");
+  KM_CHECK_ARG(!fixed || (sums && workspace), "km_warp_loss: sums/workspace required with fixed");
+  KM_CHECK_ARG((((uintptr_t)out | (uintptr_t)fixed | (uintptr_t)grid) & 15) == 0,
+               "km_warp_loss: pointers must be 16-byte aligned");
+  size_t smem = 0;
+  if (coord_mode == KM_COORD_AFFINE) {
+    KM_CHECK_ARG(mat_or_ctrl, "km_warp_loss: affine matrix missing");
+  } else if (coord_mode == KM_COORD_TPS) {
+    KM_CHECK_ARG(mat_or_ctrl && theta && K > 0, "km_warp_loss: TPS parameters missing");
+    smem = (size_t)(2 * K + 3) * sizeof(float4);
+    KM_CHECK_ARG(smem <= 40 * 1024, "km_warp_loss: K=%d too large", K);
+  } else if (coord_mode == KM_COORD_GRID) {
+    KM_CHECK_ARG(grid, "km_warp_loss: grid missing");
+  } else {
+    km_set_error("km_warp_loss: bad coord_mode %d", coord_mode);
+    return KM_EINVAL;
+  }
+  const dim3 g(KM_RED_BLOCKS, N);
+  float* part = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = km_cs(stream);
+  const bool fast = g_tps_fast != 0;
+#define KM_WL(COORD)                                                                              \
+  do {                                                                                            \
+    if (C == 1)                                                                                   \
+      launch_warp_loss<COORD, 1>(fast, g, smem, st, mat_or_ctrl, theta, K, grid, moving, fixed,   \
+                                 out, part, N, C, D, H, W, mode);                                 \
+    else                                                                                          \
+      launch_warp_loss<COORD, 16>(fast, g, smem, st, mat_or_ctrl, theta, K, grid, moving, fixed,  \
+                                  out, part, N, C, D, H, W, mode);                                \
+  } while (0)
+  if (coord_mode == KM_COORD_AFFINE) KM_WL(KM_COORD_AFFINE);
+  else if (coord_mode == KM_COORD_TPS) KM_WL(KM_COORD_TPS);
+  else KM_WL(KM_COORD_GRID);
+#undef KM_WL
+  KM_LAUNCH_OK("warp_loss_kernel");
+  if (fixed) {
+    const int NC4 = N * C * 4;
+    sum_partials4_kernel<<<(NC4 + 127) / 128, 128, 0, st>>>(part, KM_RED_BLOCKS, NC4, sums);
+    KM_LAUNCH_OK("sum_partials4_kernel");
+  }
+  return KM_OK;
+}
+
+extern "C" int km_argmax_channels(const float* pred, int32_t* labels, int N, int C, long long M,
+                                  km_stream_t stream) {
+  KM_CHECK_ARG(pred && labels && N > 0 && C > 0 && M > 0, "km_argmax_channels: bad arguments");
+  argmax_channels_kernel<<<dim3(blocks_for(M, 256, 148 * 16), N), 256, 0, km_cs(stream)>>>(
+      pred, labels, C, M);
+  KM_LAUNCH_OK("argmax_channels_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_pair_stats(const float* pred, const float* target, double* sums, void* workspace,
+                             int N, int C, long long M, int hard, km_stream_t stream) {
+  KM_CHECK_ARG(pred && target && sums && workspace && N > 0 && C > 0 && M > 0,
+               "km_pair_stats: bad arguments");
+  KM_CHECK_ARG(C <= 65535 && N <= 65535, "km_pair_stats: too many channels");
+  float* part = reinterpret_cast<float*>(workspace);
+  // hard Dice: the label map lives behind the partials in the workspace
+  int32_t* labels = nullptr;
+  if (hard) {
+    labels = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) +
+                                        pair_partials_bytes(N, C));
+    int rc = km_argmax_channels(pred, labels, N, C, M, stream);
+    if (rc != KM_OK) return rc;
+  }
+  // fewer blocks per channel when there are many channels: keep ~148*8 blocks in flight
+  int bx = KM_RED_BLOCKS;
+  pair_stats_kernel<<<dim3(bx, C, N), KM_RED_THREADS, 0, km_cs(stream)>>>(pred, target, labels, part,
+                                                                          N, C, M);
+  KM_LAUNCH_OK("pair_stats_kernel");
+  const int NC4 = N * C * 4;
+  sum_partials4_kernel<<<(NC4 + 127) / 128, 128, 0, km_cs(stream)>>>(part, bx, NC4, sums);
+  KM_LAUNCH_OK("sum_partials4_kernel");
+  return KM_OK;
+}

@@ -1,0 +1,389 @@
+"""Tensor-level wrappers over the C ABI: torch owns device memory and streams, the kernels do
+the work.  Every function requires CUDA tensors and raises otherwise (no CPU path)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import (KM_CONV_COM, KM_CONV_RELU, KM_CONV_STATS, KM_COORD_AFFINE, KM_COORD_GRID,
+                   KM_COORD_TPS, KM_INTERP_BILINEAR, KM_INTERP_NEAREST)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.KMError("keymorph_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _mode(mode: str) -> int:
+    if mode in ("bilinear", "trilinear"):
+        return KM_INTERP_BILINEAR
+    if mode == "nearest":
+        return KM_INTERP_NEAREST
+    raise ValueError(f"unsupported interpolation mode {mode!r}")
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------- warp
+def grid_sample3d(x, grid, mode="bilinear"):
+    """F.grid_sample(x, grid, mode, padding_mode='border', align_corners=False) for 5-D inputs."""
+    _need_cuda(x, grid)
+    x, grid = _f32c(x), _f32c(grid)
+    N, Cc, Di, Hi, Wi = x.shape
+    assert grid.shape[0] == N and grid.shape[-1] == 3 and grid.dim() == 5
+    _, Do, Ho, Wo, _ = grid.shape
+    out = torch.empty((N, Cc, Do, Ho, Wo), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("km_grid_sample3d", _ptr(x), _ptr(grid), _ptr(out), N, Cc, Di, Hi, Wi, Do, Ho,
+                  Wo, _mode(mode), _stream())
+    return out
+
+
+def flow_field_affine(mat34, shape):
+    """mat34: (N,3,4) rows in (z,y,x); shape: (D,H,W) -> grid (N,D,H,W,3) in (x,y,z) order."""
+    _need_cuda(mat34)
+    mat34 = _f32c(mat34)
+    N = mat34.shape[0]
+    D, H, W = (int(s) for s in shape)
+    grid = torch.empty((N, D, H, W, 3), dtype=torch.float32, device=mat34.device)
+    with torch.cuda.device(mat34.device):
+        _lib.call("km_flow_field_affine", _ptr(mat34), _ptr(grid), N, D, H, W, _stream())
+    return grid
+
+
+def flow_field_tps(ctrl, theta, shape):
+    _need_cuda(ctrl, theta)
+    ctrl, theta = _f32c(ctrl), _f32c(theta)
+    N, K, _ = ctrl.shape
+    assert theta.shape == (N, K + 4, 3)
+    D, H, W = (int(s) for s in shape)
+    grid = torch.empty((N, D, H, W, 3), dtype=torch.float32, device=ctrl.device)
+    with torch.cuda.device(ctrl.device):
+        _lib.call("km_flow_field_tps", _ptr(ctrl), _ptr(theta), _ptr(grid), N, K, D, H, W,
+                  _stream())
+    return grid
+
+
+def points_transform_affine(mat34, pts):
+    _need_cuda(mat34, pts)
+    mat34, pts = _f32c(mat34), _f32c(pts)
+    N, P, _ = pts.shape
+    out = torch.empty_like(pts)
+    with torch.cuda.device(pts.device):
+        _lib.call("km_points_transform_affine", _ptr(mat34), _ptr(pts), _ptr(out), N, P, _stream())
+    return out
+
+
+def points_transform_tps(ctrl, theta, pts):
+    _need_cuda(ctrl, theta, pts)
+    ctrl, theta, pts = _f32c(ctrl), _f32c(theta), _f32c(pts)
+    N, K, _ = ctrl.shape
+    P = pts.shape[1]
+    out = torch.empty_like(pts)
+    with torch.cuda.device(pts.device):
+        _lib.call("km_points_transform_tps", _ptr(ctrl), _ptr(theta), _ptr(pts), _ptr(out), N, K,
+                  P, _stream())
+    return out
+
+
+def warp_loss(moving, fixed=None, *, mat34=None, ctrl=None, theta=None, grid=None,
+              mode="bilinear", store=True):
+    """Fused warp (+ loss sums).  Exactly one of mat34 / (ctrl, theta) / grid selects where the
+    sampling coordinates come from.  Returns (warped or None, sums (N,C,4) fp64 or None) with
+    sums[..., :] = [sum (a-f)^2, sum a*f, sum a*a, sum f*f]."""
+    _need_cuda(moving, fixed, mat34, ctrl, theta, grid)
+    moving, fixed = _f32c(moving), _f32c(fixed)
+    N, Cc, D, H, W = moving.shape
+    K = 0
+    a = th = g = None
+    if mat34 is not None:
+        coord, a = KM_COORD_AFFINE, _f32c(mat34)
+    elif ctrl is not None:
+        coord, a, th = KM_COORD_TPS, _f32c(ctrl), _f32c(theta)
+        K = a.shape[1]
+    elif grid is not None:
+        coord, g = KM_COORD_GRID, _f32c(grid)
+        assert g.shape == (N, D, H, W, 3)
+    else:
+        raise ValueError("warp_loss needs mat34, (ctrl, theta) or grid")
+    out = torch.empty_like(moving) if store else None
+    sums = ws = None
+    if fixed is not None:
+        assert fixed.shape == moving.shape
+        sums = torch.empty((N, Cc, 4), dtype=torch.float64, device=moving.device)
+        ws = _ws(_lib.query("km_warp_loss_workspace_bytes", N, Cc), moving.device)
+    with torch.cuda.device(moving.device):
+        _lib.call("km_warp_loss", coord, _ptr(a), _ptr(th), K, _ptr(g), _ptr(moving), _ptr(fixed),
+                  _ptr(out), _ptr(sums), _ptr(ws), N, Cc, D, H, W, _mode(mode), _stream())
+    return out, sums
+
+
+def pair_stats(pred, target, hard=False):
+    """sums (N,C,4) fp64 = [sum (p-t)^2, sum p*t, sum p*p, sum t*t] over the flattened spatial dims;
+    hard=True replaces pred by one_hot(argmax_c pred)."""
+    _need_cuda(pred, target)
+    pred, target = _f32c(pred), _f32c(target)
+    assert pred.shape == target.shape
+    N, Cc = pred.shape[0], pred.shape[1]
+    M = pred[0, 0].numel()
+    sums = torch.empty((N, Cc, 4), dtype=torch.float64, device=pred.device)
+    ws = _ws(_lib.query("km_pair_stats_workspace_bytes", N, Cc, M, int(hard)), pred.device)
+    with torch.cuda.device(pred.device):
+        _lib.call("km_pair_stats", _ptr(pred), _ptr(target), _ptr(sums), _ptr(ws), N, Cc, M,
+                  int(hard), _stream())
+    return sums
+
+
+def argmax_channels(pred):
+    _need_cuda(pred)
+    pred = _f32c(pred)
+    N, Cc = pred.shape[0], pred.shape[1]
+    M = pred[0, 0].numel()
+    labels = torch.empty((N,) + tuple(pred.shape[2:]), dtype=torch.int32, device=pred.device)
+    with torch.cuda.device(pred.device):
+        _lib.call("km_argmax_channels", _ptr(pred), _ptr(labels), N, Cc, M, _stream())
+    return labels
+
+
+# --------------------------------------------------------------------------------------- CoM
+def com3d(heat, ij=True, return_mass=False):
+    _need_cuda(heat)
+    heat = _f32c(heat)
+    N, K, D, H, W = heat.shape
+    pts = torch.empty((N, K, 3), dtype=torch.float32, device=heat.device)
+    mass = torch.empty((N, K), dtype=torch.float32, device=heat.device) if return_mass else None
+    ws = _ws(_lib.query("km_com3d_workspace_bytes", N, K), heat.device)
+    with torch.cuda.device(heat.device):
+        _lib.call("km_com3d", _ptr(heat), _ptr(pts), _ptr(mass), _ptr(ws), N, K, D, H, W, int(ij),
+                  _stream())
+    return (pts, mass) if return_mass else pts
+
+
+# --------------------------------------------------------------------------------------- fits
+def _fit(name, x, y, w):
+    _need_cuda(x, y, w)
+    x, y, w = _f32c(x), _f32c(y), _f32c(w)
+    N, K, d = x.shape
+    assert d == 3 and y.shape == x.shape
+    A = torch.empty((N, 4, 4), dtype=torch.float32, device=x.device)
+    Ainv = torch.empty_like(A)
+    status = torch.empty((N,), dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call(name, _ptr(x), _ptr(y), _ptr(w), _ptr(A), _ptr(Ainv), _ptr(status), N, K,
+                  _stream())
+    return A, Ainv, status
+
+
+def fit_affine(x, y, w=None):
+    """A44 = square(argmin_A |y - A [x;1]|), its inverse and a per-sample singularity status."""
+    return _fit("km_fit_affine", x, y, w)
+
+
+def fit_rigid(x, y, w=None):
+    return _fit("km_fit_rigid", x, y, w)
+
+
+def inverse44(m):
+    _need_cuda(m)
+    m = _f32c(m)
+    N = m.shape[0]
+    inv = torch.empty_like(m)
+    status = torch.empty((N,), dtype=torch.int32, device=m.device)
+    with torch.cuda.device(m.device):
+        _lib.call("km_inverse44", _ptr(m), _ptr(inv), _ptr(status), N, _stream())
+    return inv, status
+
+
+def tps_fit(c_src, c_dst, lmbda, w=None):
+    """theta (N,K+4,3) solving the TPS system that maps c_src -> c_dst (fp64 LU on the device)."""
+    _need_cuda(c_src, c_dst, lmbda, w)
+    c_src, c_dst, w = _f32c(c_src), _f32c(c_dst), _f32c(w)
+    N, K, _ = c_src.shape
+    lmbda = _f32c(lmbda.to(c_src.device)).reshape(-1)
+    if lmbda.numel() == 1 and N > 1:
+        lmbda = lmbda.repeat(N)
+    assert lmbda.numel() == N
+    theta = torch.empty((N, K + 4, 3), dtype=torch.float32, device=c_src.device)
+    status = torch.empty((N,), dtype=torch.int32, device=c_src.device)
+    ws = _ws(_lib.query("km_tps_fit_workspace_bytes", N, K), c_src.device)
+    with torch.cuda.device(c_src.device):
+        _lib.call("km_tps_fit", _ptr(c_src), _ptr(c_dst), _ptr(lmbda), _ptr(w), _ptr(theta),
+                  _ptr(status), _ptr(ws), N, K, _stream())
+    return theta, status
+
+
+# --------------------------------------------------------------------------------------- backbone
+def pack_weights(w):
+    """fp32 (Cout,Cin,kd,kh,kw) -> bf16 [tap][Cout][Cin]."""
+    _need_cuda(w)
+    w = _f32c(w)
+    Cout, Cin = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    out = torch.empty((taps, Cout, Cin), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.call("km_pack_weights", _ptr(w), _ptr(out), Cout, Cin, taps, _stream())
+    return out
+
+
+def conv_nparts():
+    return _lib.query("km_conv_nparts")
+
+
+def red_nparts():
+    return _lib.query("km_pool_nparts")
+
+
+def conv3d_tc(x, wp, bias=None, relu=False, want_stats=False, want_com=False, store=True):
+    """x: bf16 (N,D,H,W,Cin); wp: bf16 (taps,Cout,Cin).  Returns (out|None, stats|None, com|None)."""
+    _need_cuda(x, wp, bias)
+    assert x.dtype == torch.bfloat16 and wp.dtype == torch.bfloat16
+    x, wp = x.contiguous(), wp.contiguous()
+    N, D, H, W, Cin = x.shape
+    taps, Cout, Cin2 = wp.shape
+    assert Cin2 == Cin
+    flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0) | \
+        (KM_CONV_COM if want_com else 0)
+    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device) if store else None
+    nparts = conv_nparts()
+    stats = torch.empty((nparts, N, Cout, 2), dtype=torch.float32, device=x.device) \
+        if want_stats else None
+    com = torch.empty((nparts, N, Cout, 4), dtype=torch.float32, device=x.device) \
+        if want_com else None
+    bias = _f32c(bias)
+    with torch.cuda.device(x.device):
+        _lib.call("km_conv3d_tc", _ptr(x), _ptr(wp), _ptr(bias), _ptr(out), _ptr(stats), _ptr(com),
+                  N, Cin, Cout, D, H, W, taps, flags, _stream())
+    return out, stats, com
+
+
+def com_finalize(com, return_mass=False):
+    nparts, N, K, _ = com.shape
+    pts = torch.empty((N, K, 3), dtype=torch.float32, device=com.device)
+    mass = torch.empty((N, K), dtype=torch.float32, device=com.device) if return_mass else None
+    with torch.cuda.device(com.device):
+        _lib.call("km_com_finalize", _ptr(com), nparts, _ptr(pts), _ptr(mass), N, K, _stream())
+    return (pts, mass) if return_mass else pts
+
+
+def volume_stats(x):
+    """x: fp32 (N, ...) -> partial stats (nparts, N, 1, 2)."""
+    _need_cuda(x)
+    x = _f32c(x)
+    N = x.shape[0]
+    M = x[0].numel()
+    stats = torch.empty((red_nparts(), N, 1, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("km_volume_stats", _ptr(x), _ptr(stats), N, M, _stream())
+    return stats
+
+
+def channel_stats(x):
+    """x: bf16 NDHWC -> partial stats (nparts, N, C, 2)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    N, Cc = x.shape[0], x.shape[-1]
+    nvox = x[0, ..., 0].numel()
+    stats = torch.empty((red_nparts(), N, Cc, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("km_channel_stats", _ptr(x), _ptr(stats), N, Cc, nvox, _stream())
+    return stats
+
+
+def norm_finalize(stats0, count0, gamma, beta, groups, eps=1e-5, stats1=None, count1=0.0, rep1=1.0):
+    """partial stats -> per-(n,c) scale / shift of GroupNorm(groups) (InstanceNorm: groups=C)."""
+    nparts0, N, C0, _ = stats0.shape
+    C1 = 0 if stats1 is None else stats1.shape[2]
+    nparts1 = 0 if stats1 is None else stats1.shape[0]
+    Cc = C0 + C1
+    scale = torch.empty((N, Cc), dtype=torch.float32, device=stats0.device)
+    shift = torch.empty_like(scale)
+    gamma, beta = _f32c(gamma), _f32c(beta)
+    with torch.cuda.device(stats0.device):
+        _lib.call("km_norm_finalize", _ptr(stats0), nparts0, C0, float(count0), _ptr(stats1),
+                  nparts1, C1, float(count1), float(rep1), _ptr(gamma), _ptr(beta), int(groups),
+                  float(eps), _ptr(scale), _ptr(shift), N, _stream())
+    return scale, shift
+
+
+def norm_apply(src0, scale, shift, src1=None, relu=False, pool=False, out=None):
+    """bf16 NDHWC normalise (+ReLU) (+concat of the nearest-upsampled src1) (+MaxPool3d(2))."""
+    _need_cuda(src0, src1, scale, shift)
+    src0 = src0.contiguous()
+    N, D, H, W, C0 = src0.shape
+    C1 = D1 = H1 = W1 = 0
+    if src1 is not None:
+        src1 = src1.contiguous()
+        _, D1, H1, W1, C1 = src1.shape
+    oshape = (N, D // 2, H // 2, W // 2, C0) if pool else (N, D, H, W, C0 + C1)
+    if out is None:
+        out = torch.empty(oshape, dtype=torch.bfloat16, device=src0.device)
+    assert tuple(out.shape) == oshape and out.is_contiguous()
+    with torch.cuda.device(src0.device):
+        _lib.call("km_norm_apply", _ptr(src0), C0, _ptr(src1), C1, D1, H1, W1, _ptr(scale),
+                  _ptr(shift), _ptr(out), N, D, H, W, int(relu), int(pool), _stream())
+    return out
+
+
+def maxpool2_stats(x):
+    _need_cuda(x)
+    x = x.contiguous()
+    N, D, H, W, Cc = x.shape
+    out = torch.empty((N, D // 2, H // 2, W // 2, Cc), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((red_nparts(), N, Cc, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("km_maxpool2_stats", _ptr(x), _ptr(out), _ptr(stats), N, Cc, D, H, W, _stream())
+    return out, stats
+
+
+def conv3d_stem(x, w, bias=None, in_scale=None, in_shift=None, relu=True):
+    """x: fp32 (N,1,D,H,W); w: fp32 (Cout,1,3,3,3) -> bf16 (N,D,H,W,Cout) + partial stats."""
+    _need_cuda(x, w)
+    x, w, bias = _f32c(x), _f32c(w), _f32c(bias)
+    N, Cin, D, H, W = x.shape
+    assert Cin == 1
+    Cout = w.shape[0]
+    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((red_nparts(), N, Cout, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("km_conv3d_stem", _ptr(x), _ptr(w), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
+                  _ptr(out), _ptr(stats), N, Cout, D, H, W, int(relu), _stream())
+    return out, stats
+
+
+def ndhwc_to_ncdhw(x):
+    _need_cuda(x)
+    x = x.contiguous()
+    N, D, H, W, Cc = x.shape
+    out = torch.empty((N, Cc, D, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("km_ndhwc_bf16_to_ncdhw_f32", _ptr(x), _ptr(out), N, Cc, D, H, W, _stream())
+    return out
+
+
+def ncdhw_to_ndhwc(x):
+    _need_cuda(x)
+    x = _f32c(x)
+    N, Cc, D, H, W = x.shape
+    out = torch.empty((N, D, H, W, Cc), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("km_ncdhw_f32_to_ndhwc_bf16", _ptr(x), _ptr(out), N, Cc, D, H, W, _stream())
+    return out

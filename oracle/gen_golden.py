@@ -1,0 +1,231 @@
+"""Generate tests/golden/*.npz by running the REFERENCE ITSELF (alanqrwang/keymorph, read-only at
+/root/reference) on seeded inputs.  Runs only in the build container (the GPU box has no
+/root/reference); the fixtures it writes are committed and pin oracle/keymorph_oracle.py.
+
+    python oracle/gen_golden.py            # rewrites tests/golden/
+
+The reference's package __init__ eagerly imports nibabel / skimage / h5py / torchio / matplotlib,
+none of which is installed or used on the hot path; they are replaced by MagicMock modules.
+"""
+from __future__ import annotations
+
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import tempfile
+from unittest import mock
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden")
+REF = os.environ.get("KEYMORPH_REFERENCE", "/root/reference")
+_MOCKED = {"nibabel", "skimage", "h5py", "torchio", "matplotlib"}
+
+
+class _MockFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, name, path=None, target=None):
+        if name.split(".")[0] in _MOCKED:
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = mock.MagicMock(name=spec.name)
+        m.__path__ = []
+        m.__spec__ = spec
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+def import_reference():
+    sys.meta_path.insert(0, _MockFinder())
+    sys.path.insert(0, REF)
+    import keymorph  # noqa: F401
+    return keymorph
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    conv = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        conv[k] = np.asarray(v)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **conv)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB, keys {sorted(conv)}")
+
+
+def main():
+    import_reference()
+    sys.path.insert(0, ROOT)
+    from keymorph import layers, loss_ops, utils
+    from keymorph.augmentation import affine_augment
+    from keymorph.keypoint_aligners import TPS, AffineKeypointAligner, RigidKeypointAligner
+    from keymorph.model import KeyMorph
+    from keymorph.net import ConvNet
+    from keymorph.unet3d.model import TruncatedUNet3D, UNet3D
+    from oracle.keymorph_oracle import gaussian_phantom
+
+    torch.set_num_threads(8)
+
+    # ---------------------------------------------------------------- aligners
+    g = torch.Generator().manual_seed(11)
+    K = 32
+    pm = torch.rand(1, K, 3, generator=g) * 1.2 - 0.6
+    lin = torch.eye(3) + 0.15 * torch.randn(3, 3, generator=g)
+    pf = pm @ lin.T + 0.05 * torch.randn(1, K, 3, generator=g) + torch.tensor([0.05, -0.1, 0.02])
+    w = torch.rand(1, K, generator=g)
+    w = w / w.sum()
+    shape = (1, 1, 8, 10, 12)
+    out = {"points_m": pm, "points_f": pf, "w": w, "shape": np.array(shape)}
+    for tag, cls in (("affine", AffineKeypointAligner), ("rigid", RigidKeypointAligner)):
+        for wtag, ww in (("", None), ("_w", w)):
+            al = cls(pm, pf, w=ww, dim=3)
+            out[f"{tag}{wtag}_matrix"] = al.transform_matrix
+            out[f"{tag}{wtag}_inverse"] = al.inverse_transform_matrix
+            out[f"{tag}{wtag}_grid"] = al.get_flow_field(shape)
+            out[f"{tag}{wtag}_points_a"] = al.get_forward_transformed_points(pm)
+            out[f"{tag}{wtag}_points_inv"] = al.get_inverse_transformed_points(pf)
+    save("aligners", **out)
+
+    # ---------------------------------------------------------------- TPS
+    K = 24
+    pm = torch.rand(1, K, 3, generator=g) * 1.2 - 0.6
+    pf = pm + 0.08 * torch.randn(1, K, 3, generator=g)
+    w = torch.rand(1, K, generator=g)
+    w = w / w.sum()
+    out = {"points_m": pm, "points_f": pf, "w": w, "shape": np.array(shape)}
+    for lam in (0.0, 0.1, 10.0):
+        for wtag, ww in (("", None), ("_w", w)):
+            if ww is not None and lam != 0.1:
+                continue
+            tps = TPS(pm, pf, torch.tensor([lam]), w=ww, dim=3, num_subgrids=4)
+            tag = f"lam{lam:g}{wtag}"
+            out[f"{tag}_inverse_theta"] = tps.inverse_theta
+            out[f"{tag}_grid"] = tps.get_flow_field(shape, compute_on_subgrids=True)
+            out[f"{tag}_points_a"] = tps.get_forward_transformed_points(pm)
+            out[f"{tag}_theta"] = tps.theta
+    save("tps", **out)
+
+    # ---------------------------------------------------------------- warp + losses
+    x = torch.randn(2, 3, 9, 10, 11, generator=g)
+    grid = torch.rand(2, 7, 8, 12, 3, generator=g) * 2.4 - 1.2
+    # exact half-way coordinates exercise round-half-even in nearest mode
+    grid[0, 0, 0, :4, 0] = torch.tensor([-1 + 1.0 / 11, -1 + 3.0 / 11, -1 + 5.0 / 11, 1.0])
+    out = {"x": x, "grid": grid,
+           "bilinear": utils.align_img(grid, x, "bilinear"),
+           "nearest": utils.align_img(grid, x, "nearest")}
+    lab_p = torch.randint(0, 5, (2, 1, 6, 7, 8), generator=g)
+    lab_t = torch.randint(0, 5, (2, 1, 6, 7, 8), generator=g)
+    seg_t = torch.nn.functional.one_hot(lab_t)[:, 0].permute(0, 4, 1, 2, 3).float()
+    soft_p = torch.softmax(torch.randn(2, 5, 6, 7, 8, generator=g) +
+                           2 * torch.nn.functional.one_hot(lab_p)[:, 0].permute(0, 4, 1, 2, 3).float(), 1)
+    out.update(seg_pred=soft_p, seg_target=seg_t)
+    out["mse"] = loss_ops.MSELoss()(soft_p, seg_t)
+    for hard in (False, True):
+        for ign in (False, True):
+            out[f"dice_h{int(hard)}_i{int(ign)}"] = loss_ops.DiceLoss(hard=hard)(soft_p, seg_t, ign_first_ch=ign)
+            out[f"dice_regions_h{int(hard)}_i{int(ign)}"] = loss_ops.DiceLoss(hard=hard, return_regions=True)(
+                soft_p, seg_t, ign_first_ch=ign)
+    save("warp_loss", **out)
+
+    # ---------------------------------------------------------------- CoM on a random heat map
+    heat = torch.randn(2, 5, 9, 12, 16, generator=g)
+    save("com", heat=heat, points_ij=layers.CenterOfMass3d(indexing="ij")(heat),
+         points_xy=layers.CenterOfMass3d(indexing="xy")(heat))
+
+    # ---------------------------------------------------------------- augmentation
+    img = gaussian_phantom(16, 5)
+    seg = (img > 0.3).float()
+    params = (0.1, 0.05, 0.3, 0.02)
+    a_img, a_seg = affine_augment(img, params, seg=seg)
+    save("augment", img=img, seg=seg, params=np.array(params), img_aug=a_img, seg_aug=a_seg)
+
+    # ---------------------------------------------------------------- backbones (seed 23 init)
+    def state_checksums(net):
+        sd = net.state_dict()
+        keys = sorted(sd)
+        return keys, np.array([float(sd[k].double().abs().sum()) for k in keys])
+
+    img32 = gaussian_phantom(32, 1000)
+    img64 = gaussian_phantom(64, 1001)
+    com = layers.CenterOfMass3d(indexing="ij")
+
+    torch.manual_seed(23)
+    tnet = TruncatedUNet3D(1, 16, 1, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8,
+                           num_levels=4, is_segmentation=False, conv_padding=1).eval()
+    keys, sums = state_checksums(tnet)
+    with torch.no_grad():
+        h32 = tnet(img32)
+        h64 = tnet(img64)
+    save("truncunet_k16", keys=np.array(keys), checksums=sums, heat32=h32, points32=com(h32),
+         points64=com(h64), heat64_sub=h64[:, :, ::4, ::4, ::4])
+
+    torch.manual_seed(23)
+    unet = UNet3D(1, 16, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8, num_levels=4,
+                  is_segmentation=False, conv_padding=1).eval()
+    keys, sums = state_checksums(unet)
+    with torch.no_grad():
+        h64 = unet(img64)
+    save("unet_k16", keys=np.array(keys), checksums=sums, points64=com(h64),
+         heat64_sub=h64[:, :, ::8, ::8, ::8])
+
+    torch.manual_seed(23)
+    cnet = ConvNet(3, 1, 16, norm_type="instance").eval()
+    keys, sums = state_checksums(cnet)
+    with torch.no_grad():
+        h64 = cnet(gaussian_phantom(128, 1002))
+    save("convnet_k16", keys=np.array(keys), checksums=sums, heat=h64, points=com(h64))
+
+    # ---------------------------------------------------------------- KeyMorph.forward (32^3)
+    torch.manual_seed(23)
+    tnet = TruncatedUNet3D(1, 16, 1, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8,
+                           num_levels=4, is_segmentation=False, conv_padding=1)
+    for wk in (None, "power"):
+        model = KeyMorph(torch.nn.DataParallel(tnet), 16, 3, weight_keypoints=wk).eval()
+        img_f = gaussian_phantom(32, 1000)
+        img_m = affine_augment(gaussian_phantom(32, 1000), (0.05, 0.03, 0.15, 0.01))
+        types = ["rigid", "affine", "tps_10", "tps_0.1"]
+        with torch.no_grad():
+            res = model(img_f, img_m, transform_type=types, return_aligned_points=True)
+        out = {"img_f": img_f, "img_m": img_m}
+        for t in types:
+            r = res[t]
+            out[f"{t}_grid"] = r["grid"]
+            out[f"{t}_points_f"] = r["points_f"]
+            out[f"{t}_points_m"] = r["points_m"]
+            out[f"{t}_points_a"] = r["points_a"]
+            if "matrix" in r:
+                out[f"{t}_matrix"] = r["matrix"]
+            if r["points_weights"] is not None:
+                out[f"{t}_weights"] = r["points_weights"]
+            out[f"{t}_img_a"] = utils.align_img(r["grid"], img_m)
+        save("forward32" + ("_power" if wk else ""), **out)
+
+    # ---------------------------------------------------------------- groupwise (directory mode)
+    model = KeyMorph(torch.nn.DataParallel(tnet), 16, 3).eval()
+    with tempfile.TemporaryDirectory() as d, torch.no_grad():
+        subj = [affine_augment(gaussian_phantom(32, 1000), (0.02 * i, 0.02 * i - 0.03, 0.1 * i, 0.0))
+                for i in range(4)]
+        for i, s in enumerate(subj):
+            np.savez(os.path.join(d, f"img_m_{i:03}.npz"), img=s.numpy())
+        sd = os.path.join(d, "out")
+        os.makedirs(sd)
+        res = model.groupwise_register(d, transform_type=["rigid", "affine", "tps_1"], device="cpu", num_iters=3,
+                                       log_to_console=False, save_dir=sd, save_results_to_disk=True)
+        out = {"subjects": torch.cat(subj, 0)}
+        for t in ("rigid", "affine", "tps_1"):
+            out[f"{t}_points_m"] = res[t]["grouppoints_m"]
+            out[f"{t}_points_a"] = res[t]["grouppoints_a"]
+            for i in range(4):
+                out[f"{t}_grid_{i}"] = np.load(os.path.join(sd, f"{t}_grid_{i:03}.npy"))[:, ::2, ::2, ::2]
+        save("groupwise32", **out)
+
+
+if __name__ == "__main__":
+    main()
