@@ -87,12 +87,28 @@ def load() -> C.CDLL:
     return lib
 
 
+# kernels launched by one call of each entry point (bench.py's "gpu_launches" claim)
+KERNELS_PER_CALL = {
+    "km_warp_loss": 2, "km_pair_stats": 2, "km_com3d": 2, "km_tps_fit": 2,
+}
+launch_count = 0
+# optional tracer: callable(name, phase) with phase in {"pre", "post"}; bench.py installs one that
+# records CUDA events around km_conv3d_tc / km_warp_loss launches on the launching stream
+TRACE = None
+
+
 def call(name: str, *args):
     """Call an int-returning entry point and raise KMError with km_last_error() on failure."""
+    global launch_count
     lib = load()
+    if TRACE is not None:
+        TRACE(name, "pre")
     rc = getattr(lib, name)(*args)
+    if TRACE is not None:
+        TRACE(name, "post")
     if rc != 0:
         raise KMError(f"{name} failed ({rc}): {lib.km_last_error().decode()}")
+    launch_count += KERNELS_PER_CALL.get(name, 1)
 
 
 def query(name: str, *args):

@@ -468,7 +468,9 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   g.TW = pow2_le(W, 128);
   g.TH = pow2_le(H, 128 / g.TW);
   g.TD = 128 / (g.TW * g.TH);
-  KM_CHECK_ARG(g.TD <= D, "km_conv3d_tc: volume %dx%dx%d has fewer than 128 voxels per brick", D, H, W);
+  // volumes with fewer than 128 voxels (deepest level of small test inputs): the brick sticks out
+  // of the tensor in D; TMA zero-fills the out-of-bounds part and the epilogue masks those rows.
+  KM_CHECK_ARG(g.TD <= 256, "km_conv3d_tc: volume %dx%dx%d too small", D, H, W);
   g.tiles_x = (W + g.TW - 1) / g.TW;
   g.tiles_y = (H + g.TH - 1) / g.TH;
   g.tiles_z = (D + g.TD - 1) / g.TD;

@@ -1,0 +1,217 @@
+"""Backbone executor: runs a UNet3D / TruncatedUNet3D / ConvNet parameter container on the CUDA
+kernels (bf16 NDHWC activations, fp32 accumulation) and returns keypoints directly.
+
+Layer schedule of the UNet path (reference: keymorph/unet3d/model.py:115-151):
+
+    volume_stats -> norm_finalize                     GroupNorm(1) of the 1-channel input
+    conv3d_stem (GN on load, ReLU, stats)             enc0.SingleConv1   1 -> 16      CUDA cores
+    norm_finalize, norm_apply, conv3d_tc(ReLU,stats)  every other SingleConv          tcgen05
+    maxpool2_stats                                    encoder transitions (stats of the pooled map)
+    norm_apply(src0 = skip, src1 = x)                 decoder: GN + nearest-upsample + concat fused
+    conv3d_tc(taps=1, bias, CoM)                      final 1x1x1 conv + ReLU + centre of mass; the
+                                                      heat map is never written unless asked for
+
+GroupNorm statistics are produced by the epilogue of the kernel that writes the tensor, so no
+tensor is read just to be measured.  Inference only (no autograd through the kernels).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _unwrap(module):
+    # torch.nn.DataParallel(network) as in scripts/register.py:264
+    return module.module if isinstance(module, torch.nn.DataParallel) else module
+
+
+def backbone_engine(module):
+    """Engine cached on the parameter container (None for foreign modules)."""
+    from .net import ConvNet
+    from .unet3d import _UNetBase
+    m = _unwrap(module)
+    if isinstance(m, _UNetBase):
+        if m._engine is None:
+            object.__setattr__(m, "_engine", UNetEngine(m))
+        return m._engine
+    if isinstance(m, ConvNet):
+        if m._engine is None:
+            object.__setattr__(m, "_engine", ConvNetEngine(m))
+        return m._engine
+    return None
+
+
+class _WeightCache:
+    """Packed (bf16, [tap][Cout][Cin]) copies of the conv weights, refreshed when a parameter
+    changes (load_state_dict, .to(device), in-place updates bump `_version`)."""
+
+    def __init__(self):
+        self._packed = {}
+
+    def get(self, key, param, pad_out_to=None):
+        sig = (param.data_ptr(), param._version, str(param.device), tuple(param.shape), pad_out_to)
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        w = param.detach()
+        if pad_out_to is not None and w.shape[0] % pad_out_to:
+            extra = pad_out_to - w.shape[0] % pad_out_to
+            w = torch.cat([w, w.new_zeros((extra,) + tuple(w.shape[1:]))], 0)
+        packed = ops.pack_weights(w)
+        self._packed[key] = (sig, packed)
+        return packed
+
+
+def _padded(vec, multiple):
+    if vec is None or vec.shape[0] % multiple == 0:
+        return vec
+    return torch.cat([vec, vec.new_zeros(multiple - vec.shape[0] % multiple)], 0)
+
+
+class _EngineBase:
+    def __init__(self, module):
+        self.m = module
+        self.weights = _WeightCache()
+
+    def _check_input(self, x):
+        if not x.is_cuda:
+            raise ops._lib.KMError("keymorph_b200 backbones run on CUDA only (no CPU fallback)")
+        if x.dim() != 5 or x.shape[1] != 1:
+            raise ValueError(f"expected (N,1,D,H,W) input, got {tuple(x.shape)}")
+        p = next(self.m.parameters())
+        if p.device != x.device:
+            raise ValueError(f"input on {x.device} but backbone weights on {p.device}")
+        if torch.is_grad_enabled() and any(q.requires_grad for q in self.m.parameters()) \
+                and self.m.training:
+            raise NotImplementedError("keymorph_b200 kernels are inference-only: call .eval() / "
+                                      "torch.no_grad() (training is out of scope, SURVEY.md 3.4)")
+        return x.float().contiguous()
+
+    def keypoints(self, x, want_mass=False, want_feat=False):
+        raise NotImplementedError
+
+    def heatmap(self, x):
+        return self.keypoints(x, want_feat=True)[2]
+
+
+class UNetEngine(_EngineBase):
+    def _single_conv(self, key, sc_mod, x_norm):
+        wp = self.weights.get(key, sc_mod.conv.weight)
+        out, stats, _ = ops.conv3d_tc(x_norm, wp, relu=True, want_stats=True)
+        return out, stats
+
+    @torch.no_grad()
+    def keypoints(self, x, want_mass=False, want_feat=False):
+        m = self.m
+        x = self._check_input(x)
+        N, _, D, H, W = x.shape
+        enc = m.encoders
+
+        def nvox(t):
+            return t.shape[1] * t.shape[2] * t.shape[3]
+
+        # ---- encoder 0: GN(1 group) -> conv 1->16 (stem) -> GN -> conv
+        sc0 = enc[0].basic_module.SingleConv1
+        st = ops.volume_stats(x)
+        scale, shift = ops.norm_finalize(st, D * H * W, sc0.groupnorm.weight, sc0.groupnorm.bias,
+                                         sc0.groupnorm.num_groups, sc0.groupnorm.eps)
+        a, st = ops.conv3d_stem(x, sc0.conv.weight.detach(), None, scale.reshape(-1),
+                                shift.reshape(-1), relu=True)
+        sc1 = enc[0].basic_module.SingleConv2
+        scale, shift = ops.norm_finalize(st, nvox(a), sc1.groupnorm.weight, sc1.groupnorm.bias,
+                                         sc1.groupnorm.num_groups, sc1.groupnorm.eps)
+        a = ops.norm_apply(a, scale, shift, out=a)
+        cur, cur_st = self._single_conv("enc0.c2", sc1, a)
+        del a
+        feats = [(cur, cur_st)]
+        # ---- encoders 1..L-1: pool -> (GN, conv) x 2
+        for i in range(1, len(enc)):
+            dc = enc[i].basic_module
+            p, st = ops.maxpool2_stats(cur)
+            g = dc.SingleConv1.groupnorm
+            scale, shift = ops.norm_finalize(st, nvox(p), g.weight, g.bias, g.num_groups, g.eps)
+            p = ops.norm_apply(p, scale, shift, out=p)
+            c1, st = self._single_conv(f"enc{i}.c1", dc.SingleConv1, p)
+            del p
+            g = dc.SingleConv2.groupnorm
+            scale, shift = ops.norm_finalize(st, nvox(c1), g.weight, g.bias, g.num_groups, g.eps)
+            c1 = ops.norm_apply(c1, scale, shift, out=c1)
+            cur, cur_st = self._single_conv(f"enc{i}.c2", dc.SingleConv2, c1)
+            del c1
+            feats.append((cur, cur_st))
+        # the truncated net never consumes the first encoder's full-resolution output as a skip
+        skips = feats[:-1][::-1]
+        del feats
+        # ---- decoders: GN(upsample(x) ++ skip) fused into one pass, then (conv, GN, conv)
+        for j, dec in enumerate(m.decoders):
+            dc = dec.basic_module
+            skip, skip_st = skips[j]
+            g = dc.SingleConv1.groupnorm
+            exact = all(skip.shape[d] == 2 * cur.shape[d] for d in (1, 2, 3))
+            if exact:
+                scale, shift = ops.norm_finalize(skip_st, nvox(skip), g.weight, g.bias,
+                                                 g.num_groups, g.eps, stats1=cur_st,
+                                                 count1=nvox(cur), rep1=8.0)
+                cat = ops.norm_apply(skip, scale, shift, src1=cur)
+            else:
+                C = skip.shape[-1] + cur.shape[-1]
+                ones = torch.ones((N, C), device=x.device)
+                cat = ops.norm_apply(skip, ones, torch.zeros_like(ones), src1=cur)
+                st = ops.channel_stats(cat)
+                scale, shift = ops.norm_finalize(st, nvox(cat), g.weight, g.bias, g.num_groups,
+                                                 g.eps)
+                cat = ops.norm_apply(cat, scale, shift, out=cat)
+            skips[j] = None
+            c1, st = self._single_conv(f"dec{j}.c1", dc.SingleConv1, cat)
+            del cat
+            g = dc.SingleConv2.groupnorm
+            scale, shift = ops.norm_finalize(st, nvox(c1), g.weight, g.bias, g.num_groups, g.eps)
+            c1 = ops.norm_apply(c1, scale, shift, out=c1)
+            cur, cur_st = self._single_conv(f"dec{j}.c2", dc.SingleConv2, c1)
+            del c1
+        # ---- final 1x1x1 conv (+bias) fused with ReLU + centre of mass
+        K = m.final_conv.out_channels
+        wp = self.weights.get("final", m.final_conv.weight, pad_out_to=32)
+        bias = _padded(m.final_conv.bias.detach(), 32)
+        heat, _, com = ops.conv3d_tc(cur, wp, bias=bias, want_com=True, store=want_feat)
+        pts, mass = ops.com_finalize(com, return_mass=True)
+        pts, mass = pts[:, :K], mass[:, :K]
+        feat = ops.ndhwc_to_ncdhw(heat)[:, :K] if want_feat else None
+        return pts, (mass if want_mass else None), feat
+
+
+class ConvNetEngine(_EngineBase):
+    @torch.no_grad()
+    def keypoints(self, x, want_mass=False, want_feat=False):
+        m = self.m
+        x = self._check_input(x)
+        N = x.shape[0]
+        blocks = m.blocks()
+        K = blocks[-1].conv.out_channels
+        b0 = blocks[0]
+        raw, st = ops.conv3d_stem(x, b0.conv.weight.detach(), b0.conv.bias.detach(), None, None,
+                                  relu=False)
+        for b, blk in enumerate(blocks):
+            C = raw.shape[-1]
+            nv = raw.shape[1] * raw.shape[2] * raw.shape[3]
+            if blk.norm is not None:
+                scale, shift = ops.norm_finalize(st, nv, None, None, C, blk.norm.eps)
+            else:
+                scale = torch.ones((N, C), device=x.device)
+                shift = torch.zeros_like(scale)
+            if b == len(blocks) - 1:
+                heat = ops.norm_apply(raw, scale, shift, relu=True)
+                break
+            y = ops.norm_apply(raw, scale, shift, relu=True, pool=blk.down_sample,
+                               out=None if blk.down_sample else raw)
+            nxt = blocks[b + 1]
+            last = b + 1 == len(blocks) - 1
+            wp = self.weights.get(f"block{b + 2}", nxt.conv.weight, pad_out_to=16 if last else None)
+            bias = nxt.conv.bias.detach()
+            raw, st, _ = ops.conv3d_tc(y, wp, bias=_padded(bias, 16) if last else bias, relu=False,
+                                       want_stats=True)
+            del y
+        feat = ops.ndhwc_to_ncdhw(heat)[:, :K].contiguous()
+        pts, mass = ops.com3d(feat, ij=True, return_mass=True)
+        return pts, (mass if want_mass else None), (feat if want_feat else None)

@@ -196,7 +196,7 @@ def main():
         out = {"img_f": img_f, "img_m": img_m}
         for t in types:
             r = res[t]
-            out[f"{t}_grid"] = r["grid"]
+            out[f"{t}_grid"] = r["grid"][:, ::2, ::2, ::2]
             out[f"{t}_points_f"] = r["points_f"]
             out[f"{t}_points_m"] = r["points_m"]
             out[f"{t}_points_a"] = r["points_a"]
@@ -204,7 +204,7 @@ def main():
                 out[f"{t}_matrix"] = r["matrix"]
             if r["points_weights"] is not None:
                 out[f"{t}_weights"] = r["points_weights"]
-            out[f"{t}_img_a"] = utils.align_img(r["grid"], img_m)
+            out[f"{t}_img_a"] = utils.align_img(r["grid"], img_m)[:, :, ::2, ::2, ::2]
         save("forward32" + ("_power" if wk else ""), **out)
 
     # ---------------------------------------------------------------- groupwise (directory mode)

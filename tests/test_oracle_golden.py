@@ -1,0 +1,210 @@
+"""The CPU oracle (oracle/keymorph_oracle.py) against (a) the reference's own known-answer tests
+(test/test.py, restated here) and (b) golden vectors produced by the reference itself
+(oracle/gen_golden.py).  No GPU involved."""
+import numpy as np
+import pytest
+import torch
+from scipy import ndimage
+from torch.testing import assert_close
+
+from oracle import keymorph_oracle as O
+
+
+# ---------------------------------------------------------------- reference KATs: CenterOfMass3d
+def _blob(shape, at, sigma=5):
+    img = np.zeros(shape)
+    img[at] = 1
+    return torch.tensor(ndimage.gaussian_filter(img, sigma)).float()
+
+
+def test_com_kats():
+    """test/test.py:117-253."""
+    pt = torch.zeros(3, 3, 3)
+    pt[1, 1, 1] = 1
+    assert_close(O.center_of_mass3d(pt.view(1, 1, 3, 3, 3), ij=False), torch.zeros(1, 1, 3))
+    three = torch.zeros(3, 3, 3)
+    three[0, 0, 0] = three[1, 1, 1] = three[2, 2, 2] = 1
+    assert_close(O.center_of_mass3d(three.view(1, 1, 3, 3, 3), ij=False), torch.zeros(1, 1, 3))
+    assert_close(O.center_of_mass3d(_blob((101, 101, 101), (50, 50, 50))[None, None], ij=False),
+                 torch.zeros(1, 1, 3))
+    assert_close(O.center_of_mass3d(_blob((101, 51, 51), (50, 25, 25))[None, None], ij=False),
+                 torch.zeros(1, 1, 3))
+    off = _blob((101, 101, 101), (50, 25, 25))[None, None]
+    assert_close(O.center_of_mass3d(off, ij=False), torch.tensor([[[-0.5, -0.5, 0.0]]]))
+    two = torch.stack([_blob((101, 101, 101), (50, 25, 25)), _blob((101, 101, 101), (25, 50, 50))])[:, None]
+    assert_close(O.center_of_mass3d(two, ij=False), torch.tensor([[[-0.5, -0.5, 0]], [[0, 0, -0.5]]]))
+    assert_close(O.center_of_mass3d(two, ij=True), torch.tensor([[[0, -0.5, -0.5]], [[-0.5, 0, 0]]]))
+
+
+# ---------------------------------------------------------------- reference KATs: rigid / affine
+RIGID_KATS = [
+    # (points_m, points_f, weights, expected transform_matrix)  test/test.py:259-413
+    ([[0, 0, 0], [0, 0, 0.1], [0, 0, 0.2], [0, 0, 0.3]], [[0, 0, 0.1], [0, 0, 0.2], [0, 0, 0.3], [0, 0, 0.4]],
+     None, [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0.1], [0, 0, 0, 1]]),
+    ([[0.1, -0.1, 0.1], [0.3, -0.2, 0.2], [0.5, -0.3, 0.3], [0.7, -0.4, 0.4]],
+     [[0.3, 0, 0], [0.5, -0.1, 0.1], [0.7, -0.2, 0.2], [0.9, -0.3, 0.3]],
+     None, [[1, 0, 0, 0.2], [0, 1, 0, 0.1], [0, 0, 1, -0.1], [0, 0, 0, 1]]),
+    ([[1, 0, 0], [0, -1, 0], [-1, 0, 0], [0, 1, 0]], [[0, -1, 0], [-1, 0, 0], [0, 1, 0], [1, 0, 0]],
+     None, [[0, 1, 0, 0], [-1, 0, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]),
+    ([[1, 0, 0], [0, -1, 0], [-1, 0, 0], [0, 1, 0]], [[0, -0.5, 0], [-0.5, 0, 0], [0, 0.5, 0], [0.5, 0, 0]],
+     None, [[0, 1, 0, 0], [-1, 0, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]),
+    ([[1, 0, 0], [0, -1, 0], [-1, 0, 0], [0, 1, 0]], [[0, -0.5, 0], [-0.5, 0, 0], [0, 0.5, 0], [0.5, 0, 0]],
+     [1, 1, 1, 1], [[0, 1, 0, 0], [-1, 0, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]),
+]
+
+
+@pytest.mark.parametrize("pm,pf,w,expected", RIGID_KATS)
+def test_rigid_kats(pm, pf, w, expected):
+    pm, pf = torch.tensor(pm).float()[None], torch.tensor(pf).float()[None]
+    w = None if w is None else torch.tensor(w).float()[None]
+    tm, inv = O.aligner_matrices(pm, pf, w, "rigid")
+    assert_close(tm, torch.tensor(expected).float()[None])
+
+
+def test_rigid_forward_inverse_symmetry():
+    """test/test.py:279-299."""
+    a = torch.tensor(RIGID_KATS[0][0]).float()[None]
+    b = torch.tensor(RIGID_KATS[0][1]).float()[None]
+    f12, i12 = O.aligner_matrices(a, b, None, "rigid")
+    f21, i21 = O.aligner_matrices(b, a, None, "rigid")
+    assert_close(f12, i21)
+    assert_close(f21, i12)
+
+
+def test_affine_singular_raises():
+    """test/test.py:462-480 (test_affine_2 errors in the reference: all z == 0)."""
+    pm = torch.tensor([[1, 0, 0], [0, -1, 0], [-1, 0, 0], [0, 1, 0]]).float()[None]
+    pf = torch.tensor([[0, -1, 0], [-1, 0, 0], [0, 1, 0], [1, 0, 0]]).float()[None]
+    with pytest.raises(Exception):
+        O.aligner_matrices(pm, pf, None, "affine")
+
+
+# ---------------------------------------------------------------- golden vectors from the reference
+def test_golden_aligners(golden):
+    g = golden("aligners")
+    pm, pf, w = g["points_m"], g["points_f"], g["w"]
+    shape = tuple(int(s) for s in g["shape"][2:])
+    for kind in ("affine", "rigid"):
+        for tag, ww in (("", None), ("_w", w)):
+            tm, inv = O.aligner_matrices(pm, pf, ww, kind)
+            assert_close(tm, g[f"{kind}{tag}_matrix"], rtol=0, atol=0)
+            assert_close(inv, g[f"{kind}{tag}_inverse"], rtol=0, atol=0)
+            assert_close(O.affine_flow_field(inv, shape), g[f"{kind}{tag}_grid"], rtol=0, atol=0)
+            assert_close(O.transform_points(tm, pm), g[f"{kind}{tag}_points_a"], rtol=0, atol=0)
+            assert_close(O.transform_points(inv, pf), g[f"{kind}{tag}_points_inv"], rtol=0, atol=0)
+
+
+def test_golden_tps(golden):
+    g = golden("tps")
+    pm, pf, w = g["points_m"], g["points_f"], g["w"]
+    shape = tuple(int(s) for s in g["shape"][2:])
+    for lam, tag, ww in ((0.0, "lam0", None), (0.1, "lam0.1", None), (10.0, "lam10", None),
+                         (0.1, "lam0.1_w", w)):
+        lmbda = torch.tensor([lam])
+        assert_close(O.tps_fit(pf, pm, lmbda, ww), g[f"{tag}_inverse_theta"], rtol=0, atol=0)
+        assert_close(O.tps_fit(pm, pf, lmbda, ww), g[f"{tag}_theta"], rtol=0, atol=0)
+        # the reference evaluates 4 sub-grids; chunking does not change per-voxel arithmetic but
+        # may change the BLAS blocking, hence a tolerance at rounding level
+        assert_close(O.tps_flow_field(pm, pf, lmbda, shape, ww), g[f"{tag}_grid"], rtol=1e-5, atol=2e-5)
+        assert_close(O.tps_forward_points(pm, pf, lmbda, pm, ww), g[f"{tag}_points_a"], rtol=1e-5, atol=1e-5)
+
+
+def test_golden_warp_and_losses(golden):
+    g = golden("warp_loss")
+    for mode in ("bilinear", "nearest"):
+        assert_close(O.align_img(g["grid"], g["x"], mode), g[mode], rtol=0, atol=0)
+        mine = torch.from_numpy(O.grid_sample3d_numpy(g["x"].numpy(), g["grid"].numpy(), mode))
+        if mode == "nearest":
+            assert torch.equal(mine, g[mode])          # pure gather: bit exact
+        else:
+            assert_close(mine, g[mode], rtol=1e-6, atol=1e-6)
+    p, t = g["seg_pred"], g["seg_target"]
+    assert_close(O.mse_loss(p, t), g["mse"], rtol=0, atol=0)
+    for hard in (0, 1):
+        for ign in (0, 1):
+            assert_close(O.dice_loss(p, t, bool(hard), bool(ign)), g[f"dice_h{hard}_i{ign}"], rtol=0, atol=0)
+            assert_close(O.dice_loss(p, t, bool(hard), bool(ign), True), g[f"dice_regions_h{hard}_i{ign}"],
+                         rtol=0, atol=0)
+
+
+def test_golden_com(golden):
+    g = golden("com")
+    assert_close(O.center_of_mass3d(g["heat"], ij=True), g["points_ij"], rtol=0, atol=0)
+    assert_close(O.center_of_mass3d(g["heat"], ij=False), g["points_xy"], rtol=0, atol=0)
+
+
+def test_golden_augment(golden):
+    g = golden("augment")
+    params = tuple(float(v) for v in g["params"])
+    img, seg = O.affine_augment(g["img"], params, seg=g["seg"])
+    assert_close(img, g["img_aug"], rtol=1e-6, atol=1e-6)
+    assert (seg != g["seg_aug"]).float().mean() < 1e-3   # nearest: a coordinate may sit on a tie
+
+
+def _seeded(cls_name, **kw):
+    import keymorph_b200 as kb
+    torch.manual_seed(23)
+    if cls_name == "trunc":
+        return kb.TruncatedUNet3D(1, 16, 1, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8,
+                                  num_levels=4, is_segmentation=False, conv_padding=1)
+    if cls_name == "unet":
+        return kb.UNet3D(1, 16, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8, num_levels=4,
+                         is_segmentation=False, conv_padding=1)
+    return kb.ConvNet(3, 1, 16, norm_type="instance")
+
+
+def test_golden_backbones(golden):
+    """Functional backbones of the oracle == the reference modules (same seeded weights)."""
+    g = golden("truncunet_k16")
+    sd = _seeded("trunc").state_dict()
+    h32 = O.unet3d_forward(sd, O.gaussian_phantom(32, 1000), 4, 1)
+    assert_close(h32, g["heat32"], rtol=1e-5, atol=1e-5)
+    assert_close(O.center_of_mass3d(h32), g["points32"], rtol=1e-5, atol=1e-5)
+    h64 = O.unet3d_forward(sd, O.gaussian_phantom(64, 1001), 4, 1)
+    assert_close(O.center_of_mass3d(h64), g["points64"], rtol=1e-5, atol=1e-5)
+
+    g = golden("unet_k16")
+    h64 = O.unet3d_forward(_seeded("unet").state_dict(), O.gaussian_phantom(64, 1001), 4, 0)
+    assert_close(O.center_of_mass3d(h64), g["points64"], rtol=1e-5, atol=1e-5)
+    assert_close(h64[:, :, ::8, ::8, ::8], g["heat64_sub"], rtol=1e-4, atol=1e-4)
+
+    g = golden("convnet_k16")
+    h = O.convnet_forward(_seeded("conv").state_dict(), O.gaussian_phantom(128, 1002))
+    assert_close(h, g["heat"], rtol=1e-4, atol=1e-4)
+    assert_close(O.center_of_mass3d(h), g["points"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("power", [False, True])
+def test_golden_forward(golden, power):
+    g = golden("forward32_power" if power else "forward32")
+    sd = _seeded("trunc").state_dict()
+    types = ["rigid", "affine", "tps_10", "tps_0.1"]
+    res = O.keymorph_forward("truncatedunet", sd, g["img_f"], g["img_m"], types,
+                             weight_keypoints="power" if power else None)
+    for t in types:
+        r = res[t]
+        assert_close(r["points_f"], g[f"{t}_points_f"], rtol=1e-5, atol=1e-5)
+        assert_close(r["points_m"], g[f"{t}_points_m"], rtol=1e-5, atol=1e-5)
+        tol = 2e-4 if t.startswith("tps") else 5e-5
+        assert_close(r["points_a"], g[f"{t}_points_a"], rtol=tol, atol=tol)
+        assert_close(r["grid"][:, ::2, ::2, ::2], g[f"{t}_grid"], rtol=tol, atol=tol)
+        if "matrix" in r:
+            assert_close(r["matrix"], g[f"{t}_matrix"], rtol=tol, atol=tol)
+        if power:
+            assert_close(r["points_weights"], g[f"{t}_weights"], rtol=1e-4, atol=1e-6)
+        img_a = O.align_img(r["grid"], g["img_m"])
+        assert_close(img_a[:, :, ::2, ::2, ::2], g[f"{t}_img_a"], rtol=1e-3, atol=1e-3)
+
+
+def test_golden_groupwise(golden):
+    g = golden("groupwise32")
+    sd = _seeded("trunc").state_dict()
+    subj = g["subjects"]
+    pts = torch.cat([O.center_of_mass3d(O.unet3d_forward(sd, subj[i:i + 1], 4, 1)) for i in range(len(subj))])
+    for t in ("rigid", "affine", "tps_1"):
+        assert_close(pts, g[f"{t}_points_m"], rtol=1e-5, atol=1e-5)
+        cur, mean = O.groupwise_points(pts, t, 3)
+        assert_close(cur, g[f"{t}_points_a"], rtol=1e-4, atol=1e-4)
+        for i in range(len(subj)):
+            grid = O.register_points(mean, pts[i:i + 1], t, subj.shape[2:], None, False)["grid"]
+            assert_close(grid[:, ::2, ::2, ::2], g[f"{t}_grid_{i}"], rtol=2e-4, atol=2e-4)
