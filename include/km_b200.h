@@ -41,6 +41,9 @@ int km_sm_count(void);
 /* runtime options: key KM_OPT_TPS_FAST (default 1): evaluate the TPS radial basis of the dense
  * flow field with lg2.approx / rsqrt.approx instead of logf / sqrtf. */
 #define KM_OPT_TPS_FAST 1
+/* key KM_OPT_CONV_FORCE_GENERIC (default 0): make km_conv3d_tc use the one-TMA-box-per-tap data
+ * path even where the x-halo-reuse path applies (A/B testing of the two paths). */
+#define KM_OPT_CONV_FORCE_GENERIC 2
 int km_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------ *

@@ -24,6 +24,8 @@ constexpr int kTileM = 128;
 constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr int kFstagePitch = 33;  // floats, conflict-free transposed access
+constexpr int kMaxStages = 12;
+int g_force_mode0 = 0;            // km_set_option(KM_OPT_CONV_FORCE_GENERIC): A/B the two data paths
 
 struct ConvGeom {
   int N, D, H, W, Cin, Cout;
@@ -35,7 +37,13 @@ struct ConvGeom {
   int stages;
   int flags;
   int has_out;
-  uint32_t a_bytes, b_bytes, b_stride;  // per stage
+  int mode;            // 0: one TMA box per tap (generic brick); 1: x-halo box shared by 3 dx taps
+  int sub;             // sub-iterations (A box + B box) packed into one pipeline stage
+  int ntap;            // MMAs groups per sub-iteration: 1 (mode 0) or 3 (mode 1: dx = -1, 0, +1)
+  int subiters;        // sub-iterations per tile: taps*chunks (mode 0) or 9*chunks (mode 1)
+  uint32_t a_sub_bytes, b_sub_bytes;      // TMA bytes per sub-iteration
+  uint32_t a_sub_stride, b_sub_stride;    // 1024-aligned slots inside a stage
+  uint32_t stage_stride;
   uint32_t off_staging, off_fstage, off_rowinfo, off_stats, off_com, off_scratch, off_bars;
   uint32_t staging_pitch;               // bytes per staged row (BN*2 + 16)
   uint32_t tmem_cols;
@@ -49,6 +57,19 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// accumulator row -> offset inside the output brick
+__device__ __forceinline__ void row_to_voxel(const ConvGeom& g, int row, int& tx, int& ty, int& tz) {
+  if (g.mode == 0) {
+    tx = row % g.TW;
+    ty = (row / g.TW) % g.TH;
+    tz = row / (g.TW * g.TH);
+  } else {  // rows are stored y-fastest so that an x step is a whole 8-row swizzle atom
+    ty = row & 7;
+    tx = row >> 3;
+    tz = 0;
+  }
 }
 
 struct TileCoord {
@@ -80,7 +101,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = g.stages;
-  const uint32_t stage_stride = g.a_bytes + g.b_stride;
+  const uint32_t stage_stride = g.stage_stride;
 
   const uint32_t bars = base + g.off_bars;  // full[stages], empty[stages], tfull[2], tempty[2]
   auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
@@ -121,31 +142,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int kiters = g.taps * g.chunks;
-
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       long long it = 0;
       for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(g, tile);
-        for (int tap = 0; tap < g.taps; ++tap) {
-          int dz = 0, dy = 0, dx = 0;
-          if (g.taps == 27) {
-            dz = tap / 9 - 1;
-            dy = (tap / 3) % 3 - 1;
-            dx = tap % 3 - 1;
-          }
-          for (int ch = 0; ch < g.chunks; ++ch, ++it) {
-            const int s = (int)(it % stages);
-            const uint32_t ph = (uint32_t)((it / stages) & 1);
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            mbar_arrive_expect_tx(full_bar(s), g.a_bytes + g.b_bytes);
-            const uint32_t a_dst = base + (uint32_t)s * stage_stride;
-            const uint32_t b_dst = a_dst + g.a_bytes;
-            tma_load_5d(a_dst, &tmA, full_bar(s), ch * g.kc, tc.x0 + dx, tc.y0 + dy, tc.z0 + dz,
-                        tc.n);
-            tma_load_3d(b_dst, &tmB, full_bar(s), ch * g.kc, tc.nb * g.BN, tap);
+        for (int si = 0; si < g.subiters; si += g.sub, ++it) {
+          const int nsub = min(g.sub, g.subiters - si);
+          const int s = (int)(it % stages);
+          const uint32_t ph = (uint32_t)((it / stages) & 1);
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), (uint32_t)nsub * (g.a_sub_bytes + g.b_sub_bytes));
+          const uint32_t a_base = base + (uint32_t)s * stage_stride;
+          const uint32_t b_base = a_base + (uint32_t)g.sub * g.a_sub_stride;
+          for (int u = 0; u < nsub; ++u) {
+            const int qi = si + u;
+            const int grp = qi / g.chunks, ch = qi % g.chunks;
+            const uint32_t a_dst = a_base + (uint32_t)u * g.a_sub_stride;
+            const uint32_t b_dst = b_base + (uint32_t)u * g.b_sub_stride;
+            if (g.mode == 0) {
+              int dz = 0, dy = 0, dx = 0;
+              if (g.taps == 27) {
+                dz = grp / 9 - 1;
+                dy = (grp / 3) % 3 - 1;
+                dx = grp % 3 - 1;
+              }
+              tma_load_5d(a_dst, &tmA, full_bar(s), ch * g.kc, tc.x0 + dx, tc.y0 + dy, tc.z0 + dz,
+                          tc.n);
+              tma_load_3d(b_dst, &tmB, full_bar(s), ch * g.kc, tc.nb * g.BN, grp);
+            } else {
+              // tensor map dims are (C, H, W, D, N): rows land as h + 8 * w, 18 x-columns incl. halo
+              const int dz = grp / 3 - 1, dy = grp % 3 - 1;
+              tma_load_5d(a_dst, &tmA, full_bar(s), ch * g.kc, tc.y0 + dy, tc.x0 - 1, tc.z0 + dz,
+                          tc.n);
+              tma_load_3d(b_dst, &tmB, full_bar(s), ch * g.kc, tc.nb * g.BN, grp * 3);
+            }
           }
         }
       }
@@ -162,17 +194,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.BN);
-        for (int ki = 0; ki < kiters; ++ki, ++it) {
+        uint32_t accum = 0;
+        const uint32_t a_tap = 8u * (uint32_t)(g.kc * 2);           // one 8-row swizzle atom = one x step
+        const uint32_t b_tap = (uint32_t)g.BN * (uint32_t)(g.kc * 2);
+        for (int si = 0; si < g.subiters; si += g.sub, ++it) {
+          const int nsub = min(g.sub, g.subiters - si);
           const int s = (int)(it % stages);
           const uint32_t ph = (uint32_t)((it / stages) & 1);
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t a_addr = base + (uint32_t)s * stage_stride;
-          const uint32_t b_addr = a_addr + g.a_bytes;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t adesc = umma_smem_desc(a_addr + 32u * kk, g.sbo, g.layout);
-            const uint64_t bdesc = umma_smem_desc(b_addr + 32u * kk, g.sbo, g.layout);
-            umma_bf16(d_tmem, adesc, bdesc, g.idesc, (ki > 0 || kk > 0) ? 1u : 0u);
+          const uint32_t a_base = base + (uint32_t)s * stage_stride;
+          const uint32_t b_base = a_base + (uint32_t)g.sub * g.a_sub_stride;
+          for (int u = 0; u < nsub; ++u) {
+            const uint32_t a_addr = a_base + (uint32_t)u * g.a_sub_stride;
+            const uint32_t b_addr = b_base + (uint32_t)u * g.b_sub_stride;
+            for (int t = 0; t < g.ntap; ++t) {
+              for (int kk = 0; kk < ksteps; ++kk) {
+                const uint64_t adesc = umma_smem_desc(a_addr + t * a_tap + 32u * kk, g.sbo, g.layout);
+                const uint64_t bdesc = umma_smem_desc(b_addr + t * b_tap + 32u * kk, g.sbo, g.layout);
+                umma_bf16(d_tmem, adesc, bdesc, g.idesc, accum);
+                accum = 1u;
+              }
+            }
           }
           umma_commit(empty_bar(s));  // frees the smem stage when these MMAs have read it
         }
@@ -207,9 +250,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = tc.nb * BN;
 
       // voxel of this row
-      const int tx = row % g.TW;
-      const int ty = (row / g.TW) % g.TH;
-      const int tz = row / (g.TW * g.TH);
+      int tx, ty, tz;
+      row_to_voxel(g, row, tx, ty, tz);
       const int vx = tc.x0 + tx, vy = tc.y0 + ty, vz = tc.z0 + tz;
       const bool valid = (vx < g.W) && (vy < g.H) && (vz < g.D);
       rowvalid[row] = valid ? 1 : 0;
@@ -329,11 +371,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (has_out) {
         const int total_chunks = kTileM * cpr;
         for (int id = et; id < total_chunks; id += kEpiThreads) {
-          const int r2 = id / cpr, j = id % cpr;
+          const int j = id % cpr;
+          int r2 = id / cpr;
+          if (g.mode == 1) r2 = ((r2 & 15) << 3) | (r2 >> 4);   // walk x fastest for coalescing
           if (!rowvalid[r2]) continue;
-          const int x2 = tc.x0 + r2 % g.TW;
-          const int y2 = tc.y0 + (r2 / g.TW) % g.TH;
-          const int z2 = tc.z0 + r2 / (g.TW * g.TH);
+          int tx2, ty2, tz2;
+          row_to_voxel(g, r2, tx2, ty2, tz2);
+          const int x2 = tc.x0 + tx2, y2 = tc.y0 + ty2, z2 = tc.z0 + tz2;
           const size_t vox = (((size_t)tc.n * g.D + z2) * g.H + y2) * g.W + x2;
           const uint4 v = *reinterpret_cast<const uint4*>(staging + (size_t)r2 * pitch + j * 16);
           *reinterpret_cast<uint4*>(out + vox * g.Cout + n0 + j * 8) = v;
@@ -425,6 +469,7 @@ inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 }  // namespace
 
 extern "C" int km_sm_count(void) { return sm_count(); }
+void km_conv_set_force_generic(int v) { g_force_mode0 = v ? 1 : 0; }
 extern "C" int km_conv_nparts(void) { return sm_count(); }
 
 extern "C" int km_pack_weights(const float* w, void* packed, int Cout, int Cin, int taps,
@@ -463,34 +508,48 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   g.has_out = out ? 1 : 0;
   g.kc = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
   g.chunks = Cin / g.kc;
-  // output brick: as long a W-run as possible, then H, then D (power-of-two factors of 128)
-  auto pow2_le = [](int v, int cap) { int p = 1; while (p * 2 <= v && p * 2 <= cap) p *= 2; return p; };
-  g.TW = pow2_le(W, 128);
-  g.TH = pow2_le(H, 128 / g.TW);
-  g.TD = 128 / (g.TW * g.TH);
-  // volumes with fewer than 128 voxels (deepest level of small test inputs): the brick sticks out
-  // of the tensor in D; TMA zero-fills the out-of-bounds part and the epilogue masks those rows.
-  KM_CHECK_ARG(g.TD <= 256, "km_conv3d_tc: volume %dx%dx%d too small", D, H, W);
-  g.tiles_x = (W + g.TW - 1) / g.TW;
-  g.tiles_y = (H + g.TH - 1) / g.TH;
-  g.tiles_z = (D + g.TD - 1) / g.TD;
-  // output-channel block: largest divisor of Cout that is <= 256 and a multiple of 16 (32 for CoM)
+  const int row_bytes = g.kc * 2;
+  // mode 1 (x-halo reuse): the brick is 16(x) x 8(y) x 1(z); ONE TMA box of 18 x-columns serves the
+  // three dx taps (an x step is a whole 8-row swizzle atom, so the tap is selected by the start
+  // address of the UMMA descriptor) -> 9 instead of 27 activation boxes per Cin chunk.
+  g.mode = (taps == 27 && H >= 8 && W >= 16 && !g_force_mode0) ? 1 : 0;
   const int gran = (flags & KM_CONV_COM) ? 32 : 16;
   KM_CHECK_ARG(Cout % gran == 0, "km_conv3d_tc: Cout must be a multiple of %d in this mode", gran);
+  const int bn_cap = g.mode == 1 ? 128 : 256;
   g.BN = 0;
-  for (int bn = 256; bn >= gran; bn -= gran)
+  for (int bn = bn_cap; bn >= gran; bn -= gran)
     if (Cout % bn == 0) { g.BN = bn; break; }
   KM_CHECK_ARG(g.BN > 0, "km_conv3d_tc: no channel block for Cout=%d", Cout);
   g.n_blocks = Cout / g.BN;
+  if (g.mode == 1) {
+    g.TW = 16; g.TH = 8; g.TD = 1;
+    g.ntap = 3;
+    g.subiters = 9 * g.chunks;
+    g.a_sub_bytes = 18u * 8u * row_bytes;
+    g.b_sub_bytes = 3u * (uint32_t)g.BN * row_bytes;
+  } else {
+    // generic brick: as long a W-run as possible, then H, then D (power-of-two factors of 128).
+    // Volumes with fewer than 128 voxels (deepest level of small inputs): the brick sticks out of
+    // the tensor; TMA zero-fills the out-of-bounds part and the epilogue masks those rows.
+    auto pow2_le = [](int v, int cap) { int p = 1; while (p * 2 <= v && p * 2 <= cap) p *= 2; return p; };
+    g.TW = pow2_le(W, 128);
+    g.TH = pow2_le(H, 128 / g.TW);
+    g.TD = 128 / (g.TW * g.TH);
+    g.ntap = 1;
+    g.subiters = taps * g.chunks;
+    g.a_sub_bytes = (uint32_t)kTileM * row_bytes;
+    g.b_sub_bytes = (uint32_t)g.BN * row_bytes;
+  }
+  g.a_sub_stride = round_up(g.a_sub_bytes, 1024);
+  g.b_sub_stride = round_up(g.b_sub_bytes, 1024);
+  g.tiles_x = (W + g.TW - 1) / g.TW;
+  g.tiles_y = (H + g.TH - 1) / g.TH;
+  g.tiles_z = (D + g.TD - 1) / g.TD;
   g.total_tiles = (long long)N * g.tiles_z * g.tiles_y * g.tiles_x * g.n_blocks;
 
-  const int row_bytes = g.kc * 2;
   g.layout = umma_layout_for_row_bytes(row_bytes);
   g.sbo = 8u * (uint32_t)row_bytes;
   g.idesc = umma_idesc_bf16(kTileM, g.BN);
-  g.a_bytes = (uint32_t)kTileM * row_bytes;
-  g.b_bytes = (uint32_t)g.BN * row_bytes;
-  g.b_stride = round_up(g.b_bytes, 1024);
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)g.BN) cols *= 2;
   g.tmem_cols = cols;
@@ -499,25 +558,32 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   // shared-memory carve-up (offsets relative to the 1024-aligned base)
   const uint32_t kSmemMax = 232448 - 1024;  // 227 KB minus alignment slack
   g.staging_pitch = (uint32_t)g.BN * 2 + 16;
-  uint32_t fixed = 0;
   const uint32_t staging_bytes = g.has_out ? round_up(kTileM * g.staging_pitch, 16) : 0;
   const uint32_t fstage_bytes = (flags & KM_CONV_COM) ? 2u * kTileM * kFstagePitch * 4u : 0;
   const uint32_t rowinfo_bytes = 3u * kTileM * 4u + kTileM;
   const uint32_t stats_bytes = (flags & KM_CONV_STATS) ? (uint32_t)N * Cout * 2u * 4u : 0;
   const uint32_t com_bytes = (flags & KM_CONV_COM) ? (uint32_t)N * Cout * 4u * 4u : 0;
   const uint32_t scratch_bytes = (flags & KM_CONV_COM) ? 2u * 4u * 32u * 4u * 4u : 0;
-  const uint32_t bars_bytes = 8u * (2u * 8u + 4u) + 16u;
-  fixed = staging_bytes + fstage_bytes + rowinfo_bytes + stats_bytes + com_bytes + scratch_bytes +
-          bars_bytes + 64;
-  const uint32_t stage_stride = g.a_bytes + g.b_stride;
-  KM_CHECK_ARG(fixed + 2 * stage_stride <= kSmemMax,
+  const uint32_t bars_bytes = 8u * (2u * kMaxStages + 4u) + 16u;
+  const uint32_t fixed = staging_bytes + fstage_bytes + rowinfo_bytes + stats_bytes + com_bytes +
+                         scratch_bytes + bars_bytes + 64;
+  const uint32_t unit = g.a_sub_stride + g.b_sub_stride;
+  KM_CHECK_ARG(fixed + 2 * unit <= kSmemMax,
                "km_conv3d_tc: shared memory budget exceeded (N*Cout too large: N=%d Cout=%d)", N, Cout);
-  int stages = (int)((kSmemMax - fixed) / stage_stride);
-  if (stages > 8) stages = 8;
-  const int kiters = taps * g.chunks;
-  (void)kiters;
+  const uint32_t avail = kSmemMax - fixed;
+  // pack sub-iterations into a stage until it holds ~40 KB (fewer barrier round trips, more bytes
+  // in flight per barrier) while keeping at least 3 stages
+  int sub = 1;
+  while (sub < g.subiters && (uint32_t)(sub + 1) * unit <= 40u * 1024u &&
+         (uint32_t)(sub + 1) * unit * 3u <= avail)
+    ++sub;
+  g.sub = sub;
+  g.stage_stride = (uint32_t)sub * unit;
+  int stages = (int)(avail / g.stage_stride);
+  if (stages > kMaxStages) stages = kMaxStages;
+  KM_CHECK_ARG(stages >= 2, "km_conv3d_tc: not enough shared memory for a 2-stage pipeline");
   g.stages = stages;
-  uint32_t off = (uint32_t)stages * stage_stride;
+  uint32_t off = (uint32_t)stages * g.stage_stride;
   g.off_staging = off; off += staging_bytes;
   g.off_fstage = off; off += fstage_bytes;
   g.off_rowinfo = off; off += round_up(rowinfo_bytes, 16);
@@ -543,6 +609,12 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2,
                              (cuuint64_t)H * W * Cin * 2, (cuuint64_t)D * H * W * Cin * 2};
     cuuint32_t box[5] = {(cuuint32_t)g.kc, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TD, 1};
+    if (g.mode == 1) {
+      // (C, H, W, D, N): y is the fastest spatial index in shared memory (8 rows = one swizzle atom)
+      dims[1] = (cuuint64_t)H; dims[2] = (cuuint64_t)W;
+      strides[0] = (cuuint64_t)W * Cin * 2; strides[1] = (cuuint64_t)Cin * 2;
+      box[1] = 8; box[2] = 18; box[3] = 1;
+    }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -555,7 +627,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)g.kc, (cuuint32_t)g.BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)g.kc, (cuuint32_t)g.BN, (cuuint32_t)(g.mode == 1 ? 3 : 1)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wp), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,

@@ -53,12 +53,9 @@ __host__ __device__ __forceinline__ float km_linspace(float start, float end, in
   if (n <= 1) return start;
   const float step = (end - start) / (float)(n - 1);
   const int half = n / 2;
-#ifdef __CUDA_ARCH__
-  return (i < half) ? __fadd_rn(start, __fmul_rn(step, (float)i))
-                    : __fsub_rn(end, __fmul_rn(step, (float)(n - 1 - i)));
-#else
-  return (i < half) ? (start + step * (float)i) : (end - step * (float)(n - 1 - i));
-#endif
+  // torch's CPU (AVX2) and CUDA kernels both contract start + step*i into one FMA; verified
+  // bit-for-bit against torch.linspace for n in 2..512 (tests/test_gpu_parity.py)
+  return (i < half) ? fmaf(step, (float)i, start) : fmaf(-step, (float)(n - 1 - i), end);
 }
 
 __device__ __forceinline__ float km_warp_sum(float v) {

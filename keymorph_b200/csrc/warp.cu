@@ -13,6 +13,9 @@
 namespace {
 
 int g_tps_fast = 1;
+}  // namespace
+void km_conv_set_force_generic(int v);
+namespace {
 
 // ---- ATen grid_sampler_3d source-index arithmetic (align_corners=False, padding "border"),
 // written without FMA contraction so that it rounds like the scalar CPU reference.
@@ -449,6 +452,10 @@ inline int blocks_for(long long items, int threads, int cap) {
 extern "C" int km_set_option(int key, int value) {
   if (key == KM_OPT_TPS_FAST) {
     g_tps_fast = value ? 1 : 0;
+    return KM_OK;
+  }
+  if (key == KM_OPT_CONV_FORCE_GENERIC) {
+    km_conv_set_force_generic(value);
     return KM_OK;
   }
   km_set_error("km_set_option: unknown key %d", key);

@@ -336,6 +336,7 @@ def _conv_case(N, Cin, Cout, D, H, W, taps, relu, bias):
 
 
 def run_conv():
+    from keymorph_b200 import _lib
     ok = True
     cases = [
         (1, 64, 64, 8, 8, 8, 27, True, False),     # SW128, single tile row
@@ -351,12 +352,18 @@ def run_conv():
         (1, 64, 64, 10, 12, 20, 27, True, False),  # clipped bricks
         (1, 32, 64, 64, 64, 64, 27, True, False),
     ]
-    for c in cases:
-        try:
-            ok &= _conv_case(*c)
-        except Exception as e:  # noqa: BLE001
-            print(f"  [FAIL] conv case {c}: {type(e).__name__}: {e}", flush=True)
-            return False
+    cases += [(1, 64, 64, 4, 4, 4, 27, True, False), (2, 128, 128, 4, 4, 4, 27, True, False),
+              (1, 64, 64, 8, 24, 40, 27, True, False), (1, 32, 64, 5, 9, 17, 27, True, False)]
+    for force in (0, 1):
+        _lib.call("km_set_option", _lib.KM_OPT_CONV_FORCE_GENERIC, force)
+        print(f"  -- force generic path = {force}")
+        for c in cases:
+            try:
+                ok &= _conv_case(*c)
+            except Exception as e:  # noqa: BLE001
+                print(f"  [FAIL] conv case {c}: {type(e).__name__}: {e}", flush=True)
+                return False
+    _lib.call("km_set_option", _lib.KM_OPT_CONV_FORCE_GENERIC, 0)
     return ok
 
 
