@@ -5,14 +5,24 @@
 // 1x1x1 conv), the latter fused with keymorph/layers.py:92-134 (ReLU + centre of mass) so that the
 // heat map never has to reach HBM.
 //
-// GEMM view:  D[128 voxels x BN] += A[128 voxels x kc] * B[BN x kc]^T  for every (tap, Cin chunk)
-//   A = activation brick (TW x TH x TD = 128 voxels) shifted by the tap offset, fetched by ONE TMA
-//       box copy from the bf16 NDHWC tensor (out-of-bounds rows are zero-filled = conv padding);
+// GEMM view:  D[128 voxels x BN] += A[128 voxels x KC] * B[BN x KC]^T  for every (tap, Cin chunk)
+//   A = activation brick shifted by the tap offset, fetched by TMA from the bf16 NDHWC tensor
+//       (out-of-bounds rows are zero-filled = conv padding);
 //   B = weights [tap][Cout][Cin], K-major, fetched by TMA;
 //   D = fp32 accumulator in TMEM, double buffered so the epilogue of tile i overlaps tile i+1.
 // Roles (192 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
 // warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU -> bf16 staging in smem -> coalesced stores,
 // per-channel sum / sum-of-squares for the next GroupNorm, or centre-of-mass partials).
+//
+// Two data paths (template parameter MODE):
+//   MODE 1 "x-halo reuse" (3x3x3, H >= 8, W >= 16): brick 16(x) x 8(y) x 1(z).  The tensor map
+//     orders the dims (C, H, W, D, N) so that shared-memory rows run y-fastest; an x step is then
+//     exactly one 8-row swizzle atom and the three dx taps read the SAME 18-column box through UMMA
+//     descriptors whose start address differs by one atom: 9 activation boxes per Cin chunk
+//     instead of 27.
+//   MODE 0 generic (1x1x1, tiny volumes): one box per tap, brick = longest W-run x H x D.
+// The single-thread producer / issuer loops are kept free of divisions and descriptor rebuilds:
+// with one thread feeding the tensor core, instruction count per MMA is what limits throughput.
 #include "km_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -30,17 +40,16 @@ int g_force_mode0 = 0;            // km_set_option(KM_OPT_CONV_FORCE_GENERIC): A
 struct ConvGeom {
   int N, D, H, W, Cin, Cout;
   int taps;
-  int kc, chunks;      // Cin chunk per k-iteration, number of chunks
+  int chunks;          // Cin / KC
   int TW, TH, TD;      // output brick, TW*TH*TD == 128
   int tiles_x, tiles_y, tiles_z;
   int BN, n_blocks;    // output-channel block
   int stages;
   int flags;
   int has_out;
-  int mode;            // 0: one TMA box per tap (generic brick); 1: x-halo box shared by 3 dx taps
   int sub;             // sub-iterations (A box + B box) packed into one pipeline stage
-  int ntap;            // MMAs groups per sub-iteration: 1 (mode 0) or 3 (mode 1: dx = -1, 0, +1)
   int subiters;        // sub-iterations per tile: taps*chunks (mode 0) or 9*chunks (mode 1)
+  int stat_parts;      // row groups that accumulate channel statistics independently
   uint32_t a_sub_bytes, b_sub_bytes;      // TMA bytes per sub-iteration
   uint32_t a_sub_stride, b_sub_stride;    // 1024-aligned slots inside a stage
   uint32_t stage_stride;
@@ -48,8 +57,7 @@ struct ConvGeom {
   uint32_t staging_pitch;               // bytes per staged row (BN*2 + 16)
   uint32_t tmem_cols;
   uint32_t idesc;
-  uint32_t sbo, layout;
-  long long total_tiles;
+  int total_tiles;
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -60,8 +68,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // accumulator row -> offset inside the output brick
+template <int MODE>
 __device__ __forceinline__ void row_to_voxel(const ConvGeom& g, int row, int& tx, int& ty, int& tz) {
-  if (g.mode == 0) {
+  if (MODE == 0) {
     tx = row % g.TW;
     ty = (row / g.TW) % g.TH;
     tz = row / (g.TW * g.TH);
@@ -75,24 +84,31 @@ __device__ __forceinline__ void row_to_voxel(const ConvGeom& g, int row, int& tx
 struct TileCoord {
   int nb, n, x0, y0, z0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, long long t) {
+__device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int t) {
   TileCoord c;
-  c.nb = (int)(t % g.n_blocks);
+  c.nb = t % g.n_blocks;
   t /= g.n_blocks;
-  c.x0 = (int)(t % g.tiles_x) * g.TW;
+  c.x0 = (t % g.tiles_x) * g.TW;
   t /= g.tiles_x;
-  c.y0 = (int)(t % g.tiles_y) * g.TH;
+  c.y0 = (t % g.tiles_y) * g.TH;
   t /= g.tiles_y;
-  c.z0 = (int)(t % g.tiles_z) * g.TD;
+  c.z0 = (t % g.tiles_z) * g.TD;
   t /= g.tiles_z;
-  c.n = (int)t;
+  c.n = t;
   return c;
 }
 
+template <int KC, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvGeom g, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                float* __restrict__ stats, float* __restrict__ com) {
+  constexpr int kRowBytes = KC * 2;
+  constexpr int kSteps = KC / 16;
+  constexpr int kNtap = MODE == 1 ? 3 : 1;
+  constexpr uint32_t kLayout = kRowBytes == 128 ? 2u : (kRowBytes == 64 ? 4u : 6u);
+  constexpr uint32_t kSbo = 8u * kRowBytes;
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -133,7 +149,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);
     float* s_com = reinterpret_cast<float*>(sm + g.off_com);
     if (g.flags & KM_CONV_STATS)
-      for (int i = threadIdx.x; i < g.N * g.Cout * 2; i += kThreads) s_stats[i] = 0.f;
+      for (int i = threadIdx.x; i < g.stat_parts * g.N * g.Cout * 2; i += kThreads) s_stats[i] = 0.f;
     if (g.flags & KM_CONV_COM)
       for (int i = threadIdx.x; i < g.N * g.Cout * 4; i += kThreads) s_com[i] = 0.f;
   }
@@ -142,42 +158,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  const int sub = g.sub;
+  const int n_stage_iters = (g.subiters + sub - 1) / sub;
+  const int last_nsub = g.subiters - (n_stage_iters - 1) * sub;
+
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      long long it = 0;
-      for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t sub_tx = g.a_sub_bytes + g.b_sub_bytes;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(g, tile);
-        for (int si = 0; si < g.subiters; si += g.sub, ++it) {
-          const int nsub = min(g.sub, g.subiters - si);
-          const int s = (int)(it % stages);
-          const uint32_t ph = (uint32_t)((it / stages) & 1);
+        const int bn0 = tc.nb * g.BN;
+        int grp = 0, ch = 0;  // grp: tap (mode 0) or (dz,dy) pair (mode 1); ch: Cin chunk
+        int dz = g.taps == 27 ? -1 : 0, dy = dz, dx = dz;
+        for (int si = 0; si < n_stage_iters; ++si) {
+          const int nsub = (si == n_stage_iters - 1) ? last_nsub : sub;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_arrive_expect_tx(full_bar(s), (uint32_t)nsub * (g.a_sub_bytes + g.b_sub_bytes));
-          const uint32_t a_base = base + (uint32_t)s * stage_stride;
-          const uint32_t b_base = a_base + (uint32_t)g.sub * g.a_sub_stride;
+          mbar_arrive_expect_tx(full_bar(s), (uint32_t)nsub * sub_tx);
+          uint32_t a_dst = base + (uint32_t)s * stage_stride;
+          uint32_t b_dst = a_dst + (uint32_t)sub * g.a_sub_stride;
           for (int u = 0; u < nsub; ++u) {
-            const int qi = si + u;
-            const int grp = qi / g.chunks, ch = qi % g.chunks;
-            const uint32_t a_dst = a_base + (uint32_t)u * g.a_sub_stride;
-            const uint32_t b_dst = b_base + (uint32_t)u * g.b_sub_stride;
-            if (g.mode == 0) {
-              int dz = 0, dy = 0, dx = 0;
-              if (g.taps == 27) {
-                dz = grp / 9 - 1;
-                dy = (grp / 3) % 3 - 1;
-                dx = grp % 3 - 1;
-              }
-              tma_load_5d(a_dst, &tmA, full_bar(s), ch * g.kc, tc.x0 + dx, tc.y0 + dy, tc.z0 + dz,
+            if (MODE == 0) {
+              tma_load_5d(a_dst, &tmA, full_bar(s), ch * KC, tc.x0 + dx, tc.y0 + dy, tc.z0 + dz,
                           tc.n);
-              tma_load_3d(b_dst, &tmB, full_bar(s), ch * g.kc, tc.nb * g.BN, grp);
+              tma_load_3d(b_dst, &tmB, full_bar(s), ch * KC, bn0, grp);
             } else {
               // tensor map dims are (C, H, W, D, N): rows land as h + 8 * w, 18 x-columns incl. halo
-              const int dz = grp / 3 - 1, dy = grp % 3 - 1;
-              tma_load_5d(a_dst, &tmA, full_bar(s), ch * g.kc, tc.y0 + dy, tc.x0 - 1, tc.z0 + dz,
+              tma_load_5d(a_dst, &tmA, full_bar(s), ch * KC, tc.y0 + dy, tc.x0 - 1, tc.z0 + dz,
                           tc.n);
-              tma_load_3d(b_dst, &tmB, full_bar(s), ch * g.kc, tc.nb * g.BN, grp * 3);
+              tma_load_3d(b_dst, &tmB, full_bar(s), ch * KC, bn0, grp * 3);
             }
+            a_dst += g.a_sub_stride;
+            b_dst += g.b_sub_stride;
+            if (++ch == g.chunks) {
+              ch = 0;
+              ++grp;
+              if (MODE == 0) {
+                if (++dx == 2) {
+                  dx = -1;
+                  if (++dy == 2) {
+                    dy = -1;
+                    ++dz;
+                  }
+                }
+              } else {
+                if (++dy == 2) {
+                  dy = -1;
+                  ++dz;
+                }
+              }
+            }
+          }
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1u;
           }
         }
       }
@@ -185,41 +221,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     if (lane == 0) {
-      long long it = 0;
-      long long tcount = 0;
-      const int ksteps = g.kc / 16;
-      for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tcount) {
-        const int acc = (int)(tcount & 1);
-        const uint32_t acc_ph = (uint32_t)((tcount >> 1) & 1);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t tcount = 0;
+      // UMMA smem descriptor: hi word is constant, lo word = (addr >> 4) | LBO(=1) << 16
+      const uint64_t desc_hi =
+          ((uint64_t)((kSbo >> 4) | (1u << 14) | (kLayout << 29))) << 32;
+      const uint32_t lo_flag = 1u << 16;
+      const uint32_t a_tap16 = (8u * kRowBytes) >> 4;                 // one swizzle atom = one x step
+      const uint32_t b_tap16 = ((uint32_t)g.BN * kRowBytes) >> 4;
+      const uint32_t a_sub16 = g.a_sub_stride >> 4, b_sub16 = g.b_sub_stride >> 4;
+      const uint32_t base16 = (base & 0x3FFFFu) >> 4;
+      const uint32_t stage16 = stage_stride >> 4;
+      const uint32_t boff16 = ((uint32_t)sub * g.a_sub_stride) >> 4;
+      const uint32_t idesc = g.idesc;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u;
+        const uint32_t acc_ph = (tcount >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.BN);
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)g.BN;
         uint32_t accum = 0;
-        const uint32_t a_tap = 8u * (uint32_t)(g.kc * 2);           // one 8-row swizzle atom = one x step
-        const uint32_t b_tap = (uint32_t)g.BN * (uint32_t)(g.kc * 2);
-        for (int si = 0; si < g.subiters; si += g.sub, ++it) {
-          const int nsub = min(g.sub, g.subiters - si);
-          const int s = (int)(it % stages);
-          const uint32_t ph = (uint32_t)((it / stages) & 1);
+        for (int si = 0; si < n_stage_iters; ++si) {
+          const int nsub = (si == n_stage_iters - 1) ? last_nsub : sub;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t a_base = base + (uint32_t)s * stage_stride;
-          const uint32_t b_base = a_base + (uint32_t)g.sub * g.a_sub_stride;
+          uint32_t a16 = base16 + (uint32_t)s * stage16;
+          uint32_t b16 = a16 + boff16;
           for (int u = 0; u < nsub; ++u) {
-            const uint32_t a_addr = a_base + (uint32_t)u * g.a_sub_stride;
-            const uint32_t b_addr = b_base + (uint32_t)u * g.b_sub_stride;
-            for (int t = 0; t < g.ntap; ++t) {
-              for (int kk = 0; kk < ksteps; ++kk) {
-                const uint64_t adesc = umma_smem_desc(a_addr + t * a_tap + 32u * kk, g.sbo, g.layout);
-                const uint64_t bdesc = umma_smem_desc(b_addr + t * b_tap + 32u * kk, g.sbo, g.layout);
-                umma_bf16(d_tmem, adesc, bdesc, g.idesc, accum);
+#pragma unroll
+            for (int t = 0; t < kNtap; ++t) {
+#pragma unroll
+              for (int kk = 0; kk < kSteps; ++kk) {
+                const uint64_t adesc = desc_hi | (uint64_t)((a16 + t * a_tap16 + 2u * kk) | lo_flag);
+                const uint64_t bdesc = desc_hi | (uint64_t)((b16 + t * b_tap16 + 2u * kk) | lo_flag);
+                umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
                 accum = 1u;
               }
             }
+            a16 += a_sub16;
+            b16 += b_sub16;
           }
           umma_commit(empty_bar(s));  // frees the smem stage when these MMAs have read it
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        umma_commit(tfull_bar((int)acc));  // accumulator complete -> epilogue
       }
     }
   } else {
@@ -231,7 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* fstage = reinterpret_cast<float*>(sm + g.off_fstage);
     float* rowlin = reinterpret_cast<float*>(sm + g.off_rowinfo);          // [3][128] lz, ly, lx
     uint8_t* rowvalid = sm + g.off_rowinfo + 3 * kTileM * sizeof(float);   // [128]
-    float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);
+    float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);           // [parts][N][Cout][2]
     float* s_com = reinterpret_cast<float*>(sm + g.off_com);
     float* scratch = reinterpret_cast<float*>(sm + g.off_scratch);         // [2][4][32][4]
     const bool do_relu = (g.flags & KM_CONV_RELU) != 0;
@@ -241,17 +290,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int BN = g.BN;
     const uint32_t pitch = g.staging_pitch;
     const int cpr = BN / 8;  // 16-byte chunks per staged row
+    const int parts = g.stat_parts;
+    const int rows_per_part = kTileM / parts;
 
-    long long tcount = 0;
-    for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tcount) {
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tcount) {
       const TileCoord tc = decode_tile(g, tile);
-      const int acc = (int)(tcount & 1);
-      const uint32_t acc_ph = (uint32_t)((tcount >> 1) & 1);
+      const uint32_t acc = tcount & 1u;
+      const uint32_t acc_ph = (tcount >> 1) & 1u;
       const int n0 = tc.nb * BN;
 
       // voxel of this row
       int tx, ty, tz;
-      row_to_voxel(g, row, tx, ty, tz);
+      row_to_voxel<MODE>(g, row, tx, ty, tz);
       const int vx = tc.x0 + tx, vy = tc.y0 + ty, vz = tc.z0 + tz;
       const bool valid = (vx < g.W) && (vy < g.H) && (vz < g.D);
       rowvalid[row] = valid ? 1 : 0;
@@ -261,9 +312,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         rowlin[2 * kTileM + row] = km_linspace(0.f, 1.f, g.W, vx);
       }
 
-      mbar_wait(tfull_bar(acc), acc_ph);
+      mbar_wait(tfull_bar((int)acc), acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN;
 
       if (!do_com) {
         for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -283,14 +334,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               a = fmaxf(a, 0.f);
               b = fmaxf(b, 0.f);
             }
-            pk[j] = pack_bf16(a, b);
+            // rows outside the volume are staged as zeros so that the statistics need no mask
+            pk[j] = valid ? pack_bf16(a, b) : 0u;
           }
           uint4* dst = reinterpret_cast<uint4*>(staging + (size_t)row * pitch + (size_t)c0 * 2);
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
+        mbar_arrive(tempty_bar((int)acc));
         epi_bar();
       } else {
         // final conv + centre of mass: 32-column chunks, transposed through fp32 smem
@@ -323,7 +375,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (cc == nchunks - 1) {
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            mbar_arrive(tempty_bar((int)acc));
           }
           epi_bar();
           // combine the previous chunk's quarter partials (written before this barrier)
@@ -373,10 +425,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int id = et; id < total_chunks; id += kEpiThreads) {
           const int j = id % cpr;
           int r2 = id / cpr;
-          if (g.mode == 1) r2 = ((r2 & 15) << 3) | (r2 >> 4);   // walk x fastest for coalescing
+          if (MODE == 1) r2 = ((r2 & 15) << 3) | (r2 >> 4);   // walk x fastest for coalescing
           if (!rowvalid[r2]) continue;
           int tx2, ty2, tz2;
-          row_to_voxel(g, r2, tx2, ty2, tz2);
+          row_to_voxel<MODE>(g, r2, tx2, ty2, tz2);
           const int x2 = tc.x0 + tx2, y2 = tc.y0 + ty2, z2 = tc.z0 + tz2;
           const size_t vox = (((size_t)tc.n * g.D + z2) * g.H + y2) * g.W + x2;
           const uint4 v = *reinterpret_cast<const uint4*>(staging + (size_t)r2 * pitch + j * 16);
@@ -384,16 +436,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       if (do_stats) {
-        for (int col = et; col < BN; col += kEpiThreads) {
+        // thread -> (column, row group); every (part, column) slot is owned by one thread
+        for (int id = et; id < parts * BN; id += kEpiThreads) {
+          const int col = id % BN, part = id / BN;
+          const uint8_t* p = staging + (size_t)(part * rows_per_part) * pitch + (size_t)col * 2;
           float s = 0.f, ss = 0.f;
-          for (int r2 = 0; r2 < kTileM; ++r2) {
-            if (!rowvalid[r2]) continue;
-            const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
-                staging + (size_t)r2 * pitch + (size_t)col * 2));
+#pragma unroll 8
+          for (int rr = 0; rr < rows_per_part; ++rr) {
+            const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
+            p += pitch;
             s += v;
             ss = fmaf(v, v, ss);
           }
-          float* d = s_stats + ((size_t)tc.n * g.Cout + n0 + col) * 2;
+          float* d = s_stats + (((size_t)part * g.N + tc.n) * g.Cout + n0 + col) * 2;
           d[0] += s;
           d[1] += ss;
         }
@@ -405,7 +460,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     epi_bar();
     if (do_stats) {
       float* dst = stats + (size_t)blockIdx.x * g.N * g.Cout * 2;
-      for (int i = et; i < g.N * g.Cout * 2; i += kEpiThreads) dst[i] = s_stats[i];
+      const int n = g.N * g.Cout * 2;
+      for (int i = et; i < n; i += kEpiThreads) {
+        float a = 0.f;
+        for (int p = 0; p < parts; ++p) a += s_stats[(size_t)p * n + i];
+        dst[i] = a;
+      }
     }
     if (do_com) {
       float* dst = com + (size_t)blockIdx.x * g.N * g.Cout * 4;
@@ -466,6 +526,20 @@ int sm_count() {
 
 inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
+typedef void (*ConvKernel)(const CUtensorMap, const CUtensorMap, const ConvGeom, const float*,
+                           __nv_bfloat16*, float*, float*);
+
+ConvKernel pick_kernel(int kc, int mode) {
+  if (mode == 1) {
+    if (kc == 64) return conv_tc_kernel<64, 1>;
+    if (kc == 32) return conv_tc_kernel<32, 1>;
+    return conv_tc_kernel<16, 1>;
+  }
+  if (kc == 64) return conv_tc_kernel<64, 0>;
+  if (kc == 32) return conv_tc_kernel<32, 0>;
+  return conv_tc_kernel<16, 0>;
+}
+
 }  // namespace
 
 extern "C" int km_sm_count(void) { return sm_count(); }
@@ -506,24 +580,20 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   g.taps = taps;
   g.flags = flags;
   g.has_out = out ? 1 : 0;
-  g.kc = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
-  g.chunks = Cin / g.kc;
-  const int row_bytes = g.kc * 2;
-  // mode 1 (x-halo reuse): the brick is 16(x) x 8(y) x 1(z); ONE TMA box of 18 x-columns serves the
-  // three dx taps (an x step is a whole 8-row swizzle atom, so the tap is selected by the start
-  // address of the UMMA descriptor) -> 9 instead of 27 activation boxes per Cin chunk.
-  g.mode = (taps == 27 && H >= 8 && W >= 16 && !g_force_mode0) ? 1 : 0;
+  const int kc = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
+  g.chunks = Cin / kc;
+  const int row_bytes = kc * 2;
+  const int mode = (taps == 27 && H >= 8 && W >= 16 && !g_force_mode0) ? 1 : 0;
   const int gran = (flags & KM_CONV_COM) ? 32 : 16;
   KM_CHECK_ARG(Cout % gran == 0, "km_conv3d_tc: Cout must be a multiple of %d in this mode", gran);
-  const int bn_cap = g.mode == 1 ? 128 : 256;
+  const int bn_cap = mode == 1 ? 128 : 256;
   g.BN = 0;
   for (int bn = bn_cap; bn >= gran; bn -= gran)
     if (Cout % bn == 0) { g.BN = bn; break; }
   KM_CHECK_ARG(g.BN > 0, "km_conv3d_tc: no channel block for Cout=%d", Cout);
   g.n_blocks = Cout / g.BN;
-  if (g.mode == 1) {
+  if (mode == 1) {
     g.TW = 16; g.TH = 8; g.TD = 1;
-    g.ntap = 3;
     g.subiters = 9 * g.chunks;
     g.a_sub_bytes = 18u * 8u * row_bytes;
     g.b_sub_bytes = 3u * (uint32_t)g.BN * row_bytes;
@@ -535,7 +605,6 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
     g.TW = pow2_le(W, 128);
     g.TH = pow2_le(H, 128 / g.TW);
     g.TD = 128 / (g.TW * g.TH);
-    g.ntap = 1;
     g.subiters = taps * g.chunks;
     g.a_sub_bytes = (uint32_t)kTileM * row_bytes;
     g.b_sub_bytes = (uint32_t)g.BN * row_bytes;
@@ -545,10 +614,11 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   g.tiles_x = (W + g.TW - 1) / g.TW;
   g.tiles_y = (H + g.TH - 1) / g.TH;
   g.tiles_z = (D + g.TD - 1) / g.TD;
-  g.total_tiles = (long long)N * g.tiles_z * g.tiles_y * g.tiles_x * g.n_blocks;
+  const long long tiles = (long long)N * g.tiles_z * g.tiles_y * g.tiles_x * g.n_blocks;
+  KM_CHECK_ARG(tiles < (1ll << 31), "km_conv3d_tc: too many tiles");
+  g.total_tiles = (int)tiles;
+  g.stat_parts = (g.BN <= kTileM && kTileM % g.BN == 0) ? kTileM / g.BN : 1;
 
-  g.layout = umma_layout_for_row_bytes(row_bytes);
-  g.sbo = 8u * (uint32_t)row_bytes;
   g.idesc = umma_idesc_bf16(kTileM, g.BN);
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)g.BN) cols *= 2;
@@ -561,7 +631,8 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   const uint32_t staging_bytes = g.has_out ? round_up(kTileM * g.staging_pitch, 16) : 0;
   const uint32_t fstage_bytes = (flags & KM_CONV_COM) ? 2u * kTileM * kFstagePitch * 4u : 0;
   const uint32_t rowinfo_bytes = 3u * kTileM * 4u + kTileM;
-  const uint32_t stats_bytes = (flags & KM_CONV_STATS) ? (uint32_t)N * Cout * 2u * 4u : 0;
+  const uint32_t stats_bytes =
+      (flags & KM_CONV_STATS) ? (uint32_t)g.stat_parts * N * Cout * 2u * 4u : 0;
   const uint32_t com_bytes = (flags & KM_CONV_COM) ? (uint32_t)N * Cout * 4u * 4u : 0;
   const uint32_t scratch_bytes = (flags & KM_CONV_COM) ? 2u * 4u * 32u * 4u * 4u : 0;
   const uint32_t bars_bytes = 8u * (2u * kMaxStages + 4u) + 16u;
@@ -608,8 +679,8 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2,
                              (cuuint64_t)H * W * Cin * 2, (cuuint64_t)D * H * W * Cin * 2};
-    cuuint32_t box[5] = {(cuuint32_t)g.kc, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TD, 1};
-    if (g.mode == 1) {
+    cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TD, 1};
+    if (mode == 1) {
       // (C, H, W, D, N): y is the fastest spatial index in shared memory (8 rows = one swizzle atom)
       dims[1] = (cuuint64_t)H; dims[2] = (cuuint64_t)W;
       strides[0] = (cuuint64_t)W * Cin * 2; strides[1] = (cuuint64_t)Cin * 2;
@@ -627,7 +698,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)g.kc, (cuuint32_t)g.BN, (cuuint32_t)(g.mode == 1 ? 3 : 1)};
+    cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)g.BN, (cuuint32_t)(mode == 1 ? 3 : 1)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wp), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -638,14 +709,15 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
     }
   }
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    KM_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    232448));
-    attr_set = true;
+  ConvKernel kernel = pick_kernel(kc, mode);
+  static bool attr_set[2][3] = {{false, false, false}, {false, false, false}};
+  const int ki = kc == 64 ? 2 : (kc == 32 ? 1 : 0);
+  if (!attr_set[mode][ki]) {
+    KM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set[mode][ki] = true;
   }
   const int nsm = sm_count();
-  const int grid = (int)(g.total_tiles < nsm ? g.total_tiles : nsm);
+  const int grid = g.total_tiles < nsm ? g.total_tiles : nsm;
   // partial slots of CTAs that are not launched must still be defined
   if (grid < nsm) {
     if (flags & KM_CONV_STATS)
@@ -653,7 +725,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
     if (flags & KM_CONV_COM)
       KM_CUDA_OK(cudaMemsetAsync(com, 0, (size_t)nsm * N * Cout * 4 * sizeof(float), km_cs(stream)));
   }
-  conv_tc_kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(
+  kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(
       tmA, tmB, g, bias, reinterpret_cast<__nv_bfloat16*>(out), stats, com);
   KM_LAUNCH_OK("conv_tc_kernel");
   return KM_OK;

@@ -73,6 +73,11 @@ class _EngineBase:
     def __init__(self, module):
         self.m = module
         self.weights = _WeightCache()
+        self.debug = None      # set to a dict to capture every layer's raw output (tools/diag_*)
+
+    def _dbg(self, key, t):
+        if self.debug is not None:
+            self.debug[key] = t.clone()
 
     def _check_input(self, x):
         if not x.is_cuda:
@@ -99,6 +104,7 @@ class UNetEngine(_EngineBase):
     def _single_conv(self, key, sc_mod, x_norm):
         wp = self.weights.get(key, sc_mod.conv.weight)
         out, stats, _ = ops.conv3d_tc(x_norm, wp, relu=True, want_stats=True)
+        self._dbg(key, out)
         return out, stats
 
     @torch.no_grad()
@@ -118,6 +124,7 @@ class UNetEngine(_EngineBase):
                                          sc0.groupnorm.num_groups, sc0.groupnorm.eps)
         a, st = ops.conv3d_stem(x, sc0.conv.weight.detach(), None, scale.reshape(-1),
                                 shift.reshape(-1), relu=True)
+        self._dbg("enc0.c1", a)
         sc1 = enc[0].basic_module.SingleConv2
         scale, shift = ops.norm_finalize(st, nvox(a), sc1.groupnorm.weight, sc1.groupnorm.bias,
                                          sc1.groupnorm.num_groups, sc1.groupnorm.eps)
@@ -141,7 +148,7 @@ class UNetEngine(_EngineBase):
             del c1
             feats.append((cur, cur_st))
         # the truncated net never consumes the first encoder's full-resolution output as a skip
-        skips = feats[:-1][::-1]
+        skips = feats[:-1][::-1][:len(m.decoders)]
         del feats
         # ---- decoders: GN(upsample(x) ++ skip) fused into one pass, then (conv, GN, conv)
         for j, dec in enumerate(m.decoders):

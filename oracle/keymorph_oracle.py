@@ -88,7 +88,7 @@ def center_of_mass3d(vol, ij=True):
     eps = 1e-8
     outs = []
     for size, keep in ((dx, (2, 3)), (dy, (2, 4)), (dz, (3, 4))):
-        lin = torch.linspace(0, 1, size).to(v.dtype).view(1, 1, -1)
+        lin = torch.linspace(0, 1, size).to(v).view(1, 1, -1)
         m = v.sum(dim=keep)
         total = m.sum(dim=-1, keepdim=True) + eps
         outs.append((lin * m).sum(dim=-1, keepdim=True) / total)
