@@ -44,6 +44,9 @@ int km_sm_count(void);
 /* key KM_OPT_CONV_FORCE_GENERIC (default 0): make km_conv3d_tc use the one-TMA-box-per-tap data
  * path even where the x-halo-reuse path applies (A/B testing of the two paths). */
 #define KM_OPT_CONV_FORCE_GENERIC 2
+/* key KM_OPT_CONV_NO_RESIDENT_WEIGHTS (default 0): stream the weights of small layers per tile
+ * instead of keeping them in shared memory (A/B testing). */
+#define KM_OPT_CONV_NO_RESIDENT_WEIGHTS 3
 int km_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------ *

@@ -62,6 +62,7 @@ KM_INTERP_BILINEAR, KM_INTERP_NEAREST = 0, 1
 KM_COORD_AFFINE, KM_COORD_TPS, KM_COORD_GRID = 0, 1, 2
 KM_OPT_TPS_FAST = 1
 KM_OPT_CONV_FORCE_GENERIC = 2
+KM_OPT_CONV_NO_RESIDENT_WEIGHTS = 3
 
 _lib = None
 

@@ -65,16 +65,21 @@ com3d_kernel(const float* __restrict__ heat, float* __restrict__ partials, int N
 // partials (nparts, NK, 4) -> points (NK, 3), mass (NK)
 __global__ void com_finalize_kernel(const float* __restrict__ com, int nparts, float* points,
                                     float* mass, int NK, int ij) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per keypoint channel: lanes stride over the partial slots
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= NK) return;
   double s[4] = {0, 0, 0, 0};
-  for (int p = 0; p < nparts; ++p) {
-    const float* c = com + ((size_t)p * NK + i) * 4;
-    s[0] += c[0];
-    s[1] += c[1];
-    s[2] += c[2];
-    s[3] += c[3];
+  for (int p = lane; p < nparts; p += 32) {
+    const float4 c = *reinterpret_cast<const float4*>(com + ((size_t)p * NK + i) * 4);
+    s[0] += c.x;
+    s[1] += c.y;
+    s[2] += c.z;
+    s[3] += c.w;
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s[k] = km_warp_sum(s[k]);
+  if (lane != 0) return;
   // keymorph/layers.py:112-134: M = sum(m) + 1e-8 (fp32); c = sum(lin*m) / M; out = c*2 - 1
   const float M = (float)s[0];
   const float den = M + 1e-8f;
@@ -103,7 +108,7 @@ extern "C" int km_com_finalize(const float* com, int nparts, float* points, floa
                                int K, km_stream_t stream) {
   KM_CHECK_ARG(com && points && nparts > 0 && N > 0 && K > 0, "km_com_finalize: bad arguments");
   const int NK = N * K;
-  com_finalize_kernel<<<(NK + 127) / 128, 128, 0, km_cs(stream)>>>(com, nparts, points, mass, NK, 1);
+  com_finalize_kernel<<<(NK + 7) / 8, 256, 0, km_cs(stream)>>>(com, nparts, points, mass, NK, 1);
   KM_LAUNCH_OK("com_finalize_kernel");
   return KM_OK;
 }
@@ -125,7 +130,7 @@ extern "C" int km_com3d(const float* heat, float* points, float* mass, void* wor
   else
     com3d_kernel<false><<<dim3(parts, NK), 256, 0, km_cs(stream)>>>(heat, partials, NK, D, H, W);
   KM_LAUNCH_OK("com3d_kernel");
-  com_finalize_kernel<<<(NK + 127) / 128, 128, 0, km_cs(stream)>>>(partials, parts, points, mass, NK,
+  com_finalize_kernel<<<(NK + 7) / 8, 256, 0, km_cs(stream)>>>(partials, parts, points, mass, NK,
                                                                   ij);
   KM_LAUNCH_OK("com_finalize_kernel");
   return KM_OK;

@@ -111,26 +111,32 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats0, int npart
   const int C = C0 + C1;
   double* csum = sd;
   double* gstat = sd + 2 * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  // one warp per channel: lanes stride over the partial slots, fixed-order shuffle reduction
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int c = wid; c < C; c += nwarps) {
     double s = 0.0, ss = 0.0;
     if (c < C0) {
-      for (int p = 0; p < nparts0; ++p) {
-        const float* q = stats0 + (((size_t)p * N + n) * C0 + c) * 2;
-        s += (double)q[0];
-        ss += (double)q[1];
+      for (int p = lane; p < nparts0; p += 32) {
+        const float2 q = *reinterpret_cast<const float2*>(stats0 + (((size_t)p * N + n) * C0 + c) * 2);
+        s += (double)q.x;
+        ss += (double)q.y;
       }
     } else {
       const int c1 = c - C0;
-      for (int p = 0; p < nparts1; ++p) {
-        const float* q = stats1 + (((size_t)p * N + n) * C1 + c1) * 2;
-        s += (double)q[0];
-        ss += (double)q[1];
+      for (int p = lane; p < nparts1; p += 32) {
+        const float2 q = *reinterpret_cast<const float2*>(stats1 + (((size_t)p * N + n) * C1 + c1) * 2);
+        s += (double)q.x;
+        ss += (double)q.y;
       }
       s *= rep1;
       ss *= rep1;
     }
-    csum[2 * c] = s;
-    csum[2 * c + 1] = ss;
+    s = km_warp_sum(s);
+    ss = km_warp_sum(ss);
+    if (lane == 0) {
+      csum[2 * c] = s;
+      csum[2 * c + 1] = ss;
+    }
   }
   __syncthreads();
   const int cpg = C / groups;
@@ -159,7 +165,11 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats0, int npart
 }
 
 // ------------------------------------------------------------------------------------------
-// out = act(scale*src + shift) with optional second (nearest-upsampled) source and optional pool
+// out = act(scale*src + shift) with optional second (nearest-upsampled) source.
+// grid (ceil(W*cg/256), ceil(H/kNormRows), N*D): (n, z) is uniform per block, a thread owns one
+// 16-byte channel group of one x position and walks kNormRows rows -> one 32-bit division per
+// thread, no 64-bit index arithmetic, scale/shift loaded once.
+constexpr int kNormRows = 8;
 __global__ void __launch_bounds__(256)
 norm_apply_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict__ src1, int C1,
                   int D1, int H1, int W1, const float* __restrict__ scale,
@@ -167,40 +177,48 @@ norm_apply_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict_
                   int W, int relu) {
   const int C = C0 + C1;
   const int cg = C / 8, cg0 = C0 / 8;
-  const long long nvox = (long long)D * H * W;
-  const long long total = (long long)N * nvox * cg;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // chunk index inside a row
+  if (i >= W * cg) return;
+  const int x = i / cg, g = i - x * cg;
+  const int n = blockIdx.z / D, z = blockIdx.z - n * D;
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)n * C + g * 8);
+  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)n * C + g * 8);
+  const float4 a0 = __ldg(sc), a1 = __ldg(sc + 1), b0 = __ldg(sh), b1 = __ldg(sh + 1);
+  const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   // ATen upsample_nearest3d: src = min(floor(dst * (in / out)), in - 1) with a float scale
-  const float sz = (float)D1 / (float)D, sy = (float)H1 / (float)H, sx = (float)W1 / (float)W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    const long long v = i / cg;
-    const int n = (int)(v / nvox);
-    uint4 raw;
-    if (g < cg0) {
-      raw = __ldg(reinterpret_cast<const uint4*>(src0 + (size_t)v * C0) + g);
-    } else {
-      const long long r = v % nvox;
-      const int x = (int)(r % W), y = (int)((r / W) % H), z = (int)(r / ((long long)W * H));
-      const int x1 = min((int)floorf(x * sx), W1 - 1);
-      const int y1 = min((int)floorf(y * sy), H1 - 1);
-      const int z1 = min((int)floorf(z * sz), D1 - 1);
-      const size_t v1 = (((size_t)n * D1 + z1) * H1 + y1) * W1 + x1;
-      raw = __ldg(reinterpret_cast<const uint4*>(src1 + v1 * C1) + (g - cg0));
-    }
-    float f[8];
-    unpack8(raw, f);
-    const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)n * C + g * 8);
-    const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)n * C + g * 8);
-    const float4 a0 = __ldg(sc), a1 = __ldg(sc + 1), b0 = __ldg(sh), b1 = __ldg(sh + 1);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const bool from1 = g >= cg0;
+  const int x1 = from1 ? min((int)floorf(x * ((float)W1 / (float)W)), W1 - 1) : 0;
+  const int z1 = from1 ? min((int)floorf(z * ((float)D1 / (float)D)), D1 - 1) : 0;
+  const float sy = from1 ? (float)H1 / (float)H : 0.f;
+  const int y_lo = blockIdx.y * kNormRows, y_hi = min(H, y_lo + kNormRows);
+  uint4 raw[kNormRows];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      f[k] = fmaf(a[k], f[k], b[k]);
-      if (relu) f[k] = fmaxf(f[k], 0.f);
+  for (int r = 0; r < kNormRows; ++r) {
+    const int y = y_lo + r;
+    if (y < y_hi) {
+      if (!from1) {
+        raw[r] = __ldg(reinterpret_cast<const uint4*>(src0 + (((size_t)blockIdx.z * H + y) * W + x) * C0) + g);
+      } else {
+        const int y1 = min((int)floorf(y * sy), H1 - 1);
+        const size_t v1 = (((size_t)n * D1 + z1) * H1 + y1) * W1 + x1;
+        raw[r] = __ldg(reinterpret_cast<const uint4*>(src1 + v1 * C1) + (g - cg0));
+      }
     }
-    reinterpret_cast<uint4*>(out)[i] = pack8(f);
+  }
+#pragma unroll
+  for (int r = 0; r < kNormRows; ++r) {
+    const int y = y_lo + r;
+    if (y < y_hi) {
+      float f[8];
+      unpack8(raw[r], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        f[k] = fmaf(a[k], f[k], b[k]);
+        if (relu) f[k] = fmaxf(f[k], 0.f);
+      }
+      reinterpret_cast<uint4*>(out + (((size_t)blockIdx.z * H + y) * W + x) * C)[g] = pack8(f);
+    }
   }
 }
 
@@ -323,7 +341,9 @@ conv_stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                  const float* __restrict__ bias, const float* __restrict__ in_scale,
                  const float* __restrict__ in_shift, bf16* __restrict__ out,
                  float* __restrict__ stats, int N, int D, int H, int W, int relu) {
-  constexpr int TX = 32, TY = 4, TZ = 2;
+  // VPT voxels per thread along x (x and x+32): every broadcast weight load feeds VPT FMAs
+  constexpr int VPT = COUT <= 16 ? 2 : 1;
+  constexpr int TX = 32 * VPT, TY = 4, TZ = 2;
   constexpr int HX = TX + 2, HY = TY + 2, HZ = TZ + 2;
   __shared__ float tile[HZ][HY][HX];
   __shared__ __align__(16) float sw[27][COUT];
@@ -342,7 +362,7 @@ conv_stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
 
   const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY, tiles_z = (D + TZ - 1) / TZ;
   const long long ntiles = (long long)tiles_x * tiles_y * tiles_z;
-  const int lx = threadIdx.x % TX, ly = (threadIdx.x / TX) % TY, lz = threadIdx.x / (TX * TY);
+  const int lx = threadIdx.x % 32, ly = (threadIdx.x / 32) % TY, lz = threadIdx.x / (32 * TY);
 
   float s[COUT], ss[COUT];
 #pragma unroll
@@ -362,39 +382,52 @@ conv_stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
       tile[hz][hy][hx] = v;
     }
     __syncthreads();
-    const int gx = x0 + lx, gy = y0 + ly, gz = z0 + lz;
-    if (gx < W && gy < H && gz < D) {
-      float acc[COUT];
+    const int gy = y0 + ly, gz = z0 + lz;
+    if (gy < H && gz < D) {
+      float acc[VPT][COUT];
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[c] = sbias[c];
+      for (int v = 0; v < VPT; ++v)
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[v][c] = sbias[c];
 #pragma unroll
       for (int tap = 0; tap < 27; ++tap) {
-        const float v = tile[lz + tap / 9][ly + (tap / 3) % 3][lx + tap % 3];
+        float in[VPT];
+#pragma unroll
+        for (int v = 0; v < VPT; ++v)
+          in[v] = tile[lz + tap / 9][ly + (tap / 3) % 3][lx + 32 * v + tap % 3];
         const float4* wr = reinterpret_cast<const float4*>(&sw[tap][0]);
 #pragma unroll
         for (int c4 = 0; c4 < COUT / 4; ++c4) {
           const float4 wv = wr[c4];
-          acc[4 * c4 + 0] = fmaf(v, wv.x, acc[4 * c4 + 0]);
-          acc[4 * c4 + 1] = fmaf(v, wv.y, acc[4 * c4 + 1]);
-          acc[4 * c4 + 2] = fmaf(v, wv.z, acc[4 * c4 + 2]);
-          acc[4 * c4 + 3] = fmaf(v, wv.w, acc[4 * c4 + 3]);
+#pragma unroll
+          for (int v = 0; v < VPT; ++v) {
+            acc[v][4 * c4 + 0] = fmaf(in[v], wv.x, acc[v][4 * c4 + 0]);
+            acc[v][4 * c4 + 1] = fmaf(in[v], wv.y, acc[v][4 * c4 + 1]);
+            acc[v][4 * c4 + 2] = fmaf(in[v], wv.z, acc[v][4 * c4 + 2]);
+            acc[v][4 * c4 + 3] = fmaf(in[v], wv.w, acc[v][4 * c4 + 3]);
+          }
         }
       }
-      uint4* dst = reinterpret_cast<uint4*>(on + (((size_t)gz * H + gy) * W + gx) * COUT);
 #pragma unroll
-      for (int c8 = 0; c8 < COUT / 8; ++c8) {
-        float f[8];
+      for (int v = 0; v < VPT; ++v) {
+        const int gx = x0 + lx + 32 * v;
+        if (gx >= W) continue;
+        uint4* dst = reinterpret_cast<uint4*>(on + (((size_t)gz * H + gy) * W + gx) * COUT);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float v = acc[8 * c8 + k];
-          if (relu) v = fmaxf(v, 0.f);
-          // statistics are taken over the values actually stored (bf16-rounded)
-          v = __bfloat162float(__float2bfloat16_rn(v));
-          f[k] = v;
-          s[8 * c8 + k] += v;
-          ss[8 * c8 + k] = fmaf(v, v, ss[8 * c8 + k]);
+        for (int c8 = 0; c8 < COUT / 8; ++c8) {
+          float f[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float o = acc[v][8 * c8 + k];
+            if (relu) o = fmaxf(o, 0.f);
+            // statistics are taken over the values actually stored (bf16-rounded)
+            o = __bfloat162float(__float2bfloat16_rn(o));
+            f[k] = o;
+            s[8 * c8 + k] += o;
+            ss[8 * c8 + k] = fmaf(o, o, ss[8 * c8 + k]);
+          }
+          dst[c8] = pack8(f);
         }
-        dst[c8] = pack8(f);
       }
     }
   }
@@ -487,7 +520,7 @@ extern "C" int km_norm_finalize(const float* stats0, int nparts0, int C0, double
   KM_CHECK_ARG(groups > 0 && C % groups == 0, "km_norm_finalize: %d channels not divisible by %d groups",
                C, groups);
   const size_t smem = (size_t)(2 * C + 2 * groups) * sizeof(double);
-  norm_finalize_kernel<<<N, 256, smem, km_cs(stream)>>>(stats0, nparts0, C0, count0, stats1, nparts1,
+  norm_finalize_kernel<<<N, 1024, smem, km_cs(stream)>>>(stats0, nparts0, C0, count0, stats1, nparts1,
                                                        C1, count1, rep1, gamma, beta, groups, eps,
                                                        scale, shift, N);
   KM_LAUNCH_OK("norm_finalize_kernel");
@@ -511,8 +544,9 @@ extern "C" int km_norm_apply(const void* src0, int C0, const void* src1, int C1,
     KM_LAUNCH_OK("norm_apply_pool_kernel");
     return KM_OK;
   }
-  const long long total = (long long)N * D * H * W * ((C0 + C1) / 8);
-  norm_apply_kernel<<<blocks_for(total, 256), 256, 0, km_cs(stream)>>>(
+  KM_CHECK_ARG(H <= 65535 && (long long)N * D <= 65535, "km_norm_apply: volume too large for the grid");
+  const dim3 grid((W * ((C0 + C1) / 8) + 255) / 256, (H + kNormRows - 1) / kNormRows, N * D);
+  norm_apply_kernel<<<grid, 256, 0, km_cs(stream)>>>(
       reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1,
       C1 ? D1 : 1, C1 ? H1 : 1, C1 ? W1 : 1, scale, shift, reinterpret_cast<bf16*>(out), N, D, H, W,
       relu);

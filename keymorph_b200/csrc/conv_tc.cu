@@ -10,9 +10,10 @@
 //       (out-of-bounds rows are zero-filled = conv padding);
 //   B = weights [tap][Cout][Cin], K-major, fetched by TMA;
 //   D = fp32 accumulator in TMEM, double buffered so the epilogue of tile i overlaps tile i+1.
-// Roles (192 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU -> bf16 staging in smem -> coalesced stores,
-// per-channel sum / sum-of-squares for the next GroupNorm, or centre-of-mass partials).
+// Roles (320 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..9 = epilogue in two column groups (tcgen05.ld -> bias/ReLU -> bf16 staging in smem ->
+// coalesced stores, per-channel sum / sum-of-squares for the next GroupNorm, or centre-of-mass
+// partials).
 //
 // Two data paths (template parameter MODE):
 //   MODE 1 "x-halo reuse" (3x3x3, H >= 8, W >= 16): brick 16(x) x 8(y) x 1(z).  The tensor map
@@ -31,11 +32,12 @@ using namespace kmtc;
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiThreads = 256;
 constexpr int kFstagePitch = 33;  // floats, conflict-free transposed access
 constexpr int kMaxStages = 12;
 int g_force_mode0 = 0;            // km_set_option(KM_OPT_CONV_FORCE_GENERIC): A/B the two data paths
+int g_no_resident = 0;            // km_set_option(KM_OPT_CONV_NO_RESIDENT_WEIGHTS)
 
 struct ConvGeom {
   int N, D, H, W, Cin, Cout;
@@ -50,10 +52,12 @@ struct ConvGeom {
   int sub;             // sub-iterations (A box + B box) packed into one pipeline stage
   int subiters;        // sub-iterations per tile: taps*chunks (mode 0) or 9*chunks (mode 1)
   int stat_parts;      // row groups that accumulate channel statistics independently
+  int b_resident;      // all weight slices stay in shared memory for the whole kernel
+  uint32_t off_bres;
   uint32_t a_sub_bytes, b_sub_bytes;      // TMA bytes per sub-iteration
   uint32_t a_sub_stride, b_sub_stride;    // 1024-aligned slots inside a stage
   uint32_t stage_stride;
-  uint32_t off_staging, off_fstage, off_rowinfo, off_stats, off_com, off_scratch, off_bars;
+  uint32_t off_staging, off_fstage, off_rowinfo, off_stats, off_com, off_scratch, off_bias, off_bars;
   uint32_t staging_pitch;               // bytes per staged row (BN*2 + 16)
   uint32_t tmem_cols;
   uint32_t idesc;
@@ -124,7 +128,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(stages + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * stages + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * stages + 2 + a); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + g.off_bars + 8u * (2 * stages + 4));
+  const uint32_t bres_bar = bars + 8u * (uint32_t)(2 * stages + 4);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + g.off_bars + 8u * (2 * stages + 5));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -135,6 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiThreads);
     }
+    mbar_init(bres_bar, 1);
     fence_mbar_init();
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
@@ -152,6 +158,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = threadIdx.x; i < g.stat_parts * g.N * g.Cout * 2; i += kThreads) s_stats[i] = 0.f;
     if (g.flags & KM_CONV_COM)
       for (int i = threadIdx.x; i < g.N * g.Cout * 4; i += kThreads) s_com[i] = 0.f;
+    float* s_bias = reinterpret_cast<float*>(sm + g.off_bias);
+    for (int i = threadIdx.x; i < g.Cout; i += kThreads) s_bias[i] = bias ? bias[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -167,7 +175,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t sub_tx = g.a_sub_bytes + g.b_sub_bytes;
+      const bool resident = g.b_resident != 0;
+      const uint32_t sub_tx = g.a_sub_bytes + (resident ? 0u : g.b_sub_bytes);
+      if (resident) {
+        // weights: every (dz,dy) x Cin-chunk slice (3 dx taps each) is loaded once per CTA
+        mbar_arrive_expect_tx(bres_bar, (uint32_t)g.subiters * g.b_sub_bytes);
+        uint32_t dst = base + g.off_bres;
+        for (int grp = 0; grp < g.subiters / g.chunks; ++grp)
+          for (int ch = 0; ch < g.chunks; ++ch, dst += g.b_sub_stride)
+            tma_load_3d(dst, &tmB, bres_bar, ch * KC, 0, MODE == 1 ? grp * 3 : grp);
+      }
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(g, tile);
         const int bn0 = tc.nb * g.BN;
@@ -183,12 +200,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (MODE == 0) {
               tma_load_5d(a_dst, &tmA, full_bar(s), ch * KC, tc.x0 + dx, tc.y0 + dy, tc.z0 + dz,
                           tc.n);
-              tma_load_3d(b_dst, &tmB, full_bar(s), ch * KC, bn0, grp);
+              if (!resident) tma_load_3d(b_dst, &tmB, full_bar(s), ch * KC, bn0, grp);
             } else {
               // tensor map dims are (C, H, W, D, N): rows land as h + 8 * w, 18 x-columns incl. halo
               tma_load_5d(a_dst, &tmA, full_bar(s), ch * KC, tc.y0 + dy, tc.x0 - 1, tc.z0 + dz,
                           tc.n);
-              tma_load_3d(b_dst, &tmB, full_bar(s), ch * KC, bn0, grp * 3);
+              if (!resident) tma_load_3d(b_dst, &tmB, full_bar(s), ch * KC, bn0, grp * 3);
             }
             a_dst += g.a_sub_stride;
             b_dst += g.b_sub_stride;
@@ -235,6 +252,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t stage16 = stage_stride >> 4;
       const uint32_t boff16 = ((uint32_t)sub * g.a_sub_stride) >> 4;
       const uint32_t idesc = g.idesc;
+      const bool resident = g.b_resident != 0;
+      const uint32_t bres16 = ((base + g.off_bres) & 0x3FFFFu) >> 4;
+      if (resident) mbar_wait(bres_bar, 0u);
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u;
         const uint32_t acc_ph = (tcount >> 1) & 1u;
@@ -242,12 +262,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)g.BN;
         uint32_t accum = 0;
+        uint32_t bq16 = bres16;   // running weight slice (resident mode)
         for (int si = 0; si < n_stage_iters; ++si) {
           const int nsub = (si == n_stage_iters - 1) ? last_nsub : sub;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           uint32_t a16 = base16 + (uint32_t)s * stage16;
-          uint32_t b16 = a16 + boff16;
+          uint32_t b16 = resident ? bq16 : a16 + boff16;
           for (int u = 0; u < nsub; ++u) {
 #pragma unroll
             for (int t = 0; t < kNtap; ++t) {
@@ -262,6 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             a16 += a_sub16;
             b16 += b_sub16;
           }
+          bq16 += (uint32_t)nsub * b_sub16;
           umma_commit(empty_bar(s));  // frees the smem stage when these MMAs have read it
           if (++s == stages) {
             s = 0;
@@ -272,17 +294,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // =============================== epilogue ====================================
-    const int q = warp & 3;          // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;   // accumulator row == voxel within the brick
-    const int et = row;              // epilogue thread id 0..127
+    // =============================== epilogue (8 warps) ==========================
+    // Two groups of four warps; each warp reads its own TMEM lane quadrant (warp % 4), the groups
+    // split the accumulator COLUMNS between them so that TMEM loads, conversion and the
+    // centre-of-mass transposes of the two halves overlap.
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;       // accumulator row == voxel within the brick
+    const int half = (warp - 2) >> 2;    // 0: warps 2..5, 1: warps 6..9
+    const int et = half * kTileM + row;  // epilogue thread id 0..255
     uint8_t* staging = sm + g.off_staging;
-    float* fstage = reinterpret_cast<float*>(sm + g.off_fstage);
-    float* rowlin = reinterpret_cast<float*>(sm + g.off_rowinfo);          // [3][128] lz, ly, lx
+    float* fstage = reinterpret_cast<float*>(sm + g.off_fstage) + (size_t)half * 2 * kTileM * kFstagePitch;
+    float* rowlin = reinterpret_cast<float*>(sm + g.off_rowinfo);          // [3][128] tz, ty, tx
     uint8_t* rowvalid = sm + g.off_rowinfo + 3 * kTileM * sizeof(float);   // [128]
     float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);           // [parts][N][Cout][2]
     float* s_com = reinterpret_cast<float*>(sm + g.off_com);
-    float* scratch = reinterpret_cast<float*>(sm + g.off_scratch);         // [2][4][32][4]
+    float* scratch = reinterpret_cast<float*>(sm + g.off_scratch) + (size_t)half * 2 * 4 * 32 * 4;
+    const float* s_bias = reinterpret_cast<const float*>(sm + g.off_bias);  // [Cout], zeros if none
+    const float step_z = g.D > 1 ? 1.f / (float)(g.D - 1) : 0.f;
+    const float step_y = g.H > 1 ? 1.f / (float)(g.H - 1) : 0.f;
+    const float step_x = g.W > 1 ? 1.f / (float)(g.W - 1) : 0.f;
     const bool do_relu = (g.flags & KM_CONV_RELU) != 0;
     const bool do_stats = (g.flags & KM_CONV_STATS) != 0;
     const bool do_com = (g.flags & KM_CONV_COM) != 0;
@@ -292,6 +322,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cpr = BN / 8;  // 16-byte chunks per staged row
     const int parts = g.stat_parts;
     const int rows_per_part = kTileM / parts;
+    auto half_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); };
+    auto all_bar = [&]() { asm volatile("bar.sync 3, 256;" ::: "memory"); };
 
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tcount) {
@@ -300,16 +332,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t acc_ph = (tcount >> 1) & 1u;
       const int n0 = tc.nb * BN;
 
-      // voxel of this row
+      // voxel of this row (both groups write the same values)
       int tx, ty, tz;
       row_to_voxel<MODE>(g, row, tx, ty, tz);
       const int vx = tc.x0 + tx, vy = tc.y0 + ty, vz = tc.z0 + tz;
       const bool valid = (vx < g.W) && (vy < g.H) && (vz < g.D);
       rowvalid[row] = valid ? 1 : 0;
       if (do_com) {
-        rowlin[0 * kTileM + row] = km_linspace(0.f, 1.f, g.D, vz);
-        rowlin[1 * kTileM + row] = km_linspace(0.f, 1.f, g.H, vy);
-        rowlin[2 * kTileM + row] = km_linspace(0.f, 1.f, g.W, vx);
+        rowlin[0 * kTileM + row] = (float)tz;   // brick-local offsets (narrow-brick CoM path)
+        rowlin[1 * kTileM + row] = (float)ty;
+        rowlin[2 * kTileM + row] = (float)tx;
       }
 
       mbar_wait(tfull_bar((int)acc), acc_ph);
@@ -317,19 +349,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN;
 
       if (!do_com) {
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        const int nblk = BN / 16, split = (nblk + 1) / 2;
+        const int b_lo = half == 0 ? 0 : split, b_hi = half == 0 ? split : nblk;
+        for (int blk = b_lo; blk < b_hi; ++blk) {
+          const int c0 = blk * 16;
           uint32_t r[16];
           tmem_ld16(taddr + (uint32_t)c0, r);
           tmem_ld_wait();
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float a = __uint_as_float(r[2 * j]);
-            float b = __uint_as_float(r[2 * j + 1]);
-            if (bias) {
-              a += __ldg(bias + n0 + c0 + 2 * j);
-              b += __ldg(bias + n0 + c0 + 2 * j + 1);
-            }
+            float a = __uint_as_float(r[2 * j]) + s_bias[n0 + c0 + 2 * j];
+            float b = __uint_as_float(r[2 * j + 1]) + s_bias[n0 + c0 + 2 * j + 1];
             if (do_relu) {
               a = fmaxf(a, 0.f);
               b = fmaxf(b, 0.f);
@@ -343,80 +374,111 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         mbar_arrive(tempty_bar((int)acc));
-        epi_bar();
+        all_bar();
       } else {
-        // final conv + centre of mass: 32-column chunks, transposed through fp32 smem
-        const int nchunks = BN / 32;
-        for (int cc = 0; cc < nchunks; ++cc) {
+        // final conv + centre of mass: 32-column chunks, transposed through fp32 smem.  Sums are
+        // taken with brick-local voxel offsets (tx, ty, tz) and converted to linspace(0,1,n)
+        // coordinates once per tile: lin(i) = i / (n - 1).
+        const int nchunks = BN / 32, split = (nchunks + 1) / 2;
+        const int c_lo = half == 0 ? 0 : split, c_hi = half == 0 ? split : nchunks;
+        const bool wide = g.TW >= 32;   // a 32-row quarter is then an x-run: ty, tz constant
+        const int col = row & 31, rq = row >> 5;
+        const float q_tx = (float)((rq * 32) % g.TW);
+        const float q_ty = (float)(((rq * 32) / g.TW) % g.TH);
+        const float q_tz = (float)((rq * 32) / (g.TW * g.TH));
+        auto combine = [&](int cc, int slot) {
+          const float* sc = scratch + (size_t)slot * 4 * 32 * 4;
+          float t[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            t[k] = ((sc[(0 * 32 + row) * 4 + k] + sc[(1 * 32 + row) * 4 + k]) +
+                    sc[(2 * 32 + row) * 4 + k]) + sc[(3 * 32 + row) * 4 + k];
+          float* dstc = s_com + ((size_t)tc.n * g.Cout + n0 + cc * 32 + row) * 4;
+          dstc[0] += t[0];
+          dstc[1] += step_z * fmaf((float)tc.z0, t[0], t[1]);
+          dstc[2] += step_y * fmaf((float)tc.y0, t[0], t[2]);
+          dstc[3] += step_x * fmaf((float)tc.x0, t[0], t[3]);
+        };
+        int it_c = 0;
+        for (int cc = c_lo; cc < c_hi; ++cc, ++it_c) {
           const int c0 = cc * 32;
-          float* fs = fstage + (size_t)(cc & 1) * kTileM * kFstagePitch;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t r[16];
-            tmem_ld16(taddr + (uint32_t)(c0 + 16 * h), r);
-            tmem_ld_wait();
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float v = __uint_as_float(r[j]);
-              if (bias) v += __ldg(bias + n0 + c0 + 16 * h + j);
-              r[j] = __float_as_uint(v);
-              fs[row * kFstagePitch + 16 * h + j] = valid ? fmaxf(v, 0.f) : 0.f;
-            }
-            if (has_out) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                pk[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-              uint4* dst = reinterpret_cast<uint4*>(staging + (size_t)row * pitch +
-                                                    (size_t)(c0 + 16 * h) * 2);
-              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
-          }
-          if (cc == nchunks - 1) {
+          float* fs = fstage + (size_t)(it_c & 1) * kTileM * kFstagePitch;
+          uint32_t r0[16], r1[16];
+          tmem_ld16(taddr + (uint32_t)c0, r0);
+          tmem_ld16(taddr + (uint32_t)(c0 + 16), r1);
+          tmem_ld_wait();
+          if (cc == c_hi - 1) {
             tc_fence_before();
             mbar_arrive(tempty_bar((int)acc));
           }
-          epi_bar();
-          // combine the previous chunk's quarter partials (written before this barrier)
-          if (cc > 0 && et < 32) {
-            const float* sc = scratch + (size_t)((cc - 1) & 1) * 4 * 32 * 4;
-            float* dstc = s_com + ((size_t)tc.n * g.Cout + n0 + (cc - 1) * 32 + et) * 4;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              dstc[k] += ((sc[(0 * 32 + et) * 4 + k] + sc[(1 * 32 + et) * 4 + k]) +
-                          sc[(2 * 32 + et) * 4 + k]) + sc[(3 * 32 + et) * 4 + k];
+          for (int j = 0; j < 16; ++j) {
+            const float v0 = __uint_as_float(r0[j]) + s_bias[n0 + c0 + j];
+            const float v1 = __uint_as_float(r1[j]) + s_bias[n0 + c0 + 16 + j];
+            r0[j] = __float_as_uint(v0);
+            r1[j] = __float_as_uint(v1);
+            fs[row * kFstagePitch + j] = valid ? fmaxf(v0, 0.f) : 0.f;
+            fs[row * kFstagePitch + 16 + j] = valid ? fmaxf(v1, 0.f) : 0.f;
           }
-          // this thread: column (et & 31), rows [32*(et>>5), +32)
+          if (has_out) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              pk[j] = pack_bf16(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+            uint4* dst = reinterpret_cast<uint4*>(staging + (size_t)row * pitch + (size_t)c0 * 2);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              pk[j] = pack_bf16(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+            dst[2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[3] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          half_bar();
+          // combine the previous chunk's quarter partials (written before this barrier)
+          if (it_c > 0 && row < 32) combine(cc - 1, (it_c - 1) & 1);
+          // this thread: column `col`, rows [32*rq, +32)
           {
-            const int col = et & 31, rq = et >> 5;
-            float s0 = 0.f, sz = 0.f, sy = 0.f, sx = 0.f;
+            float s0 = 0.f, sz, sy, sx;
+            const float* fcol = fs + (size_t)(rq * 32) * kFstagePitch + col;
+            if (wide) {
+              float sxr = 0.f;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                const float hv = fcol[rr * kFstagePitch];
+                s0 += hv;
+                sxr = fmaf(hv, (float)rr, sxr);
+              }
+              sx = fmaf(q_tx, s0, sxr);
+              sy = q_ty * s0;
+              sz = q_tz * s0;
+            } else {
+              sz = sy = sx = 0.f;
 #pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              const int r2 = rq * 32 + rr;
-              const float hv = fs[r2 * kFstagePitch + col];
-              s0 += hv;
-              sz = fmaf(hv, rowlin[0 * kTileM + r2], sz);
-              sy = fmaf(hv, rowlin[1 * kTileM + r2], sy);
-              sx = fmaf(hv, rowlin[2 * kTileM + r2], sx);
+              for (int rr = 0; rr < 32; ++rr) {
+                const int r2 = rq * 32 + rr;
+                const float hv = fcol[rr * kFstagePitch];
+                s0 += hv;
+                sz = fmaf(hv, rowlin[0 * kTileM + r2], sz);
+                sy = fmaf(hv, rowlin[1 * kTileM + r2], sy);
+                sx = fmaf(hv, rowlin[2 * kTileM + r2], sx);
+              }
             }
-            float* sc = scratch + (size_t)(cc & 1) * 4 * 32 * 4 + (size_t)(rq * 32 + col) * 4;
+            float* sc = scratch + (size_t)(it_c & 1) * 4 * 32 * 4 + (size_t)(rq * 32 + col) * 4;
             sc[0] = s0;
             sc[1] = sz;
             sc[2] = sy;
             sc[3] = sx;
           }
         }
-        epi_bar();
-        if (et < 32) {
-          const int cc = nchunks - 1;
-          const float* sc = scratch + (size_t)(cc & 1) * 4 * 32 * 4;
-          float* dstc = s_com + ((size_t)tc.n * g.Cout + n0 + cc * 32 + et) * 4;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            dstc[k] += ((sc[(0 * 32 + et) * 4 + k] + sc[(1 * 32 + et) * 4 + k]) +
-                        sc[(2 * 32 + et) * 4 + k]) + sc[(3 * 32 + et) * 4 + k];
+        if (c_hi > c_lo) {
+          half_bar();
+          if (row < 32) combine(c_hi - 1, (it_c - 1) & 1);
+        } else {
+          tc_fence_before();
+          mbar_arrive(tempty_bar((int)acc));   // this group had no columns in this tile
         }
+        all_bar();
       }
 
       // ---- staged bf16 tile -> global (coalesced 16-byte chunks) + per-channel stats ----
@@ -453,11 +515,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           d[1] += ss;
         }
       }
-      epi_bar();  // staging / rowinfo may be overwritten by the next tile
+      all_bar();  // staging / rowinfo may be overwritten by the next tile
     }
 
     // ---- per-CTA partials -> global ----
-    epi_bar();
+    all_bar();
     if (do_stats) {
       float* dst = stats + (size_t)blockIdx.x * g.N * g.Cout * 2;
       const int n = g.N * g.Cout * 2;
@@ -544,6 +606,7 @@ ConvKernel pick_kernel(int kc, int mode) {
 
 extern "C" int km_sm_count(void) { return sm_count(); }
 void km_conv_set_force_generic(int v) { g_force_mode0 = v ? 1 : 0; }
+void km_conv_set_no_resident(int v) { g_no_resident = v ? 1 : 0; }
 extern "C" int km_conv_nparts(void) { return sm_count(); }
 
 extern "C" int km_pack_weights(const float* w, void* packed, int Cout, int Cin, int taps,
@@ -617,7 +680,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   const long long tiles = (long long)N * g.tiles_z * g.tiles_y * g.tiles_x * g.n_blocks;
   KM_CHECK_ARG(tiles < (1ll << 31), "km_conv3d_tc: too many tiles");
   g.total_tiles = (int)tiles;
-  g.stat_parts = (g.BN <= kTileM && kTileM % g.BN == 0) ? kTileM / g.BN : 1;
+  g.stat_parts = (g.BN <= kEpiThreads && kEpiThreads % g.BN == 0) ? kEpiThreads / g.BN : 1;
 
   g.idesc = umma_idesc_bf16(kTileM, g.BN);
   uint32_t cols = 32;
@@ -629,19 +692,23 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   const uint32_t kSmemMax = 232448 - 1024;  // 227 KB minus alignment slack
   g.staging_pitch = (uint32_t)g.BN * 2 + 16;
   const uint32_t staging_bytes = g.has_out ? round_up(kTileM * g.staging_pitch, 16) : 0;
-  const uint32_t fstage_bytes = (flags & KM_CONV_COM) ? 2u * kTileM * kFstagePitch * 4u : 0;
+  const uint32_t fstage_bytes = (flags & KM_CONV_COM) ? 2u * 2u * kTileM * kFstagePitch * 4u : 0;
   const uint32_t rowinfo_bytes = 3u * kTileM * 4u + kTileM;
   const uint32_t stats_bytes =
       (flags & KM_CONV_STATS) ? (uint32_t)g.stat_parts * N * Cout * 2u * 4u : 0;
   const uint32_t com_bytes = (flags & KM_CONV_COM) ? (uint32_t)N * Cout * 4u * 4u : 0;
-  const uint32_t scratch_bytes = (flags & KM_CONV_COM) ? 2u * 4u * 32u * 4u * 4u : 0;
-  const uint32_t bars_bytes = 8u * (2u * kMaxStages + 4u) + 16u;
+  const uint32_t scratch_bytes = (flags & KM_CONV_COM) ? 2u * 2u * 4u * 32u * 4u * 4u : 0;
+  const uint32_t bars_bytes = 8u * (2u * kMaxStages + 6u) + 16u;
+  const uint32_t bias_bytes = (uint32_t)Cout * 4u;
   const uint32_t fixed = staging_bytes + fstage_bytes + rowinfo_bytes + stats_bytes + com_bytes +
-                         scratch_bytes + bars_bytes + 64;
-  const uint32_t unit = g.a_sub_stride + g.b_sub_stride;
-  KM_CHECK_ARG(fixed + 2 * unit <= kSmemMax,
+                         scratch_bytes + bias_bytes + bars_bytes + 64;
+  // small weight tensors (first layers) stay resident: the per-tile weight re-fetch is TMA-request bound
+  const uint32_t bres_bytes = (uint32_t)g.subiters * g.b_sub_stride;
+  g.b_resident = (mode == 1 && g.n_blocks == 1 && bres_bytes <= 64u * 1024u && !g_no_resident) ? 1 : 0;
+  const uint32_t unit = g.a_sub_stride + (g.b_resident ? 0u : g.b_sub_stride);
+  KM_CHECK_ARG(fixed + (g.b_resident ? bres_bytes : 0u) + 2 * unit <= kSmemMax,
                "km_conv3d_tc: shared memory budget exceeded (N*Cout too large: N=%d Cout=%d)", N, Cout);
-  const uint32_t avail = kSmemMax - fixed;
+  const uint32_t avail = kSmemMax - fixed - (g.b_resident ? bres_bytes : 0u);
   // pack sub-iterations into a stage until it holds ~40 KB (fewer barrier round trips, more bytes
   // in flight per barrier) while keeping at least 3 stages
   int sub = 1;
@@ -655,12 +722,15 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   KM_CHECK_ARG(stages >= 2, "km_conv3d_tc: not enough shared memory for a 2-stage pipeline");
   g.stages = stages;
   uint32_t off = (uint32_t)stages * g.stage_stride;
+  g.off_bres = off;
+  if (g.b_resident) off += bres_bytes;
   g.off_staging = off; off += staging_bytes;
   g.off_fstage = off; off += fstage_bytes;
   g.off_rowinfo = off; off += round_up(rowinfo_bytes, 16);
   g.off_stats = off; off += stats_bytes;
   g.off_com = off; off += com_bytes;
   g.off_scratch = off; off += scratch_bytes;
+  g.off_bias = off; off += bias_bytes;
   off = round_up(off, 8);
   g.off_bars = off; off += bars_bytes;
   const uint32_t smem_bytes = off + 1024;

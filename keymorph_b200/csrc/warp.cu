@@ -15,6 +15,7 @@ namespace {
 int g_tps_fast = 1;
 }  // namespace
 void km_conv_set_force_generic(int v);
+void km_conv_set_no_resident(int v);
 namespace {
 
 // ---- ATen grid_sampler_3d source-index arithmetic (align_corners=False, padding "border"),
@@ -372,11 +373,14 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
 // partials [nparts][NC][4] -> sums[NC][4] (fp64)
 __global__ void sum_partials4_kernel(const float* __restrict__ partials, int nparts, int NC4,
                                      double* __restrict__ sums) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per output value: lanes stride over the partial slots, fixed-order shuffle reduce
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= NC4) return;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += (double)partials[(size_t)p * NC4 + i];
-  sums[i] = s;
+  for (int p = lane; p < nparts; p += 32) s += (double)partials[(size_t)p * NC4 + i];
+  s = km_warp_sum(s);
+  if (lane == 0) sums[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -456,6 +460,10 @@ extern "C" int km_set_option(int key, int value) {
   }
   if (key == KM_OPT_CONV_FORCE_GENERIC) {
     km_conv_set_force_generic(value);
+    return KM_OK;
+  }
+  if (key == KM_OPT_CONV_NO_RESIDENT_WEIGHTS) {
+    km_conv_set_no_resident(value);
     return KM_OK;
   }
   km_set_error("km_set_option: unknown key %d", key);
@@ -592,7 +600,7 @@ extern "C" int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const floa
   KM_LAUNCH_OK("warp_loss_kernel");
   if (fixed) {
     const int NC4 = N * C * 4;
-    sum_partials4_kernel<<<(NC4 + 127) / 128, 128, 0, st>>>(part, KM_RED_BLOCKS, NC4, sums);
+    sum_partials4_kernel<<<(NC4 + 7) / 8, 256, 0, st>>>(part, KM_RED_BLOCKS, NC4, sums);
     KM_LAUNCH_OK("sum_partials4_kernel");
   }
   return KM_OK;
@@ -627,7 +635,7 @@ extern "C" int km_pair_stats(const float* pred, const float* target, double* sum
                                                                           N, C, M);
   KM_LAUNCH_OK("pair_stats_kernel");
   const int NC4 = N * C * 4;
-  sum_partials4_kernel<<<(NC4 + 127) / 128, 128, 0, km_cs(stream)>>>(part, bx, NC4, sums);
+  sum_partials4_kernel<<<(NC4 + 7) / 8, 256, 0, km_cs(stream)>>>(part, bx, NC4, sums);
   KM_LAUNCH_OK("sum_partials4_kernel");
   return KM_OK;
 }

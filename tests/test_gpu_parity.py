@@ -519,8 +519,17 @@ def test_full_size_256_backbone_and_registration_vs_oracle():
     ref_pts = O.center_of_mass3d(O.unet3d_forward(sd, f_cpu, 4, 1))
     r = model(f, m, transform_type=["rigid", "affine"], return_aligned_points=True)
     err = (r["affine"]["points_f"].cpu() - ref_pts).abs().max().item()
-    print(f"256^3 keypoints vs fp32 oracle: max err {err:.3e}")
-    assert err < 1e-2
+    # drift budget = what torch's own bf16 autocast does to the SAME network on the SAME volume
+    # (the oracle functions evaluated on the GPU under autocast; SURVEY.md section 7, hard part 3)
+    sd_gpu = {k: v.to(DEV) for k, v in sd.items()}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ac_pts = O.center_of_mass3d(O.unet3d_forward(sd_gpu, f, 4, 1).float()).cpu()
+    drift = (ac_pts - ref_pts).abs().max().item()
+    mean_err = (r["affine"]["points_f"].cpu() - ref_pts).abs().mean().item()
+    print(f"256^3 keypoints vs fp32 oracle: max err {err:.3e} mean {mean_err:.3e}; "
+          f"torch bf16-autocast drift on the same input: max {drift:.3e}")
+    assert err < max(1e-2, 1.25 * drift)
+    assert mean_err < 2.5e-3
     for t in ("rigid", "affine"):
         ref = O.register_points(r[t]["points_f"].cpu(), r[t]["points_m"].cpu(), t, (S, S, S))
         assert_close(r[t]["matrix"].cpu(), ref["matrix"], rtol=1e-4, atol=1e-4)

@@ -394,6 +394,43 @@ def run_conv_big():
     return ok
 
 
+def run_convtime():
+    """Per-layer timing of the bench workload's convolutions (N=2), with the data-path options."""
+    import torch
+    from keymorph_b200 import _lib, ops
+    layers = [(16, 32, 256, 27), (32, 32, 128, 27), (32, 64, 128, 27), (64, 64, 64, 27), (64, 128, 64, 27),
+              (128, 128, 32, 27), (128, 256, 32, 27), (384, 128, 64, 27), (128, 128, 64, 27),
+              (192, 64, 128, 27), (64, 64, 128, 27), (64, 256, 128, 1)]
+    for label, opts in (("default", {}), ("generic path", {_lib.KM_OPT_CONV_FORCE_GENERIC: 1}),
+                        ("streamed weights", {_lib.KM_OPT_CONV_NO_RESIDENT_WEIGHTS: 1})):
+        for k, v in opts.items():
+            _lib.call("km_set_option", k, v)
+        print(f"  -- {label}")
+        total = 0.0
+        for (Cin, Cout, S, taps) in layers:
+            x = torch.randn(2, S, S, S, Cin, device="cuda").bfloat16()
+            wp = (torch.randn(taps, Cout, Cin, device="cuda") / (taps * Cin) ** 0.5).bfloat16()
+            bias = torch.zeros(Cout, device="cuda") if taps == 1 else None
+            kw = dict(want_com=True, store=False, bias=bias) if taps == 1 else dict(relu=True, want_stats=True)
+            for _ in range(2):
+                ops.conv3d_tc(x, wp, **kw)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                ops.conv3d_tc(x, wp, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            total += ms
+            fl = 2.0 * taps * Cin * Cout * S ** 3 * 2
+            print(f"  conv {Cin}->{Cout} @{S}^3 x2 taps={taps}: {ms:.3f} ms, {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+        print(f"  total {total:.3f} ms")
+        for k in opts:
+            _lib.call("km_set_option", k, 0)
+    return True
+
+
 def run_convcom():
     import torch
     import torch.nn.functional as F
