@@ -47,6 +47,9 @@ int km_sm_count(void);
 /* key KM_OPT_CONV_NO_RESIDENT_WEIGHTS (default 0): stream the weights of small layers per tile
  * instead of keeping them in shared memory (A/B testing). */
 #define KM_OPT_CONV_NO_RESIDENT_WEIGHTS 3
+/* key KM_OPT_CONV_MAX_BRICKS (default 4): how many x-adjacent 16x8 bricks may share one weight
+ * fetch in km_conv3d_tc (1, 2 or 4). */
+#define KM_OPT_CONV_MAX_BRICKS 4
 int km_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------ *

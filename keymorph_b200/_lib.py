@@ -63,6 +63,7 @@ KM_COORD_AFFINE, KM_COORD_TPS, KM_COORD_GRID = 0, 1, 2
 KM_OPT_TPS_FAST = 1
 KM_OPT_CONV_FORCE_GENERIC = 2
 KM_OPT_CONV_NO_RESIDENT_WEIGHTS = 3
+KM_OPT_CONV_MAX_BRICKS = 4
 
 _lib = None
 

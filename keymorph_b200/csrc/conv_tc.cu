@@ -38,6 +38,7 @@ constexpr int kFstagePitch = 33;  // floats, conflict-free transposed access
 constexpr int kMaxStages = 12;
 int g_force_mode0 = 0;            // km_set_option(KM_OPT_CONV_FORCE_GENERIC): A/B the two data paths
 int g_no_resident = 0;            // km_set_option(KM_OPT_CONV_NO_RESIDENT_WEIGHTS)
+int g_max_mt = 4;                 // km_set_option(KM_OPT_CONV_MAX_BRICKS)
 
 struct ConvGeom {
   int N, D, H, W, Cin, Cout;
@@ -53,6 +54,7 @@ struct ConvGeom {
   int subiters;        // sub-iterations per tile: taps*chunks (mode 0) or 9*chunks (mode 1)
   int stat_parts;      // row groups that accumulate channel statistics independently
   int b_resident;      // all weight slices stay in shared memory for the whole kernel
+  int mt;              // mode 1: x-adjacent 16x8 bricks that share one weight fetch (1, 2 or 4)
   uint32_t off_bres;
   uint32_t a_sub_bytes, b_sub_bytes;      // TMA bytes per sub-iteration
   uint32_t a_sub_stride, b_sub_stride;    // 1024-aligned slots inside a stage
@@ -260,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t acc_ph = (tcount >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)g.BN;
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)(g.mt * g.BN);
         uint32_t accum = 0;
         uint32_t bq16 = bres16;   // running weight slice (resident mode)
         for (int si = 0; si < n_stage_iters; ++si) {
@@ -270,16 +272,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t a16 = base16 + (uint32_t)s * stage16;
           uint32_t b16 = resident ? bq16 : a16 + boff16;
           for (int u = 0; u < nsub; ++u) {
+            for (int m = 0; m < g.mt; ++m) {   // bricks sharing this weight slice
+              const uint32_t am16 = a16 + (uint32_t)(16 * m) * a_tap16;
+              const uint32_t dm = d_tmem + (uint32_t)(m * g.BN);
 #pragma unroll
-            for (int t = 0; t < kNtap; ++t) {
+              for (int t = 0; t < kNtap; ++t) {
 #pragma unroll
-              for (int kk = 0; kk < kSteps; ++kk) {
-                const uint64_t adesc = desc_hi | (uint64_t)((a16 + t * a_tap16 + 2u * kk) | lo_flag);
-                const uint64_t bdesc = desc_hi | (uint64_t)((b16 + t * b_tap16 + 2u * kk) | lo_flag);
-                umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
-                accum = 1u;
+                for (int kk = 0; kk < kSteps; ++kk) {
+                  const uint64_t adesc = desc_hi | (uint64_t)((am16 + t * a_tap16 + 2u * kk) | lo_flag);
+                  const uint64_t bdesc = desc_hi | (uint64_t)((b16 + t * b_tap16 + 2u * kk) | lo_flag);
+                  umma_bf16(dm, adesc, bdesc, idesc, (accum | (uint32_t)(t | kk)) ? 1u : 0u);
+                }
               }
             }
+            accum = 1u;
             a16 += a_sub16;
             b16 += b_sub16;
           }
@@ -327,10 +333,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tcount) {
-      const TileCoord tc = decode_tile(g, tile);
+      const TileCoord tc0 = decode_tile(g, tile);
       const uint32_t acc = tcount & 1u;
       const uint32_t acc_ph = (tcount >> 1) & 1u;
-      const int n0 = tc.nb * BN;
+      const int n0 = tc0.nb * BN;
+      mbar_wait(tfull_bar((int)acc), acc_ph);
+      tc_fence_after();
+      int m_last = 0;   // last brick of the group that lies (partly) inside the volume
+      while (m_last + 1 < g.mt && tc0.x0 + 16 * (m_last + 1) < g.W) ++m_last;
+      for (int m = 0; m <= m_last; ++m) {
+      TileCoord tc = tc0;
+      tc.x0 += 16 * m;
+      const bool last_sub = m == m_last;
 
       // voxel of this row (both groups write the same values)
       int tx, ty, tz;
@@ -344,9 +358,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         rowlin[2 * kTileM + row] = (float)tx;
       }
 
-      mbar_wait(tfull_bar((int)acc), acc_ph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                             (acc * (uint32_t)g.mt + (uint32_t)m) * (uint32_t)BN;
 
       if (!do_com) {
         const int nblk = BN / 16, split = (nblk + 1) / 2;
@@ -372,8 +385,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
-        tc_fence_before();
-        mbar_arrive(tempty_bar((int)acc));
+        if (last_sub) {
+          tc_fence_before();
+          mbar_arrive(tempty_bar((int)acc));
+        }
         all_bar();
       } else {
         // final conv + centre of mass: 32-column chunks, transposed through fp32 smem.  Sums are
@@ -381,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // coordinates once per tile: lin(i) = i / (n - 1).
         const int nchunks = BN / 32, split = (nchunks + 1) / 2;
         const int c_lo = half == 0 ? 0 : split, c_hi = half == 0 ? split : nchunks;
-        const bool wide = g.TW >= 32;   // a 32-row quarter is then an x-run: ty, tz constant
+        const bool wide = MODE == 0 && g.TW >= 32;   // a 32-row quarter is then an x-run: ty, tz constant
         const int col = row & 31, rq = row >> 5;
         const float q_tx = (float)((rq * 32) % g.TW);
         const float q_ty = (float)(((rq * 32) / g.TW) % g.TH);
@@ -407,7 +422,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld16(taddr + (uint32_t)c0, r0);
           tmem_ld16(taddr + (uint32_t)(c0 + 16), r1);
           tmem_ld_wait();
-          if (cc == c_hi - 1) {
+          if (cc == c_hi - 1 && last_sub) {
             tc_fence_before();
             mbar_arrive(tempty_bar((int)acc));
           }
@@ -474,7 +489,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (c_hi > c_lo) {
           half_bar();
           if (row < 32) combine(c_hi - 1, (it_c - 1) & 1);
-        } else {
+        } else if (last_sub) {
           tc_fence_before();
           mbar_arrive(tempty_bar((int)acc));   // this group had no columns in this tile
         }
@@ -515,7 +530,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           d[1] += ss;
         }
       }
-      all_bar();  // staging / rowinfo may be overwritten by the next tile
+      all_bar();  // staging / rowinfo may be overwritten by the next brick / tile
+      }
     }
 
     // ---- per-CTA partials -> global ----
@@ -607,6 +623,7 @@ ConvKernel pick_kernel(int kc, int mode) {
 extern "C" int km_sm_count(void) { return sm_count(); }
 void km_conv_set_force_generic(int v) { g_force_mode0 = v ? 1 : 0; }
 void km_conv_set_no_resident(int v) { g_no_resident = v ? 1 : 0; }
+void km_conv_set_max_mt(int v) { g_max_mt = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
 extern "C" int km_conv_nparts(void) { return sm_count(); }
 
 extern "C" int km_pack_weights(const float* w, void* packed, int Cout, int Cin, int taps,
@@ -655,10 +672,19 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
     if (Cout % bn == 0) { g.BN = bn; break; }
   KM_CHECK_ARG(g.BN > 0, "km_conv3d_tc: no channel block for Cout=%d", Cout);
   g.n_blocks = Cout / g.BN;
+  g.mt = 1;
   if (mode == 1) {
-    g.TW = 16; g.TH = 8; g.TD = 1;
+    // bricks that share one weight fetch: as many as TMEM (2 buffers x mt x BN columns) allows,
+    // not more than the row holds; shared memory is checked below
+    int mt = g_max_mt;
+    while (mt > 1 && (2 * mt * g.BN > 512 || 16 * (mt / 2) >= W)) mt /= 2;
+    while (mt > 1 && round_up((16u * mt + 2u) * 8u * row_bytes, 1024) +
+                             round_up(3u * (uint32_t)g.BN * row_bytes, 1024) > 96u * 1024u)
+      mt /= 2;
+    g.mt = mt;
+    g.TW = 16 * mt; g.TH = 8; g.TD = 1;
     g.subiters = 9 * g.chunks;
-    g.a_sub_bytes = 18u * 8u * row_bytes;
+    g.a_sub_bytes = (16u * mt + 2u) * 8u * row_bytes;
     g.b_sub_bytes = 3u * (uint32_t)g.BN * row_bytes;
   } else {
     // generic brick: as long a W-run as possible, then H, then D (power-of-two factors of 128).
@@ -684,7 +710,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
 
   g.idesc = umma_idesc_bf16(kTileM, g.BN);
   uint32_t cols = 32;
-  while (cols < 2u * (uint32_t)g.BN) cols *= 2;
+  while (cols < 2u * (uint32_t)(g.mt * g.BN)) cols *= 2;
   g.tmem_cols = cols;
   KM_CHECK_ARG(cols <= 512, "km_conv3d_tc: TMEM overflow");
 
@@ -754,7 +780,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
       // (C, H, W, D, N): y is the fastest spatial index in shared memory (8 rows = one swizzle atom)
       dims[1] = (cuuint64_t)H; dims[2] = (cuuint64_t)W;
       strides[0] = (cuuint64_t)W * Cin * 2; strides[1] = (cuuint64_t)Cin * 2;
-      box[1] = 8; box[2] = 18; box[3] = 1;
+      box[1] = 8; box[2] = (cuuint32_t)(16 * g.mt + 2); box[3] = 1;
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims,
