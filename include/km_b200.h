@@ -50,6 +50,8 @@ int km_sm_count(void);
 /* key KM_OPT_CONV_MAX_BRICKS (default 4): how many x-adjacent 16x8 bricks may share one weight
  * fetch in km_conv3d_tc (1, 2 or 4). */
 #define KM_OPT_CONV_MAX_BRICKS 4
+/* key KM_OPT_CONV_NO_EPILOGUE_BATCH (default 0): stage one brick per epilogue round (A/B). */
+#define KM_OPT_CONV_NO_EPILOGUE_BATCH 5
 int km_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------ *

@@ -64,6 +64,7 @@ KM_OPT_TPS_FAST = 1
 KM_OPT_CONV_FORCE_GENERIC = 2
 KM_OPT_CONV_NO_RESIDENT_WEIGHTS = 3
 KM_OPT_CONV_MAX_BRICKS = 4
+KM_OPT_CONV_NO_EPILOGUE_BATCH = 5
 
 _lib = None
 

@@ -39,6 +39,7 @@ constexpr int kMaxStages = 12;
 int g_force_mode0 = 0;            // km_set_option(KM_OPT_CONV_FORCE_GENERIC): A/B the two data paths
 int g_no_resident = 0;            // km_set_option(KM_OPT_CONV_NO_RESIDENT_WEIGHTS)
 int g_max_mt = 4;                 // km_set_option(KM_OPT_CONV_MAX_BRICKS)
+int g_no_epi_batch = 0;           // km_set_option(KM_OPT_CONV_NO_EPILOGUE_BATCH)
 
 struct ConvGeom {
   int N, D, H, W, Cin, Cout;
@@ -55,6 +56,7 @@ struct ConvGeom {
   int stat_parts;      // row groups that accumulate channel statistics independently
   int b_resident;      // all weight slices stay in shared memory for the whole kernel
   int mt;              // mode 1: x-adjacent 16x8 bricks that share one weight fetch (1, 2 or 4)
+  int eb;              // bricks staged together per epilogue round (<= mt)
   uint32_t off_bres;
   uint32_t a_sub_bytes, b_sub_bytes;      // TMA bytes per sub-iteration
   uint32_t a_sub_stride, b_sub_stride;    // 1024-aligned slots inside a stage
@@ -311,7 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* staging = sm + g.off_staging;
     float* fstage = reinterpret_cast<float*>(sm + g.off_fstage) + (size_t)half * 2 * kTileM * kFstagePitch;
     float* rowlin = reinterpret_cast<float*>(sm + g.off_rowinfo);          // [3][128] tz, ty, tx
-    uint8_t* rowvalid = sm + g.off_rowinfo + 3 * kTileM * sizeof(float);   // [128]
+    uint8_t* rowvalid = sm + g.off_rowinfo + 3 * kTileM * sizeof(float);   // [eb][128]
     float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);           // [parts][N][Cout][2]
     float* s_com = reinterpret_cast<float*>(sm + g.off_com);
     float* scratch = reinterpret_cast<float*>(sm + g.off_scratch) + (size_t)half * 2 * 4 * 32 * 4;
@@ -341,17 +343,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       int m_last = 0;   // last brick of the group that lies (partly) inside the volume
       while (m_last + 1 < g.mt && tc0.x0 + 16 * (m_last + 1) < g.W) ++m_last;
-      for (int m = 0; m <= m_last; ++m) {
+      const int eb = g.eb;
+      for (int m = 0; m <= m_last; m += eb) {
+      // one epilogue round: nb bricks staged together (fewer barriers per brick for narrow BN)
+      const int nb = min(eb, m_last + 1 - m);
       TileCoord tc = tc0;
       tc.x0 += 16 * m;
-      const bool last_sub = m == m_last;
+      const bool last_sub = m + nb - 1 == m_last;
 
       // voxel of this row (both groups write the same values)
       int tx, ty, tz;
       row_to_voxel<MODE>(g, row, tx, ty, tz);
-      const int vx = tc.x0 + tx, vy = tc.y0 + ty, vz = tc.z0 + tz;
-      const bool valid = (vx < g.W) && (vy < g.H) && (vz < g.D);
-      rowvalid[row] = valid ? 1 : 0;
+      const int vy = tc.y0 + ty, vz = tc.z0 + tz;
+      uint32_t vmask = 0;
+      for (int mb = 0; mb < nb; ++mb) {
+        const bool v = (tc.x0 + 16 * mb + tx < g.W) && (vy < g.H) && (vz < g.D);
+        vmask |= (v ? 1u : 0u) << mb;
+        rowvalid[mb * kTileM + row] = v ? 1 : 0;
+      }
+      const bool valid = (vmask & 1u) != 0;
       if (do_com) {
         rowlin[0 * kTileM + row] = (float)tz;   // brick-local offsets (narrow-brick CoM path)
         rowlin[1 * kTileM + row] = (float)ty;
@@ -364,26 +374,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!do_com) {
         const int nblk = BN / 16, split = (nblk + 1) / 2;
         const int b_lo = half == 0 ? 0 : split, b_hi = half == 0 ? split : nblk;
-        for (int blk = b_lo; blk < b_hi; ++blk) {
-          const int c0 = blk * 16;
-          uint32_t r[16];
-          tmem_ld16(taddr + (uint32_t)c0, r);
-          tmem_ld_wait();
-          uint32_t pk[8];
+        for (int mb = 0; mb < nb; ++mb) {
+          const bool vrow = ((vmask >> mb) & 1u) != 0;
+          const uint32_t taddr_b = taddr + (uint32_t)(mb * BN);
+          uint8_t* srow = staging + (size_t)(mb * kTileM + row) * pitch;
+          for (int blk = b_lo; blk < b_hi; ++blk) {
+            const int c0 = blk * 16;
+            uint32_t r[16];
+            tmem_ld16(taddr_b + (uint32_t)c0, r);
+            tmem_ld_wait();
+            uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float a = __uint_as_float(r[2 * j]) + s_bias[n0 + c0 + 2 * j];
-            float b = __uint_as_float(r[2 * j + 1]) + s_bias[n0 + c0 + 2 * j + 1];
-            if (do_relu) {
-              a = fmaxf(a, 0.f);
-              b = fmaxf(b, 0.f);
+            for (int j = 0; j < 8; ++j) {
+              float a = __uint_as_float(r[2 * j]) + s_bias[n0 + c0 + 2 * j];
+              float b = __uint_as_float(r[2 * j + 1]) + s_bias[n0 + c0 + 2 * j + 1];
+              if (do_relu) {
+                a = fmaxf(a, 0.f);
+                b = fmaxf(b, 0.f);
+              }
+              // rows outside the volume are staged as zeros so that the statistics need no mask
+              pk[j] = vrow ? pack_bf16(a, b) : 0u;
             }
-            // rows outside the volume are staged as zeros so that the statistics need no mask
-            pk[j] = valid ? pack_bf16(a, b) : 0u;
+            uint4* dst = reinterpret_cast<uint4*>(srow + (size_t)c0 * 2);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          uint4* dst = reinterpret_cast<uint4*>(staging + (size_t)row * pitch + (size_t)c0 * 2);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
         if (last_sub) {
           tc_fence_before();
@@ -498,17 +513,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       // ---- staged bf16 tile -> global (coalesced 16-byte chunks) + per-channel stats ----
       if (has_out) {
-        const int total_chunks = kTileM * cpr;
+        const int total_chunks = nb * kTileM * cpr;
         for (int id = et; id < total_chunks; id += kEpiThreads) {
           const int j = id % cpr;
-          int r2 = id / cpr;
+          const int rr = id / cpr;
+          const int mb = rr >> 7;
+          int r2 = rr & (kTileM - 1);
           if (MODE == 1) r2 = ((r2 & 15) << 3) | (r2 >> 4);   // walk x fastest for coalescing
-          if (!rowvalid[r2]) continue;
+          if (!rowvalid[mb * kTileM + r2]) continue;
           int tx2, ty2, tz2;
           row_to_voxel<MODE>(g, r2, tx2, ty2, tz2);
-          const int x2 = tc.x0 + tx2, y2 = tc.y0 + ty2, z2 = tc.z0 + tz2;
+          const int x2 = tc.x0 + 16 * mb + tx2, y2 = tc.y0 + ty2, z2 = tc.z0 + tz2;
           const size_t vox = (((size_t)tc.n * g.D + z2) * g.H + y2) * g.W + x2;
-          const uint4 v = *reinterpret_cast<const uint4*>(staging + (size_t)r2 * pitch + j * 16);
+          const uint4 v = *reinterpret_cast<const uint4*>(
+              staging + (size_t)(mb * kTileM + r2) * pitch + j * 16);
           *reinterpret_cast<uint4*>(out + vox * g.Cout + n0 + j * 8) = v;
         }
       }
@@ -516,14 +534,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // thread -> (column, row group); every (part, column) slot is owned by one thread
         for (int id = et; id < parts * BN; id += kEpiThreads) {
           const int col = id % BN, part = id / BN;
-          const uint8_t* p = staging + (size_t)(part * rows_per_part) * pitch + (size_t)col * 2;
           float s = 0.f, ss = 0.f;
+          for (int mb = 0; mb < nb; ++mb) {
+            const uint8_t* p = staging + (size_t)(mb * kTileM + part * rows_per_part) * pitch +
+                               (size_t)col * 2;
 #pragma unroll 8
-          for (int rr = 0; rr < rows_per_part; ++rr) {
-            const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
-            p += pitch;
-            s += v;
-            ss = fmaf(v, v, ss);
+            for (int rr = 0; rr < rows_per_part; ++rr) {
+              const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
+              p += pitch;
+              s += v;
+              ss = fmaf(v, v, ss);
+            }
           }
           float* d = s_stats + (((size_t)part * g.N + tc.n) * g.Cout + n0 + col) * 2;
           d[0] += s;
@@ -624,6 +645,7 @@ extern "C" int km_sm_count(void) { return sm_count(); }
 void km_conv_set_force_generic(int v) { g_force_mode0 = v ? 1 : 0; }
 void km_conv_set_no_resident(int v) { g_no_resident = v ? 1 : 0; }
 void km_conv_set_max_mt(int v) { g_max_mt = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
+void km_conv_set_no_epi_batch(int v) { g_no_epi_batch = v ? 1 : 0; }
 extern "C" int km_conv_nparts(void) { return sm_count(); }
 
 extern "C" int km_pack_weights(const float* w, void* packed, int Cout, int Cin, int taps,
@@ -717,9 +739,15 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   // shared-memory carve-up (offsets relative to the 1024-aligned base)
   const uint32_t kSmemMax = 232448 - 1024;  // 227 KB minus alignment slack
   g.staging_pitch = (uint32_t)g.BN * 2 + 16;
-  const uint32_t staging_bytes = g.has_out ? round_up(kTileM * g.staging_pitch, 16) : 0;
+  // bricks staged per epilogue round: all bricks of a group when that costs <= 48 KB
+  g.eb = 1;
+  if (g.has_out && !(flags & KM_CONV_COM) && !g_no_epi_batch) {
+    g.eb = g.mt;
+    while (g.eb > 1 && (uint32_t)g.eb * kTileM * g.staging_pitch > 48u * 1024u) g.eb /= 2;
+  }
+  const uint32_t staging_bytes = g.has_out ? round_up((uint32_t)g.eb * kTileM * g.staging_pitch, 16) : 0;
   const uint32_t fstage_bytes = (flags & KM_CONV_COM) ? 2u * 2u * kTileM * kFstagePitch * 4u : 0;
-  const uint32_t rowinfo_bytes = 3u * kTileM * 4u + kTileM;
+  const uint32_t rowinfo_bytes = 3u * kTileM * 4u + 4u * kTileM;
   const uint32_t stats_bytes =
       (flags & KM_CONV_STATS) ? (uint32_t)g.stat_parts * N * Cout * 2u * 4u : 0;
   const uint32_t com_bytes = (flags & KM_CONV_COM) ? (uint32_t)N * Cout * 4u * 4u : 0;

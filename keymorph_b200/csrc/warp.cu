@@ -17,6 +17,7 @@ int g_tps_fast = 1;
 void km_conv_set_force_generic(int v);
 void km_conv_set_no_resident(int v);
 void km_conv_set_max_mt(int v);
+void km_conv_set_no_epi_batch(int v);
 namespace {
 
 // ---- ATen grid_sampler_3d source-index arithmetic (align_corners=False, padding "border"),
@@ -469,6 +470,10 @@ extern "C" int km_set_option(int key, int value) {
   }
   if (key == KM_OPT_CONV_MAX_BRICKS) {
     km_conv_set_max_mt(value);
+    return KM_OK;
+  }
+  if (key == KM_OPT_CONV_NO_EPILOGUE_BATCH) {
+    km_conv_set_no_epi_batch(value);
     return KM_OK;
   }
   km_set_error("km_set_option: unknown key %d", key);

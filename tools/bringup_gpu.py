@@ -401,8 +401,7 @@ def run_convtime():
     layers = [(16, 32, 256, 27), (32, 32, 128, 27), (32, 64, 128, 27), (64, 64, 64, 27), (64, 128, 64, 27),
               (128, 128, 32, 27), (128, 256, 32, 27), (384, 128, 64, 27), (128, 128, 64, 27),
               (192, 64, 128, 27), (64, 64, 128, 27), (64, 256, 128, 1)]
-    for label, opts in (("default", {}), ("max 2 bricks per weight fetch", {_lib.KM_OPT_CONV_MAX_BRICKS: 2}),
-                        ("1 brick per weight fetch", {_lib.KM_OPT_CONV_MAX_BRICKS: 1}),
+    for label, opts in (("default", {}), ("one brick per epilogue round", {_lib.KM_OPT_CONV_NO_EPILOGUE_BATCH: 1}),
                         ("streamed weights", {_lib.KM_OPT_CONV_NO_RESIDENT_WEIGHTS: 1})):
         _lib.call("km_set_option", _lib.KM_OPT_CONV_MAX_BRICKS, 4)
         for k, v in opts.items():
