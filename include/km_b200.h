@@ -52,6 +52,9 @@ int km_sm_count(void);
 #define KM_OPT_CONV_MAX_BRICKS 4
 /* key KM_OPT_CONV_NO_EPILOGUE_BATCH (default 0): stage one brick per epilogue round (A/B). */
 #define KM_OPT_CONV_NO_EPILOGUE_BATCH 5
+/* key KM_OPT_CONV_HALO_AXIS (default 2): axis along which the three taps share one TMA box in
+ * km_conv3d_tc: 2 = y (shared-memory atoms are x-runs, contiguous in global memory), 1 = x. */
+#define KM_OPT_CONV_HALO_AXIS 6
 int km_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------ *

@@ -65,6 +65,7 @@ KM_OPT_CONV_FORCE_GENERIC = 2
 KM_OPT_CONV_NO_RESIDENT_WEIGHTS = 3
 KM_OPT_CONV_MAX_BRICKS = 4
 KM_OPT_CONV_NO_EPILOGUE_BATCH = 5
+KM_OPT_CONV_HALO_AXIS = 6
 
 _lib = None
 

@@ -40,6 +40,7 @@ int g_force_mode0 = 0;            // km_set_option(KM_OPT_CONV_FORCE_GENERIC): A
 int g_no_resident = 0;            // km_set_option(KM_OPT_CONV_NO_RESIDENT_WEIGHTS)
 int g_max_mt = 4;                 // km_set_option(KM_OPT_CONV_MAX_BRICKS)
 int g_no_epi_batch = 0;           // km_set_option(KM_OPT_CONV_NO_EPILOGUE_BATCH)
+int g_halo_axis = 2;              // km_set_option(KM_OPT_CONV_HALO_AXIS): 1 = x-shift, 2 = y-shift
 
 struct ConvGeom {
   int N, D, H, W, Cin, Cout;
@@ -82,9 +83,13 @@ __device__ __forceinline__ void row_to_voxel(const ConvGeom& g, int row, int& tx
     tx = row % g.TW;
     ty = (row / g.TW) % g.TH;
     tz = row / (g.TW * g.TH);
-  } else {  // rows are stored y-fastest so that an x step is a whole 8-row swizzle atom
+  } else if (MODE == 1) {  // rows are stored y-fastest: an x step is a whole 8-row swizzle atom
     ty = row & 7;
     tx = row >> 3;
+    tz = 0;
+  } else {                 // MODE 2: rows are stored x-fastest: a y step is a whole swizzle atom
+    tx = row & 7;
+    ty = row >> 3;
     tz = 0;
   }
 }
@@ -113,7 +118,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                float* __restrict__ stats, float* __restrict__ com) {
   constexpr int kRowBytes = KC * 2;
   constexpr int kSteps = KC / 16;
-  constexpr int kNtap = MODE == 1 ? 3 : 1;
+  constexpr int kNtap = MODE >= 1 ? 3 : 1;
   constexpr uint32_t kLayout = kRowBytes == 128 ? 2u : (kRowBytes == 64 ? 4u : 6u);
   constexpr uint32_t kSbo = 8u * kRowBytes;
 
@@ -187,7 +192,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t dst = base + g.off_bres;
         for (int grp = 0; grp < g.subiters / g.chunks; ++grp)
           for (int ch = 0; ch < g.chunks; ++ch, dst += g.b_sub_stride)
-            tma_load_3d(dst, &tmB, bres_bar, ch * KC, 0, MODE == 1 ? grp * 3 : grp);
+            if (MODE == 2) tma_load_5d(dst, &tmB, bres_bar, ch * KC, 0, grp % 3, 0, grp / 3);
+            else tma_load_3d(dst, &tmB, bres_bar, ch * KC, 0, MODE == 1 ? grp * 3 : grp);
       }
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(g, tile);
@@ -205,11 +211,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_5d(a_dst, &tmA, full_bar(s), ch * KC, tc.x0 + dx, tc.y0 + dy, tc.z0 + dz,
                           tc.n);
               if (!resident) tma_load_3d(b_dst, &tmB, full_bar(s), ch * KC, bn0, grp);
-            } else {
+            } else if (MODE == 1) {
               // tensor map dims are (C, H, W, D, N): rows land as h + 8 * w, 18 x-columns incl. halo
               tma_load_5d(a_dst, &tmA, full_bar(s), ch * KC, tc.y0 + dy, tc.x0 - 1, tc.z0 + dz,
                           tc.n);
               if (!resident) tma_load_3d(b_dst, &tmB, full_bar(s), ch * KC, bn0, grp * 3);
+            } else {
+              // MODE 2: dims (C, W, H, D, N), box 8 x-voxels (one atom, contiguous in global memory)
+              // by 16*mt+2 y-rows; here `dy` counts the dx tap of this (dz, dx) group.  The weights
+              // come through a 5-D map (Cin, Cout, dx, dy, dz): all three dy slices of (dz, dx).
+              tma_load_5d(a_dst, &tmA, full_bar(s), ch * KC, tc.x0 + dy, tc.y0 - 1, tc.z0 + dz,
+                          tc.n);
+              if (!resident) tma_load_5d(b_dst, &tmB, full_bar(s), ch * KC, bn0, dy + 1, 0, dz + 1);
             }
             a_dst += g.a_sub_stride;
             b_dst += g.b_sub_stride;
@@ -241,30 +254,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0) {
+    // The whole warp runs this loop with warp-uniform values (so that the compiler keeps the UMMA
+    // descriptors in uniform registers); only the elected lane issues tcgen05.mma / commit.
+    {
+      const uint32_t issue = elect_one();   // 1 in exactly one lane
       int s = 0;
       uint32_t ph = 0;
       uint32_t tcount = 0;
       // UMMA smem descriptor: hi word is constant, lo word = (addr >> 4) | LBO(=1) << 16
-      const uint64_t desc_hi =
-          ((uint64_t)((kSbo >> 4) | (1u << 14) | (kLayout << 29))) << 32;
+      constexpr uint32_t desc_hi = (kSbo >> 4) | (1u << 14) | (kLayout << 29);
       const uint32_t lo_flag = 1u << 16;
-      const uint32_t a_tap16 = (8u * kRowBytes) >> 4;                 // one swizzle atom = one x step
+      const uint32_t a_tap16 = (8u * kRowBytes) >> 4;                 // one swizzle atom = one tap step
       const uint32_t b_tap16 = ((uint32_t)g.BN * kRowBytes) >> 4;
       const uint32_t a_sub16 = g.a_sub_stride >> 4, b_sub16 = g.b_sub_stride >> 4;
-      const uint32_t base16 = (base & 0x3FFFFu) >> 4;
+      const uint32_t base16 = ((base & 0x3FFFFu) >> 4) | lo_flag;
       const uint32_t stage16 = stage_stride >> 4;
       const uint32_t boff16 = ((uint32_t)sub * g.a_sub_stride) >> 4;
       const uint32_t idesc = g.idesc;
       const bool resident = g.b_resident != 0;
-      const uint32_t bres16 = ((base + g.off_bres) & 0x3FFFFu) >> 4;
+      const uint32_t bres16 = (((base + g.off_bres) & 0x3FFFFu) >> 4) | lo_flag;
+      const int mt = g.mt;
+      const uint32_t bn = (uint32_t)g.BN;
       if (resident) mbar_wait(bres_bar, 0u);
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u;
         const uint32_t acc_ph = (tcount >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)(g.mt * g.BN);
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)mt * bn;
         uint32_t accum = 0;
         uint32_t bq16 = bres16;   // running weight slice (resident mode)
         for (int si = 0; si < n_stage_iters; ++si) {
@@ -274,31 +291,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t a16 = base16 + (uint32_t)s * stage16;
           uint32_t b16 = resident ? bq16 : a16 + boff16;
           for (int u = 0; u < nsub; ++u) {
-            for (int m = 0; m < g.mt; ++m) {   // bricks sharing this weight slice
-              const uint32_t am16 = a16 + (uint32_t)(16 * m) * a_tap16;
-              const uint32_t dm = d_tmem + (uint32_t)(m * g.BN);
+            uint32_t am16 = a16, dm = d_tmem;
+            for (int m = 0; m < mt; ++m) {   // bricks sharing this weight slice
 #pragma unroll
               for (int t = 0; t < kNtap; ++t) {
 #pragma unroll
                 for (int kk = 0; kk < kSteps; ++kk) {
-                  const uint64_t adesc = desc_hi | (uint64_t)((am16 + t * a_tap16 + 2u * kk) | lo_flag);
-                  const uint64_t bdesc = desc_hi | (uint64_t)((b16 + t * b_tap16 + 2u * kk) | lo_flag);
-                  umma_bf16(dm, adesc, bdesc, idesc, (accum | (uint32_t)(t | kk)) ? 1u : 0u);
+                  umma_bf16_pred(dm, am16 + t * a_tap16 + 2u * kk, b16 + t * b_tap16 + 2u * kk,
+                                 desc_hi, idesc, (t | kk) ? 1u : accum, issue);
                 }
               }
+              am16 += 16u * a_tap16;
+              dm += bn;
             }
             accum = 1u;
             a16 += a_sub16;
             b16 += b_sub16;
           }
           bq16 += (uint32_t)nsub * b_sub16;
-          umma_commit(empty_bar(s));  // frees the smem stage when these MMAs have read it
+          umma_commit_pred(empty_bar(s), issue);  // frees the smem stage when these MMAs have read it
           if (++s == stages) {
             s = 0;
             ph ^= 1u;
           }
         }
-        umma_commit(tfull_bar((int)acc));  // accumulator complete -> epilogue
+        umma_commit_pred(tfull_bar((int)acc), issue);  // accumulator complete -> epilogue
       }
     }
   } else {
@@ -342,22 +359,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar((int)acc), acc_ph);
       tc_fence_after();
       int m_last = 0;   // last brick of the group that lies (partly) inside the volume
-      while (m_last + 1 < g.mt && tc0.x0 + 16 * (m_last + 1) < g.W) ++m_last;
+      if (MODE == 2) {
+        while (m_last + 1 < g.mt && tc0.y0 + 16 * (m_last + 1) < g.H) ++m_last;
+      } else {
+        while (m_last + 1 < g.mt && tc0.x0 + 16 * (m_last + 1) < g.W) ++m_last;
+      }
       const int eb = g.eb;
       for (int m = 0; m <= m_last; m += eb) {
       // one epilogue round: nb bricks staged together (fewer barriers per brick for narrow BN)
       const int nb = min(eb, m_last + 1 - m);
       TileCoord tc = tc0;
-      tc.x0 += 16 * m;
+      if (MODE == 2) tc.y0 += 16 * m;
+      else tc.x0 += 16 * m;
       const bool last_sub = m + nb - 1 == m_last;
 
       // voxel of this row (both groups write the same values)
       int tx, ty, tz;
       row_to_voxel<MODE>(g, row, tx, ty, tz);
-      const int vy = tc.y0 + ty, vz = tc.z0 + tz;
+      const int vz = tc.z0 + tz;
       uint32_t vmask = 0;
       for (int mb = 0; mb < nb; ++mb) {
-        const bool v = (tc.x0 + 16 * mb + tx < g.W) && (vy < g.H) && (vz < g.D);
+        const int vx = tc.x0 + tx + (MODE == 2 ? 0 : 16 * mb);
+        const int vy = tc.y0 + ty + (MODE == 2 ? 16 * mb : 0);
+        const bool v = (vx < g.W) && (vy < g.H) && (vz < g.D);
         vmask |= (v ? 1u : 0u) << mb;
         rowvalid[mb * kTileM + row] = v ? 1 : 0;
       }
@@ -523,7 +547,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!rowvalid[mb * kTileM + r2]) continue;
           int tx2, ty2, tz2;
           row_to_voxel<MODE>(g, r2, tx2, ty2, tz2);
-          const int x2 = tc.x0 + 16 * mb + tx2, y2 = tc.y0 + ty2, z2 = tc.z0 + tz2;
+          const int x2 = tc.x0 + tx2 + (MODE == 2 ? 0 : 16 * mb);
+          const int y2 = tc.y0 + ty2 + (MODE == 2 ? 16 * mb : 0), z2 = tc.z0 + tz2;
           const size_t vox = (((size_t)tc.n * g.D + z2) * g.H + y2) * g.W + x2;
           const uint4 v = *reinterpret_cast<const uint4*>(
               staging + (size_t)(mb * kTileM + r2) * pitch + j * 16);
@@ -629,6 +654,11 @@ typedef void (*ConvKernel)(const CUtensorMap, const CUtensorMap, const ConvGeom,
                            __nv_bfloat16*, float*, float*);
 
 ConvKernel pick_kernel(int kc, int mode) {
+  if (mode == 2) {
+    if (kc == 64) return conv_tc_kernel<64, 2>;
+    if (kc == 32) return conv_tc_kernel<32, 2>;
+    return conv_tc_kernel<16, 2>;
+  }
   if (mode == 1) {
     if (kc == 64) return conv_tc_kernel<64, 1>;
     if (kc == 32) return conv_tc_kernel<32, 1>;
@@ -646,6 +676,7 @@ void km_conv_set_force_generic(int v) { g_force_mode0 = v ? 1 : 0; }
 void km_conv_set_no_resident(int v) { g_no_resident = v ? 1 : 0; }
 void km_conv_set_max_mt(int v) { g_max_mt = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
 void km_conv_set_no_epi_batch(int v) { g_no_epi_batch = v ? 1 : 0; }
+void km_conv_set_halo_axis(int v) { g_halo_axis = v == 1 ? 1 : 2; }
 extern "C" int km_conv_nparts(void) { return sm_count(); }
 
 extern "C" int km_pack_weights(const float* w, void* packed, int Cout, int Cin, int taps,
@@ -685,26 +716,36 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   const int kc = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
   g.chunks = Cin / kc;
   const int row_bytes = kc * 2;
-  const int mode = (taps == 27 && H >= 8 && W >= 16 && !g_force_mode0) ? 1 : 0;
+  // halo-reuse paths: 2 = y is the shifted axis (atoms are x-runs, contiguous in global memory),
+  // 1 = x is the shifted axis; 0 = generic
+  int mode = 0;
+  if (taps == 27 && !g_force_mode0) {
+    if (g_halo_axis == 2 && W >= 8 && H >= 16) mode = 2;
+    else if (H >= 8 && W >= 16) mode = 1;
+    else if (W >= 8 && H >= 16) mode = 2;
+  }
   const int gran = (flags & KM_CONV_COM) ? 32 : 16;
   KM_CHECK_ARG(Cout % gran == 0, "km_conv3d_tc: Cout must be a multiple of %d in this mode", gran);
-  const int bn_cap = mode == 1 ? 128 : 256;
+  const int bn_cap = mode >= 1 ? 128 : 256;
   g.BN = 0;
   for (int bn = bn_cap; bn >= gran; bn -= gran)
     if (Cout % bn == 0) { g.BN = bn; break; }
   KM_CHECK_ARG(g.BN > 0, "km_conv3d_tc: no channel block for Cout=%d", Cout);
   g.n_blocks = Cout / g.BN;
   g.mt = 1;
-  if (mode == 1) {
+  if (mode >= 1) {
     // bricks that share one weight fetch: as many as TMEM (2 buffers x mt x BN columns) allows,
-    // not more than the row holds; shared memory is checked below
+    // not more than the row / column holds; shared memory is checked below
     int mt = g_max_mt;
-    while (mt > 1 && (2 * mt * g.BN > 512 || 16 * (mt / 2) >= W)) mt /= 2;
+    const int extent = mode == 1 ? W : H;
+    while (mt > 1 && (2 * mt * g.BN > 512 || 16 * (mt / 2) >= extent)) mt /= 2;
     while (mt > 1 && round_up((16u * mt + 2u) * 8u * row_bytes, 1024) +
                              round_up(3u * (uint32_t)g.BN * row_bytes, 1024) > 96u * 1024u)
       mt /= 2;
     g.mt = mt;
-    g.TW = 16 * mt; g.TH = 8; g.TD = 1;
+    if (mode == 1) { g.TW = 16 * mt; g.TH = 8; }
+    else { g.TW = 8; g.TH = 16 * mt; }
+    g.TD = 1;
     g.subiters = 9 * g.chunks;
     g.a_sub_bytes = (16u * mt + 2u) * 8u * row_bytes;
     g.b_sub_bytes = 3u * (uint32_t)g.BN * row_bytes;
@@ -758,7 +799,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
                          scratch_bytes + bias_bytes + bars_bytes + 64;
   // small weight tensors (first layers) stay resident: the per-tile weight re-fetch is TMA-request bound
   const uint32_t bres_bytes = (uint32_t)g.subiters * g.b_sub_stride;
-  g.b_resident = (mode == 1 && g.n_blocks == 1 && bres_bytes <= 64u * 1024u && !g_no_resident) ? 1 : 0;
+  g.b_resident = (mode >= 1 && g.n_blocks == 1 && bres_bytes <= 64u * 1024u && !g_no_resident) ? 1 : 0;
   const uint32_t unit = g.a_sub_stride + (g.b_resident ? 0u : g.b_sub_stride);
   KM_CHECK_ARG(fixed + (g.b_resident ? bres_bytes : 0u) + 2 * unit <= kSmemMax,
                "km_conv3d_tc: shared memory budget exceeded (N*Cout too large: N=%d Cout=%d)", N, Cout);
@@ -809,6 +850,8 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
       dims[1] = (cuuint64_t)H; dims[2] = (cuuint64_t)W;
       strides[0] = (cuuint64_t)W * Cin * 2; strides[1] = (cuuint64_t)Cin * 2;
       box[1] = 8; box[2] = (cuuint32_t)(16 * g.mt + 2); box[3] = 1;
+    } else if (mode == 2) {
+      box[1] = 8; box[2] = (cuuint32_t)(16 * g.mt + 2); box[3] = 1;   // natural (C, W, H, D, N) order
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims,
@@ -819,7 +862,22 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
       return KM_ECUDA;
     }
   }
-  {
+  if (mode == 2) {
+    // [tap = dz*9 + dy*3 + dx][Cout][Cin] viewed as (Cin, Cout, dx, dy, dz): one box = the three dy
+    // slices of a (dz, dx) group, landing as three consecutive [BN x kc] tiles
+    const cuuint64_t slice = (cuuint64_t)Cout * Cin * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 3, 3, 3};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, slice, 3 * slice, 9 * slice};
+    cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)g.BN, 1, 3, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(wp), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      km_set_error("km_conv3d_tc: cuTensorMapEncodeTiled(B5) failed with %d", (int)r);
+      return KM_ECUDA;
+    }
+  } else {
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
     cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)g.BN, (cuuint32_t)(mode == 1 ? 3 : 1)};
@@ -834,7 +892,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   }
 
   ConvKernel kernel = pick_kernel(kc, mode);
-  static bool attr_set[2][3] = {{false, false, false}, {false, false, false}};
+  static bool attr_set[3][3] = {{false, false, false}, {false, false, false}, {false, false, false}};
   const int ki = kc == 64 ? 2 : (kc == 32 ? 1 : 0);
   if (!attr_set[mode][ki]) {
     KM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));

@@ -18,6 +18,7 @@ void km_conv_set_force_generic(int v);
 void km_conv_set_no_resident(int v);
 void km_conv_set_max_mt(int v);
 void km_conv_set_no_epi_batch(int v);
+void km_conv_set_halo_axis(int v);
 namespace {
 
 // ---- ATen grid_sampler_3d source-index arithmetic (align_corners=False, padding "border"),
@@ -474,6 +475,10 @@ extern "C" int km_set_option(int key, int value) {
   }
   if (key == KM_OPT_CONV_NO_EPILOGUE_BATCH) {
     km_conv_set_no_epi_batch(value);
+    return KM_OK;
+  }
+  if (key == KM_OPT_CONV_HALO_AXIS) {
+    km_conv_set_halo_axis(value);
     return KM_OK;
   }
   km_set_error("km_set_option: unknown key %d", key);

@@ -354,9 +354,10 @@ def run_conv():
     ]
     cases += [(1, 64, 64, 4, 4, 4, 27, True, False), (2, 128, 128, 4, 4, 4, 27, True, False),
               (1, 64, 64, 8, 24, 40, 27, True, False), (1, 32, 64, 5, 9, 17, 27, True, False)]
-    for force in (0, 1):
+    for force, axis in ((0, 2), (0, 1), (1, 2)):
         _lib.call("km_set_option", _lib.KM_OPT_CONV_FORCE_GENERIC, force)
-        print(f"  -- force generic path = {force}")
+        _lib.call("km_set_option", _lib.KM_OPT_CONV_HALO_AXIS, axis)
+        print(f"  -- force generic path = {force}, halo axis = {axis}")
         for c in cases:
             try:
                 ok &= _conv_case(*c)
@@ -401,8 +402,9 @@ def run_convtime():
     layers = [(16, 32, 256, 27), (32, 32, 128, 27), (32, 64, 128, 27), (64, 64, 64, 27), (64, 128, 64, 27),
               (128, 128, 32, 27), (128, 256, 32, 27), (384, 128, 64, 27), (128, 128, 64, 27),
               (192, 64, 128, 27), (64, 64, 128, 27), (64, 256, 128, 1)]
-    for label, opts in (("default", {}), ("one brick per epilogue round", {_lib.KM_OPT_CONV_NO_EPILOGUE_BATCH: 1}),
+    for label, opts in (("default (halo axis y)", {}), ("halo axis x", {_lib.KM_OPT_CONV_HALO_AXIS: 1}),
                         ("streamed weights", {_lib.KM_OPT_CONV_NO_RESIDENT_WEIGHTS: 1})):
+        _lib.call("km_set_option", _lib.KM_OPT_CONV_HALO_AXIS, 2)
         _lib.call("km_set_option", _lib.KM_OPT_CONV_MAX_BRICKS, 4)
         for k, v in opts.items():
             _lib.call("km_set_option", k, v)
