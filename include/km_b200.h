@@ -55,6 +55,9 @@ int km_sm_count(void);
 /* key KM_OPT_CONV_HALO_AXIS (default 2): axis along which the three taps share one TMA box in
  * km_conv3d_tc: 2 = y (shared-memory atoms are x-runs, contiguous in global memory), 1 = x. */
 #define KM_OPT_CONV_HALO_AXIS 6
+/* key KM_OPT_TPS_SINGLE_CTA (default 0): solve the TPS system with the un-blocked one-CTA LU instead
+ * of the blocked multi-CTA Gauss-Jordan elimination (A/B testing). */
+#define KM_OPT_TPS_SINGLE_CTA 7
 int km_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------ *

@@ -12,6 +12,8 @@
 
 namespace {
 
+int g_tps_single_cta = 0;   // km_set_option(KM_OPT_TPS_SINGLE_CTA): the un-blocked one-CTA LU (A/B)
+
 __device__ __forceinline__ double tps_u64(double d2) {
   const double r = sqrt(d2 + 1e-6);
   return (r * r) * log(r + 1e-6);
@@ -141,11 +143,187 @@ tps_solve_kernel(double* __restrict__ A, float* __restrict__ theta, int32_t* __r
   if (tid == 0) status[b] = s_sing;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Blocked Gauss-Jordan elimination with partial pivoting, spread over the whole GPU.
+// Rows are never moved: pivrow[k] names the pivot row of column k, elig[r] tells whether row r may
+// still become a pivot.  Per panel of kNB columns:
+//   tps_panel_kernel  (1 CTA / system, one THREAD per row, the row's kNB panel entries live in
+//                      registers): for each column pick the largest eligible entry, broadcast
+//                      the pivot row segment through smem, eliminate the column from every other
+//                      row (multipliers overwrite the eliminated entries);
+//   tps_update_kernel (many CTAs): applies the panel's kNB row operations to all remaining
+//                      columns (and the 3 right-hand sides) of ALL rows.
+// After the last panel the matrix is diagonal in the pivot order: x_k = b[pivrow[k]] / a[pivrow[k]][k].
+constexpr int kNB = 16;
+
+__global__ void __launch_bounds__(1024)
+tps_panel_kernel(double* __restrict__ A, int* __restrict__ pivrow, int* __restrict__ elig,
+                 int32_t* __restrict__ status, int n, int ld, int c0) {
+  __shared__ double s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ double s_prow[kNB];
+  __shared__ int s_piv;
+  const int b = blockIdx.x;
+  double* Ab = A + (size_t)b * n * ld;
+  int* piv = pivrow + (size_t)b * n;
+  int* el = elig + (size_t)b * n;
+  const int r = threadIdx.x, lane = r & 31, wid = r >> 5, nwarps = blockDim.x >> 5;
+  const int nb = min(kNB, n - c0);
+  const bool has_row = r < n;
+  double a[kNB];
+  bool eligible = false;
+  if (has_row) {
+    eligible = c0 == 0 ? true : (el[r] != 0);
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) a[j] = (j < nb) ? Ab[(size_t)r * ld + c0 + j] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < kNB; ++k) {
+    if (k < nb) {   // uniform
+      // ---- pivot search among eligible rows
+      double v = (has_row && eligible) ? fabs(a[k]) : -1.0;
+      int vi = r;
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+        if (ov > v || (ov == v && oi < vi)) {
+          v = ov;
+          vi = oi;
+        }
+      }
+      if (lane == 0) {
+        s_val[wid] = v;
+        s_idx[wid] = vi;
+      }
+      __syncthreads();
+      if (wid == 0) {
+        double w = lane < nwarps ? s_val[lane] : -1.0;
+        int wi = lane < nwarps ? s_idx[lane] : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, w, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+          if (ov > w || (ov == w && oi < wi)) {
+            w = ov;
+            wi = oi;
+          }
+        }
+        if (lane == 0) {
+          s_piv = wi;
+          if (!(w > 0.0) || !isfinite(w)) status[b] = 1;
+        }
+      }
+      __syncthreads();
+      const int pr = s_piv;
+      if (r == pr) {
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) s_prow[j] = a[j];
+        eligible = false;
+        piv[c0 + k] = r;
+      }
+      __syncthreads();
+      // ---- eliminate column k from every other row; the multiplier replaces the entry
+      if (has_row && r != pr) {
+        const double l = a[k] / s_prow[k];
+        a[k] = l;
+#pragma unroll
+        for (int j = 0; j < kNB; ++j)
+          if (j > k) a[j] -= l * s_prow[j];
+      }
+    }
+  }
+  if (has_row) {
+#pragma unroll
+    for (int j = 0; j < kNB; ++j)
+      if (j < nb) Ab[(size_t)r * ld + c0 + j] = a[j];
+    el[r] = eligible ? 1 : 0;
+  }
+}
+
+// U~[t][j] for the columns right of the panel: pivot row t as it was when it became the pivot, i.e.
+// corrected by the pivots t' < t of the same panel (sequential per column, columns independent).
+// Written to a side buffer because the update kernel overwrites the pivot rows themselves.
+__global__ void __launch_bounds__(64)
+tps_urow_kernel(const double* __restrict__ A, const int* __restrict__ pivrow, double* __restrict__ Ut,
+                int n, int ld, int c0) {
+  const int b = blockIdx.y;
+  const double* Ab = A + (size_t)b * n * ld;
+  const int* piv = pivrow + (size_t)b * n;
+  const int nb = min(kNB, n - c0);
+  const int j = c0 + nb + blockIdx.x * 64 + threadIdx.x;
+  if (j >= ld) return;
+  double u[kNB];
+#pragma unroll
+  for (int t = 0; t < kNB; ++t) {
+    if (t < nb) {
+      const int pr = piv[c0 + t];
+      double v = Ab[(size_t)pr * ld + j];
+#pragma unroll
+      for (int t2 = 0; t2 < kNB; ++t2)
+        if (t2 < t) v -= Ab[(size_t)pr * ld + c0 + t2] * u[t2];
+      u[t] = v;
+      Ut[((size_t)b * kNB + t) * ld + j] = v;
+    }
+  }
+}
+
+// grid (column tiles of 64, row tiles of 32, systems); 256 threads = 64 columns x 4 row lanes
+__global__ void __launch_bounds__(256)
+tps_update_kernel(double* __restrict__ A, const int* __restrict__ pivrow,
+                  const double* __restrict__ Ut, int n, int ld, int c0) {
+  __shared__ double s_u[kNB][64];     // pivot rows as they were when they became pivots
+  __shared__ double s_l[32][kNB + 1]; // multipliers of this row tile
+  __shared__ int s_pr[kNB];
+  const int b = blockIdx.z;
+  double* Ab = A + (size_t)b * n * ld;
+  const int* piv = pivrow + (size_t)b * n;
+  const int nb = min(kNB, n - c0);
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int j = c0 + nb + blockIdx.x * 64 + tx;   // column handled by this thread
+  const bool col_ok = j < ld;
+  if (threadIdx.x < kNB) s_pr[threadIdx.x] = threadIdx.x < nb ? piv[c0 + threadIdx.x] : -1;
+  __syncthreads();
+  for (int i = threadIdx.x; i < kNB * 64; i += 256) {
+    const int t = i >> 6, c = i & 63;
+    const int jj = c0 + nb + blockIdx.x * 64 + c;
+    s_u[t][c] = (t < nb && jj < ld) ? Ut[((size_t)b * kNB + t) * ld + jj] : 0.0;
+  }
+  // multipliers of the rows of this tile
+  const int r0 = blockIdx.y * 32;
+  for (int i = threadIdx.x; i < 32 * kNB; i += 256) {
+    const int rr = i / kNB, t = i % kNB;
+    const int r = r0 + rr;
+    s_l[rr][t] = (r < n && t < nb) ? Ab[(size_t)r * ld + c0 + t] : 0.0;
+  }
+  __syncthreads();
+  if (!col_ok) return;
+  for (int rr = ty; rr < 32; rr += 4) {
+    const int r = r0 + rr;
+    if (r >= n) break;
+    double v = Ab[(size_t)r * ld + j];
+#pragma unroll
+    for (int t = 0; t < kNB; ++t)
+      if (t < nb && s_pr[t] != r) v -= s_l[rr][t] * s_u[t][tx];
+    Ab[(size_t)r * ld + j] = v;
+  }
+}
+
+__global__ void tps_finish_kernel(const double* __restrict__ A, const int* __restrict__ pivrow,
+                                  float* __restrict__ theta, int n, int ld) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 3) return;
+  const int k = i / 3, d = i % 3;
+  const double* row = A + ((size_t)b * n + pivrow[(size_t)b * n + k]) * ld;
+  theta[((size_t)b * n + k) * 3 + d] = (float)(row[n + d] / row[k]);
+}
+
 }  // namespace
 
 extern "C" size_t km_tps_fit_workspace_bytes(int N, int K) {
   const size_t n = (size_t)K + 4;
-  return (size_t)N * n * (n + 3) * sizeof(double);
+  // augmented matrix (fp64) + pivot rows + eligibility flags
+  return (size_t)N * (n + kNB) * (n + 3) * sizeof(double) + 2 * (size_t)N * n * sizeof(int) + 64;
 }
 
 extern "C" int km_tps_fit(const float* c_src, const float* c_dst, const float* lmbda,
@@ -153,20 +331,43 @@ extern "C" int km_tps_fit(const float* c_src, const float* c_dst, const float* l
                           int K, km_stream_t stream) {
   KM_CHECK_ARG(c_src && c_dst && lmbda && theta && status && workspace && N > 0 && K > 0,
                "km_tps_fit: bad arguments");
-  const int n = K + 4;
-  const size_t smem = (size_t)4 * n * sizeof(double) + (size_t)n * sizeof(int);
-  KM_CHECK_ARG(smem <= 200 * 1024, "km_tps_fit: K=%d too large", K);
+  const int n = K + 4, ld = n + 3;
+  cudaStream_t st = km_cs(stream);
   double* A = reinterpret_cast<double*>(workspace);
-  const long long total = (long long)n * (n + 3);
+  const long long total = (long long)n * ld;
   int bx = (int)((total + 255) / 256);
   if (bx > 1184) bx = 1184;
-  tps_assemble_kernel<<<dim3(bx, N), 256, 0, km_cs(stream)>>>(c_src, c_dst, lmbda, w, A, K);
+  tps_assemble_kernel<<<dim3(bx, N), 256, 0, st>>>(c_src, c_dst, lmbda, w, A, K);
   KM_LAUNCH_OK("tps_assemble_kernel");
+  if (n <= 1024 && !g_tps_single_cta) {
+    double* Ut = A + (size_t)N * n * ld;
+    int* pivrow = reinterpret_cast<int*>(Ut + (size_t)N * kNB * ld);
+    int* elig = pivrow + (size_t)N * n;
+    KM_CUDA_OK(cudaMemsetAsync(status, 0, (size_t)N * sizeof(int32_t), st));
+    const int threads = (n + 31) / 32 * 32;
+    for (int c0 = 0; c0 < n; c0 += kNB) {
+      tps_panel_kernel<<<N, threads, 0, st>>>(A, pivrow, elig, status, n, ld, c0);
+      const int nb = n - c0 < kNB ? n - c0 : kNB;
+      const int rest = ld - c0 - nb;   // columns right of the panel (incl. the 3 right-hand sides)
+      tps_urow_kernel<<<dim3((rest + 63) / 64, N), 64, 0, st>>>(A, pivrow, Ut, n, ld, c0);
+      tps_update_kernel<<<dim3((rest + 63) / 64, (n + 31) / 32, N), 256, 0, st>>>(A, pivrow, Ut, n, ld,
+                                                                                 c0);
+    }
+    KM_LAUNCH_OK("tps_panel/update_kernel");
+    tps_finish_kernel<<<dim3((n * 3 + 127) / 128, N), 128, 0, st>>>(A, pivrow, theta, n, ld);
+    KM_LAUNCH_OK("tps_finish_kernel");
+    return KM_OK;
+  }
+  // very large systems: one CTA per system, matrix streamed from L2
+  const size_t smem = (size_t)4 * n * sizeof(double) + (size_t)n * sizeof(int);
+  KM_CHECK_ARG(smem <= 200 * 1024, "km_tps_fit: K=%d too large", K);
   if (smem > 48 * 1024) {
     KM_CUDA_OK(cudaFuncSetAttribute(tps_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
   }
-  tps_solve_kernel<<<N, 1024, smem, km_cs(stream)>>>(A, theta, status, K);
+  tps_solve_kernel<<<N, 1024, smem, st>>>(A, theta, status, K);
   KM_LAUNCH_OK("tps_solve_kernel");
   return KM_OK;
 }
+
+void km_tps_set_single_cta(int v) { g_tps_single_cta = v ? 1 : 0; }

@@ -19,6 +19,7 @@ void km_conv_set_no_resident(int v);
 void km_conv_set_max_mt(int v);
 void km_conv_set_no_epi_batch(int v);
 void km_conv_set_halo_axis(int v);
+void km_tps_set_single_cta(int v);
 namespace {
 
 // ---- ATen grid_sampler_3d source-index arithmetic (align_corners=False, padding "border"),
@@ -479,6 +480,10 @@ extern "C" int km_set_option(int key, int value) {
   }
   if (key == KM_OPT_CONV_HALO_AXIS) {
     km_conv_set_halo_axis(value);
+    return KM_OK;
+  }
+  if (key == KM_OPT_TPS_SINGLE_CTA) {
+    km_tps_set_single_cta(value);
     return KM_OK;
   }
   km_set_error("km_set_option: unknown key %d", key);
