@@ -368,20 +368,39 @@ conv_stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
 #pragma unroll
   for (int c = 0; c < COUT; ++c) s[c] = ss[c] = 0.f;
 
+  // software pipeline: the halo of the NEXT tile is fetched into registers while the current tile
+  // is being computed, so the global-load latency hides behind the 27-tap stencil
+  constexpr int kHalo = HZ * HY * HX;
+  constexpr int kPre = (kHalo + 255) / 256;
+  float pre[kPre];
+  auto fetch = [&](long long t) {
+    const int x0 = (int)(t % tiles_x) * TX;
+    const int y0 = (int)((t / tiles_x) % tiles_y) * TY;
+    const int z0 = (int)(t / ((long long)tiles_x * tiles_y)) * TZ;
+#pragma unroll
+    for (int j = 0; j < kPre; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      const int hx = i % HX, hy = (i / HX) % HY, hz = i / (HX * HY);
+      const int gx = x0 + hx - 1, gy = y0 + hy - 1, gz = z0 + hz - 1;
+      float v = 0.f;
+      if (i < kHalo && gx >= 0 && gx < W && gy >= 0 && gy < H && gz >= 0 && gz < D)
+        v = fmaf(a_in, __ldg(xn + ((size_t)gz * H + gy) * W + gx), b_in);
+      pre[j] = v;
+    }
+  };
+  if (blockIdx.x < ntiles) fetch(blockIdx.x);
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int x0 = (int)(t % tiles_x) * TX;
     const int y0 = (int)((t / tiles_x) % tiles_y) * TY;
     const int z0 = (int)(t / ((long long)tiles_x * tiles_y)) * TZ;
     __syncthreads();  // previous tile fully consumed (also orders the weight staging)
-    for (int i = threadIdx.x; i < HZ * HY * HX; i += 256) {
-      const int hx = i % HX, hy = (i / HX) % HY, hz = i / (HX * HY);
-      const int gx = x0 + hx - 1, gy = y0 + hy - 1, gz = z0 + hz - 1;
-      float v = 0.f;
-      if (gx >= 0 && gx < W && gy >= 0 && gy < H && gz >= 0 && gz < D)
-        v = fmaf(a_in, __ldg(xn + ((size_t)gz * H + gy) * W + gx), b_in);
-      tile[hz][hy][hx] = v;
+#pragma unroll
+    for (int j = 0; j < kPre; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      if (i < kHalo) (&tile[0][0][0])[i] = pre[j];
     }
     __syncthreads();
+    if (t + gridDim.x < ntiles) fetch(t + gridDim.x);
     const int gy = y0 + ly, gz = z0 + lz;
     if (gy < H && gz < D) {
       float acc[VPT][COUT];

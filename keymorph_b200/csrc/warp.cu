@@ -221,45 +221,42 @@ points_tps_kernel(const float* __restrict__ ctrl, const float* __restrict__ thet
 }
 
 // ------------------------------------------------------------------------------------------
-// stand-alone grid_sample: 4 output voxels per thread along W (V = 4) or 1 (V = 1)
-template <int V>
+// stand-alone grid_sample.  A warp owns 128 consecutive output voxels; lane i handles voxels
+// i, i+32, i+64, i+96 of the chunk, so every load / store instruction of the warp touches 32
+// CONSECUTIVE voxels (the gathers of a warp then fall into one or two cache lines per corner for
+// the near-identity transforms of registration) while each thread still has 4 independent voxels
+// in flight.
 __global__ void __launch_bounds__(256)
 grid_sample_kernel(const float* __restrict__ x, const float* __restrict__ grid,
                    float* __restrict__ out, int C, int Di, int Hi, int Wi, long long nvo,
                    int mode) {
   const int n = blockIdx.y;
-  const long long ngroups = nvo / V;
+  const int lane = threadIdx.x & 31;
+  const long long nchunks = (nvo + 127) / 128;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const size_t in_vol = (size_t)Di * Hi * Wi;
   const float* gn = grid + (size_t)n * nvo * 3;
-  for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < ngroups;
-       gidx += (long long)gridDim.x * blockDim.x) {
-    float g[3 * V];
-    if (V == 4) {
-      const float4* g4 = reinterpret_cast<const float4*>(gn + gidx * 12);
-      const float4 a = __ldg(g4), b = __ldg(g4 + 1), c = __ldg(g4 + 2);
-      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
-      g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
-      g[8] = c.x; g[9] = c.y; g[10] = c.z; g[11] = c.w;
-    } else {
-      g[0] = __ldg(gn + gidx * 3);
-      g[1] = __ldg(gn + gidx * 3 + 1);
-      g[2] = __ldg(gn + gidx * 3 + 2);
-    }
-    Tri t[V];
+  for (long long chunk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks;
+       chunk += warps) {
+    const long long v0 = chunk * 128 + lane;
+    Tri t[4];
+    bool ok[4];
 #pragma unroll
-    for (int k = 0; k < V; ++k) t[k] = make_tri(g[3 * k], g[3 * k + 1], g[3 * k + 2], Di, Hi, Wi);
+    for (int k = 0; k < 4; ++k) {
+      const long long v = v0 + 32 * k;
+      ok[k] = v < nvo;
+      const float* gp = gn + (ok[k] ? v : 0) * 3;
+      t[k] = make_tri(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), Di, Hi, Wi);
+    }
     for (int c = 0; c < C; ++c) {
       const float* vol = x + ((size_t)n * C + c) * in_vol;
-      float r[V];
+      float* o = out + ((size_t)n * C + c) * nvo + v0;
 #pragma unroll
-      for (int k = 0; k < V; ++k)
-        r[k] = (mode == KM_INTERP_NEAREST) ? nearest_sample(vol, t[k], Hi, Wi)
-                                           : tri_sample(vol, t[k], Di, Hi, Wi);
-      float* o = out + ((size_t)n * C + c) * nvo + gidx * V;
-      if (V == 4)
-        *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
-      else
-        o[0] = r[0];
+      for (int k = 0; k < 4; ++k) {
+        if (ok[k])
+          o[32 * k] = (mode == KM_INTERP_NEAREST) ? nearest_sample(vol, t[k], Hi, Wi)
+                                                  : tri_sample(vol, t[k], Di, Hi, Wi);
+      }
     }
   }
 }
@@ -288,8 +285,13 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
     load_tps_smem(mat_or_ctrl + (size_t)n * K * 3, theta + (size_t)n * (K + 4) * 3, K, c4, w4, aff);
   }
   const float* gn = (COORD == KM_COORD_GRID) ? grid + (size_t)n * nvox * 3 : nullptr;
-  const long long ngroups = nvox / 4;  // W % 4 == 0 is checked on the host
-  const int W4 = W / 4;
+  // a warp owns 128 consecutive voxels, lane i handles voxels i, i+32, i+64, i+96 (see
+  // grid_sample_kernel): coalesced streams AND gathers that share cache lines across the warp
+  const int lane = threadIdx.x & 31;
+  const int nv = (int)nvox;   // checked on the host
+  const int nchunks = (nv + 127) / 128;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int HW = H * W;
 
   for (int cbase = 0; cbase < C; cbase += CCH) {
     const int cn = min(CCH, C - cbase);
@@ -297,56 +299,54 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
 #pragma unroll
     for (int c = 0; c < CCH; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
 
-    for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < ngroups;
-         gidx += (long long)gridDim.x * blockDim.x) {
+    for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warps) {
+      const int v0 = chunk * 128 + lane;
       Tri t[4];
-      if (COORD == KM_COORD_GRID) {
-        const float4* g4 = reinterpret_cast<const float4*>(gn + gidx * 12);
-        const float4 a = __ldg(g4), b = __ldg(g4 + 1), c = __ldg(g4 + 2);
-        t[0] = make_tri(a.x, a.y, a.z, D, H, W);
-        t[1] = make_tri(a.w, b.x, b.y, D, H, W);
-        t[2] = make_tri(b.z, b.w, c.x, D, H, W);
-        t[3] = make_tri(c.y, c.z, c.w, D, H, W);
-      } else {
-        const int xg = (int)(gidx % W4) * 4;
-        const int y = (int)((gidx / W4) % H);
-        const int z = (int)(gidx / ((long long)W4 * H));
-        const float pz = km_linspace(-1.f, 1.f, D, z), py = km_linspace(-1.f, 1.f, H, y);
+      bool ok[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float px = km_linspace(-1.f, 1.f, W, xg + k);
-          float gx, gy, gz;
+      for (int k = 0; k < 4; ++k) {
+        const int v = v0 + 32 * k;
+        ok[k] = v < nv;
+        const int vv = ok[k] ? v : 0;
+        float gx, gy, gz;
+        if (COORD == KM_COORD_GRID) {
+          const float* gp = gn + (size_t)vv * 3;
+          gx = __ldg(gp);
+          gy = __ldg(gp + 1);
+          gz = __ldg(gp + 2);
+        } else {
+          const int z = vv / HW, rem = vv - z * HW;
+          const int y = rem / W, xx = rem - y * W;
+          const float pz = km_linspace(-1.f, 1.f, D, z), py = km_linspace(-1.f, 1.f, H, y);
+          const float px = km_linspace(-1.f, 1.f, W, xx);
           if (COORD == KM_COORD_AFFINE) {
             ac(pz, py, px, gx, gy, gz);
           } else {
             tps_eval<FAST>(c4, w4, aff, K, pz, py, px, gz, gy, gx);
           }
-          t[k] = make_tri(gx, gy, gz, D, H, W);
         }
+        t[k] = make_tri(gx, gy, gz, D, H, W);
       }
 #pragma unroll
       for (int c = 0; c < CCH; ++c) {
         if (c < cn) {
           const size_t ch = (size_t)n * C + cbase + c;
           const float* vol = moving + ch * nvox;
-          float r[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            r[k] = (mode == KM_INTERP_NEAREST) ? nearest_sample(vol, t[k], H, W)
-                                               : tri_sample(vol, t[k], D, H, W);
-          if (out)
-            *reinterpret_cast<float4*>(out + ch * nvox + gidx * 4) =
-                make_float4(r[0], r[1], r[2], r[3]);
-          if (fixed) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(fixed + ch * nvox) + gidx);
-            const float fv[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float d = r[k] - fv[k];
-              acc[c][0] = fmaf(d, d, acc[c][0]);
-              acc[c][1] = fmaf(r[k], fv[k], acc[c][1]);
-              acc[c][2] = fmaf(r[k], r[k], acc[c][2]);
-              acc[c][3] = fmaf(fv[k], fv[k], acc[c][3]);
+          for (int k = 0; k < 4; ++k) {
+            if (ok[k]) {
+              const float r = (mode == KM_INTERP_NEAREST) ? nearest_sample(vol, t[k], H, W)
+                                                          : tri_sample(vol, t[k], D, H, W);
+              const size_t idx = ch * nvox + v0 + 32 * k;
+              if (out) out[idx] = r;
+              if (fixed) {
+                const float fv = __ldg(fixed + idx);
+                const float d = r - fv;
+                acc[c][0] = fmaf(d, d, acc[c][0]);
+                acc[c][1] = fmaf(r, fv, acc[c][1]);
+                acc[c][2] = fmaf(r, r, acc[c][2]);
+                acc[c][3] = fmaf(fv, fv, acc[c][3]);
+              }
             }
           }
         }
@@ -498,14 +498,8 @@ extern "C" int km_grid_sample3d(const float* x, const float* grid, float* out, i
                "km_grid_sample3d: bad shape");
   KM_CHECK_ARG(mode == KM_INTERP_BILINEAR || mode == KM_INTERP_NEAREST, "km_grid_sample3d: bad mode");
   const long long nvo = (long long)Do * Ho * Wo;
-  const bool vec = (nvo % 4 == 0) && (((uintptr_t)grid & 15) == 0) && (((uintptr_t)out & 15) == 0);
-  if (vec) {
-    const dim3 g(blocks_for(nvo / 4, 256, 148 * 16), N);
-    grid_sample_kernel<4><<<g, 256, 0, km_cs(stream)>>>(x, grid, out, C, Di, Hi, Wi, nvo, mode);
-  } else {
-    const dim3 g(blocks_for(nvo, 256, 148 * 16), N);
-    grid_sample_kernel<1><<<g, 256, 0, km_cs(stream)>>>(x, grid, out, C, Di, Hi, Wi, nvo, mode);
-  }
+  const dim3 g(blocks_for((nvo + 3) / 4, 256, 148 * 8), N);
+  grid_sample_kernel<<<g, 256, 0, km_cs(stream)>>>(x, grid, out, C, Di, Hi, Wi, nvo, mode);
   KM_LAUNCH_OK("grid_sample_kernel");
   return KM_OK;
 }
@@ -582,11 +576,9 @@ extern "C" int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const floa
                             double* sums, void* workspace, int N, int C, int D, int H, int W,
                             int mode, km_stream_t stream) {
   KM_CHECK_ARG(moving && N > 0 && C > 0 && D > 0 && H > 0 && W > 0, "km_warp_loss: bad arguments");
-  KM_CHECK_ARG(W % 4 == 0, "km_warp_loss: W must be a multiple of 4 (got %d)", W);
+  KM_CHECK_ARG((long long)D * H * W < (1ll << 31), "km_warp_loss: volume too large");
   KM_CHECK_ARG(mode == KM_INTERP_BILINEAR || mode == KM_INTERP_NEAREST, "km_warp_loss: bad mode");
   KM_CHECK_ARG(!fixed || (sums && workspace), "km_warp_loss: sums/workspace required with fixed");
-  KM_CHECK_ARG((((uintptr_t)out | (uintptr_t)fixed | (uintptr_t)grid) & 15) == 0,
-               "km_warp_loss: pointers must be 16-byte aligned");
   size_t smem = 0;
   if (coord_mode == KM_COORD_AFFINE) {
     KM_CHECK_ARG(mat_or_ctrl, "km_warp_loss: affine matrix missing");
