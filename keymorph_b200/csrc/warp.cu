@@ -74,6 +74,31 @@ __device__ __forceinline__ float tri_sample(const float* __restrict__ vol, const
   return acc;
 }
 
+// Same value up to FMA rounding (<= 1 ulp of the result) with half the instructions: corner indices
+// are clamped instead of predicated (a clamped corner always carries weight exactly 0), the x-y
+// weight products are shared between the two z planes, 32-bit offsets, FMA accumulation.  Used by
+// the fused warp+loss kernels; km_grid_sample3d keeps the bit-exact formulation above.
+__device__ __forceinline__ float tri_sample_fast(const float* __restrict__ vol, const Tri& t, int D,
+                                                 int H, int W) {
+  const float x0f = (float)t.x0, y0f = (float)t.y0, z0f = (float)t.z0;
+  const float wx1 = t.ix - x0f, wx0 = (x0f + 1.f) - t.ix;
+  const float wy1 = t.iy - y0f, wy0 = (y0f + 1.f) - t.iy;
+  const float wz1 = t.iz - z0f, wz0 = (z0f + 1.f) - t.iz;
+  const int x1 = min(t.x0 + 1, W - 1), y1 = min(t.y0 + 1, H - 1), z1 = min(t.z0 + 1, D - 1);
+  const int r00 = (t.z0 * H + t.y0) * W, r01 = (t.z0 * H + y1) * W;
+  const int r10 = (z1 * H + t.y0) * W, r11 = (z1 * H + y1) * W;
+  const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+  float acc = __ldg(vol + r00 + t.x0) * (w00 * wz0);
+  acc = fmaf(__ldg(vol + r00 + x1), w10 * wz0, acc);
+  acc = fmaf(__ldg(vol + r01 + t.x0), w01 * wz0, acc);
+  acc = fmaf(__ldg(vol + r01 + x1), w11 * wz0, acc);
+  acc = fmaf(__ldg(vol + r10 + t.x0), w00 * wz1, acc);
+  acc = fmaf(__ldg(vol + r10 + x1), w10 * wz1, acc);
+  acc = fmaf(__ldg(vol + r11 + t.x0), w01 * wz1, acc);
+  acc = fmaf(__ldg(vol + r11 + x1), w11 * wz1, acc);
+  return acc;
+}
+
 __device__ __forceinline__ float nearest_sample(const float* __restrict__ vol, const Tri& t, int H,
                                                 int W) {
   // std::nearbyint: round half to even
@@ -301,6 +326,9 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
 
     for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warps) {
       const int v0 = chunk * 128 + lane;
+      // (z, y, x) of the chunk's first voxel: one division pair per 128 voxels
+      const int cz = (chunk * 128) / HW, crem = chunk * 128 - cz * HW;
+      const int cy = crem / W, cx = crem - cy * W;
       Tri t[4];
       bool ok[4];
 #pragma unroll
@@ -315,8 +343,15 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
           gy = __ldg(gp + 1);
           gz = __ldg(gp + 2);
         } else {
-          const int z = vv / HW, rem = vv - z * HW;
-          const int y = rem / W, xx = rem - y * W;
+          int xx = cx + lane + 32 * k, y = cy, z = cz;
+          while (xx >= W) {   // at most once per row the chunk spans
+            xx -= W;
+            if (++y == H) {
+              y = 0;
+              ++z;
+            }
+          }
+          if (!ok[k]) xx = y = z = 0;
           const float pz = km_linspace(-1.f, 1.f, D, z), py = km_linspace(-1.f, 1.f, H, y);
           const float px = km_linspace(-1.f, 1.f, W, xx);
           if (COORD == KM_COORD_AFFINE) {
@@ -336,7 +371,7 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
           for (int k = 0; k < 4; ++k) {
             if (ok[k]) {
               const float r = (mode == KM_INTERP_NEAREST) ? nearest_sample(vol, t[k], H, W)
-                                                          : tri_sample(vol, t[k], D, H, W);
+                                                          : tri_sample_fast(vol, t[k], D, H, W);
               const size_t idx = ch * nvox + v0 + 32 * k;
               if (out) out[idx] = r;
               if (fixed) {
