@@ -196,14 +196,23 @@ int km_maxpool2_stats(const void* src, void* out, float* stats, int N, int C, in
  * stats: (nparts,N,1,2), nparts = km_pool_nparts(). */
 int km_volume_stats(const float* x, float* stats, int N, long long M, km_stream_t stream);
 
-/* stem: 3x3x3 conv of the 1-channel fp32 volume with on-the-fly GroupNorm(1 group) of the input
- * (zero padding of the NORMALISED volume), + optional bias, optional ReLU -> bf16 NDHWC,
- * + per-(n,c) stats of the output.  w: fp32 (Cout,1,3,3,3), Cout in {16,32}.
- * stats: (nparts,N,Cout,2), nparts = km_stem_nparts(N,D,H,W). */
+/* stem: 3x3x3 conv (pad 1) of the 1-channel fp32 volume on the warp-level tensor-core path (TF32
+ * operands, fp32 accumulate) -- keymorph/unet3d/buildingblocks.py:39-132 (encoder 0, first SingleConv)
+ * and keymorph/layers.py:137-187 (ConvNet block 1).  w: fp32 (Cout,1,3,3,3), Cout in {16,32}.
+ *   v = conv(in_scale[n]*x + in_shift[n]) + bias      (zero padding of the NORMALISED volume;
+ *                                                      in_scale/in_shift/bias may be NULL)
+ *   v = relu(v)                                       if relu_pre
+ *   stats (nparts,N,Cout,2) += [sum v, sum v^2]       if stats != NULL, nparts = km_stem_nparts()
+ *   out = bf16(act(out_scale[n,c]*v + out_shift[n,c]))  if out != NULL (NDHWC; act = relu if relu_post;
+ *                                                      out_scale/out_shift (N,Cout) may be NULL)
+ * The layer is meant to run twice (statistics pass with out == NULL, then the store pass with the
+ * following layer's normalisation folded in) instead of normalising its 2*Cout B/voxel output in
+ * a separate pass. */
 int km_stem_nparts(int N, int D, int H, int W);
 int km_conv3d_stem(const float* x, const float* w, const float* bias, const float* in_scale,
-                   const float* in_shift, void* out, float* stats, int N, int Cout, int D, int H,
-                   int W, int relu, km_stream_t stream);
+                   const float* in_shift, const float* out_scale, const float* out_shift, void* out,
+                   float* stats, int N, int Cout, int D, int H, int W, int relu_pre, int relu_post,
+                   km_stream_t stream);
 
 /* tcgen05 implicit-GEMM convolution, kernel 3x3x3 pad 1 (taps = 27) or 1x1x1 (taps = 1).
  *   x: bf16 NDHWC (N,D,H,W,Cin), Cin % 16 == 0;  wp: bf16 [tap][Cout][Cin] from km_pack_weights;
@@ -220,6 +229,17 @@ int km_conv_nparts(void);
 int km_conv3d_tc(const void* x, const void* wp, const float* bias, void* out, float* stats,
                  float* com, int N, int Cin, int Cout, int D, int H, int W, int taps, int flags,
                  km_stream_t stream);
+
+/* Final 1x1x1 convolution fused with ReLU + centre of mass, transposed tcgen05 formulation
+ * (keymorph/unet3d/model.py:99,389 final_conv + keymorph/layers.py:92-134 + keymorph/model.py:95-109):
+ * heat^T[channel, voxel] = W . X^T, one epilogue thread per keypoint channel, sums in registers; the
+ * heat map is never materialised.
+ *   x: bf16 NDHWC (N,D,H,W,Cin), Cin % 16 == 0, Cin <= 256;  wp: bf16 [Cout][Cin] (km_pack_weights
+ *   with taps = 1), Cout % 128 == 0 (zero-pad), Cout <= 512;  bias: fp32 (Cout) or NULL;
+ *   com: (km_conv_nparts(),N,Cout,4) fp32 partial [sum h, sum h*lz, sum h*ly, sum h*lx], h = relu(conv),
+ *   l* = linspace(0,1,n) -- the same partials as KM_CONV_COM, finished by km_com_finalize. */
+int km_conv1x1_com(const void* x, const void* wp, const float* bias, float* com, int N, int Cin,
+                   int Cout, int D, int H, int W, km_stream_t stream);
 
 /* com partials -> keypoints (N,K,3) 'ij' order + optional mass (N,K)
  * (keymorph/layers.py:121-134: c = sum(lin*m)/(M+1e-8), *2-1). */

@@ -49,7 +49,8 @@ SIGNATURES = {
     "km_maxpool2_stats": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "km_volume_stats": (_i, [_p, _p, _i, _ll, _p]),
     "km_stem_nparts": (_i, [_i, _i, _i, _i]),
-    "km_conv3d_stem": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "km_conv1x1_com": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "km_conv3d_stem": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "km_conv_nparts": (_i, []),
     "km_conv3d_tc": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "km_com_finalize": (_i, [_p, _i, _p, _p, _i, _i, _p]),

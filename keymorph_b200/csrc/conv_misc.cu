@@ -1,4 +1,4 @@
-// HBM-bound companions of the tcgen05 convolution: the 1-channel stem stencil, GroupNorm /
+// HBM-bound companions of the tcgen05 convolution (the 1-channel stem lives in stem.cu): GroupNorm /
 // InstanceNorm statistics + application (with the decoder's nearest-upsample + concat folded in),
 // MaxPool3d(2) and layout converters.  All reductions are two-stage and deterministic: every block
 // writes one partial slot, the finalize kernel adds the slots in a fixed order in fp64.
@@ -332,149 +332,6 @@ maxpool2_stats_kernel(const bf16* __restrict__ src, bf16* __restrict__ out,
 }
 
 // ------------------------------------------------------------------------------------------
-// stem: 1-channel fp32 volume -> COUT bf16 channels, 3x3x3, pad 1.
-// Block tile 32(x) x 4(y) x 2(z) outputs, halo tile staged in smem already normalised
-// (zero outside the volume = padding of the normalised tensor).  grid (KM_RED_BLOCKS, N).
-template <int COUT>
-__global__ void __launch_bounds__(256)
-conv_stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                 const float* __restrict__ bias, const float* __restrict__ in_scale,
-                 const float* __restrict__ in_shift, bf16* __restrict__ out,
-                 float* __restrict__ stats, int N, int D, int H, int W, int relu) {
-  // VPT voxels per thread along x (x and x+32): every broadcast weight load feeds VPT FMAs
-  constexpr int VPT = COUT <= 16 ? 2 : 1;
-  constexpr int TX = 32 * VPT, TY = 4, TZ = 2;
-  constexpr int HX = TX + 2, HY = TY + 2, HZ = TZ + 2;
-  __shared__ float tile[HZ][HY][HX];
-  __shared__ __align__(16) float sw[27][COUT];
-  __shared__ float sbias[COUT];
-  __shared__ float red[8][2 * COUT];
-  const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < 27 * COUT; i += 256) {
-    const int co = i % COUT, tap = i / COUT;
-    sw[tap][co] = w[co * 27 + tap];
-  }
-  for (int i = threadIdx.x; i < COUT; i += 256) sbias[i] = bias ? bias[i] : 0.f;
-  const float a_in = in_scale ? in_scale[n] : 1.f;
-  const float b_in = in_shift ? in_shift[n] : 0.f;
-  const float* xn = x + (size_t)n * D * H * W;
-  bf16* on = out + (size_t)n * D * H * W * COUT;
-
-  const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY, tiles_z = (D + TZ - 1) / TZ;
-  const long long ntiles = (long long)tiles_x * tiles_y * tiles_z;
-  const int lx = threadIdx.x % 32, ly = (threadIdx.x / 32) % TY, lz = threadIdx.x / (32 * TY);
-
-  float s[COUT], ss[COUT];
-#pragma unroll
-  for (int c = 0; c < COUT; ++c) s[c] = ss[c] = 0.f;
-
-  // software pipeline: the halo of the NEXT tile is fetched into registers while the current tile
-  // is being computed, so the global-load latency hides behind the 27-tap stencil
-  constexpr int kHalo = HZ * HY * HX;
-  constexpr int kPre = (kHalo + 255) / 256;
-  float pre[kPre];
-  auto fetch = [&](long long t) {
-    const int x0 = (int)(t % tiles_x) * TX;
-    const int y0 = (int)((t / tiles_x) % tiles_y) * TY;
-    const int z0 = (int)(t / ((long long)tiles_x * tiles_y)) * TZ;
-#pragma unroll
-    for (int j = 0; j < kPre; ++j) {
-      const int i = threadIdx.x + 256 * j;
-      const int hx = i % HX, hy = (i / HX) % HY, hz = i / (HX * HY);
-      const int gx = x0 + hx - 1, gy = y0 + hy - 1, gz = z0 + hz - 1;
-      float v = 0.f;
-      if (i < kHalo && gx >= 0 && gx < W && gy >= 0 && gy < H && gz >= 0 && gz < D)
-        v = fmaf(a_in, __ldg(xn + ((size_t)gz * H + gy) * W + gx), b_in);
-      pre[j] = v;
-    }
-  };
-  if (blockIdx.x < ntiles) fetch(blockIdx.x);
-  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int x0 = (int)(t % tiles_x) * TX;
-    const int y0 = (int)((t / tiles_x) % tiles_y) * TY;
-    const int z0 = (int)(t / ((long long)tiles_x * tiles_y)) * TZ;
-    __syncthreads();  // previous tile fully consumed (also orders the weight staging)
-#pragma unroll
-    for (int j = 0; j < kPre; ++j) {
-      const int i = threadIdx.x + 256 * j;
-      if (i < kHalo) (&tile[0][0][0])[i] = pre[j];
-    }
-    __syncthreads();
-    if (t + gridDim.x < ntiles) fetch(t + gridDim.x);
-    const int gy = y0 + ly, gz = z0 + lz;
-    if (gy < H && gz < D) {
-      float acc[VPT][COUT];
-#pragma unroll
-      for (int v = 0; v < VPT; ++v)
-#pragma unroll
-        for (int c = 0; c < COUT; ++c) acc[v][c] = sbias[c];
-#pragma unroll
-      for (int tap = 0; tap < 27; ++tap) {
-        float in[VPT];
-#pragma unroll
-        for (int v = 0; v < VPT; ++v)
-          in[v] = tile[lz + tap / 9][ly + (tap / 3) % 3][lx + 32 * v + tap % 3];
-        const float4* wr = reinterpret_cast<const float4*>(&sw[tap][0]);
-#pragma unroll
-        for (int c4 = 0; c4 < COUT / 4; ++c4) {
-          const float4 wv = wr[c4];
-#pragma unroll
-          for (int v = 0; v < VPT; ++v) {
-            acc[v][4 * c4 + 0] = fmaf(in[v], wv.x, acc[v][4 * c4 + 0]);
-            acc[v][4 * c4 + 1] = fmaf(in[v], wv.y, acc[v][4 * c4 + 1]);
-            acc[v][4 * c4 + 2] = fmaf(in[v], wv.z, acc[v][4 * c4 + 2]);
-            acc[v][4 * c4 + 3] = fmaf(in[v], wv.w, acc[v][4 * c4 + 3]);
-          }
-        }
-      }
-#pragma unroll
-      for (int v = 0; v < VPT; ++v) {
-        const int gx = x0 + lx + 32 * v;
-        if (gx >= W) continue;
-        uint4* dst = reinterpret_cast<uint4*>(on + (((size_t)gz * H + gy) * W + gx) * COUT);
-#pragma unroll
-        for (int c8 = 0; c8 < COUT / 8; ++c8) {
-          float f[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float o = acc[v][8 * c8 + k];
-            if (relu) o = fmaxf(o, 0.f);
-            // statistics are taken over the values actually stored (bf16-rounded)
-            o = __bfloat162float(__float2bfloat16_rn(o));
-            f[k] = o;
-            s[8 * c8 + k] += o;
-            ss[8 * c8 + k] = fmaf(o, o, ss[8 * c8 + k]);
-          }
-          dst[c8] = pack8(f);
-        }
-      }
-    }
-  }
-  // deterministic block reduction of the per-thread accumulators
-#pragma unroll
-  for (int c = 0; c < COUT; ++c) {
-    s[c] = km_warp_sum(s[c]);
-    ss[c] = km_warp_sum(ss[c]);
-  }
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) {
-      red[threadIdx.x >> 5][2 * c] = s[c];
-      red[threadIdx.x >> 5][2 * c + 1] = ss[c];
-    }
-  }
-  __syncthreads();
-  if (stats) {
-    for (int i = threadIdx.x; i < 2 * COUT; i += 256) {
-      float a = 0.f;
-      for (int wv = 0; wv < 8; ++wv) a += red[wv][i];
-      stats[((size_t)blockIdx.x * N + n) * COUT * 2 + i] = a;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 __global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int N,
                                       int C, long long nvox) {
   const long long total = (long long)N * C * nvox;
@@ -509,7 +366,6 @@ inline int blocks_for(long long work_items, int threads) {
 }  // namespace
 
 extern "C" int km_pool_nparts(void) { return KM_RED_BLOCKS; }
-extern "C" int km_stem_nparts(int, int, int, int) { return KM_RED_BLOCKS; }
 
 extern "C" int km_volume_stats(const float* x, float* stats, int N, long long M,
                                km_stream_t stream) {
@@ -582,24 +438,6 @@ extern "C" int km_maxpool2_stats(const void* src, void* out, float* stats, int N
   maxpool2_stats_kernel<<<dim3(KM_RED_BLOCKS, N), 256, 0, km_cs(stream)>>>(
       reinterpret_cast<const bf16*>(src), reinterpret_cast<bf16*>(out), stats, N, C, D, H, W);
   KM_LAUNCH_OK("maxpool2_stats_kernel");
-  return KM_OK;
-}
-
-extern "C" int km_conv3d_stem(const float* x, const float* w, const float* bias,
-                              const float* in_scale, const float* in_shift, void* out, float* stats,
-                              int N, int Cout, int D, int H, int W, int relu, km_stream_t stream) {
-  KM_CHECK_ARG(x && w && out && N > 0 && D > 0 && H > 0 && W > 0, "km_conv3d_stem: bad arguments");
-  KM_CHECK_ARG(Cout == 16 || Cout == 32, "km_conv3d_stem: Cout must be 16 or 32 (got %d)", Cout);
-  const dim3 grid(KM_RED_BLOCKS, N);
-  if (Cout == 16)
-    conv_stem_kernel<16><<<grid, 256, 0, km_cs(stream)>>>(x, w, bias, in_scale, in_shift,
-                                                         reinterpret_cast<bf16*>(out), stats, N, D,
-                                                         H, W, relu);
-  else
-    conv_stem_kernel<32><<<grid, 256, 0, km_cs(stream)>>>(x, w, bias, in_scale, in_shift,
-                                                         reinterpret_cast<bf16*>(out), stats, N, D,
-                                                         H, W, relu);
-  KM_LAUNCH_OK("conv_stem_kernel");
   return KM_OK;
 }
 

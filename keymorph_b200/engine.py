@@ -4,7 +4,8 @@ kernels (bf16 NDHWC activations, fp32 accumulation) and returns keypoints direct
 Layer schedule of the UNet path (reference: keymorph/unet3d/model.py:115-151):
 
     volume_stats -> norm_finalize                     GroupNorm(1) of the 1-channel input
-    conv3d_stem (GN on load, ReLU, stats)             enc0.SingleConv1   1 -> 16      CUDA cores
+    conv3d_stem x2 (GN on load, ReLU; pass 1 = stats, enc0.SingleConv1   1 -> 16      mma.sync TF32
+                    pass 2 = next GN folded, store)
     norm_finalize, norm_apply, conv3d_tc(ReLU,stats)  every other SingleConv          tcgen05
     maxpool2_stats                                    encoder transitions (stats of the pooled map)
     norm_apply(src0 = skip, src1 = x)                 decoder: GN + nearest-upsample + concat fused
@@ -122,13 +123,18 @@ class UNetEngine(_EngineBase):
         st = ops.volume_stats(x)
         scale, shift = ops.norm_finalize(st, D * H * W, sc0.groupnorm.weight, sc0.groupnorm.bias,
                                          sc0.groupnorm.num_groups, sc0.groupnorm.eps)
-        a, st = ops.conv3d_stem(x, sc0.conv.weight.detach(), None, scale.reshape(-1),
-                                shift.reshape(-1), relu=True)
-        self._dbg("enc0.c1", a)
+        # the stem runs twice: a statistics pass, then a store pass with the next GroupNorm folded in
+        w0 = sc0.conv.weight.detach()
+        in_sc, in_sh = scale.reshape(-1), shift.reshape(-1)
+        _, st = ops.conv3d_stem(x, w0, None, in_sc, in_sh, relu_pre=True, store=False)
         sc1 = enc[0].basic_module.SingleConv2
-        scale, shift = ops.norm_finalize(st, nvox(a), sc1.groupnorm.weight, sc1.groupnorm.bias,
+        scale, shift = ops.norm_finalize(st, D * H * W, sc1.groupnorm.weight, sc1.groupnorm.bias,
                                          sc1.groupnorm.num_groups, sc1.groupnorm.eps)
-        a = ops.norm_apply(a, scale, shift, out=a)
+        if self.debug is not None:
+            self._dbg("enc0.c1", ops.conv3d_stem(x, w0, None, in_sc, in_sh, relu_pre=True,
+                                                 want_stats=False)[0])
+        a, _ = ops.conv3d_stem(x, w0, None, in_sc, in_sh, scale, shift, relu_pre=True,
+                               want_stats=False)
         cur, cur_st = self._single_conv("enc0.c2", sc1, a)
         del a
         feats = [(cur, cur_st)]
@@ -179,9 +185,14 @@ class UNetEngine(_EngineBase):
             del c1
         # ---- final 1x1x1 conv (+bias) fused with ReLU + centre of mass
         K = m.final_conv.out_channels
-        wp = self.weights.get("final", m.final_conv.weight, pad_out_to=32)
-        bias = _padded(m.final_conv.bias.detach(), 32)
-        heat, _, com = ops.conv3d_tc(cur, wp, bias=bias, want_com=True, store=want_feat)
+        if not want_feat and K <= 512 and cur.shape[-1] <= 256:
+            # transposed formulation: one epilogue thread per keypoint channel, no heat map at all
+            wp = self.weights.get("final.t", m.final_conv.weight, pad_out_to=128)
+            heat, com = None, ops.conv1x1_com(cur, wp, _padded(m.final_conv.bias.detach(), 128))
+        else:
+            wp = self.weights.get("final", m.final_conv.weight, pad_out_to=32)
+            bias = _padded(m.final_conv.bias.detach(), 32)
+            heat, _, com = ops.conv3d_tc(cur, wp, bias=bias, want_com=True, store=want_feat)
         pts, mass = ops.com_finalize(com, return_mass=True)
         pts, mass = pts[:, :K], mass[:, :K]
         feat = ops.ndhwc_to_ncdhw(heat)[:, :K] if want_feat else None
@@ -197,21 +208,32 @@ class ConvNetEngine(_EngineBase):
         blocks = m.blocks()
         K = blocks[-1].conv.out_channels
         b0 = blocks[0]
-        raw, st = ops.conv3d_stem(x, b0.conv.weight.detach(), b0.conv.bias.detach(), None, None,
-                                  relu=False)
+        w0, bias0 = b0.conv.weight.detach(), b0.conv.bias.detach()
+        # block 1 (stem): statistics pass, then a store pass with InstanceNorm + ReLU folded in
+        _, st = ops.conv3d_stem(x, w0, bias0, store=False)
+        raw = None
         for b, blk in enumerate(blocks):
-            C = raw.shape[-1]
-            nv = raw.shape[1] * raw.shape[2] * raw.shape[3]
+            if b == 0:
+                C, nv = w0.shape[0], x.shape[2] * x.shape[3] * x.shape[4]
+            else:
+                C = raw.shape[-1]
+                nv = raw.shape[1] * raw.shape[2] * raw.shape[3]
             if blk.norm is not None:
                 scale, shift = ops.norm_finalize(st, nv, None, None, C, blk.norm.eps)
             else:
                 scale = torch.ones((N, C), device=x.device)
                 shift = torch.zeros_like(scale)
-            if b == len(blocks) - 1:
-                heat = ops.norm_apply(raw, scale, shift, relu=True)
-                break
-            y = ops.norm_apply(raw, scale, shift, relu=True, pool=blk.down_sample,
-                               out=None if blk.down_sample else raw)
+            if b == 0 and len(blocks) > 1 and not blk.down_sample:
+                y, _ = ops.conv3d_stem(x, w0, bias0, None, None, scale, shift, relu_post=True,
+                                       want_stats=False)
+            else:
+                if b == 0:
+                    raw, _ = ops.conv3d_stem(x, w0, bias0, want_stats=False)
+                if b == len(blocks) - 1:
+                    heat = ops.norm_apply(raw, scale, shift, relu=True)
+                    break
+                y = ops.norm_apply(raw, scale, shift, relu=True, pool=blk.down_sample,
+                                   out=None if blk.down_sample else raw)
             nxt = blocks[b + 1]
             last = b + 1 == len(blocks) - 1
             wp = self.weights.get(f"block{b + 2}", nxt.conv.weight, pad_out_to=16 if last else None)

@@ -275,6 +275,23 @@ def conv3d_tc(x, wp, bias=None, relu=False, want_stats=False, want_com=False, st
     return out, stats, com
 
 
+def conv1x1_com(x, wp, bias=None):
+    """Final 1x1x1 conv + ReLU + centre-of-mass partials without the heat map.
+    x: bf16 (N,D,H,W,Cin); wp: bf16 (1,Cout,Cin) with Cout % 128 == 0 -> com (nparts,N,Cout,4)."""
+    _need_cuda(x, wp, bias)
+    assert x.dtype == torch.bfloat16 and wp.dtype == torch.bfloat16
+    x, wp = x.contiguous(), wp.contiguous()
+    N, D, H, W, Cin = x.shape
+    taps, Cout, Cin2 = wp.shape
+    assert taps == 1 and Cin2 == Cin
+    com = torch.empty((conv_nparts(), N, Cout, 4), dtype=torch.float32, device=x.device)
+    bias = _f32c(bias)
+    with torch.cuda.device(x.device):
+        _lib.call("km_conv1x1_com", _ptr(x), _ptr(wp), _ptr(bias), _ptr(com), N, Cin, Cout, D, H, W,
+                  _stream())
+    return com
+
+
 def com_finalize(com, return_mass=False):
     nparts, N, K, _ = com.shape
     pts = torch.empty((N, K, 3), dtype=torch.float32, device=com.device)
@@ -354,18 +371,26 @@ def maxpool2_stats(x):
     return out, stats
 
 
-def conv3d_stem(x, w, bias=None, in_scale=None, in_shift=None, relu=True):
-    """x: fp32 (N,1,D,H,W); w: fp32 (Cout,1,3,3,3) -> bf16 (N,D,H,W,Cout) + partial stats."""
+def conv3d_stem(x, w, bias=None, in_scale=None, in_shift=None, out_scale=None, out_shift=None,
+                relu_pre=False, relu_post=False, store=True, want_stats=True):
+    """x: fp32 (N,1,D,H,W); w: fp32 (Cout,1,3,3,3).  v = [relu_pre](conv(in_scale*x+in_shift)+bias);
+    returns (bf16 (N,D,H,W,Cout) of [relu_post](out_scale*v+out_shift) or None, partial stats of v
+    or None).  store=False is the statistics pass (nothing is written but the partials)."""
     _need_cuda(x, w)
     x, w, bias = _f32c(x), _f32c(w), _f32c(bias)
+    out_scale, out_shift = _f32c(out_scale), _f32c(out_shift)
     N, Cin, D, H, W = x.shape
     assert Cin == 1
     Cout = w.shape[0]
-    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device)
-    stats = torch.empty((red_nparts(), N, Cout, 2), dtype=torch.float32, device=x.device)
+    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device) if store else None
+    stats = None
+    if want_stats:
+        nparts = _lib.query("km_stem_nparts", N, D, H, W)
+        stats = torch.empty((nparts, N, Cout, 2), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.call("km_conv3d_stem", _ptr(x), _ptr(w), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
-                  _ptr(out), _ptr(stats), N, Cout, D, H, W, int(relu), _stream())
+                  _ptr(out_scale), _ptr(out_shift), _ptr(out), _ptr(stats), N, Cout, D, H, W,
+                  int(relu_pre), int(relu_post), _stream())
     return out, stats
 
 

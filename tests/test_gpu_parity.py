@@ -120,6 +120,38 @@ def test_com_golden_and_empty_channels(golden):
     assert_close(kb.CenterOfMass3d("ij")(cu(neg)).cpu(), O.center_of_mass3d(neg))
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 200, 32, 32, 32), (1, 32, 130, 5, 6, 20), (1, 16, 70, 3, 9, 48),
+                                   (2, 128, 512, 8, 16, 16), (1, 64, 256, 64, 64, 64)])
+def test_conv1x1_com_transposed_vs_fp32(shape):
+    """km_conv1x1_com (final 1x1x1 conv + ReLU + CoM, transposed tcgen05 formulation, no heat map)
+    against the fp32 conv of the same bf16-rounded operands + the oracle's CenterOfMass3d / power
+    mass.  Covers partial bricks, narrow volumes (generic epilogue path), 1-2 passes, 1-4 Cin chunks."""
+    import torch.nn.functional as F
+    N, Cin, K, D, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(N, Cin, D, H, W, generator=g)
+    w = torch.randn(K, Cin, 1, 1, 1, generator=g) / Cin ** 0.5
+    bias = torch.randn(K, generator=g) * 0.3
+    Kp = (K + 127) // 128 * 128
+    wpad = torch.cat([w, torch.zeros(Kp - K, Cin, 1, 1, 1)])
+    bpad = torch.cat([bias, torch.zeros(Kp - K)])
+    xb = ops.ncdhw_to_ndhwc(cu(x))
+    com = ops.conv1x1_com(xb, ops.pack_weights(cu(wpad)), cu(bpad))
+    pts, mass = ops.com_finalize(com, return_mass=True)
+    heat = F.conv3d(ops.ndhwc_to_ncdhw(xb).cpu().double(), w.bfloat16().double(), bias.double())
+    ref_pts = O.center_of_mass3d(heat).float()
+    ref_mass = F.relu(heat).flatten(2).sum(-1).float()
+    assert_close(mass[:, :K].cpu(), ref_mass, rtol=2e-5, atol=1e-3)
+    assert_close(pts[:, :K].cpu(), ref_pts, rtol=0, atol=2e-5)
+    assert float(mass[:, K:].abs().max()) == 0.0 if Kp > K else True
+    # same partials as the KM_CONV_COM path of the general convolution
+    wp32 = ops.pack_weights(cu(torch.cat([w, torch.zeros((32 - K % 32) % 32, Cin, 1, 1, 1)])))
+    b32 = cu(torch.cat([bias, torch.zeros((32 - K % 32) % 32)]))
+    _, _, com2 = ops.conv3d_tc(xb, wp32, bias=b32, want_com=True, store=False)
+    pts2 = ops.com_finalize(com2)
+    assert_close(pts[:, :K], pts2[:, :K], rtol=0, atol=2e-5)
+
+
 # ------------------------------------------------------------------------------------ aligners
 RIGID_KATS = [
     ([[0, 0, 0], [0, 0, 0.1], [0, 0, 0.2], [0, 0, 0.3]], [[0, 0, 0.1], [0, 0, 0.2], [0, 0, 0.3], [0, 0, 0.4]],
@@ -293,6 +325,41 @@ def _seeded(kind, K=16):
     else:
         net = kb.ConvNet(3, 1, K, norm_type="instance")
     return net.eval()
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 16, 16, 32), (2, 32, 9, 11, 35), (1, 16, 5, 70, 130)])
+def test_stem_two_pass_vs_torch_fp32(shape):
+    """stem (mma.sync TF32): statistics pass + store pass with the next normalisation folded in,
+    against fp32 torch ops of the same layer (GroupNorm(1) -> Conv3d -> ReLU -> GroupNorm(8)).
+    Tolerance: TF32 operand rounding (2^-11 relative per operand over 27 taps) + bf16 storage."""
+    import torch.nn.functional as F
+    N, Cout, D, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.rand(N, 1, D, H, W, generator=g)
+    w = torch.randn(Cout, 1, 3, 3, 3, generator=g) * 0.2
+    bias = torch.randn(Cout, generator=g) * 0.1
+    gam0, bet0 = torch.rand(1, generator=g) + 0.5, torch.randn(1, generator=g) * 0.1
+    gam1, bet1 = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g) * 0.1
+    ref_v = F.relu(F.conv3d(F.group_norm(x, 1, gam0, bet0, 1e-5), w, bias, padding=1))
+    ref = F.group_norm(ref_v, 8, gam1, bet1, 1e-5)
+    xd = cu(x)
+    st = ops.volume_stats(xd)
+    sc, sh = ops.norm_finalize(st, D * H * W, cu(gam0), cu(bet0), 1)
+    none, st = ops.conv3d_stem(xd, cu(w), cu(bias), sc.reshape(-1), sh.reshape(-1), relu_pre=True, store=False)
+    assert none is None
+    sums = st.double().sum(0).cpu()
+    assert_close(sums[..., 0], ref_v.double().flatten(2).sum(-1), rtol=1e-3, atol=1e-2)
+    assert_close(sums[..., 1], (ref_v.double() ** 2).flatten(2).sum(-1), rtol=2e-3, atol=1e-2)
+    sc1, sh1 = ops.norm_finalize(st, D * H * W, cu(gam1), cu(bet1), 8)
+    out, none = ops.conv3d_stem(xd, cu(w), cu(bias), sc.reshape(-1), sh.reshape(-1), sc1, sh1, relu_pre=True,
+                                want_stats=False)
+    assert none is None
+    got = ops.ndhwc_to_ncdhw(out).cpu()
+    assert_close(got, ref, rtol=1e-2, atol=1e-2)
+    assert (got - ref).abs().mean().item() < 2e-3
+    # plain (un-normalised, no ReLU) store == conv + bias
+    raw, _ = ops.conv3d_stem(xd, cu(w), cu(bias), want_stats=False)
+    assert_close(ops.ndhwc_to_ncdhw(raw).cpu(), F.conv3d(x, w, bias, padding=1), rtol=1e-2, atol=1e-2)
 
 
 def _heat_report(name, got, ref):
@@ -525,11 +592,14 @@ def test_full_size_256_backbone_and_registration_vs_oracle():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         ac_pts = O.center_of_mass3d(O.unet3d_forward(sd_gpu, f, 4, 1).float()).cpu()
     drift = (ac_pts - ref_pts).abs().max().item()
+    drift_mean = (ac_pts - ref_pts).abs().mean().item()
     mean_err = (r["affine"]["points_f"].cpu() - ref_pts).abs().mean().item()
     print(f"256^3 keypoints vs fp32 oracle: max err {err:.3e} mean {mean_err:.3e}; "
-          f"torch bf16-autocast drift on the same input: max {drift:.3e}")
-    assert err < max(1e-2, 1.25 * drift)
-    assert mean_err < 2.5e-3
+          f"torch bf16-autocast drift on the same input: max {drift:.3e} mean {drift_mean:.3e}")
+    # the MEAN error must not exceed torch's own bf16-autocast drift; the max over the K keypoints is
+    # one worst, weakly localised blob in either run, so it only has to stay within 2x of it
+    assert mean_err < max(1e-3, 1.1 * drift_mean)
+    assert err < max(1e-2, 2.0 * drift)
     for t in ("rigid", "affine"):
         ref = O.register_points(r[t]["points_f"].cpu(), r[t]["points_m"].cpu(), t, (S, S, S))
         assert_close(r[t]["matrix"].cpu(), ref["matrix"], rtol=1e-4, atol=1e-4)

@@ -266,7 +266,7 @@ def run_misc():
         gam, bet = torch.rand(1, device=dev) + 0.5, torch.randn(1, device=dev) * 0.1
         st = ops.volume_stats(x)
         sc, sh = ops.norm_finalize(st, D * H * W, gam, bet, 1)
-        out, stats = ops.conv3d_stem(x, w, None, sc.reshape(-1), sh.reshape(-1), relu=True)
+        out, stats = ops.conv3d_stem(x, w, None, sc.reshape(-1), sh.reshape(-1), relu_pre=True)
         ref = F.relu(F.conv3d(F.group_norm(x, 1, gam, bet, 1e-5), w, padding=1))
         ok &= _report(f"stem conv Cout={Cout}", ops.ndhwc_to_ncdhw(out), ref, 1e-2)
         s = stats.double().sum(0)
