@@ -239,13 +239,14 @@ def run_engine(args):
                 "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": None,
                 "flops_per_step": tc_flops, "launches_per_step": n_conv, "kernel_ms_per_step": conv_ms,
                 "share_of_step": conv_ms / ms_step, "peak_source": peak_src}
-    # the HBM-bound kernel of the path: fused warp + MSE from a materialised grid
-    # algorithmic bytes: grid 12 + moving 4 + fixed 4 + warped-store 4 per voxel
+    # the HBM-bound kernel of the path: ONE pass writes the affine flow field (12 B/voxel), gathers the
+    # moving volume (4), reads the fixed volume (4), stores the warped volume (4) and reduces the
+    # MSE sums (fused warp + loss, grid generated in registers)
     warp_bytes = 24.0 * S ** 3
     warp_gbs = warp_bytes / (warp_ms * 1e-3) / 1e9 if warp_ms > 0 else None
-    roofline_warp = {"bound": "hbm", "kernel": "warp_loss_kernel<GRID>", "achieved": warp_gbs, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": (warp_gbs / hbm_peak) if warp_gbs else None, "traffic": None,
-                     "bytes_per_launch": warp_bytes, "kernel_ms_per_step": warp_ms}
+    roofline_warp = {"bound": "hbm", "kernel": "warp_loss_kernel<AFFINE> (+grid store, +MSE)", "achieved": warp_gbs,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": (warp_gbs / hbm_peak) if warp_gbs else None,
+                     "traffic": None, "bytes_per_launch": warp_bytes, "kernel_ms_per_step": warp_ms}
 
     # end to end through the public API with HOST (pinned) buffers: every step copies both volumes
     # host->device (prefetched on a side stream by keymorph_b200.hostio) and reads the MSE back

@@ -96,6 +96,10 @@ int km_points_transform_tps(const float* ctrl, const float* theta, const float* 
  * deterministically in two stages.
  *   sums layout per (n, c): [sum (a-f)^2, sum a*f, sum a*a, sum f*f]  (fp64, 4 doubles)
  * `fixed` may be NULL (then only the warp is performed and sums are untouched).
+ * `grid_out` (N,D,H,W,3), affine / TPS coordinate modes only, may be NULL: the flow field the
+ * coordinates were generated from, in grid_sample's (x,y,z) order -- identical to
+ * km_flow_field_affine / km_flow_field_tps -- written by the same pass, so that a registration that
+ * must return the grid (keymorph/model.py:252-262) never reads it back.
  * workspace: km_warp_loss_workspace_bytes(N, C). */
 #define KM_COORD_AFFINE 0
 #define KM_COORD_TPS 1
@@ -103,8 +107,8 @@ int km_points_transform_tps(const float* ctrl, const float* theta, const float* 
 size_t km_warp_loss_workspace_bytes(int N, int C);
 int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const float* theta, int K,
                  const float* grid, const float* moving, const float* fixed, float* out,
-                 double* sums, void* workspace, int N, int C, int D, int H, int W, int mode,
-                 km_stream_t stream);
+                 float* grid_out, double* sums, void* workspace, int N, int C, int D, int H, int W,
+                 int mode, km_stream_t stream);
 
 /* keymorph/loss_ops.py:9-13 and :16-63.  Elementwise-pair statistics of two (N,C,M) fp32 tensors:
  * sums[n,c,:] = [sum (p-t)^2, sum p*t, sum p*p, sum t*t] (fp64).  With hard != 0 pred is replaced

@@ -30,7 +30,7 @@ SIGNATURES = {
     "km_points_transform_affine": (_i, [_p, _p, _p, _i, _i, _p]),
     "km_points_transform_tps": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "km_warp_loss_workspace_bytes": (_sz, [_i, _i]),
-    "km_warp_loss": (_i, [_i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "km_warp_loss": (_i, [_i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "km_pair_stats_workspace_bytes": (_sz, [_i, _i, _ll, _i]),
     "km_pair_stats": (_i, [_p, _p, _p, _p, _i, _i, _ll, _i, _p]),
     "km_argmax_channels": (_i, [_p, _p, _i, _i, _ll, _p]),

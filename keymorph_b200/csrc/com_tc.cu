@@ -247,13 +247,17 @@ com_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             for (int ci = 0; ci < 4; ++ci) {
               if (ci < 3) tmem_ld32(taddr + 32u * (ci + 1), r[(ci + 1) & 1]);
               const uint32_t(&v)[32] = r[ci & 1];
-              float s0 = 0.f, sx = 0.f;
+              // four independent accumulator chains: with two epilogue warps per scheduler a single
+              // dependent FADD/FFMA chain would be latency bound
+              float s0p[4] = {0.f, 0.f, 0.f, 0.f}, sxp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float h = fmaxf(__uint_as_float(v[j]) + b, 0.f);
-                s0 += h;
-                sx = fmaf(h, (float)j, sx);
+                s0p[j & 3] += h;
+                sxp[j & 3] = fmaf(h, (float)j, sxp[j & 3]);
               }
+              const float s0 = (s0p[0] + s0p[1]) + (s0p[2] + s0p[3]);
+              const float sx = (sxp[0] + sxp[1]) + (sxp[2] + sxp[3]);
               const float4 o = tab[ci * 32];   // offsets of the chunk's first voxel
               t0 += s0;
               txs += fmaf(o.x, s0, sx);

@@ -8,6 +8,7 @@
 //   keymorph/loss_ops.py:9-63          MSELoss / DiceLoss
 // All kernels are HBM-bound streaming kernels: 4 consecutive x-voxels per thread, 16-byte loads
 // and stores on the contiguous streams (grid, fixed, out), gathers through the read-only path.
+#include <climits>
 #include "km_common.cuh"
 
 namespace {
@@ -287,16 +288,23 @@ grid_sample_kernel(const float* __restrict__ x, const float* __restrict__ grid,
 }
 
 // ------------------------------------------------------------------------------------------
-// fused warp (+ store) (+ loss partials).  grid (KM_RED_BLOCKS, N), 256 threads.
+// fused warp (+ store) (+ flow-field store) (+ loss partials).  grid (KM_RED_BLOCKS, N), 256 threads.
 // partials: [gridDim.x][N][C][4] floats = sum (a-f)^2, sum a*f, sum a*a, sum f*f
+//
+// The (x,y,z) triples of a warp's 128 consecutive voxels are 1536 contiguous bytes of the flow
+// field: they are moved with three 16-byte accesses per lane and transposed through a per-warp
+// shared-memory buffer (stride-3 word access is bank-conflict free), instead of 12-byte-strided
+// scalar accesses whose L1 wavefronts bound the kernel.
 template <int COORD, int CCH, bool FAST>
 __global__ void __launch_bounds__(256)
 warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict__ theta, int K,
                  const float* __restrict__ grid, const float* __restrict__ moving,
                  const float* __restrict__ fixed, float* __restrict__ out,
-                 float* __restrict__ partials, int N, int C, int D, int H, int W, int mode) {
+                 float* __restrict__ grid_out, float* __restrict__ partials, int N, int C, int D,
+                 int H, int W, int mode) {
   extern __shared__ float4 s4[];
   __shared__ float red[8][CCH * 4];
+  __shared__ __align__(16) float s_g[8][384];   // per-warp staging of 128 flow-field triples
   const int n = blockIdx.y;
   const long long nvox = (long long)D * H * W;
   AffineCoord ac;
@@ -310,6 +318,9 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
     load_tps_smem(mat_or_ctrl + (size_t)n * K * 3, theta + (size_t)n * (K + 4) * 3, K, c4, w4, aff);
   }
   const float* gn = (COORD == KM_COORD_GRID) ? grid + (size_t)n * nvox * 3 : nullptr;
+  float* gon = grid_out ? grid_out + (size_t)n * nvox * 3 : nullptr;
+  float* sg = s_g[threadIdx.x >> 5];
+  const bool g_al = (((uintptr_t)(COORD == KM_COORD_GRID ? (const void*)gn : (const void*)gon)) & 15) == 0;
   // a warp owns 128 consecutive voxels, lane i handles voxels i, i+32, i+64, i+96 (see
   // grid_sample_kernel): coalesced streams AND gathers that share cache lines across the warp
   const int lane = threadIdx.x & 31;
@@ -320,9 +331,16 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
 
   for (int cbase = 0; cbase < C; cbase += CCH) {
     const int cn = min(CCH, C - cbase);
-    float acc[CCH][4];
-#pragma unroll
-    for (int c = 0; c < CCH; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+    // single channel: loss sums in registers for the whole kernel.  Multi-channel volumes (one-hot
+    // segmentations): every channel's sums of a chunk are warp-reduced and added to the warp's
+    // shared-memory slots by lane 0 (program order: deterministic), so the channel loop stays
+    // rolled and the register count (= occupancy) matches the single-channel instantiation
+    float acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (CCH > 1) {
+      __syncthreads();
+      for (int i = lane; i < CCH * 4; i += 32) red[threadIdx.x >> 5][i] = 0.f;
+      __syncwarp();
+    }
 
     for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warps) {
       const int v0 = chunk * 128 + lane;
@@ -331,6 +349,14 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
       const int cy = crem / W, cx = crem - cy * W;
       Tri t[4];
       bool ok[4];
+      const bool vec = g_al && chunk * 128 + 128 <= nv;   // whole chunk inside, 16-byte aligned
+      if (COORD == KM_COORD_GRID && vec && cbase == 0) {
+        const float4* g4 = reinterpret_cast<const float4*>(gn + (size_t)chunk * 384);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 3; ++i) reinterpret_cast<float4*>(sg)[lane + 32 * i] = __ldg(g4 + lane + 32 * i);
+        __syncwarp();
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int v = v0 + 32 * k;
@@ -338,10 +364,17 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
         const int vv = ok[k] ? v : 0;
         float gx, gy, gz;
         if (COORD == KM_COORD_GRID) {
-          const float* gp = gn + (size_t)vv * 3;
-          gx = __ldg(gp);
-          gy = __ldg(gp + 1);
-          gz = __ldg(gp + 2);
+          if (vec && cbase == 0) {
+            const float* gp = sg + (lane + 32 * k) * 3;
+            gx = gp[0];
+            gy = gp[1];
+            gz = gp[2];
+          } else {
+            const float* gp = gn + (size_t)vv * 3;
+            gx = __ldg(gp);
+            gy = __ldg(gp + 1);
+            gz = __ldg(gp + 2);
+          }
         } else {
           int xx = cx + lane + 32 * k, y = cy, z = cz;
           while (xx >= W) {   // at most once per row the chunk spans
@@ -359,45 +392,73 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
           } else {
             tps_eval<FAST>(c4, w4, aff, K, pz, py, px, gz, gy, gx);
           }
+          if (gon && cbase == 0) {
+            if (vec) {
+              float* gp = sg + (lane + 32 * k) * 3;
+              gp[0] = gx;
+              gp[1] = gy;
+              gp[2] = gz;
+            } else if (ok[k]) {
+              float* gp = gon + (size_t)v * 3;
+              gp[0] = gx;
+              gp[1] = gy;
+              gp[2] = gz;
+            }
+          }
         }
         t[k] = make_tri(gx, gy, gz, D, H, W);
       }
+      if (COORD != KM_COORD_GRID && gon && vec && cbase == 0) {
+        float4* g4 = reinterpret_cast<float4*>(gon + (size_t)chunk * 384);
+        __syncwarp();
 #pragma unroll
-      for (int c = 0; c < CCH; ++c) {
-        if (c < cn) {
-          const size_t ch = (size_t)n * C + cbase + c;
-          const float* vol = moving + ch * nvox;
+        for (int i = 0; i < 3; ++i) g4[lane + 32 * i] = reinterpret_cast<const float4*>(sg)[lane + 32 * i];
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int c = 0; c < cn; ++c) {
+        const size_t ch = (size_t)n * C + cbase + c;
+        const float* vol = moving + ch * nvox;
+        float acc[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (ok[k]) {
-              const float r = (mode == KM_INTERP_NEAREST) ? nearest_sample(vol, t[k], H, W)
-                                                          : tri_sample_fast(vol, t[k], D, H, W);
-              const size_t idx = ch * nvox + v0 + 32 * k;
-              if (out) out[idx] = r;
-              if (fixed) {
-                const float fv = __ldg(fixed + idx);
-                const float d = r - fv;
-                acc[c][0] = fmaf(d, d, acc[c][0]);
-                acc[c][1] = fmaf(r, fv, acc[c][1]);
-                acc[c][2] = fmaf(r, r, acc[c][2]);
-                acc[c][3] = fmaf(fv, fv, acc[c][3]);
-              }
+        for (int j = 0; j < 4; ++j) acc[j] = CCH > 1 ? 0.f : acc1[j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (ok[k]) {
+            const float r = (mode == KM_INTERP_NEAREST) ? nearest_sample(vol, t[k], H, W)
+                                                        : tri_sample_fast(vol, t[k], D, H, W);
+            const size_t idx = ch * nvox + v0 + 32 * k;
+            if (out) out[idx] = r;
+            if (fixed) {
+              const float fv = __ldg(fixed + idx);
+              const float d = r - fv;
+              acc[0] = fmaf(d, d, acc[0]);
+              acc[1] = fmaf(r, fv, acc[1]);
+              acc[2] = fmaf(r, r, acc[2]);
+              acc[3] = fmaf(fv, fv, acc[3]);
             }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (CCH > 1) {
+            if (fixed) {
+              const float v = km_warp_sum(acc[j]);
+              if (lane == 0) red[threadIdx.x >> 5][c * 4 + j] += v;
+            }
+          } else {
+            acc1[j] = acc[j];
           }
         }
       }
     }
     if (fixed) {
+      if (CCH == 1) {
 #pragma unroll
-      for (int c = 0; c < CCH; ++c)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[c][k] = km_warp_sum(acc[c][k]);
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int c = 0; c < CCH; ++c)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) red[threadIdx.x >> 5][c * 4 + k] = acc[c][k];
+        for (int j = 0; j < 4; ++j) {
+          const float v = km_warp_sum(acc1[j]);
+          if (lane == 0) red[threadIdx.x >> 5][j] = v;
+        }
       }
       __syncthreads();
       for (int i = threadIdx.x; i < cn * 4; i += blockDim.x) {
@@ -596,20 +657,20 @@ extern "C" size_t km_pair_stats_workspace_bytes(int N, int C, long long M, int h
 template <int COORD, int CCH>
 static void launch_warp_loss(bool fast, dim3 grid, size_t smem, cudaStream_t st, const float* a,
                              const float* theta, int K, const float* g, const float* mov,
-                             const float* fix, float* out, float* part, int N, int C, int D, int H,
-                             int W, int mode) {
+                             const float* fix, float* out, float* gout, float* part, int N, int C,
+                             int D, int H, int W, int mode) {
   if (fast)
-    warp_loss_kernel<COORD, CCH, true><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, part,
-                                                                N, C, D, H, W, mode);
+    warp_loss_kernel<COORD, CCH, true><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, gout,
+                                                                part, N, C, D, H, W, mode);
   else
-    warp_loss_kernel<COORD, CCH, false><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, part,
-                                                                 N, C, D, H, W, mode);
+    warp_loss_kernel<COORD, CCH, false><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, gout,
+                                                                 part, N, C, D, H, W, mode);
 }
 
 extern "C" int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const float* theta, int K,
                             const float* grid, const float* moving, const float* fixed, float* out,
-                            double* sums, void* workspace, int N, int C, int D, int H, int W,
-                            int mode, km_stream_t stream) {
+                            float* grid_out, double* sums, void* workspace, int N, int C, int D,
+                            int H, int W, int mode, km_stream_t stream) {
   KM_CHECK_ARG(moving && N > 0 && C > 0 && D > 0 && H > 0 && W > 0, "km_warp_loss: bad arguments");
   KM_CHECK_ARG((long long)D * H * W < (1ll << 31), "km_warp_loss: volume too large");
   KM_CHECK_ARG(mode == KM_INTERP_BILINEAR || mode == KM_INTERP_NEAREST, "km_warp_loss: bad mode");
@@ -620,9 +681,10 @@ extern "C" int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const floa
   } else if (coord_mode == KM_COORD_TPS) {
     KM_CHECK_ARG(mat_or_ctrl && theta && K > 0, "km_warp_loss: TPS parameters missing");
     smem = (size_t)(2 * K + 3) * sizeof(float4);
-    KM_CHECK_ARG(smem <= 40 * 1024, "km_warp_loss: K=%d too large", K);
+    KM_CHECK_ARG(smem <= 32 * 1024, "km_warp_loss: K=%d too large", K);
   } else if (coord_mode == KM_COORD_GRID) {
     KM_CHECK_ARG(grid, "km_warp_loss: grid missing");
+    KM_CHECK_ARG(!grid_out, "km_warp_loss: grid_out is for the affine / TPS coordinate modes");
   } else {
     km_set_error("km_warp_loss: bad coord_mode %d", coord_mode);
     return KM_EINVAL;
@@ -635,10 +697,10 @@ extern "C" int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const floa
   do {                                                                                            \
     if (C == 1)                                                                                   \
       launch_warp_loss<COORD, 1>(fast, g, smem, st, mat_or_ctrl, theta, K, grid, moving, fixed,   \
-                                 out, part, N, C, D, H, W, mode);                                 \
+                                 out, grid_out, part, N, C, D, H, W, mode);                       \
     else                                                                                          \
       launch_warp_loss<COORD, 16>(fast, g, smem, st, mat_or_ctrl, theta, K, grid, moving, fixed,  \
-                                  out, part, N, C, D, H, W, mode);                                \
+                                  out, grid_out, part, N, C, D, H, W, mode);                      \
   } while (0)
   if (coord_mode == KM_COORD_AFFINE) KM_WL(KM_COORD_AFFINE);
   else if (coord_mode == KM_COORD_TPS) KM_WL(KM_COORD_TPS);

@@ -147,7 +147,14 @@ class KeyMorph(nn.Module):
             aligner = self._make_aligner(align_type, points_m, points_f, weights, tps_lmbda, aff_f,
                                          aff_m, shape_f, shape_m,
                                          self.align_keypoints_in_real_world_coords)
-            grid = aligner.get_flow_field(img_f.shape, compute_on_subgrids=not self.training)
+            fused = None
+            if self.fused_warp and align_type in ("rigid", "affine") and img_m.shape == img_f.shape:
+                # one pass generates the flow field, warps the moving image and takes the loss sums
+                img_a, sums, grid = ops.warp_loss(img_m, img_f, mat34=aligner._grid_matrix(),
+                                                  want_grid=True)
+                fused = (img_a, sums)
+            else:
+                grid = aligner.get_flow_field(img_f.shape, compute_on_subgrids=not self.training)
             if return_aligned_points:
                 points_a = aligner.get_forward_transformed_points(points_m)
             align_time = time.time() - start_time
@@ -166,15 +173,15 @@ class KeyMorph(nn.Module):
             if return_aligned_points:
                 res["points_a"] = points_a
             if self.fused_warp:
-                self._fused_outputs(res, grid, img_f, img_m, kwargs)
+                self._fused_outputs(res, grid, img_f, img_m, kwargs, fused)
             result_dict[align_type_str] = res
         return result_dict
 
-    def _fused_outputs(self, res, grid, img_f, img_m, kwargs):
-        """Warped image / segmentation and loss sums in the same pass that reads the grid
-        (scripts/pairwise_register_eval.py:137-162,303-321 would otherwise call align_img and the
-        losses separately)."""
-        img_a, sums = ops.warp_loss(img_m, img_f, grid=grid)
+    def _fused_outputs(self, res, grid, img_f, img_m, kwargs, fused=None):
+        """Warped image / segmentation and loss sums in the same pass that reads (or, for rigid /
+        affine, writes) the grid (scripts/pairwise_register_eval.py:137-162,303-321 would otherwise
+        call align_img and the losses separately)."""
+        img_a, sums = fused if fused is not None else ops.warp_loss(img_m, img_f, grid=grid)
         res["img_a"] = img_a
         res["mse"] = (sums[..., 0].sum() / img_f.numel()).float()
         seg_f, seg_m = kwargs.get("seg_f"), kwargs.get("seg_m")

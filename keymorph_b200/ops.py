@@ -106,10 +106,11 @@ def points_transform_tps(ctrl, theta, pts):
 
 
 def warp_loss(moving, fixed=None, *, mat34=None, ctrl=None, theta=None, grid=None,
-              mode="bilinear", store=True):
+              mode="bilinear", store=True, want_grid=False):
     """Fused warp (+ loss sums).  Exactly one of mat34 / (ctrl, theta) / grid selects where the
     sampling coordinates come from.  Returns (warped or None, sums (N,C,4) fp64 or None) with
-    sums[..., :] = [sum (a-f)^2, sum a*f, sum a*a, sum f*f]."""
+    sums[..., :] = [sum (a-f)^2, sum a*f, sum a*a, sum f*f]; with want_grid=True (mat34 / TPS modes)
+    a third value, the (N,D,H,W,3) flow field written by the same pass."""
     _need_cuda(moving, fixed, mat34, ctrl, theta, grid)
     moving, fixed = _f32c(moving), _f32c(fixed)
     N, Cc, D, H, W = moving.shape
@@ -126,6 +127,11 @@ def warp_loss(moving, fixed=None, *, mat34=None, ctrl=None, theta=None, grid=Non
     else:
         raise ValueError("warp_loss needs mat34, (ctrl, theta) or grid")
     out = torch.empty_like(moving) if store else None
+    gout = None
+    if want_grid:
+        if g is not None:
+            raise ValueError("want_grid needs mat34 or (ctrl, theta)")
+        gout = torch.empty((N, D, H, W, 3), dtype=torch.float32, device=moving.device)
     sums = ws = None
     if fixed is not None:
         assert fixed.shape == moving.shape
@@ -133,8 +139,8 @@ def warp_loss(moving, fixed=None, *, mat34=None, ctrl=None, theta=None, grid=Non
         ws = _ws(_lib.query("km_warp_loss_workspace_bytes", N, Cc), moving.device)
     with torch.cuda.device(moving.device):
         _lib.call("km_warp_loss", coord, _ptr(a), _ptr(th), K, _ptr(g), _ptr(moving), _ptr(fixed),
-                  _ptr(out), _ptr(sums), _ptr(ws), N, Cc, D, H, W, _mode(mode), _stream())
-    return out, sums
+                  _ptr(out), _ptr(gout), _ptr(sums), _ptr(ws), N, Cc, D, H, W, _mode(mode), _stream())
+    return (out, sums, gout) if want_grid else (out, sums)
 
 
 def pair_stats(pred, target, hard=False):

@@ -89,6 +89,41 @@ def test_fused_warp_loss_vs_oracle():
         assert torch.equal(outn.cpu(), O.align_img(grid, mov, "nearest"))
 
 
+@pytest.mark.parametrize("shape", [(1, 1, 40, 48, 56), (2, 3, 17, 23, 37), (1, 14, 24, 24, 24)])
+def test_fused_warp_modes_vs_oracle(shape):
+    """km_warp_loss under a 0.3 rad rotation + shear: the affine mode that also writes the flow
+    field (bit-identical to km_flow_field_affine, coalesced 16-byte stores through the per-warp
+    staging buffer), the grid mode, and a random grid with out-of-range coordinates in both
+    interpolation modes.  All must agree with the oracle."""
+    N, C, D, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    mov, fix = torch.rand(N, C, D, H, W, generator=g), torch.rand(N, C, D, H, W, generator=g)
+    inv = O.affine_matrix_3d(0.1, 0.05, 0.3, 0.02).repeat(N, 1, 1)        # 0.3 rad rotation + shear
+    inv[:, :3, 3] += 0.05 * torch.randn(N, 3, generator=g)
+    grid = torch.cat([O.affine_flow_field(inv[i:i + 1], (D, H, W)) for i in range(N)])
+    ref = O.align_img(grid, mov)
+    rs = torch.stack([((ref - fix) ** 2).flatten(2).sum(-1), (ref * fix).flatten(2).sum(-1),
+                      (ref ** 2).flatten(2).sum(-1), (fix ** 2).flatten(2).sum(-1)], -1).double()
+    out, sums, gout = ops.warp_loss(cu(mov), cu(fix), mat34=cu(inv[:, :3]), want_grid=True)
+    assert torch.equal(gout, ops.flow_field_affine(cu(inv[:, :3]), (D, H, W)))   # same arithmetic
+    assert_close(gout.cpu(), grid, rtol=0, atol=2e-6)
+    assert_close(out.cpu(), ref, rtol=0, atol=1e-5)      # coordinates from the matrix: fp32 FMA order
+    assert_close(sums.cpu(), rs, rtol=1e-5, atol=1e-4)
+    out2, sums2 = ops.warp_loss(cu(mov), cu(fix), grid=cu(grid))
+    assert_close(out2.cpu(), ref, rtol=0, atol=2e-6)
+    assert_close(sums2.cpu(), rs, rtol=1e-5, atol=1e-4)
+    for mode in ("bilinear", "nearest"):
+        wild = torch.rand(N, D, H, W, 3, generator=g) * 2.6 - 1.3        # incoherent + out of range
+        refw = O.align_img(wild, mov, mode)
+        outw, _ = ops.warp_loss(cu(mov), None, grid=cu(wild), mode=mode)
+        if mode == "nearest":
+            assert torch.equal(outw.cpu(), refw)
+            assert torch.equal(ops.warp_loss(cu(mov), None, grid=cu(grid), mode=mode)[0].cpu(),
+                               O.align_img(grid, mov, mode))
+        else:
+            assert_close(outw.cpu(), refw, rtol=0, atol=2e-6)
+
+
 # ------------------------------------------------------------------------------------ CoM
 def _blob(shape, at, sigma=5):
     img = np.zeros(shape)
