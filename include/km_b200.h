@@ -58,6 +58,13 @@ int km_sm_count(void);
 /* key KM_OPT_TPS_SINGLE_CTA (default 0): solve the TPS system with the un-blocked one-CTA LU instead
  * of the blocked multi-CTA Gauss-Jordan elimination (A/B testing). */
 #define KM_OPT_TPS_SINGLE_CTA 7
+/* key KM_OPT_CONV_INTERLEAVE_BRICKS (default 0): km_conv3d_tc issues the MMAs of the bricks that
+ * share a weight slice round-robin (consecutive tcgen05.mma accumulate into different TMEM tiles)
+ * instead of brick by brick (A/B testing; measured slower: the issue loop needs more instructions). */
+#define KM_OPT_CONV_INTERLEAVE_BRICKS 8
+/* key KM_OPT_CONV_TWO_ISSUERS (default 128): layers whose output-channel block is at most this wide
+ * split the bricks of a group between two MMA issuer warps (0 = always one issuer; A/B testing). */
+#define KM_OPT_CONV_TWO_ISSUERS 9
 int km_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------ *

@@ -67,6 +67,8 @@ KM_OPT_CONV_NO_RESIDENT_WEIGHTS = 3
 KM_OPT_CONV_MAX_BRICKS = 4
 KM_OPT_CONV_NO_EPILOGUE_BATCH = 5
 KM_OPT_CONV_HALO_AXIS = 6
+KM_OPT_TPS_SINGLE_CTA = 7
+KM_OPT_CONV_INTERLEAVE_BRICKS = 8
 
 _lib = None
 

@@ -32,7 +32,7 @@ using namespace kmtc;
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kThreads = 352;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 second MMA issuer
 constexpr int kEpiThreads = 256;
 constexpr int kFstagePitch = 33;  // floats, conflict-free transposed access
 constexpr int kMaxStages = 12;
@@ -41,6 +41,8 @@ int g_no_resident = 0;            // km_set_option(KM_OPT_CONV_NO_RESIDENT_WEIGH
 int g_max_mt = 4;                 // km_set_option(KM_OPT_CONV_MAX_BRICKS)
 int g_no_epi_batch = 0;           // km_set_option(KM_OPT_CONV_NO_EPILOGUE_BATCH)
 int g_halo_axis = 2;              // km_set_option(KM_OPT_CONV_HALO_AXIS): 1 = x-shift, 2 = y-shift
+int g_two_issuers = 128;          // km_set_option(KM_OPT_CONV_TWO_ISSUERS): max BN that gets 2 issuer warps (0 = off)
+int g_interleave = 0;             // km_set_option(KM_OPT_CONV_INTERLEAVE_BRICKS)
 
 struct ConvGeom {
   int N, D, H, W, Cin, Cout;
@@ -58,6 +60,8 @@ struct ConvGeom {
   int b_resident;      // all weight slices stay in shared memory for the whole kernel
   int mt;              // mode 1: x-adjacent 16x8 bricks that share one weight fetch (1, 2 or 4)
   int eb;              // bricks staged together per epilogue round (<= mt)
+  int interleave;      // issue order: bricks innermost (1) or taps innermost (0)
+  int issuers;         // MMA issuer warps (1 or 2)
   uint32_t off_bres;
   uint32_t a_sub_bytes, b_sub_bytes;      // TMA bytes per sub-iteration
   uint32_t a_sub_stride, b_sub_stride;    // 1024-aligned slots inside a stage
@@ -143,10 +147,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), (uint32_t)g.issuers);     // one tcgen05.commit per issuer warp
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
+      mbar_init(tfull_bar(a), (uint32_t)g.issuers);
       mbar_init(tempty_bar(a), kEpiThreads);
     }
     mbar_init(bres_bar, 1);
@@ -252,8 +256,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer =================================
+  } else if (warp == 1 || warp == 10) {
+    // =============================== MMA issuer(s) ==============================
+    // With g.issuers == 2 the bricks of a group are split between warp 1 and warp 10: one thread
+    // cannot issue the short (N <= 64) MMAs of the narrow layers fast enough to keep the tensor
+    // pipe busy.  Each issuer commits to the stage / accumulator barriers (arrival count 2).
+    if (warp == 10 && g.issuers < 2) goto issuer_done;
     // The whole warp runs this loop with warp-uniform values (so that the compiler keeps the UMMA
     // descriptors in uniform registers); only the elected lane issues tcgen05.mma / commit.
     {
@@ -273,15 +281,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = g.idesc;
       const bool resident = g.b_resident != 0;
       const uint32_t bres16 = (((base + g.off_bres) & 0x3FFFFu) >> 4) | lo_flag;
-      const int mt = g.mt;
       const uint32_t bn = (uint32_t)g.BN;
+      const bool g_interleave = g.interleave != 0;
+      // this issuer's bricks [m_lo, m_lo + mt) of the group
+      const int m_lo = (g.issuers == 2 && warp == 10) ? g.mt / 2 : 0;
+      const int mt = g.issuers == 2 ? (warp == 10 ? g.mt - g.mt / 2 : g.mt / 2) : g.mt;
       if (resident) mbar_wait(bres_bar, 0u);
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u;
         const uint32_t acc_ph = (tcount >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)mt * bn;
+        const uint32_t d_tmem = tmem_base + (acc * (uint32_t)g.mt + (uint32_t)m_lo) * bn;
         uint32_t accum = 0;
         uint32_t bq16 = bres16;   // running weight slice (resident mode)
         for (int si = 0; si < n_stage_iters; ++si) {
@@ -290,7 +301,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           uint32_t a16 = base16 + (uint32_t)s * stage16;
           uint32_t b16 = resident ? bq16 : a16 + boff16;
+          a16 += (uint32_t)m_lo * 16u * a_tap16;
           for (int u = 0; u < nsub; ++u) {
+            if (g_interleave) {
+              // bricks innermost: consecutive MMAs accumulate into DIFFERENT TMEM tiles, so the
+              // accumulator read-after-write latency of the tensor pipe overlaps across bricks
+#pragma unroll
+              for (int t = 0; t < kNtap; ++t) {
+#pragma unroll
+                for (int kk = 0; kk < kSteps; ++kk) {
+                  uint32_t am16 = a16 + t * a_tap16 + 2u * kk, dm = d_tmem;
+                  const uint32_t bb16 = b16 + t * b_tap16 + 2u * kk;
+                  const uint32_t acc_flag = (t | kk) ? 1u : accum;
+                  for (int m = 0; m < mt; ++m) {
+                    umma_bf16_pred(dm, am16, bb16, desc_hi, idesc, acc_flag, issue);
+                    am16 += 16u * a_tap16;
+                    dm += bn;
+                  }
+                }
+              }
+            } else {
             uint32_t am16 = a16, dm = d_tmem;
             for (int m = 0; m < mt; ++m) {   // bricks sharing this weight slice
 #pragma unroll
@@ -303,6 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               am16 += 16u * a_tap16;
               dm += bn;
+            }
             }
             accum = 1u;
             a16 += a_sub16;
@@ -318,6 +349,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit_pred(tfull_bar((int)acc), issue);  // accumulator complete -> epilogue
       }
     }
+  issuer_done:;
   } else {
     // =============================== epilogue (8 warps) ==========================
     // Two groups of four warps; each warp reads its own TMEM lane quadrant (warp % 4), the groups
@@ -677,6 +709,8 @@ void km_conv_set_no_resident(int v) { g_no_resident = v ? 1 : 0; }
 void km_conv_set_max_mt(int v) { g_max_mt = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
 void km_conv_set_no_epi_batch(int v) { g_no_epi_batch = v ? 1 : 0; }
 void km_conv_set_halo_axis(int v) { g_halo_axis = v == 1 ? 1 : 2; }
+void km_conv_set_interleave(int v) { g_interleave = v ? 1 : 0; }
+void km_conv_set_two_issuers(int v) { g_two_issuers = v; }
 extern "C" int km_conv_nparts(void) { return sm_count(); }
 
 extern "C" int km_pack_weights(const float* w, void* packed, int Cout, int Cin, int taps,
@@ -733,6 +767,8 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   KM_CHECK_ARG(g.BN > 0, "km_conv3d_tc: no channel block for Cout=%d", Cout);
   g.n_blocks = Cout / g.BN;
   g.mt = 1;
+  g.interleave = g_interleave;
+  g.issuers = 1;
   if (mode >= 1) {
     // bricks that share one weight fetch: as many as TMEM (2 buffers x mt x BN columns) allows,
     // not more than the row / column holds; shared memory is checked below
@@ -743,6 +779,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
                              round_up(3u * (uint32_t)g.BN * row_bytes, 1024) > 96u * 1024u)
       mt /= 2;
     g.mt = mt;
+    g.issuers = (g_two_issuers && mt >= 2 && g.BN <= g_two_issuers) ? 2 : 1;
     if (mode == 1) { g.TW = 16 * mt; g.TH = 8; }
     else { g.TW = 8; g.TH = 16 * mt; }
     g.TD = 1;

@@ -20,6 +20,8 @@ void km_conv_set_no_resident(int v);
 void km_conv_set_max_mt(int v);
 void km_conv_set_no_epi_batch(int v);
 void km_conv_set_halo_axis(int v);
+void km_conv_set_interleave(int v);
+void km_conv_set_two_issuers(int v);
 void km_tps_set_single_cta(int v);
 namespace {
 
@@ -576,6 +578,14 @@ extern "C" int km_set_option(int key, int value) {
   }
   if (key == KM_OPT_CONV_HALO_AXIS) {
     km_conv_set_halo_axis(value);
+    return KM_OK;
+  }
+  if (key == KM_OPT_CONV_INTERLEAVE_BRICKS) {
+    km_conv_set_interleave(value);
+    return KM_OK;
+  }
+  if (key == KM_OPT_CONV_TWO_ISSUERS) {
+    km_conv_set_two_issuers(value);
     return KM_OK;
   }
   if (key == KM_OPT_TPS_SINGLE_CTA) {
