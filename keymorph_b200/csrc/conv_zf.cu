@@ -1,0 +1,468 @@
+// "z-folded" tcgen05 implicit-GEMM 3x3x3 convolution for the backbone's first tensor-core layer
+// (Cin = 16 -> Cout = 32 at full resolution: keymorph/unet3d/buildingblocks.py:50-52, second
+// SingleConv of encoder 0).
+//
+// Why a second kernel: with Cin = 16 every tcgen05.mma of the general kernel (conv_tc.cu) is a
+// 128 x 32 x 16 sliver: 27 of them per 128 voxels, each re-reading a 4 KB activation slice from
+// shared memory and each fed by its own piece of nine TMA boxes per brick group.  That layer ran
+// at ~0.48 PFLOP/s.  Here the three dz taps are folded into the N dimension instead:
+//
+//     D[voxel(z'), (j, cout)] += A[voxel(z') shifted by (dy, dx), cin] . W[dz(j), dy, dx][cout][cin]
+//
+// i.e. one plane z' of the input contributes, with ONE pass over its data and 9 MMAs of N = 96
+// per brick, to the three output planes z'+1 (dz=0), z' (dz=1) and z'-1 (dz=2).  The three column
+// blocks j of the accumulator are a ring of output planes that lives in TMEM across the CTA's walk
+// along z: block (p+2)%3 is complete after plane p, the epilogue drains it (ReLU, bf16, stats) and
+// zeroes it (tcgen05.st) so that it becomes the fresh plane z'+2 of the next step; all MMAs after
+// a unit's first plane accumulate.  Because the ring rotates, the weights are kept in the three
+// row rotations r = p % 3 (dz(j, r) = (r + 1 - j) mod 3), all resident in shared memory (81 KB).
+// Per plane: 3 TMA activation boxes (dx) instead of 9 (dz, dx), a third of the MMAs, a third of the
+// shared-memory operand reads.
+//
+// A work unit is a column of bricks: 8(x) x 32(y) voxels (two 8x16 bricks sharing every weight
+// slice, y taps through UMMA descriptor offsets exactly as MODE 2 of conv_tc.cu) x a z segment of
+// up to 64 planes (+2 halo planes, zero-filled by TMA outside the volume).  A CTA interleaves two
+// units plane by plane (TMEM sets 0 / 1) so that the epilogue of one overlaps the MMAs of the other.
+// Roles (320 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..9 = epilogue.
+#include "km_common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace kmtc;
+
+namespace {
+
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int kKC = 16;                 // input channels (one K step)
+constexpr int kCout = 32;
+constexpr int kN3 = 3 * kCout;          // MMA N: three output planes x Cout
+constexpr int kMT = 2;                  // bricks per unit (stacked in y)
+constexpr int kRowBytes = kKC * 2;      // 32 B rows, SWIZZLE_32B
+constexpr int kBoxRows = 8 * (16 * kMT + 2);
+constexpr uint32_t kASub = 9216;        // 272 rows x 32 B = 8704, rounded up to 1 KB
+constexpr uint32_t kAStage = 3 * kASub; // one plane: dx = 0, 1, 2
+constexpr uint32_t kBTile = kN3 * kRowBytes;          // 3072 B
+constexpr uint32_t kBBytes = 27 * kBTile;             // [r][dx][dy] = 82944 B
+constexpr int kStages = 4;
+constexpr int kLZ = 64;                 // z planes per unit
+constexpr uint32_t kStagePitch = kCout * 2 + 16;      // staged output row (bf16) + pad
+
+struct ZfGeom {
+  int N, D, H, W;
+  int tiles_x, tiles_y, zsegs, units;
+  int flags;
+  uint32_t off_b, off_staging, off_rowvalid, off_stats, off_bars;
+  int stat_parts;
+};
+
+struct Unit {
+  int n, x0, y0, zs, planes;   // planes = segment length + 2
+};
+
+__device__ __forceinline__ Unit decode_unit(const ZfGeom& g, int u) {
+  Unit r;
+  r.x0 = (u % g.tiles_x) * 8;
+  u /= g.tiles_x;
+  r.y0 = (u % g.tiles_y) * (16 * kMT);
+  u /= g.tiles_y;
+  r.zs = (u % g.zsegs) * kLZ;
+  r.n = u / g.zsegs;
+  r.planes = min(kLZ, g.D - r.zs) + 2;
+  return r;
+}
+
+// The tile sequence of this CTA, identical for the three roles: units blockIdx.x + k*gridDim.x are
+// taken in pairs and interleaved plane by plane; fn(set, unit, p, cnt) with cnt = tiles already
+// done on that TMEM set.
+template <typename F>
+__device__ __forceinline__ void for_each_tile(const ZfGeom& g, F&& fn) {
+  uint32_t cnt[2] = {0u, 0u};
+  const int G = (int)gridDim.x;
+  for (int ua = (int)blockIdx.x; ua < g.units; ua += 2 * G) {
+    const int ub = ua + G;
+    const Unit a = decode_unit(g, ua);
+    Unit b = a;
+    b.planes = 0;
+    if (ub < g.units) b = decode_unit(g, ub);
+    const int pmax = max(a.planes, b.planes);
+    for (int p = 0; p < pmax; ++p) {
+      if (p < a.planes) fn(0u, a, p, cnt[0]++);
+      if (p < b.planes) fn(1u, b, p, cnt[1]++);
+    }
+  }
+}
+
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const ZfGeom g, __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
+  constexpr uint32_t kLayout = 6u;                 // SWIZZLE_32B
+  constexpr uint32_t kSbo = 8u * kRowBytes;        // 256 B between 8-row groups
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_u32);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t bars = base + g.off_bars;   // full[S], empty[S], tfull[2], tempty[2], wfull
+  auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(kStages + s); };
+  auto tfull_bar = [&](uint32_t a) { return bars + 8u * (uint32_t)(2 * kStages + a); };
+  auto tempty_bar = [&](uint32_t a) { return bars + 8u * (uint32_t)(2 * kStages + 2 + a); };
+  const uint32_t w_bar = bars + 8u * (uint32_t)(2 * kStages + 4);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + g.off_bars + 8u * (2 * kStages + 5));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (uint32_t a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kEpiThreads);
+    }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  {
+    float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);
+    if (g.flags & KM_CONV_STATS)
+      for (int i = threadIdx.x; i < g.stat_parts * g.N * kCout * 2; i += kThreads) s_stats[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, kBBytes);
+      for (int t = 0; t < 27; ++t) tma_load_3d(base + g.off_b + (uint32_t)t * kBTile, &tmB, w_bar, 0, 0, t);
+      int s = 0;
+      uint32_t ph = 0;
+      for_each_tile(g, [&](uint32_t, const Unit& u, int p, uint32_t) {
+        const int z = u.zs - 1 + p;   // input plane; outside [0, D) -> TMA zero fill
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_arrive_expect_tx(full_bar(s), 3u * (uint32_t)(kBoxRows * kRowBytes));
+        const uint32_t dst = base + (uint32_t)s * kAStage;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+          tma_load_5d(dst + (uint32_t)dx * kASub, &tmA, full_bar(s), 0, u.x0 + dx - 1, u.y0 - 1, z, u.n);
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      });
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    const uint32_t issue = elect_one();
+    constexpr uint32_t desc_hi = (kSbo >> 4) | (1u << 14) | (kLayout << 29);
+    const uint32_t lo_flag = 1u << 16;
+    const uint32_t a_base16 = ((base & 0x3FFFFu) >> 4) | lo_flag;
+    const uint32_t b_base16 = (((base + g.off_b) & 0x3FFFFu) >> 4) | lo_flag;
+    const uint32_t idesc = umma_idesc_bf16(128, kN3);
+    int s = 0;
+    uint32_t ph = 0;
+    mbar_wait(w_bar, 0u);
+    for_each_tile(g, [&](uint32_t set, const Unit&, int p, uint32_t cnt) {
+      mbar_wait(tempty_bar(set), (cnt & 1u) ^ 1u);   // previous plane of this set drained + zeroed
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + set * 256u;
+      const uint32_t a16 = a_base16 + (uint32_t)s * (kAStage >> 4);
+      const uint32_t b16 = b_base16 + (uint32_t)(p % 3) * 9u * (kBTile >> 4);
+      uint32_t accum = p == 0 ? 0u : 1u;   // a unit's first plane overwrites the whole ring
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const uint32_t bb = b16 + (uint32_t)(dx * 3 + dy) * (kBTile >> 4);
+#pragma unroll
+          for (int m = 0; m < kMT; ++m) {
+            // rows of brick m shifted by dy: (16 m + dy) atoms of 8 rows x 32 B
+            const uint32_t aa = a16 + (uint32_t)dx * (kASub >> 4) + (uint32_t)(16 * m + dy) * (kSbo >> 4);
+            umma_bf16_pred(d_tmem + (uint32_t)m * kN3, aa, bb, desc_hi, idesc, accum, issue);
+          }
+          accum = 1u;
+        }
+      }
+      umma_commit_pred(empty_bar(s), issue);
+      umma_commit_pred(tfull_bar(set), issue);
+      if (++s == kStages) {
+        s = 0;
+        ph ^= 1u;
+      }
+    });
+  } else {
+    // =============================== epilogue (8 warps) ==========================
+    const int q = warp & 3;               // TMEM lane quadrant
+    const int row = q * 32 + lane;        // voxel within a brick: tx = row & 7, ty = row >> 3
+    const int half = (warp - 2) >> 2;     // column half [16 half, 16 half + 16)
+    const int et = half * 128 + row;
+    uint8_t* staging = sm + g.off_staging;
+    uint8_t* rowvalid = sm + g.off_rowvalid;   // [kMT][128]
+    float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);
+    const bool do_relu = (g.flags & KM_CONV_RELU) != 0;
+    const bool do_stats = (g.flags & KM_CONV_STATS) != 0;
+    const int parts = g.stat_parts, rows_per_part = 128 / parts;
+    auto all_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    const int tx = row & 7, ty = row >> 3;
+
+    for_each_tile(g, [&](uint32_t set, const Unit& u, int p, uint32_t cnt) {
+      const int zo = u.zs - 2 + p;                   // the output plane completed by this tile
+      const bool store = p >= 2 && zo < g.D;         // (zo >= zs by construction)
+      const uint32_t slot = (uint32_t)((p + 2) % 3);
+      mbar_wait(tfull_bar(set), cnt & 1u);
+      tc_fence_after();
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int m = 0; m < kMT; ++m) {
+        const bool v = (u.x0 + tx < g.W) && (u.y0 + 16 * m + ty < g.H);
+        vmask |= (v ? 1u : 0u) << m;
+        if (store && half == 0) rowvalid[m * 128 + row] = v ? 1 : 0;
+      }
+#pragma unroll
+      for (int m = 0; m < kMT; ++m) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256u + (uint32_t)m * kN3 +
+                               slot * kCout + (uint32_t)half * 16u;
+        if (store) {
+          uint32_t r[16];
+          tmem_ld16(taddr, r);
+          tmem_ld_wait();
+          const bool vrow = ((vmask >> m) & 1u) != 0;
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
+            if (do_relu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            }
+            pk[j] = vrow ? pack_bf16(a, b) : 0u;   // rows outside the volume: zeros (stats need no mask)
+          }
+          uint4* dst = reinterpret_cast<uint4*>(staging + (size_t)(m * 128 + row) * kStagePitch + half * 32);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        tmem_st16_zero(taddr);   // the drained block becomes the fresh output plane z' + 2
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(set));
+      if (store) {
+        all_bar();
+        // staged bf16 rows -> global (coalesced 16-byte chunks)
+        constexpr int cpr = kCout / 8;
+        for (int id = et; id < kMT * 128 * cpr; id += kEpiThreads) {
+          const int j = id % cpr, rr = id / cpr;
+          const int mb = rr >> 7, r2 = rr & 127;
+          if (!rowvalid[mb * 128 + r2]) continue;
+          const int x2 = u.x0 + (r2 & 7), y2 = u.y0 + 16 * mb + (r2 >> 3);
+          const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
+          *reinterpret_cast<uint4*>(out + vox * kCout + j * 8) =
+              *reinterpret_cast<const uint4*>(staging + (size_t)(mb * 128 + r2) * kStagePitch + j * 16);
+        }
+        if (do_stats) {
+          for (int id = et; id < parts * kCout; id += kEpiThreads) {
+            const int col = id % kCout, part = id / kCout;
+            float s = 0.f, ss = 0.f;
+#pragma unroll
+            for (int mb = 0; mb < kMT; ++mb) {
+              const uint8_t* pp = staging + (size_t)(mb * 128 + part * rows_per_part) * kStagePitch + (size_t)col * 2;
+#pragma unroll 8
+              for (int rr = 0; rr < rows_per_part; ++rr) {
+                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(pp));
+                pp += kStagePitch;
+                s += v;
+                ss = fmaf(v, v, ss);
+              }
+            }
+            float* d = s_stats + (((size_t)part * g.N + u.n) * kCout + col) * 2;
+            d[0] += s;
+            d[1] += ss;
+          }
+        }
+        all_bar();   // staging / rowvalid may be overwritten by the next tile
+      }
+    });
+
+    all_bar();
+    if (do_stats) {
+      float* dst = stats + (size_t)blockIdx.x * g.N * kCout * 2;
+      const int n = g.N * kCout * 2;
+      for (int i = et; i < n; i += kEpiThreads) {
+        float a = 0.f;
+        for (int pp = 0; pp < parts; ++pp) a += s_stats[(size_t)pp * n + i];
+        dst[i] = a;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// fp32 (Cout, Cin, 3, 3, 3) -> bf16 [r][dx][dy][j][Cout][Cin], dz(j, r) = (r + 1 - j) mod 3
+__global__ void pack_weights_zf_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int Cout,
+                                       int Cin) {
+  const int total = 27 * 3 * Cout * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t = i;
+    const int ci = t % Cin;
+    t /= Cin;
+    const int co = t % Cout;
+    t /= Cout;
+    const int j = t % 3;
+    t /= 3;
+    const int dy = t % 3;
+    t /= 3;
+    const int dx = t % 3;
+    const int r = t / 3;
+    const int dz = (r + 1 - j + 3) % 3;
+    p[i] = __float2bfloat16_rn(w[((size_t)co * Cin + ci) * 27 + dz * 9 + dy * 3 + dx]);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled zf_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+inline uint32_t zf_round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" int km_sm_count(void);
+
+extern "C" int km_conv3d_zfold_supported(int Cin, int Cout, int D, int H, int W) {
+  return (Cin == kKC && Cout == kCout && W >= 8 && H >= 16 && D >= 1) ? 1 : 0;
+}
+
+extern "C" size_t km_pack_weights_zfold_bytes(int Cout, int Cin) {
+  return (size_t)27 * 3 * Cout * Cin * 2;
+}
+
+extern "C" int km_pack_weights_zfold(const float* w, void* packed, int Cout, int Cin, km_stream_t stream) {
+  KM_CHECK_ARG(w && packed && Cout == kCout && Cin == kKC, "km_pack_weights_zfold: needs Cin=%d, Cout=%d", kKC, kCout);
+  pack_weights_zf_kernel<<<64, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
+  KM_LAUNCH_OK("pack_weights_zf_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_conv3d_zfold(const void* x, const void* wz, void* out, float* stats, int N, int Cin,
+                               int Cout, int D, int H, int W, int flags, km_stream_t stream) {
+  KM_CHECK_ARG(x && wz && out, "km_conv3d_zfold: null argument");
+  KM_CHECK_ARG(km_conv3d_zfold_supported(Cin, Cout, D, H, W), "km_conv3d_zfold: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
+  KM_CHECK_ARG(N > 0, "km_conv3d_zfold: bad batch");
+  KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "km_conv3d_zfold: KM_CONV_STATS needs stats");
+  KM_CHECK_ARG(!(flags & KM_CONV_COM), "km_conv3d_zfold: KM_CONV_COM is not supported");
+  KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wz & 15) == 0 && ((uintptr_t)out & 15) == 0,
+               "km_conv3d_zfold: pointers must be 16-byte aligned");
+  ZfGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = N; g.D = D; g.H = H; g.W = W;
+  g.flags = flags;
+  g.tiles_x = (W + 7) / 8;
+  g.tiles_y = (H + 16 * kMT - 1) / (16 * kMT);
+  g.zsegs = (D + kLZ - 1) / kLZ;
+  const long long units = (long long)N * g.zsegs * g.tiles_y * g.tiles_x;
+  KM_CHECK_ARG(units < (1ll << 30), "km_conv3d_zfold: too many units");
+  g.units = (int)units;
+  g.stat_parts = kEpiThreads / kCout;
+  const uint32_t stats_bytes = (flags & KM_CONV_STATS) ? (uint32_t)g.stat_parts * N * kCout * 2u * 4u : 0u;
+  uint32_t off = (uint32_t)kStages * kAStage;
+  g.off_b = off; off += kBBytes;
+  g.off_staging = off; off += zf_round_up((uint32_t)kMT * 128u * kStagePitch, 16);
+  g.off_rowvalid = off; off += kMT * 128;
+  g.off_stats = off; off += stats_bytes;
+  off = zf_round_up(off, 8);
+  g.off_bars = off; off += 8u * (2u * kStages + 6u) + 16u;
+  const uint32_t smem_bytes = off + 1024;
+  KM_CHECK_ARG(smem_bytes <= 232448, "km_conv3d_zfold: shared memory overflow (%u; batch too large)", smem_bytes);
+
+  PFN_encodeTiled encode = zf_encode_fn();
+  if (!encode) {
+    km_set_error("km_conv3d_zfold: cuTensorMapEncodeTiled unavailable");
+    return KM_ECUDA;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
+                             (cuuint64_t)D * H * W * Cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)kKC, 8, (cuuint32_t)(16 * kMT + 2), 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      km_set_error("km_conv3d_zfold: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+      return KM_ECUDA;
+    }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)kN3, 27};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)kN3 * Cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kKC, (cuuint32_t)kN3, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wz), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      km_set_error("km_conv3d_zfold: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+      return KM_ECUDA;
+    }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  const int nsm = km_sm_count();
+  const int grid = g.units < nsm ? g.units : nsm;
+  if (grid < nsm && (flags & KM_CONV_STATS))
+    KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * kCout * 2 * sizeof(float), km_cs(stream)));
+  conv_zf_kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
+                                                               stats);
+  KM_LAUNCH_OK("conv_zf_kernel");
+  return KM_OK;
+}

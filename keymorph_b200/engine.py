@@ -50,7 +50,7 @@ class _WeightCache:
     def __init__(self):
         self._packed = {}
 
-    def get(self, key, param, pad_out_to=None):
+    def get(self, key, param, pad_out_to=None, zfold=False):
         sig = (param.data_ptr(), param._version, str(param.device), tuple(param.shape), pad_out_to)
         hit = self._packed.get(key)
         if hit is not None and hit[0] == sig:
@@ -59,7 +59,7 @@ class _WeightCache:
         if pad_out_to is not None and w.shape[0] % pad_out_to:
             extra = pad_out_to - w.shape[0] % pad_out_to
             w = torch.cat([w, w.new_zeros((extra,) + tuple(w.shape[1:]))], 0)
-        packed = ops.pack_weights(w)
+        packed = ops.pack_weights_zfold(w) if zfold else ops.pack_weights(w)
         self._packed[key] = (sig, packed)
         return packed
 
@@ -103,8 +103,14 @@ class _EngineBase:
 
 class UNetEngine(_EngineBase):
     def _single_conv(self, key, sc_mod, x_norm):
-        wp = self.weights.get(key, sc_mod.conv.weight)
-        out, stats, _ = ops.conv3d_tc(x_norm, wp, relu=True, want_stats=True)
+        w = sc_mod.conv.weight
+        _, D, H, W, Cin = x_norm.shape
+        if ops.zfold_supported(Cin, w.shape[0], D, H, W):
+            # first tensor-core layer (16 -> 32 at full resolution): dz taps folded into MMA N
+            out, stats = ops.conv3d_zfold(x_norm, self.weights.get(key + ".zf", w, zfold=True),
+                                          relu=True, want_stats=True)
+        else:
+            out, stats, _ = ops.conv3d_tc(x_norm, self.weights.get(key, w), relu=True, want_stats=True)
         self._dbg(key, out)
         return out, stats
 

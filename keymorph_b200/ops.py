@@ -281,6 +281,38 @@ def conv3d_tc(x, wp, bias=None, relu=False, want_stats=False, want_com=False, st
     return out, stats, com
 
 
+def zfold_supported(Cin, Cout, D, H, W):
+    return bool(_lib.query("km_conv3d_zfold_supported", Cin, Cout, D, H, W))
+
+
+def pack_weights_zfold(w):
+    """fp32 (Cout,Cin,3,3,3) -> bf16 (3 rotations, 9 (dx,dy), 3*Cout, Cin) for conv3d_zfold."""
+    _need_cuda(w)
+    w = _f32c(w)
+    Cout, Cin = w.shape[0], w.shape[1]
+    out = torch.empty((3, 9, 3 * Cout, Cin), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.call("km_pack_weights_zfold", _ptr(w), _ptr(out), Cout, Cin, _stream())
+    return out
+
+
+def conv3d_zfold(x, wz, relu=False, want_stats=False):
+    """z-folded tcgen05 conv (Cin=16 -> Cout=32, 3x3x3, pad 1).  x: bf16 (N,D,H,W,16)."""
+    _need_cuda(x, wz)
+    assert x.dtype == torch.bfloat16 and wz.dtype == torch.bfloat16
+    x, wz = x.contiguous(), wz.contiguous()
+    N, D, H, W, Cin = x.shape
+    Cout = wz.shape[2] // 3
+    flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
+    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x.device) \
+        if want_stats else None
+    with torch.cuda.device(x.device):
+        _lib.call("km_conv3d_zfold", _ptr(x), _ptr(wz), _ptr(out), _ptr(stats), N, Cin, Cout, D, H, W,
+                  flags, _stream())
+    return out, stats
+
+
 def conv1x1_com(x, wp, bias=None):
     """Final 1x1x1 conv + ReLU + centre-of-mass partials without the heat map.
     x: bf16 (N,D,H,W,Cin); wp: bf16 (1,Cout,Cin) with Cout % 128 == 0 -> com (nparts,N,Cout,4)."""

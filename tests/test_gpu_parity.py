@@ -155,6 +155,30 @@ def test_com_golden_and_empty_channels(golden):
     assert_close(kb.CenterOfMass3d("ij")(cu(neg)).cpu(), O.center_of_mass3d(neg))
 
 
+@pytest.mark.parametrize("shape", [(1, 32, 32, 32), (2, 70, 40, 24), (1, 5, 16, 8), (1, 130, 17, 9)])
+def test_conv3d_zfold_vs_general_kernel_and_fp32(shape):
+    """km_conv3d_zfold (dz taps folded into MMA N, output planes as a TMEM ring along z) against
+    km_conv3d_tc and the fp32 conv of the same bf16-rounded operands.  Shapes cover two z segments
+    (D > 64), partial bricks in x / y, odd sizes and a volume shallower than the ring."""
+    import torch.nn.functional as F
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(N, 16, D, H, W, generator=g)
+    w = torch.randn(32, 16, 3, 3, 3, generator=g) / (27 * 16) ** 0.5
+    xb = ops.ncdhw_to_ndhwc(cu(x))
+    assert ops.zfold_supported(16, 32, D, H, W)
+    out, st = ops.conv3d_zfold(xb, ops.pack_weights_zfold(cu(w)), relu=True, want_stats=True)
+    out2, st2, _ = ops.conv3d_tc(xb, ops.pack_weights(cu(w)), relu=True, want_stats=True)
+    a, b = ops.ndhwc_to_ncdhw(out).cpu(), ops.ndhwc_to_ncdhw(out2).cpu()
+    ref = F.relu(F.conv3d(ops.ndhwc_to_ncdhw(xb).cpu().double(), w.bfloat16().double(), padding=1)).float()
+    assert_close(a, ref, rtol=1e-2, atol=1e-2)            # bf16 storage of the result
+    assert_close(a, b, rtol=1e-2, atol=1e-2)              # fp32 accumulation order differs
+    assert (a - b).abs().mean().item() < 1e-4
+    assert_close(st.double().sum(0).cpu(), st2.double().sum(0).cpu(), rtol=1e-3, atol=0.5)
+    s_ref = torch.stack([a.double().flatten(2).sum(-1), (a.double() ** 2).flatten(2).sum(-1)], -1)
+    assert_close(st.double().sum(0).cpu(), s_ref, rtol=1e-4, atol=1e-2)   # stats of the stored values
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 200, 32, 32, 32), (1, 32, 130, 5, 6, 20), (1, 16, 70, 3, 9, 48),
                                    (2, 128, 512, 8, 16, 16), (1, 64, 256, 64, 64, 64)])
 def test_conv1x1_com_transposed_vs_fp32(shape):

@@ -37,3 +37,17 @@ for name, cin, cout, e in LAYERS:
     print(f"{name:8s} {cin:4d}->{cout:4d} @{e:3d}^3 x{N}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s", flush=True)
     del x
 print(f"total {tot:.1f} us")
+# the z-folded kernel on the first tensor-core layer
+x = torch.randn(N, S, S, S, 16, device="cuda").bfloat16()
+wz = ops.pack_weights_zfold(torch.randn(32, 16, 3, 3, 3, device="cuda") / (27 * 16) ** 0.5)
+for _ in range(2):
+    ops.conv3d_zfold(x, wz, relu=True, want_stats=True)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    ops.conv3d_zfold(x, wz, relu=True, want_stats=True)
+e1.record()
+torch.cuda.synchronize()
+us = e0.elapsed_time(e1) / 5 * 1e3
+print(f"enc0.c2 z-folded: {us:8.1f} us  {2.0 * 27 * 16 * 32 * S ** 3 * N / us / 1e6:7.1f} TFLOP/s")
