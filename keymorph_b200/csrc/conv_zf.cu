@@ -44,15 +44,14 @@ constexpr uint32_t kASub = 9216;        // 272 rows x 32 B = 8704, rounded up to
 constexpr uint32_t kAStage = 3 * kASub; // one plane: dx = 0, 1, 2
 constexpr uint32_t kBTile = kN3 * kRowBytes;          // 3072 B
 constexpr uint32_t kBBytes = 27 * kBTile;             // [r][dx][dy] = 82944 B
-constexpr int kStages = 4;
+constexpr int kStages = 5;
 constexpr int kLZ = 64;                 // z planes per unit
-constexpr uint32_t kStagePitch = kCout * 2 + 16;      // staged output row (bf16) + pad
 
 struct ZfGeom {
   int N, D, H, W;
   int tiles_x, tiles_y, zsegs, units;
   int flags;
-  uint32_t off_b, off_staging, off_rowvalid, off_stats, off_bars;
+  uint32_t off_b, off_staging, off_stats, off_bars;
   int stat_parts;
 };
 
@@ -150,7 +149,7 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   {
     float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);
     if (g.flags & KM_CONV_STATS)
-      for (int i = threadIdx.x; i < g.stat_parts * g.N * kCout * 2; i += kThreads) s_stats[i] = 0.f;
+      for (int i = threadIdx.x; i < g.N * kCout * 2; i += kThreads) s_stats[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -220,41 +219,66 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     });
   } else {
     // =============================== epilogue (8 warps) ==========================
+    // A thread owns one voxel row of each brick (TMEM lane) and 16 of the 32 output channels.
+    // Nothing is staged: the bf16 row piece (32 B = one full sector) goes straight to global
+    // memory, and the GroupNorm statistics of the stored values are accumulated per thread in
+    // registers over all tiles of an image; they are reduced across the CTA only when the image
+    // changes (fixed order: shuffles, then the four warps of a column half one after the other).
     const int q = warp & 3;               // TMEM lane quadrant
     const int row = q * 32 + lane;        // voxel within a brick: tx = row & 7, ty = row >> 3
     const int half = (warp - 2) >> 2;     // column half [16 half, 16 half + 16)
     const int et = half * 128 + row;
-    uint8_t* staging = sm + g.off_staging;
-    uint8_t* rowvalid = sm + g.off_rowvalid;   // [kMT][128]
-    float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);
+    float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);     // [N][Cout][2]
+    float* s_wred = reinterpret_cast<float*>(sm + g.off_staging);    // [8 warps][32] flush scratch
     const bool do_relu = (g.flags & KM_CONV_RELU) != 0;
     const bool do_stats = (g.flags & KM_CONV_STATS) != 0;
-    const int parts = g.stat_parts, rows_per_part = 128 / parts;
     auto all_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     const int tx = row & 7, ty = row >> 3;
+    float ssum[16], ssq[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ssum[j] = ssq[j] = 0.f;
+    int n_cur = -1;
+    auto flush_stats = [&](int n) {
+      // per-thread sums -> s_stats[n][half*16 + j][2]
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float a = km_warp_sum(ssum[j]), b = km_warp_sum(ssq[j]);
+        if (lane == 0) {
+          s_wred[(warp - 2) * 32 + 2 * j] = a;
+          s_wred[(warp - 2) * 32 + 2 * j + 1] = b;
+        }
+        ssum[j] = ssq[j] = 0.f;
+      }
+      all_bar();
+      if (et < 64) {   // thread -> (column half h, column j, sum | sumsq)
+        const int h = et >> 5, i = et & 31;
+        float a = 0.f;
+        for (int w4 = 0; w4 < 4; ++w4) a += s_wred[(h * 4 + w4) * 32 + i];
+        s_stats[((size_t)n * kCout + h * 16 + (i >> 1)) * 2 + (i & 1)] += a;
+      }
+      all_bar();
+    };
 
     for_each_tile(g, [&](uint32_t set, const Unit& u, int p, uint32_t cnt) {
       const int zo = u.zs - 2 + p;                   // the output plane completed by this tile
       const bool store = p >= 2 && zo < g.D;         // (zo >= zs by construction)
       const uint32_t slot = (uint32_t)((p + 2) % 3);
+      if (do_stats && u.n != n_cur) {                // CTA-uniform: the tile sequence is shared
+        if (n_cur >= 0) flush_stats(n_cur);
+        n_cur = u.n;
+      }
       mbar_wait(tfull_bar(set), cnt & 1u);
       tc_fence_after();
-      uint32_t vmask = 0;
-#pragma unroll
-      for (int m = 0; m < kMT; ++m) {
-        const bool v = (u.x0 + tx < g.W) && (u.y0 + 16 * m + ty < g.H);
-        vmask |= (v ? 1u : 0u) << m;
-        if (store && half == 0) rowvalid[m * 128 + row] = v ? 1 : 0;
-      }
 #pragma unroll
       for (int m = 0; m < kMT; ++m) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256u + (uint32_t)m * kN3 +
                                slot * kCout + (uint32_t)half * 16u;
-        if (store) {
+        const int x2 = u.x0 + tx, y2 = u.y0 + 16 * m + ty;
+        if (store) {   // warp-uniform: tcgen05.ld is a warp-collective operation
           uint32_t r[16];
           tmem_ld16(taddr, r);
           tmem_ld_wait();
-          const bool vrow = ((vmask >> m) & 1u) != 0;
+          if (x2 < g.W && y2 < g.H) {
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -263,63 +287,32 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               a = fmaxf(a, 0.f);
               b = fmaxf(b, 0.f);
             }
-            pk[j] = vrow ? pack_bf16(a, b) : 0u;   // rows outside the volume: zeros (stats need no mask)
+            pk[j] = pack_bf16(a, b);
+            if (do_stats) {   // statistics of the values actually stored (bf16-rounded)
+              const float ar = __uint_as_float(pk[j] << 16), br = __uint_as_float(pk[j] & 0xffff0000u);
+              ssum[2 * j] += ar;
+              ssq[2 * j] = fmaf(ar, ar, ssq[2 * j]);
+              ssum[2 * j + 1] += br;
+              ssq[2 * j + 1] = fmaf(br, br, ssq[2 * j + 1]);
+            }
           }
-          uint4* dst = reinterpret_cast<uint4*>(staging + (size_t)(m * 128 + row) * kStagePitch + half * 32);
+          const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
+          uint4* dst = reinterpret_cast<uint4*>(out + vox * kCout + half * 16);
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
         }
         tmem_st16_zero(taddr);   // the drained block becomes the fresh output plane z' + 2
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(tempty_bar(set));
-      if (store) {
-        all_bar();
-        // staged bf16 rows -> global (coalesced 16-byte chunks)
-        constexpr int cpr = kCout / 8;
-        for (int id = et; id < kMT * 128 * cpr; id += kEpiThreads) {
-          const int j = id % cpr, rr = id / cpr;
-          const int mb = rr >> 7, r2 = rr & 127;
-          if (!rowvalid[mb * 128 + r2]) continue;
-          const int x2 = u.x0 + (r2 & 7), y2 = u.y0 + 16 * mb + (r2 >> 3);
-          const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
-          *reinterpret_cast<uint4*>(out + vox * kCout + j * 8) =
-              *reinterpret_cast<const uint4*>(staging + (size_t)(mb * 128 + r2) * kStagePitch + j * 16);
-        }
-        if (do_stats) {
-          for (int id = et; id < parts * kCout; id += kEpiThreads) {
-            const int col = id % kCout, part = id / kCout;
-            float s = 0.f, ss = 0.f;
-#pragma unroll
-            for (int mb = 0; mb < kMT; ++mb) {
-              const uint8_t* pp = staging + (size_t)(mb * 128 + part * rows_per_part) * kStagePitch + (size_t)col * 2;
-#pragma unroll 8
-              for (int rr = 0; rr < rows_per_part; ++rr) {
-                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(pp));
-                pp += kStagePitch;
-                s += v;
-                ss = fmaf(v, v, ss);
-              }
-            }
-            float* d = s_stats + (((size_t)part * g.N + u.n) * kCout + col) * 2;
-            d[0] += s;
-            d[1] += ss;
-          }
-        }
-        all_bar();   // staging / rowvalid may be overwritten by the next tile
-      }
     });
 
-    all_bar();
     if (do_stats) {
+      if (n_cur >= 0) flush_stats(n_cur);
       float* dst = stats + (size_t)blockIdx.x * g.N * kCout * 2;
-      const int n = g.N * kCout * 2;
-      for (int i = et; i < n; i += kEpiThreads) {
-        float a = 0.f;
-        for (int pp = 0; pp < parts; ++pp) a += s_stats[(size_t)pp * n + i];
-        dst[i] = a;
-      }
+      for (int i = et; i < g.N * kCout * 2; i += kEpiThreads) dst[i] = s_stats[i];
     }
   }
 
@@ -407,12 +400,11 @@ extern "C" int km_conv3d_zfold(const void* x, const void* wz, void* out, float* 
   const long long units = (long long)N * g.zsegs * g.tiles_y * g.tiles_x;
   KM_CHECK_ARG(units < (1ll << 30), "km_conv3d_zfold: too many units");
   g.units = (int)units;
-  g.stat_parts = kEpiThreads / kCout;
-  const uint32_t stats_bytes = (flags & KM_CONV_STATS) ? (uint32_t)g.stat_parts * N * kCout * 2u * 4u : 0u;
+  g.stat_parts = 1;
+  const uint32_t stats_bytes = (flags & KM_CONV_STATS) ? (uint32_t)N * kCout * 2u * 4u : 0u;
   uint32_t off = (uint32_t)kStages * kAStage;
   g.off_b = off; off += kBBytes;
-  g.off_staging = off; off += zf_round_up((uint32_t)kMT * 128u * kStagePitch, 16);
-  g.off_rowvalid = off; off += kMT * 128;
+  g.off_staging = off; off += 8u * 32u * 4u;   // per-warp scratch of the statistics flush
   g.off_stats = off; off += stats_bytes;
   off = zf_round_up(off, 8);
   g.off_bars = off; off += 8u * (2u * kStages + 6u) + 16u;
