@@ -246,12 +246,15 @@ int km_conv3d_tc(const void* x, const void* wp, const float* bias, void* out, fl
  * folded into the MMA N dimension and the output planes live as a rotating ring in TMEM while the
  * CTA walks along z (csrc/conv_zf.cu).  Same tensors / flags / stats as km_conv3d_tc (KM_CONV_RELU,
  * KM_CONV_STATS); wz comes from km_pack_weights_zfold (fp32 (Cout,Cin,3,3,3) -> bf16
- * [rotation][dx][dy][3*Cout][Cin], km_pack_weights_zfold_bytes bytes). */
+ * [rotation][dx][dy][3*Cout][Cin], km_pack_weights_zfold_bytes bytes).
+ * pooled (N,D/2,H/2,W/2,Cout), may be NULL: MaxPool3d(2) of the activated output
+ * (keymorph/unet3d/buildingblocks.py:363,387) taken in the epilogue's registers; `stats` then describe
+ * the POOLED tensor and `out` may be NULL (the truncated UNet never reads the full-resolution map). */
 int km_conv3d_zfold_supported(int Cin, int Cout, int D, int H, int W);
 size_t km_pack_weights_zfold_bytes(int Cout, int Cin);
 int km_pack_weights_zfold(const float* w, void* packed, int Cout, int Cin, km_stream_t stream);
-int km_conv3d_zfold(const void* x, const void* wz, void* out, float* stats, int N, int Cin, int Cout,
-                    int D, int H, int W, int flags, km_stream_t stream);
+int km_conv3d_zfold(const void* x, const void* wz, void* out, void* pooled, float* stats, int N, int Cin,
+                    int Cout, int D, int H, int W, int flags, km_stream_t stream);
 
 /* Final 1x1x1 convolution fused with ReLU + centre of mass, transposed tcgen05 formulation
  * (keymorph/unet3d/model.py:99,389 final_conv + keymorph/layers.py:92-134 + keymorph/model.py:95-109):

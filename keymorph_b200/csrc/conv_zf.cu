@@ -25,6 +25,7 @@
 // units plane by plane (TMEM sets 0 / 1) so that the epilogue of one overlaps the MMAs of the other.
 // Roles (320 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
 // warps 2..9 = epilogue.
+#include <type_traits>
 #include "km_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -86,8 +87,8 @@ __device__ __forceinline__ void for_each_tile(const ZfGeom& g, F&& fn) {
     if (ub < g.units) b = decode_unit(g, ub);
     const int pmax = max(a.planes, b.planes);
     for (int p = 0; p < pmax; ++p) {
-      if (p < a.planes) fn(0u, a, p, cnt[0]++);
-      if (p < b.planes) fn(1u, b, p, cnt[1]++);
+      if (p < a.planes) fn(std::integral_constant<uint32_t, 0u>{}, a, p, cnt[0]++);
+      if (p < b.planes) fn(std::integral_constant<uint32_t, 1u>{}, b, p, cnt[1]++);
     }
   }
 }
@@ -103,6 +104,16 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a),
+                                   *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -110,7 +121,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const ZfGeom g, __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
+               const ZfGeom g, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
+               float* __restrict__ stats) {
   constexpr uint32_t kLayout = 6u;                 // SWIZZLE_32B
   constexpr uint32_t kSbo = 8u * kRowBytes;        // 256 B between 8-row groups
   extern __shared__ uint8_t smem_raw[];
@@ -163,7 +175,7 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = 0; t < 27; ++t) tma_load_3d(base + g.off_b + (uint32_t)t * kBTile, &tmB, w_bar, 0, 0, t);
       int s = 0;
       uint32_t ph = 0;
-      for_each_tile(g, [&](uint32_t, const Unit& u, int p, uint32_t) {
+      for_each_tile(g, [&](auto, const Unit& u, int p, uint32_t) {
         const int z = u.zs - 1 + p;   // input plane; outside [0, D) -> TMA zero fill
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_arrive_expect_tx(full_bar(s), 3u * (uint32_t)(kBoxRows * kRowBytes));
@@ -188,7 +200,8 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int s = 0;
     uint32_t ph = 0;
     mbar_wait(w_bar, 0u);
-    for_each_tile(g, [&](uint32_t set, const Unit&, int p, uint32_t cnt) {
+    for_each_tile(g, [&](auto set_c, const Unit&, int p, uint32_t cnt) {
+      constexpr uint32_t set = decltype(set_c)::value;
       mbar_wait(tempty_bar(set), (cnt & 1u) ^ 1u);   // previous plane of this set drained + zeroed
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
@@ -237,6 +250,13 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float ssum[16], ssq[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) ssum[j] = ssq[j] = 0.f;
+    uint32_t zprev[2][kMT][8];   // xy-pooled even plane of each unit in flight (pool mode)
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int m = 0; m < kMT; ++m)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zprev[a][m][j] = 0u;
     int n_cur = -1;
     auto flush_stats = [&](int n) {
       // per-thread sums -> s_stats[n][half*16 + j][2]
@@ -259,7 +279,8 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       all_bar();
     };
 
-    for_each_tile(g, [&](uint32_t set, const Unit& u, int p, uint32_t cnt) {
+    for_each_tile(g, [&](auto set_c, const Unit& u, int p, uint32_t cnt) {
+      constexpr uint32_t set = decltype(set_c)::value;
       const int zo = u.zs - 2 + p;                   // the output plane completed by this tile
       const bool store = p >= 2 && zo < g.D;         // (zo >= zs by construction)
       const uint32_t slot = (uint32_t)((p + 2) % 3);
@@ -278,7 +299,6 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t r[16];
           tmem_ld16(taddr, r);
           tmem_ld_wait();
-          if (x2 < g.W && y2 < g.H) {
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -288,18 +308,47 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               b = fmaxf(b, 0.f);
             }
             pk[j] = pack_bf16(a, b);
-            if (do_stats) {   // statistics of the values actually stored (bf16-rounded)
+          }
+          const bool inside = x2 < g.W && y2 < g.H;
+          if (out && inside) {
+            // one 256-bit store = one full 32-byte sector per lane (two 16-byte stores would be two
+            // half-sector requests on the L1 -> crossbar path, which then bounds the kernel)
+            const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
+            st_global_v8(out + vox * kCout + half * 16, pk);
+          }
+          bool acc_stats = inside && !pooled;
+          if (pooled) {
+            // MaxPool3d(2) (keymorph/unet3d/buildingblocks.py:363,387) in registers: x / y
+            // neighbours are lanes ^1 / ^8 of the same warp, the z neighbour is the previous plane
+            // of this unit (kept per TMEM set); max commutes with the bf16 rounding
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              pk[j] = hmax2_u32(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
+              pk[j] = hmax2_u32(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 8));
+            }
+            if ((zo & 1) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) zprev[set][m][j] = pk[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pk[j] = hmax2_u32(pk[j], zprev[set][m][j]);
+              const int xp = x2 >> 1, yp = y2 >> 1, zp = zo >> 1;
+              if (((tx | ty) & 1) == 0 && xp < (g.W >> 1) && yp < (g.H >> 1)) {
+                const size_t vox = (((size_t)u.n * (g.D >> 1) + zp) * (g.H >> 1) + yp) * (g.W >> 1) + xp;
+                st_global_v8(pooled + vox * kCout + half * 16, pk);
+                acc_stats = true;   // statistics of the pooled map (what the next GroupNorm needs)
+              }
+            }
+          }
+          if (do_stats && acc_stats) {   // statistics of the values actually stored (bf16-rounded)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
               const float ar = __uint_as_float(pk[j] << 16), br = __uint_as_float(pk[j] & 0xffff0000u);
               ssum[2 * j] += ar;
               ssq[2 * j] = fmaf(ar, ar, ssq[2 * j]);
               ssum[2 * j + 1] += br;
               ssq[2 * j + 1] = fmaf(br, br, ssq[2 * j + 1]);
             }
-          }
-          const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
-          uint4* dst = reinterpret_cast<uint4*>(out + vox * kCout + half * 16);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
         tmem_st16_zero(taddr);   // the drained block becomes the fresh output plane z' + 2
@@ -381,9 +430,13 @@ extern "C" int km_pack_weights_zfold(const float* w, void* packed, int Cout, int
   return KM_OK;
 }
 
-extern "C" int km_conv3d_zfold(const void* x, const void* wz, void* out, float* stats, int N, int Cin,
-                               int Cout, int D, int H, int W, int flags, km_stream_t stream) {
-  KM_CHECK_ARG(x && wz && out, "km_conv3d_zfold: null argument");
+extern "C" int km_conv3d_zfold(const void* x, const void* wz, void* out, void* pooled, float* stats,
+                               int N, int Cin, int Cout, int D, int H, int W, int flags,
+                               km_stream_t stream) {
+  KM_CHECK_ARG(x && wz && (out || pooled), "km_conv3d_zfold: null argument");
+  KM_CHECK_ARG(!pooled || (D >= 2 && H >= 2 && W >= 2), "km_conv3d_zfold: volume too small to pool");
+  KM_CHECK_ARG(((uintptr_t)pooled & 31) == 0 && ((uintptr_t)out & 31) == 0,
+               "km_conv3d_zfold: outputs must be 32-byte aligned");
   KM_CHECK_ARG(km_conv3d_zfold_supported(Cin, Cout, D, H, W), "km_conv3d_zfold: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
   KM_CHECK_ARG(N > 0, "km_conv3d_zfold: bad batch");
   KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "km_conv3d_zfold: KM_CONV_STATS needs stats");
@@ -454,7 +507,7 @@ extern "C" int km_conv3d_zfold(const void* x, const void* wz, void* out, float* 
   if (grid < nsm && (flags & KM_CONV_STATS))
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * kCout * 2 * sizeof(float), km_cs(stream)));
   conv_zf_kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
-                                                               stats);
+                                                               reinterpret_cast<__nv_bfloat16*>(pooled), stats);
   KM_LAUNCH_OK("conv_zf_kernel");
   return KM_OK;
 }

@@ -141,13 +141,29 @@ class UNetEngine(_EngineBase):
                                                  want_stats=False)[0])
         a, _ = ops.conv3d_stem(x, w0, None, in_sc, in_sh, scale, shift, relu_pre=True,
                                want_stats=False)
-        cur, cur_st = self._single_conv("enc0.c2", sc1, a)
+        # the truncated net never consumes the first encoder's full-resolution output as a skip:
+        # then the z-folded kernel pools in its epilogue and the 32-channel full-resolution map
+        # (2.1 GB for a 256^3 pair) is never written
+        need_full0 = len(m.decoders) >= len(enc) - 1 or self.debug is not None or len(enc) < 2
+        pooled0 = None
+        w1 = sc1.conv.weight
+        if not need_full0 and ops.zfold_supported(a.shape[-1], w1.shape[0], D, H, W) \
+                and min(D, H, W) >= 2:
+            _, p0, st0 = ops.conv3d_zfold(a, self.weights.get("enc0.c2.zf", w1, zfold=True), relu=True,
+                                          want_stats=True, pool=True, store=False)
+            pooled0 = (p0, st0)
+            cur = cur_st = None
+        else:
+            cur, cur_st = self._single_conv("enc0.c2", sc1, a)
         del a
         feats = [(cur, cur_st)]
         # ---- encoders 1..L-1: pool -> (GN, conv) x 2
         for i in range(1, len(enc)):
             dc = enc[i].basic_module
-            p, st = ops.maxpool2_stats(cur)
+            if i == 1 and pooled0 is not None:
+                p, st = pooled0
+            else:
+                p, st = ops.maxpool2_stats(cur)
             g = dc.SingleConv1.groupnorm
             scale, shift = ops.norm_finalize(st, nvox(p), g.weight, g.bias, g.num_groups, g.eps)
             p = ops.norm_apply(p, scale, shift, out=p)

@@ -296,21 +296,25 @@ def pack_weights_zfold(w):
     return out
 
 
-def conv3d_zfold(x, wz, relu=False, want_stats=False):
-    """z-folded tcgen05 conv (Cin=16 -> Cout=32, 3x3x3, pad 1).  x: bf16 (N,D,H,W,16)."""
+def conv3d_zfold(x, wz, relu=False, want_stats=False, pool=False, store=True):
+    """z-folded tcgen05 conv (Cin=16 -> Cout=32, 3x3x3, pad 1).  x: bf16 (N,D,H,W,16).
+    Returns (out | None, stats | None) or, with pool=True, (out | None, pooled, stats | None) where
+    pooled = MaxPool3d(2)(out) and the stats describe the pooled tensor."""
     _need_cuda(x, wz)
     assert x.dtype == torch.bfloat16 and wz.dtype == torch.bfloat16
     x, wz = x.contiguous(), wz.contiguous()
     N, D, H, W, Cin = x.shape
     Cout = wz.shape[2] // 3
     flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
-    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device) if store else None
+    pooled = torch.empty((N, D // 2, H // 2, W // 2, Cout), dtype=torch.bfloat16, device=x.device) \
+        if pool else None
     stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x.device) \
         if want_stats else None
     with torch.cuda.device(x.device):
-        _lib.call("km_conv3d_zfold", _ptr(x), _ptr(wz), _ptr(out), _ptr(stats), N, Cin, Cout, D, H, W,
-                  flags, _stream())
-    return out, stats
+        _lib.call("km_conv3d_zfold", _ptr(x), _ptr(wz), _ptr(out), _ptr(pooled), _ptr(stats), N, Cin,
+                  Cout, D, H, W, flags, _stream())
+    return (out, pooled, stats) if pool else (out, stats)
 
 
 def conv1x1_com(x, wp, bias=None):

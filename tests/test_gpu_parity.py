@@ -177,6 +177,17 @@ def test_conv3d_zfold_vs_general_kernel_and_fp32(shape):
     assert_close(st.double().sum(0).cpu(), st2.double().sum(0).cpu(), rtol=1e-3, atol=0.5)
     s_ref = torch.stack([a.double().flatten(2).sum(-1), (a.double() ** 2).flatten(2).sum(-1)], -1)
     assert_close(st.double().sum(0).cpu(), s_ref, rtol=1e-4, atol=1e-2)   # stats of the stored values
+    if min(D, H, W) >= 2:
+        # MaxPool3d(2) fused into the epilogue: bit-identical to pooling the stored map, with or
+        # without the full-resolution store; the statistics then describe the pooled tensor
+        full, pooled, stp = ops.conv3d_zfold(xb, ops.pack_weights_zfold(cu(w)), relu=True, want_stats=True, pool=True)
+        none, pooled2, _ = ops.conv3d_zfold(xb, ops.pack_weights_zfold(cu(w)), relu=True, want_stats=True, pool=True,
+                                            store=False)
+        assert none is None and torch.equal(full, out) and torch.equal(pooled, pooled2)
+        pref = F.max_pool3d(a, 2)
+        assert torch.equal(ops.ndhwc_to_ncdhw(pooled).cpu(), pref)
+        sp_ref = torch.stack([pref.double().flatten(2).sum(-1), (pref.double() ** 2).flatten(2).sum(-1)], -1)
+        assert_close(stp.double().sum(0).cpu(), sp_ref, rtol=1e-4, atol=1e-2)
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 200, 32, 32, 32), (1, 32, 130, 5, 6, 20), (1, 16, 70, 3, 9, 48),
