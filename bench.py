@@ -32,6 +32,9 @@ WORKLOAD = "synthetic 256^3 pair, affine, 256 keypoints, TruncatedUNet3D(levels 
 METRIC = "pairwise 256^3 registrations/sec"
 UNIT = "registrations/s"
 CPU_SLAB = 64      # the CPU arm times a 64x256x256 slab of each volume and scales by 256/64
+# dram__bytes_read.sum + dram__bytes_write.sum per step from the ncu capture of this workload
+# (profiles/r01_s2_ncu_dram_traffic.txt); filled in by hand after each profiling pass
+NCU_TRAFFIC = {}
 
 
 def conv_layers(S, K, n_img):
@@ -193,8 +196,9 @@ def run_engine(args):
         step(img_f, img_m)
     sync_all()
 
-    # tracer: CUDA events around the two kernels whose rooflines are reported
-    traced = {"km_conv3d_tc": [], "km_warp_loss": []}
+    # tracer: CUDA events around the kernels whose rooflines are reported
+    traced = {"km_conv3d_tc": [], "km_conv3d_zfold": [], "km_conv1x1_com": [], "km_conv3d_stem": [],
+              "km_warp_loss": []}
     stream = torch.cuda.current_stream()
     pending = {}
 
@@ -226,19 +230,46 @@ def run_engine(args):
     ms_step_max = t.item()
     value = world * 1e3 / ms_step_max
 
-    # roofline of the dominant kernel (tcgen05 conv): algorithmic FLOPs of the tensor-core layers
-    # of one step / summed duration of their launches in one step
+    # roofline of the dominant kernel (conv_tc_kernel, the general tcgen05 3x3x3 convolution): algorithmic
+    # FLOPs of the layers it runs in one step / summed duration of its launches in one step.  The
+    # other tensor-core kernels of the backbone are reported next to it with the same definition.
     hbm_peak, tc_peak, peak_src = measured_peaks()
-    conv_ms = sum(a.elapsed_time(b) for a, b in traced["km_conv3d_tc"]) / args.steps
-    warp_ms = sum(a.elapsed_time(b) for a, b in traced["km_warp_loss"]) / args.steps
-    layers = conv_layers(S, K, 2)
-    tc_flops = sum(l[5] for l in layers if l[0] != "enc0.c1")
+
+    def per_step_ms(name):
+        return sum(a.elapsed_time(b) for a, b in traced[name]) / args.steps
+
+    conv_ms, zf_ms, com_ms = per_step_ms("km_conv3d_tc"), per_step_ms("km_conv3d_zfold"), per_step_ms("km_conv1x1_com")
+    stem_ms, warp_ms = per_step_ms("km_conv3d_stem"), per_step_ms("km_warp_loss")
+    layers = {l[0]: l[5] for l in conv_layers(S, K, 2)}
+    zf_flops = layers["enc0.c2"] if zf_ms > 0 else 0.0
+    com_flops = layers["final"] if com_ms > 0 else 0.0
+    tc_flops = sum(v for k, v in layers.items() if k != "enc0.c1") - zf_flops - com_flops
     achieved = tc_flops / (conv_ms * 1e-3) / 1e12
     n_conv = len(traced["km_conv3d_tc"]) // args.steps
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": achieved, "peak": tc_peak,
-                "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": NCU_TRAFFIC.get("conv_tc_kernel"),
                 "flops_per_step": tc_flops, "launches_per_step": n_conv, "kernel_ms_per_step": conv_ms,
-                "share_of_step": conv_ms / ms_step, "peak_source": peak_src}
+                "share_of_step": conv_ms / ms_step, "peak_source": peak_src,
+                "traffic_note": "DRAM bytes (read+write) summed over the kernel's launches of one step, ncu "
+                                "capture in profiles/ (see DESIGN.md section 6)"}
+    backbone_ms = conv_ms + zf_ms + com_ms + stem_ms
+    all_flops = sum(layers.values())
+    roofline_other = []
+    if zf_ms > 0:
+        roofline_other.append({"bound": "tensor", "kernel": "conv_zf_kernel (16->32 @256^3, dz folded into N, pool fused)",
+                               "achieved": zf_flops / (zf_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
+                               "frac": zf_flops / (zf_ms * 1e-3) / 1e12 / tc_peak, "kernel_ms_per_step": zf_ms,
+                               "traffic": NCU_TRAFFIC.get("conv_zf_kernel")})
+    if com_ms > 0:
+        roofline_other.append({"bound": "tensor", "kernel": "com_tc_kernel (final 1x1x1 conv + ReLU + centre of mass)",
+                               "achieved": com_flops / (com_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
+                               "frac": com_flops / (com_ms * 1e-3) / 1e12 / tc_peak, "kernel_ms_per_step": com_ms,
+                               "hbm_gbs": 2 * (S // 2) ** 3 * 64 * 2 / (com_ms * 1e-3) / 1e9,
+                               "traffic": NCU_TRAFFIC.get("com_tc_kernel")})
+    roofline_other.append({"bound": "tensor", "kernel": "whole backbone (stem x2 + conv_zf + conv_tc + com_tc)",
+                           "achieved": all_flops / (backbone_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
+                           "frac": all_flops / (backbone_ms * 1e-3) / 1e12 / tc_peak,
+                           "kernel_ms_per_step": backbone_ms})
     # the HBM-bound kernel of the path: ONE pass writes the affine flow field (12 B/voxel), gathers the
     # moving volume (4), reads the fixed volume (4), stores the warped volume (4) and reduces the
     # MSE sums (fused warp + loss, grid generated in registers)
@@ -273,7 +304,7 @@ def run_engine(args):
             "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "parallelism": f"pairs sharded x{world}",
                        "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "roofline_warp": roofline_warp, "mse": float(mse.item()), "loss_e2e": loss}
+            "roofline_warp": roofline_warp, "roofline_other": roofline_other, "mse": float(mse.item()), "loss_e2e": loss}
 
     if rank == 0 and world == 1 and not args.no_cpu:
         sec, _ = cpu_sample_seconds(sd_cpu, steps=1, warmup=0)
