@@ -45,6 +45,11 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
@@ -109,61 +114,102 @@ conv_stem_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
   for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = ss[nt][0] = ss[nt][1] = 0.f;
 
   // software pipeline: the halo of the NEXT tile is fetched into registers while the current one
-  // is being multiplied
-  // (raw values + a validity mask travel in registers; the input normalisation is applied when the
-  // tile is written to shared memory, so that nothing waits on the loads before the MMA loop)
-  float pre[kPre];
+  // is being multiplied (raw values + a validity mask travel in registers; the input normalisation
+  // is applied when the tile is written to shared memory, so that nothing waits on the loads before
+  // the MMA loop).  Thread -> halo elements: column hx = t & 63 of rows (t >> 6) + 4 j, j = 0..8
+  // (row = hz * 6 + hy), plus the two extra columns 64 / 65 of row t >> 1 for t < 72: the index
+  // arithmetic per element is a handful of instructions and the row offsets are immediates.
+  constexpr int kRowsPerThread = (kHZ * kHY) / 4;   // 9
+  static_assert(kHZ * kHY == 36 && kHX == 66, "halo mapping assumes a 66 x 6 x 6 tile");
+  float pre[kRowsPerThread + 1];
   uint32_t pre_ok = 0;
-  auto fetch = [&](int tl) {
-    const int x0 = (tl % tiles_x) * kTX - 1;
-    const int y0 = ((tl / tiles_x) % tiles_y) * kTY - 1;
-    const int z0 = (tl / (tiles_x * tiles_y)) * kTZ - 1;
+  const int f_hx = threadIdx.x & 63, f_r0 = threadIdx.x >> 6;
+  const int e_r = threadIdx.x >> 1, e_hx = 64 + (threadIdx.x & 1);   // extra columns (t < 72)
+  const int HW = H * W;
+  int ftl = blockIdx.x;   // tile being fetched, decoded incrementally (no divisions per tile)
+  int ftx = ftl % tiles_x, fty = (ftl / tiles_x) % tiles_y, ftz = ftl / (tiles_x * tiles_y);
+  const int stx = (int)gridDim.x % tiles_x, sty = ((int)gridDim.x / tiles_x) % tiles_y;
+  const int stz = (int)gridDim.x / (tiles_x * tiles_y);
+  int cx0 = 0, cy0 = 0, cz0 = 0;   // origin of the tile whose halo sits in `pre`
+  auto fetch = [&]() {
+    cx0 = ftx * kTX;
+    cy0 = fty * kTY;
+    cz0 = ftz * kTZ;
+    const int gx = cx0 - 1 + f_hx;
+    const bool okx = (unsigned)gx < (unsigned)W;
     pre_ok = 0;
 #pragma unroll
-    for (int j = 0; j < kPre; ++j) {
-      const int i = threadIdx.x + 256 * j;
-      const int hx = i % kHX, hy = (i / kHX) % kHY, hz = i / (kHX * kHY);
-      const int gx = x0 + hx, gy = y0 + hy, gz = z0 + hz;
-      const bool ok = i < kHalo && (unsigned)gx < (unsigned)W && (unsigned)gy < (unsigned)H &&
-                      (unsigned)gz < (unsigned)D;
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      const int r = f_r0 + 4 * j;
+      const int hz = (r * 43) >> 8, hy = r - 6 * hz;   // r / 6, r % 6 for r < 36
+      const int gy = cy0 - 1 + hy, gz = cz0 - 1 + hz;
       pre[j] = 0.f;
-      if (ok) {
-        pre[j] = __ldg(xn + ((size_t)gz * H + gy) * W + gx);
+      if (okx && (unsigned)gy < (unsigned)H && (unsigned)gz < (unsigned)D) {
+        pre[j] = __ldg(xn + (gz * HW + gy * W + gx));
         pre_ok |= 1u << j;
       }
     }
+    pre[kRowsPerThread] = 0.f;
+    if (threadIdx.x < 72) {
+      const int hz = (e_r * 43) >> 8, hy = e_r - 6 * hz;
+      const int ex = cx0 - 1 + e_hx, gy = cy0 - 1 + hy, gz = cz0 - 1 + hz;
+      if ((unsigned)ex < (unsigned)W && (unsigned)gy < (unsigned)H && (unsigned)gz < (unsigned)D) {
+        pre[kRowsPerThread] = __ldg(xn + (gz * HW + gy * W + ex));
+        pre_ok |= 1u << kRowsPerThread;
+      }
+    }
+    // advance to this CTA's next tile (mixed-radix add with carries)
+    ftl += gridDim.x;
+    ftx += stx;
+    int c = 0;
+    if (ftx >= tiles_x) { ftx -= tiles_x; c = 1; }
+    fty += sty + c;
+    c = 0;
+    if (fty >= tiles_y) { fty -= tiles_y; c = 1; }
+    ftz += stz + c;
   };
 
   const int wy = wid & 3, wz = (wid >> 2) * 2;   // the warp's row (y) and first z plane in the tile
   unsigned char* my_stage = stage[wid];
+  // shared-memory byte addresses of this thread's A-fragment taps, relative to the tile's x group 0
+  // and z plane wz (tile independent: the loops below only add immediates)
+  uint32_t aaddr[4][2];
+  {
+    const uint32_t rowbase = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)(((wz * kHY + wy) * kSX + g) * 4);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) aaddr[ks][j] = rowbase + (uint32_t)aoff[ks][j] * 4u;
+  }
+  float* st_main = tile + f_r0 * kSX + f_hx;
+  float* st_extra = tile + e_r * kSX + e_hx;
 
-  if ((int)blockIdx.x < ntiles) fetch(blockIdx.x);
+  if ((int)blockIdx.x < ntiles) fetch();
   for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
-    const int x0 = (tl % tiles_x) * kTX;
-    const int y0 = ((tl / tiles_x) % tiles_y) * kTY;
-    const int z0 = (tl / (tiles_x * tiles_y)) * kTZ;
+    const int x0 = cx0, y0 = cy0, z0 = cz0;
     __syncthreads();   // previous tile fully consumed
 #pragma unroll
-    for (int j = 0; j < kPre; ++j) {
-      const int i = threadIdx.x + 256 * j;
-      if (i < kHalo) {
-        const int hx = i % kHX, r = i / kHX;   // r = hz * kHY + hy
-        const float v = ((pre_ok >> j) & 1u) ? fmaf(a_in, pre[j], b_in) : 0.f;
-        tile[r * kSX + hx] = __uint_as_float(to_tf32(v));
-      }
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      const float v = ((pre_ok >> j) & 1u) ? fmaf(a_in, pre[j], b_in) : 0.f;
+      st_main[4 * j * kSX] = __uint_as_float(to_tf32(v));
+    }
+    if (threadIdx.x < 72) {
+      const float v = ((pre_ok >> kRowsPerThread) & 1u) ? fmaf(a_in, pre[kRowsPerThread], b_in) : 0.f;
+      *st_extra = __uint_as_float(to_tf32(v));
     }
     __syncthreads();
-    if (tl + (int)gridDim.x < ntiles) fetch(tl + gridDim.x);
+    if (tl + (int)gridDim.x < ntiles) fetch();
 
     const int gy = y0 + wy;
     if (gy >= H) continue;   // warp-uniform; the loop-top barriers are still reached by everyone
-    // two m-tiles (the warp's two z planes, same 16 x positions) per iteration: 2*NT independent
-    // accumulator chains keep the tensor pipe busy with only 4 warps per scheduler
-#pragma unroll 1
+    // two m-tiles (the warp's two z planes, same 16 x positions) per step: 2*NT independent
+    // accumulator chains keep the tensor pipe busy with only 4 warps per scheduler.  The four x
+    // groups are fully unrolled so that every LDS is [register + immediate].
+    const bool xfull = x0 + kTX <= W;   // no per-voxel masks needed
+#pragma unroll
     for (int xi = 0; xi < 4; ++xi) {
       const int xg = xi * 16;
-      if (x0 + xg >= W) break;   // warp-uniform
-      const float* base = tile + (wz * kHY + wy) * kSX + xg + g;
+      if (x0 + xg < W) {   // warp-uniform
       float acc[2][NT][4];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
@@ -179,11 +225,11 @@ conv_stem_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
         uint32_t a[2][4];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const float* bu = base + u * (kHY * kSX);
-          a[u][0] = __float_as_uint(bu[aoff[ks][0]]);
-          a[u][1] = __float_as_uint(bu[aoff[ks][0] + 8]);
-          a[u][2] = __float_as_uint(bu[aoff[ks][1]]);
-          a[u][3] = __float_as_uint(bu[aoff[ks][1] + 8]);
+          const int imm = (u * kHY * kSX + xg) * 4;
+          a[u][0] = lds_u32(aaddr[ks][0] + imm);        // constant offsets fold into the LDS immediate
+          a[u][1] = lds_u32(aaddr[ks][0] + imm + 32);
+          a[u][2] = lds_u32(aaddr[ks][1] + imm);
+          a[u][3] = lds_u32(aaddr[ks][1] + imm + 32);
         }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
@@ -192,25 +238,36 @@ conv_stem_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
             mma_tf32(acc[u][nt], a[u][0], a[u][1], a[u][2], a[u][3], bfrag[ks][nt][0], bfrag[ks][nt][1]);
       }
       // rows of this thread: voxel x = x0 + xg + g (acc[..][0..1]) and + 8 (acc[..][2..3])
-      const bool ok0 = x0 + xg + g < W, ok1 = x0 + xg + g + 8 < W;
+      const bool ok0 = xfull || x0 + xg + g < W, ok1 = xfull || x0 + xg + g + 8 < W;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int gz = z0 + wz + u;
-        if (gz >= D) break;   // warp-uniform
+        if (gz < D) {   // warp-uniform
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (relu_pre) acc[u][nt][j] = fmaxf(acc[u][nt][j], 0.f);
         if (stats) {
+          if (xfull) {
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const float v0 = ok0 ? acc[u][nt][j] : 0.f, v1 = ok1 ? acc[u][nt][2 + j] : 0.f;
-              s[nt][j] += v0 + v1;
-              ss[nt][j] = fmaf(v0, v0, fmaf(v1, v1, ss[nt][j]));
-            }
+              for (int j = 0; j < 2; ++j) {
+                const float v0 = acc[u][nt][j], v1 = acc[u][nt][2 + j];
+                s[nt][j] += v0 + v1;
+                ss[nt][j] = fmaf(v0, v0, fmaf(v1, v1, ss[nt][j]));
+              }
+          } else {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const float v0 = ok0 ? acc[u][nt][j] : 0.f, v1 = ok1 ? acc[u][nt][2 + j] : 0.f;
+                s[nt][j] += v0 + v1;
+                ss[nt][j] = fmaf(v0, v0, fmaf(v1, v1, ss[nt][j]));
+              }
+          }
         }
         if (on) {
           // normalise for the next layer, round to bf16, transpose through the warp's staging
@@ -230,17 +287,19 @@ conv_stem_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
             *reinterpret_cast<uint32_t*>(my_stage + (g + 8) * kStage + nt * 16 + t * 4) = pack_bf16x2(o[2], o[3]);
           }
           __syncwarp();
-          bf16* dst = on + (((size_t)gz * H + gy) * W + x0 + xg) * COUT;
+          bf16* dst = on + ((size_t)(gz * HW + gy * W + x0 + xg)) * COUT;
 #pragma unroll
           for (int i = 0; i < NT / 2; ++i) {
             const int c = lane + 32 * i;            // 16-byte chunk id inside the 16-voxel segment
             const int v = c / NT, q = c % NT;
-            if (x0 + xg + v < W) {
+            if (xfull || x0 + xg + v < W) {
               const uint4 val = *reinterpret_cast<const uint4*>(my_stage + v * kStage + q * 16);
               *reinterpret_cast<uint4*>(dst + (size_t)v * COUT + q * 8) = val;
             }
           }
         }
+        }
+      }
       }
     }
   }
