@@ -262,8 +262,10 @@ int km_conv3d_zfold(const void* x, const void* wz, void* out, void* pooled, floa
  * heat map is never materialised.
  *   x: bf16 NDHWC (N,D,H,W,Cin), Cin % 16 == 0, Cin <= 256;  wp: bf16 [Cout][Cin] (km_pack_weights
  *   with taps = 1), Cout % 128 == 0 (zero-pad), Cout <= 512;  bias: fp32 (Cout) or NULL;
- *   com: (km_conv_nparts(),N,Cout,4) fp32 partial [sum h, sum h*lz, sum h*ly, sum h*lx], h = relu(conv),
- *   l* = linspace(0,1,n) -- the same partials as KM_CONV_COM, finished by km_com_finalize. */
+ *   com: (km_conv1x1_com_nparts(),N,Cout,4) fp32 partial [sum h, sum h*lz, sum h*ly, sum h*lx],
+ *   h = relu(conv), l* = linspace(0,1,n) -- the same partials as KM_CONV_COM, finished by
+ *   km_com_finalize. */
+int km_conv1x1_com_nparts(void);
 int km_conv1x1_com(const void* x, const void* wp, const float* bias, float* com, int N, int Cin,
                    int Cout, int D, int H, int W, km_stream_t stream);
 

@@ -53,6 +53,7 @@ SIGNATURES = {
     "km_pack_weights_zfold_bytes": (C.c_size_t, [_i, _i]),
     "km_pack_weights_zfold": (_i, [_p, _p, _i, _i, _p]),
     "km_conv3d_zfold": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "km_conv1x1_com_nparts": (_i, []),
     "km_conv1x1_com": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "km_conv3d_stem": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "km_conv_nparts": (_i, []),

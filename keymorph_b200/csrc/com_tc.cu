@@ -14,8 +14,10 @@
 // no shared-memory transposes, no atomics, ~4 instructions per heat-map element.  The K x (S/2)^3
 // heat map (2.1 GB fp32 per volume at K=256, S=256) never exists anywhere.
 //
-// Roles (320 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warps 2..9 = epilogue (two M-tiles of 128 channels x four TMEM lane quadrants).
+// Roles (576 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..17 = epilogue (two M-tiles of 128 channels x four TMEM lane quadrants x two halves of
+// the brick's 128 voxel columns; the epilogue is the kernel's critical path, so it gets four
+// warps per scheduler).  The two column halves write separate partial slots.
 // TMEM: 2 buffers x 2 M-tiles x 128 columns = 512 columns; a work unit is (brick, pass) where pass
 // p covers channels [256p, 256p+256).
 #include "km_common.cuh"
@@ -25,8 +27,8 @@ using namespace kmtc;
 
 namespace {
 
-constexpr int kThreads = 320;
-constexpr int kEpiThreads = 256;
+constexpr int kThreads = 576;       // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
+constexpr int kEpiThreads = 512;
 constexpr int kBrick = 128;        // voxels per brick = MMA N
 constexpr int kMaxStages = 12;
 constexpr int kMaxPasses = 2;      // Cout <= 512
@@ -185,9 +187,11 @@ com_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       }
     }
   } else {
-    // =============================== epilogue (8 warps) ==========================
+    // =============================== epilogue (16 warps) =========================
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
-    const int hm = (warp - 2) >> 2;       // M-tile of the pass handled by this warp
+    const int ew = warp - 2;
+    const int hm = (ew >> 2) & 1;         // M-tile of the pass handled by this warp
+    const int ch2 = ew >> 3;              // half of the brick's voxel columns: [64 ch2, 64 ch2 + 64)
     const int crow = q * 32 + lane;       // channel within the M-tile == TMEM lane
     const float4* tab = reinterpret_cast<const float4*>(sm + g.off_tab);
     const float step_z = g.D > 1 ? 1.f / (float)(g.D - 1) : 0.f;
@@ -207,7 +211,7 @@ com_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       for (int p = 0; p < kMaxPasses; ++p) {
         const int c = (2 * p + hm) * 128 + crow;
         if (p < passes && c < g.Cout) {
-          *reinterpret_cast<float4*>(com + (((size_t)blockIdx.x * g.N + n) * g.Cout + c) * 4) =
+          *reinterpret_cast<float4*>(com + (((size_t)(2 * blockIdx.x + ch2) * g.N + n) * g.Cout + c) * 4) =
               make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
         }
         acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.f;
@@ -239,20 +243,18 @@ com_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)hm * 128u;
           const float b = bch[p];
           float t0 = 0.f, tzs = 0.f, tys = 0.f, txs = 0.f;   // brick-local sums
-          uint32_t r[2][32];
-          tmem_ld32(taddr, r[0]);
-          tmem_ld_wait();
-          if (xrun && full) {
-#pragma unroll
-            for (int ci = 0; ci < 4; ++ci) {
-              if (ci < 3) tmem_ld32(taddr + 32u * (ci + 1), r[(ci + 1) & 1]);
-              const uint32_t(&v)[32] = r[ci & 1];
-              // four independent accumulator chains: with two epilogue warps per scheduler a single
-              // dependent FADD/FFMA chain would be latency bound
+          uint32_t r[32];
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {
+            const int ci = 2 * ch2 + cc;          // 32-column chunk of the brick
+            tmem_ld32(taddr + 32u * (uint32_t)ci, r);
+            tmem_ld_wait();
+            if (xrun && full) {
+              // four independent accumulator chains per sum
               float s0p[4] = {0.f, 0.f, 0.f, 0.f}, sxp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float h = fmaxf(__uint_as_float(v[j]) + b, 0.f);
+                const float h = fmaxf(__uint_as_float(r[j]) + b, 0.f);
                 s0p[j & 3] += h;
                 sxp[j & 3] = fmaf(h, (float)j, sxp[j & 3]);
               }
@@ -263,22 +265,14 @@ com_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               txs += fmaf(o.x, s0, sx);
               tys = fmaf(o.y, s0, tys);
               tzs = fmaf(o.z, s0, tzs);
-              if (ci < 3) tmem_ld_wait();
-            }
-          } else {
-            // bricks that stick out of the volume (TMA zero-fill would read as relu(bias)) and
-            // narrow volumes: per-column offsets from the table, invalid voxels masked
-#pragma unroll 1
-            for (int ci = 0; ci < 4; ++ci) {
-              if (ci > 0) {
-                tmem_ld32(taddr + 32u * ci, r[0]);
-                tmem_ld_wait();
-              }
+            } else {
+              // bricks that stick out of the volume (TMA zero-fill would read as relu(bias)) and
+              // narrow volumes: per-column offsets from the table, invalid voxels masked
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float4 o = tab[ci * 32 + j];
                 const bool ok = x0 + (int)o.x < g.W && y0 + (int)o.y < g.H && z0 + (int)o.z < g.D;
-                const float h = ok ? fmaxf(__uint_as_float(r[0][j]) + b, 0.f) : 0.f;
+                const float h = ok ? fmaxf(__uint_as_float(r[j]) + b, 0.f) : 0.f;
                 t0 += h;
                 txs = fmaf(h, o.x, txs);
                 tys = fmaf(h, o.y, tys);
@@ -331,6 +325,8 @@ typedef void (*ComKernel)(const CUtensorMap, const CUtensorMap, const ComGeom, c
 }  // namespace
 
 extern "C" int km_sm_count(void);
+
+extern "C" int km_conv1x1_com_nparts(void) { return 2 * km_sm_count(); }
 
 extern "C" int km_conv1x1_com(const void* x, const void* wp, const float* bias, float* com, int N,
                               int Cin, int Cout, int D, int H, int W, km_stream_t stream) {
@@ -423,7 +419,7 @@ extern "C" int km_conv1x1_com(const void* x, const void* wp, const float* bias, 
   const int nsm = km_sm_count();
   const int grid = g.total_tiles < nsm ? g.total_tiles : nsm;
   // a CTA only writes the (image, channel) slots of the images it worked on
-  KM_CUDA_OK(cudaMemsetAsync(com, 0, (size_t)nsm * N * Cout * 4 * sizeof(float), km_cs(stream)));
+  KM_CUDA_OK(cudaMemsetAsync(com, 0, (size_t)2 * nsm * N * Cout * 4 * sizeof(float), km_cs(stream)));
   kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmX, tmW, g, bias, com);
   KM_LAUNCH_OK("com_tc_kernel");
   return KM_OK;

@@ -99,21 +99,21 @@ channel_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, long
 }
 
 // ------------------------------------------------------------------------------------------
-// GroupNorm / InstanceNorm finalize: one block per sample
-__global__ void norm_finalize_kernel(const float* __restrict__ stats0, int nparts0, int C0,
-                                     double count0, const float* __restrict__ stats1, int nparts1,
-                                     int C1, double count1, double rep1,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     int groups, float eps, float* __restrict__ scale,
-                                     float* __restrict__ shift, int N) {
-  extern __shared__ double sd[];  // [C][2] then [groups][2]
-  const int n = blockIdx.x;
+// GroupNorm / InstanceNorm finalize: one block per (sample, group), 128 threads
+__global__ void __launch_bounds__(128)
+norm_finalize_kernel(const float* __restrict__ stats0, int nparts0, int C0, double count0,
+                     const float* __restrict__ stats1, int nparts1, int C1, double count1, double rep1,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, int groups,
+                     float eps, float* __restrict__ scale, float* __restrict__ shift, int N) {
+  __shared__ double wsum[4][3];
+  const int n = blockIdx.x, g = blockIdx.y;
   const int C = C0 + C1;
-  double* csum = sd;
-  double* gstat = sd + 2 * C;
-  // one warp per channel: lanes stride over the partial slots, fixed-order shuffle reduction
+  const int cpg = C / groups;
+  // one warp per channel of the group: lanes stride over the partial slots, fixed-order shuffle
+  // reduction; the warp then carries its channels' totals
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int c = wid; c < C; c += nwarps) {
+  double gs = 0.0, gss = 0.0, gcnt = 0.0;
+  for (int c = g * cpg + wid; c < (g + 1) * cpg; c += nwarps) {
     double s = 0.0, ss = 0.0;
     if (c < C0) {
       for (int p = lane; p < nparts0; p += 32) {
@@ -131,32 +131,27 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats0, int npart
       s *= rep1;
       ss *= rep1;
     }
-    s = km_warp_sum(s);
-    ss = km_warp_sum(ss);
-    if (lane == 0) {
-      csum[2 * c] = s;
-      csum[2 * c + 1] = ss;
-    }
+    gs += km_warp_sum(s);
+    gss += km_warp_sum(ss);
+    gcnt += (c < C0) ? count0 : count1 * rep1;
+  }
+  if (lane == 0) {
+    wsum[wid][0] = gs;
+    wsum[wid][1] = gss;
+    wsum[wid][2] = gcnt;
   }
   __syncthreads();
-  const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    double s = 0.0, ss = 0.0, cnt = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      s += csum[2 * c];
-      ss += csum[2 * c + 1];
-      cnt += (c < C0) ? count0 : count1 * rep1;
-    }
-    const double mean = s / cnt;
-    double var = ss / cnt - mean * mean;  // biased variance (torch group_norm / instance_norm)
-    if (var < 0.0) var = 0.0;
-    gstat[2 * g] = mean;
-    gstat[2 * g + 1] = 1.0 / sqrt(var + (double)eps);
+  double s = 0.0, ss = 0.0, cnt = 0.0;
+  for (int w = 0; w < nwarps; ++w) {
+    s += wsum[w][0];
+    ss += wsum[w][1];
+    cnt += wsum[w][2];
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const double mean = gstat[2 * g], rstd = gstat[2 * g + 1];
+  const double mean = s / cnt;
+  double var = ss / cnt - mean * mean;  // biased variance (torch group_norm / instance_norm)
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  for (int c = g * cpg + threadIdx.x; c < (g + 1) * cpg; c += blockDim.x) {
     const double ga = gamma ? (double)gamma[c] : 1.0;
     const double be = beta ? (double)beta[c] : 0.0;
     scale[(size_t)n * C + c] = (float)(ga * rstd);
@@ -394,10 +389,10 @@ extern "C" int km_norm_finalize(const float* stats0, int nparts0, int C0, double
   const int C = C0 + C1;
   KM_CHECK_ARG(groups > 0 && C % groups == 0, "km_norm_finalize: %d channels not divisible by %d groups",
                C, groups);
-  const size_t smem = (size_t)(2 * C + 2 * groups) * sizeof(double);
-  norm_finalize_kernel<<<N, 1024, smem, km_cs(stream)>>>(stats0, nparts0, C0, count0, stats1, nparts1,
-                                                       C1, count1, rep1, gamma, beta, groups, eps,
-                                                       scale, shift, N);
+  KM_CHECK_ARG(groups <= 65535, "km_norm_finalize: too many groups");
+  norm_finalize_kernel<<<dim3(N, groups), 128, 0, km_cs(stream)>>>(stats0, nparts0, C0, count0, stats1, nparts1,
+                                                                  C1, count1, rep1, gamma, beta, groups, eps,
+                                                                  scale, shift, N);
   KM_LAUNCH_OK("norm_finalize_kernel");
   return KM_OK;
 }

@@ -326,7 +326,8 @@ def conv1x1_com(x, wp, bias=None):
     N, D, H, W, Cin = x.shape
     taps, Cout, Cin2 = wp.shape
     assert taps == 1 and Cin2 == Cin
-    com = torch.empty((conv_nparts(), N, Cout, 4), dtype=torch.float32, device=x.device)
+    com = torch.empty((_lib.query("km_conv1x1_com_nparts"), N, Cout, 4), dtype=torch.float32,
+                      device=x.device)
     bias = _f32c(bias)
     with torch.cuda.device(x.device):
         _lib.call("km_conv1x1_com", _ptr(x), _ptr(wp), _ptr(bias), _ptr(com), N, Cin, Cout, D, H, W,
