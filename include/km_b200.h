@@ -117,6 +117,21 @@ int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const float* theta, i
                  float* grid_out, double* sums, void* workspace, int N, int C, int D, int H, int W,
                  int mode, km_stream_t stream);
 
+/* Label-map fast path for segmentation warp + Dice.  Replaces one_hot -> align_img
+ * -> DiceLoss(soft) + DiceLoss(hard) of scripts/pairwise_register_eval.py:99-108,156-157,303-321 on
+ * uint8 label volumes (N,D,H,W) with values < C <= 255: the one-hot volumes are never built.
+ *   soft_sums (N,C,4) fp64 = [sum (a-t)^2, sum a*t, sum a*a, sum t*t] with a = trilinear warp of
+ *   one_hot(labels_m)[c] (same per-voxel arithmetic as km_warp_loss), t = one_hot(labels_f)[c];
+ *   hard_sums (N,C,4) fp64: the same with a replaced by one_hot(argmax_c a) (first maximum wins);
+ *   labels_out (N,D,H,W) uint8, may be NULL: argmax_c a, i.e. the hard warped segmentation.
+ * coord_mode KM_COORD_AFFINE (mat (N,3,4)) or KM_COORD_GRID (grid (N,D,H,W,3)).
+ * workspace: km_warp_labels_workspace_bytes(N, C). */
+size_t km_warp_labels_workspace_bytes(int N, int C);
+int km_warp_labels_dice(int coord_mode, const float* mat, const float* grid, const uint8_t* labels_m,
+                        const uint8_t* labels_f, uint8_t* labels_out, double* soft_sums,
+                        double* hard_sums, void* workspace, int N, int C, int D, int H, int W,
+                        km_stream_t stream);
+
 /* keymorph/loss_ops.py:9-13 and :16-63.  Elementwise-pair statistics of two (N,C,M) fp32 tensors:
  * sums[n,c,:] = [sum (p-t)^2, sum p*t, sum p*p, sum t*t] (fp64).  With hard != 0 pred is replaced
  * by one_hot(argmax_c pred) (first maximum wins, like torch.argmax) before the products.

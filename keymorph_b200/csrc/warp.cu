@@ -472,6 +472,174 @@ warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Label-map fast path for segmentation warp + Dice.  The reference warps a C-channel
+// fp32 one-hot volume (scripts/pairwise_register_eval.py:99-108,156-157: one_hot -> align_img ->
+// DiceLoss soft and hard) -- 4*C bytes per voxel read, written and read again.  Here the integer
+// label maps are gathered directly: the trilinear value of channel c at a voxel is the sum of the
+// corner weights whose label equals c, accumulated in exactly the order tri_sample_fast would add
+// them (zero terms are exact no-ops), so the soft-Dice sums equal those of the one-hot path bit
+// for bit per voxel, and the hard-Dice sums are exact integer counts (argmax over c, first maximum
+// wins like torch.argmax, loss_ops.py:46-49).  1 + 8 label bytes per voxel instead of 12*C.
+//   soft partials [gridDim.x][N][C][4] float = sum (a-t)^2, sum a*t, sum a*a, sum t*t
+//   hard counts   [N][C][3] unsigned long long = |hard==c & t==c|, |hard==c|, |t==c| (atomics on ints)
+template <int COORD>
+__global__ void __launch_bounds__(256)
+warp_labels_kernel(const float* __restrict__ mat, const float* __restrict__ grid,
+                   const uint8_t* __restrict__ lab_m, const uint8_t* __restrict__ lab_f,
+                   uint8_t* __restrict__ lab_out, float* __restrict__ partials,
+                   unsigned long long* __restrict__ hard, int N, int C, int D, int H, int W) {
+  extern __shared__ float s_red[];            // [8 warps][C*4] soft sums, then [C*3] uint counts
+  const int n = blockIdx.y;
+  const int nv = D * H * W, HW = H * W;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* red = s_red + (size_t)wid * C * 4;
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(s_red + (size_t)8 * C * 4);
+  for (int i = threadIdx.x; i < 8 * C * 4; i += blockDim.x) s_red[i] = 0.f;
+  for (int i = threadIdx.x; i < C * 3; i += blockDim.x) cnt[i] = 0u;
+  __syncthreads();
+  AffineCoord ac;
+  if (COORD == KM_COORD_AFFINE) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) ac.m[i] = __ldg(mat + n * 12 + i);
+  }
+  const float* gn = (COORD == KM_COORD_GRID) ? grid + (size_t)n * nv * 3 : nullptr;
+  const uint8_t* lm = lab_m + (size_t)n * nv;
+  const uint8_t* lf = lab_f + (size_t)n * nv;
+  const int nchunks = (nv + 127) / 128;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warps) {
+    const int v0 = chunk * 128 + lane;
+    const int cz = (chunk * 128) / HW, crem = chunk * 128 - cz * HW;
+    const int cy = crem / W, cx = crem - cy * W;
+    float cw[4][8];        // corner weights in tri_sample_fast's accumulation order
+    uint32_t cl[4][2];     // corner labels, 4 per word
+    int tl[4];             // fixed label, -1 for voxels past the end
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int v = v0 + 32 * k;
+      const bool ok = v < nv;
+      float gx, gy, gz;
+      if (COORD == KM_COORD_GRID) {
+        const float* gp = gn + (size_t)(ok ? v : 0) * 3;
+        gx = __ldg(gp);
+        gy = __ldg(gp + 1);
+        gz = __ldg(gp + 2);
+      } else {
+        int xx = cx + lane + 32 * k, y = cy, z = cz;
+        while (xx >= W) {
+          xx -= W;
+          if (++y == H) {
+            y = 0;
+            ++z;
+          }
+        }
+        if (!ok) xx = y = z = 0;
+        ac(km_linspace(-1.f, 1.f, D, z), km_linspace(-1.f, 1.f, H, y), km_linspace(-1.f, 1.f, W, xx), gx, gy,
+           gz);
+      }
+      const Tri t = make_tri(gx, gy, gz, D, H, W);
+      const float x0f = (float)t.x0, y0f = (float)t.y0, z0f = (float)t.z0;
+      const float wx1 = t.ix - x0f, wx0 = (x0f + 1.f) - t.ix;
+      const float wy1 = t.iy - y0f, wy0 = (y0f + 1.f) - t.iy;
+      const float wz1 = t.iz - z0f, wz0 = (z0f + 1.f) - t.iz;
+      const int x1 = min(t.x0 + 1, W - 1), y1 = min(t.y0 + 1, H - 1), z1 = min(t.z0 + 1, D - 1);
+      const int r00 = (t.z0 * H + t.y0) * W, r01 = (t.z0 * H + y1) * W;
+      const int r10 = (z1 * H + t.y0) * W, r11 = (z1 * H + y1) * W;
+      const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+      cw[k][0] = w00 * wz0; cw[k][1] = w10 * wz0; cw[k][2] = w01 * wz0; cw[k][3] = w11 * wz0;
+      cw[k][4] = w00 * wz1; cw[k][5] = w10 * wz1; cw[k][6] = w01 * wz1; cw[k][7] = w11 * wz1;
+      cl[k][0] = (uint32_t)__ldg(lm + r00 + t.x0) | ((uint32_t)__ldg(lm + r00 + x1) << 8) |
+                 ((uint32_t)__ldg(lm + r01 + t.x0) << 16) | ((uint32_t)__ldg(lm + r01 + x1) << 24);
+      cl[k][1] = (uint32_t)__ldg(lm + r10 + t.x0) | ((uint32_t)__ldg(lm + r10 + x1) << 8) |
+                 ((uint32_t)__ldg(lm + r11 + t.x0) << 16) | ((uint32_t)__ldg(lm + r11 + x1) << 24);
+      tl[k] = ok ? (int)__ldg(lf + v) : -1;
+    }
+    float best[4] = {-1.f, -1.f, -1.f, -1.f};
+    int bi[4] = {0, 0, 0, 0};
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // a = sum of the corner weights whose label is c, same order / FMA chain as the one-hot gather
+        float a = (((cl[k][0]) & 0xffu) == (uint32_t)c) ? cw[k][0] : 0.f;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+          const uint32_t l = (cl[k][j >> 2] >> (8 * (j & 3))) & 0xffu;
+          if (l == (uint32_t)c) a = a + cw[k][j];     // fmaf(1, w, a)
+        }
+        if (tl[k] >= 0) {
+          const float tv = tl[k] == c ? 1.f : 0.f;
+          const float d = a - tv;
+          a0 = fmaf(d, d, a0);
+          a1 = fmaf(a, tv, a1);
+          a2 = fmaf(a, a, a2);
+          a3 = fmaf(tv, tv, a3);
+          if (a > best[k]) {      // first maximum wins
+            best[k] = a;
+            bi[k] = c;
+          }
+        }
+      }
+      a0 = km_warp_sum(a0);
+      a1 = km_warp_sum(a1);
+      a2 = km_warp_sum(a2);
+      a3 = km_warp_sum(a3);
+      if (lane == 0) {
+        red[c * 4 + 0] += a0;
+        red[c * 4 + 1] += a1;
+        red[c * 4 + 2] += a2;
+        red[c * 4 + 3] += a3;
+      }
+    }
+    // hard Dice: exact counts via warp ballots
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+      unsigned int tp = 0, pc = 0, tc = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool ok = tl[k] >= 0;
+        const unsigned bp = __ballot_sync(0xffffffffu, ok && bi[k] == c);
+        const unsigned bt = __ballot_sync(0xffffffffu, ok && tl[k] == c);
+        tp += __popc(bp & bt);
+        pc += __popc(bp);
+        tc += __popc(bt);
+      }
+      if (lane == 0 && (pc | tc)) {
+        atomicAdd(&cnt[c * 3 + 0], tp);
+        atomicAdd(&cnt[c * 3 + 1], pc);
+        atomicAdd(&cnt[c * 3 + 2], tc);
+      }
+    }
+    if (lab_out) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (tl[k] >= 0) lab_out[(size_t)n * nv + v0 + 32 * k] = (uint8_t)bi[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 4; i += blockDim.x) {
+    float a = 0.f;
+    for (int wv = 0; wv < 8; ++wv) a += s_red[(size_t)wv * C * 4 + i];
+    partials[((size_t)blockIdx.x * N + n) * C * 4 + i] = a;
+  }
+  for (int i = threadIdx.x; i < C * 3; i += blockDim.x)
+    if (cnt[i]) atomicAdd(&hard[(size_t)n * C * 3 + i], (unsigned long long)cnt[i]);
+}
+
+// hard counts -> the same [sum (p-t)^2, sum p*t, sum p*p, sum t*t] layout as the soft sums
+__global__ void hard_counts_to_sums_kernel(const unsigned long long* __restrict__ hard, double* __restrict__ sums,
+                                           int NC) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  const double tp = (double)hard[i * 3], p = (double)hard[i * 3 + 1], t = (double)hard[i * 3 + 2];
+  sums[i * 4 + 0] = p + t - 2.0 * tp;
+  sums[i * 4 + 1] = tp;
+  sums[i * 4 + 2] = p;
+  sums[i * 4 + 3] = t;
+}
+
 // partials [nparts][NC][4] -> sums[NC][4] (fp64)
 __global__ void sum_partials4_kernel(const float* __restrict__ partials, int nparts, int NC4,
                                      double* __restrict__ sums) {
@@ -722,6 +890,42 @@ extern "C" int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const floa
     sum_partials4_kernel<<<(NC4 + 7) / 8, 256, 0, st>>>(part, KM_RED_BLOCKS, NC4, sums);
     KM_LAUNCH_OK("sum_partials4_kernel");
   }
+  return KM_OK;
+}
+
+extern "C" size_t km_warp_labels_workspace_bytes(int N, int C) {
+  return (size_t)KM_RED_BLOCKS * N * C * 4 * sizeof(float) + (size_t)N * C * 3 * sizeof(unsigned long long);
+}
+
+extern "C" int km_warp_labels_dice(int coord_mode, const float* mat, const float* grid,
+                                   const uint8_t* labels_m, const uint8_t* labels_f, uint8_t* labels_out,
+                                   double* soft_sums, double* hard_sums, void* workspace, int N, int C,
+                                   int D, int H, int W, km_stream_t stream) {
+  KM_CHECK_ARG(labels_m && labels_f && soft_sums && hard_sums && workspace, "km_warp_labels_dice: null argument");
+  KM_CHECK_ARG(N > 0 && C > 0 && C <= 255 && D > 0 && H > 0 && W > 0, "km_warp_labels_dice: bad shape (C <= 255)");
+  KM_CHECK_ARG((long long)D * H * W < (1ll << 31), "km_warp_labels_dice: volume too large");
+  KM_CHECK_ARG((coord_mode == KM_COORD_AFFINE && mat) || (coord_mode == KM_COORD_GRID && grid),
+               "km_warp_labels_dice: coord_mode must be KM_COORD_AFFINE (mat) or KM_COORD_GRID (grid)");
+  float* part = reinterpret_cast<float*>(workspace);
+  unsigned long long* hard = reinterpret_cast<unsigned long long*>(
+      reinterpret_cast<uint8_t*>(workspace) + (size_t)KM_RED_BLOCKS * N * C * 4 * sizeof(float));
+  cudaStream_t st = km_cs(stream);
+  KM_CUDA_OK(cudaMemsetAsync(hard, 0, (size_t)N * C * 3 * sizeof(unsigned long long), st));
+  const size_t smem = ((size_t)8 * C * 4 + (size_t)C * 3) * sizeof(float);
+  KM_CHECK_ARG(smem <= 48 * 1024, "km_warp_labels_dice: too many classes for shared memory");
+  const dim3 g(KM_RED_BLOCKS, N);
+  if (coord_mode == KM_COORD_AFFINE)
+    warp_labels_kernel<KM_COORD_AFFINE><<<g, 256, smem, st>>>(mat, grid, labels_m, labels_f, labels_out, part,
+                                                              hard, N, C, D, H, W);
+  else
+    warp_labels_kernel<KM_COORD_GRID><<<g, 256, smem, st>>>(mat, grid, labels_m, labels_f, labels_out, part,
+                                                            hard, N, C, D, H, W);
+  KM_LAUNCH_OK("warp_labels_kernel");
+  const int NC4 = N * C * 4;
+  sum_partials4_kernel<<<(NC4 + 7) / 8, 256, 0, st>>>(part, KM_RED_BLOCKS, NC4, soft_sums);
+  KM_LAUNCH_OK("sum_partials4_kernel");
+  hard_counts_to_sums_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(hard, hard_sums, N * C);
+  KM_LAUNCH_OK("hard_counts_to_sums_kernel");
   return KM_OK;
 }
 

@@ -185,6 +185,15 @@ class KeyMorph(nn.Module):
         res["img_a"] = img_a
         res["mse"] = (sums[..., 0].sum() / img_f.numel()).float()
         seg_f, seg_m = kwargs.get("seg_f"), kwargs.get("seg_m")
+        lab_f, lab_m = kwargs.get("labels_f"), kwargs.get("labels_m")
+        if lab_f is not None and lab_m is not None:
+            # label-map fast path: integer label volumes instead of fp32 one-hot
+            # channels; same soft / hard Dice as one_hot -> align_img -> DiceLoss
+            soft, hard, lab_a = ops.warp_labels_dice(lab_m, lab_f, kwargs["num_classes"], grid=grid,
+                                                     want_labels=True)
+            res["labels_a"] = lab_a.reshape(lab_m.shape)
+            res["softdice"] = dice_from_sums(soft)
+            res["harddice"] = dice_from_sums(hard)
         if seg_f is not None and seg_m is not None:
             seg_a, ssums = ops.warp_loss(seg_m.float(), seg_f.float(), grid=grid)
             res["seg_a"] = seg_a

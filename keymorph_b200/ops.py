@@ -143,6 +143,33 @@ def warp_loss(moving, fixed=None, *, mat34=None, ctrl=None, theta=None, grid=Non
     return (out, sums, gout) if want_grid else (out, sums)
 
 
+def warp_labels_dice(labels_m, labels_f, num_classes, *, mat34=None, grid=None, want_labels=False):
+    """Segmentation warp + soft and hard Dice sums straight from uint8 label maps (N,D,H,W) or
+    (N,1,D,H,W): returns (soft_sums, hard_sums[, warped hard labels]) with the (N,C,4) fp64 layout of
+    warp_loss / pair_stats, without ever building the C-channel one-hot volumes."""
+    _need_cuda(labels_m, labels_f, mat34, grid)
+    lm = labels_m.reshape(labels_m.shape[0], *labels_m.shape[-3:]).to(torch.uint8).contiguous()
+    lf = labels_f.reshape(labels_f.shape[0], *labels_f.shape[-3:]).to(torch.uint8).contiguous()
+    assert lm.shape == lf.shape
+    N, D, H, W = lm.shape
+    Cc = int(num_classes)
+    if mat34 is not None:
+        coord, a, g = KM_COORD_AFFINE, _f32c(mat34), None
+    elif grid is not None:
+        coord, a, g = KM_COORD_GRID, None, _f32c(grid)
+        assert g.shape == (N, D, H, W, 3)
+    else:
+        raise ValueError("warp_labels_dice needs mat34 or grid")
+    soft = torch.empty((N, Cc, 4), dtype=torch.float64, device=lm.device)
+    hard = torch.empty_like(soft)
+    lout = torch.empty_like(lm) if want_labels else None
+    ws = _ws(_lib.query("km_warp_labels_workspace_bytes", N, Cc), lm.device)
+    with torch.cuda.device(lm.device):
+        _lib.call("km_warp_labels_dice", coord, _ptr(a), _ptr(g), _ptr(lm), _ptr(lf), _ptr(lout), _ptr(soft),
+                  _ptr(hard), _ptr(ws), N, Cc, D, H, W, _stream())
+    return (soft, hard, lout) if want_labels else (soft, hard)
+
+
 def pair_stats(pred, target, hard=False):
     """sums (N,C,4) fp64 = [sum (p-t)^2, sum p*t, sum p*p, sum t*t] over the flattened spatial dims;
     hard=True replaces pred by one_hot(argmax_c pred)."""

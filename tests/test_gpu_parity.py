@@ -124,6 +124,39 @@ def test_fused_warp_modes_vs_oracle(shape):
             assert_close(outw.cpu(), refw, rtol=0, atol=2e-6)
 
 
+@pytest.mark.parametrize("shape,C", [((1, 20, 24, 28), 14), ((2, 9, 11, 13), 5), ((1, 33, 17, 40), 33)])
+def test_label_map_dice_fast_path_vs_one_hot_and_oracle(shape, C):
+    """km_warp_labels_dice (uint8 label maps in, soft + hard Dice sums out) against (a) the engine's
+    own one-hot path: the soft sums must be IDENTICAL (same per-voxel arithmetic and reduction
+    structure), the hard label map identical to argmax of the warped one-hot volume; (b) the oracle's
+    one_hot -> align_img -> DiceLoss (keymorph/loss_ops.py:16-63)."""
+    import torch.nn.functional as F
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) + C)
+    coarse = torch.randint(0, C, (N, 1, D // 3 + 1, H // 3 + 1, W // 3 + 1), generator=g).float()
+    lab_m = F.interpolate(coarse, size=(D, H, W), mode="nearest").long()[:, 0]      # blocky label maps
+    lab_f = lab_m.roll(shifts=(1, 2, -1), dims=(1, 2, 3))
+    inv = O.affine_matrix_3d(0.05, 0.03, 0.2, 0.01).repeat(N, 1, 1)
+    grid = torch.cat([O.affine_flow_field(inv[i:i + 1], (D, H, W)) for i in range(N)])
+    oh_m = F.one_hot(lab_m, C).permute(0, 4, 1, 2, 3).float()
+    oh_f = F.one_hot(lab_f, C).permute(0, 4, 1, 2, 3).float()
+    soft, hard, lab_a = ops.warp_labels_dice(cu(lab_m), cu(lab_f), C, grid=cu(grid), want_labels=True)
+    seg_a, soft_ref = ops.warp_loss(cu(oh_m), cu(oh_f), grid=cu(grid))
+    assert torch.equal(soft, soft_ref)
+    assert torch.equal(lab_a.long().cpu(), seg_a.argmax(1).cpu())
+    hard_ref = ops.pair_stats(seg_a, cu(oh_f), hard=True)
+    assert torch.equal(hard, hard_ref)
+    # oracle: the reference's formulas on the one-hot volumes
+    ref_a = O.align_img(grid, oh_m)
+    for hard_flag, sums in ((False, soft), (True, hard)):
+        ref = O.dice_loss(ref_a, oh_f, hard=hard_flag)
+        assert_close(kb.loss_ops.dice_from_sums(sums).cpu(), ref, rtol=1e-5, atol=1e-6)
+    # affine coordinate mode
+    soft2, hard2 = ops.warp_labels_dice(cu(lab_m), cu(lab_f), C, mat34=cu(inv[:, :3]))
+    assert_close(soft2, soft, rtol=1e-4, atol=1e-2)
+    assert_close(kb.loss_ops.dice_from_sums(hard2), kb.loss_ops.dice_from_sums(hard), rtol=0, atol=2e-3)
+
+
 # ------------------------------------------------------------------------------------ CoM
 def _blob(shape, at, sigma=5):
     img = np.zeros(shape)

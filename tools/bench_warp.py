@@ -44,3 +44,9 @@ timed(lambda: ops.flow_field_affine(inv, (S, S, S)), 12 * N, "flow_field_affine 
 if seg is not None:
     timed(lambda: ops.warp_loss(seg, seg, grid=grid), (12 + 14 * 12) * N, "warp_loss grid C=14 + Dice sums (180 B/vox)")
     timed(lambda: ops.grid_sample3d(seg, grid), (12 + 14 * 8) * N, "grid_sample C=14 (124 B/vox)")
+if seg is not None:
+    lab_m = torch.randint(0, 14, (1, S, S, S), device=dev, dtype=torch.uint8)
+    lab_f = torch.randint(0, 14, (1, S, S, S), device=dev, dtype=torch.uint8)
+    timed(lambda: ops.warp_labels_dice(lab_m, lab_f, 14, grid=grid, want_labels=True), 15 * N,
+          "label-map warp + soft & hard Dice C=14 (15 B/vox)")
+    timed(lambda: ops.pair_stats(seg, seg, hard=True), 14 * 8 * N, "pair_stats hard Dice C=14 (one-hot path, 112 B/vox)")
