@@ -132,6 +132,17 @@ int km_warp_labels_dice(int coord_mode, const float* mat, const float* grid, con
                         double* hard_sums, void* workspace, int N, int C, int D, int H, int W,
                         km_stream_t stream);
 
+/* keymorph/loss_ops.py:161-247 (_jacobian_determinant, jdstd, jdlessthan0): statistics of
+ * the Jacobian determinant of a 3-component fp32 field over the interior cropped by 2 voxels.  The
+ * field is addressed by element strides (n, component, z, y, x), so the (N,3,D,H,W) tensor the
+ * reference passes and the (N,D,H,W,3) grid it is a permuted view of are both read in place.
+ *   out (N,4) fp64 = [std (ddof 0), count(det <= 0), mean, number of interior voxels]
+ * workspace: km_jacobian_stats_workspace_bytes(N).  Requires D, H, W > 4. */
+size_t km_jacobian_stats_workspace_bytes(int N);
+int km_jacobian_stats(const float* field, long long stride_n, long long stride_c, long long stride_z,
+                      long long stride_y, long long stride_x, double* out, void* workspace, int N,
+                      int D, int H, int W, km_stream_t stream);
+
 /* keymorph/loss_ops.py:9-13 and :16-63.  Elementwise-pair statistics of two (N,C,M) fp32 tensors:
  * sums[n,c,:] = [sum (p-t)^2, sum p*t, sum p*p, sum t*t] (fp64).  With hard != 0 pred is replaced
  * by one_hot(argmax_c pred) (first maximum wins, like torch.argmax) before the products.

@@ -640,6 +640,83 @@ __global__ void hard_counts_to_sums_kernel(const unsigned long long* __restrict_
   sums[i * 4 + 3] = t;
 }
 
+// ------------------------------------------------------------------------------------------
+// Jacobian-determinant statistics of a 3-component field (keymorph/loss_ops.py:161-247,
+// _jacobian_determinant / jdstd / jdlessthan0): central differences with weights
+// (-0.5, 0, 0.5) along z, y, x of every component (rounded to fp32 like scipy.ndimage.correlate on
+// a float32 array), J = grad + I in fp64, determinant by the reference's cofactor expansion, over
+// the interior cropped by 2 voxels on every side.  The field is addressed through element strides,
+// so both the (N,3,D,H,W) tensor the reference passes and the (N,D,H,W,3) grid it was permuted
+// from are read in place.  partials: [gridDim.x][N][3] double = sum det, sum det^2, count(det <= 0)
+__global__ void __launch_bounds__(256)
+jacobian_stats_kernel(const float* __restrict__ f, long long sn, long long sc, long long sz, long long sy,
+                      long long sx, double* __restrict__ partials, int N, int D, int H, int W) {
+  const int n = blockIdx.y;
+  const int Dz = D - 4, Hy = H - 4, Wx = W - 4;
+  const long long nint = (long long)Dz * Hy * Wx;
+  const float* fn = f + n * sn;
+  double s = 0.0, ss = 0.0, neg = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nint;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wx) + 2, y = (int)((i / Wx) % Hy) + 2, z = (int)(i / ((long long)Wx * Hy)) + 2;
+    const float* p = fn + z * sz + y * sy + x * sx;
+    double J[3][3];   // J[a][b] = d(component b) / d(direction a) + delta_ab, a in (z, y, x)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const float* q = p + b * sc;
+      J[0][b] = (double)(float)(0.5 * (double)__ldg(q + sz) - 0.5 * (double)__ldg(q - sz));
+      J[1][b] = (double)(float)(0.5 * (double)__ldg(q + sy) - 0.5 * (double)__ldg(q - sy));
+      J[2][b] = (double)(float)(0.5 * (double)__ldg(q + sx) - 0.5 * (double)__ldg(q - sx));
+    }
+    J[0][0] += 1.0;
+    J[1][1] += 1.0;
+    J[2][2] += 1.0;
+    const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -
+                       J[1][0] * (J[0][1] * J[2][2] - J[0][2] * J[2][1]) +
+                       J[2][0] * (J[0][1] * J[1][2] - J[0][2] * J[1][1]);
+    s += det;
+    ss += det * det;
+    neg += det <= 0.0 ? 1.0 : 0.0;
+  }
+  __shared__ double red[8][3];
+  s = km_warp_sum(s);
+  ss = km_warp_sum(ss);
+  neg = km_warp_sum(neg);
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5][0] = s;
+    red[threadIdx.x >> 5][1] = ss;
+    red[threadIdx.x >> 5][2] = neg;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double a = 0.0;
+    for (int w = 0; w < 8; ++w) a += red[w][threadIdx.x];
+    partials[((size_t)blockIdx.x * N + n) * 3 + threadIdx.x] = a;
+  }
+}
+
+// partials -> out[n] = (std over the interior (ddof = 0), count(det <= 0), mean, number of voxels)
+__global__ void jacobian_finalize_kernel(const double* __restrict__ partials, int nparts, double count,
+                                         double* __restrict__ out, int N) {
+  const int n = blockIdx.x;
+  const int lane = threadIdx.x;
+  double a[3] = {0.0, 0.0, 0.0};
+  for (int p = lane; p < nparts; p += 32)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a[k] += partials[((size_t)p * N + n) * 3 + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) a[k] = km_warp_sum(a[k]);
+  if (lane == 0) {
+    const double mean = a[0] / count;
+    double var = a[1] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    out[n * 4 + 0] = sqrt(var);
+    out[n * 4 + 1] = a[2];
+    out[n * 4 + 2] = mean;
+    out[n * 4 + 3] = count;
+  }
+}
+
 // partials [nparts][NC][4] -> sums[NC][4] (fp64)
 __global__ void sum_partials4_kernel(const float* __restrict__ partials, int nparts, int NC4,
                                      double* __restrict__ sums) {
@@ -926,6 +1003,25 @@ extern "C" int km_warp_labels_dice(int coord_mode, const float* mat, const float
   KM_LAUNCH_OK("sum_partials4_kernel");
   hard_counts_to_sums_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(hard, hard_sums, N * C);
   KM_LAUNCH_OK("hard_counts_to_sums_kernel");
+  return KM_OK;
+}
+
+extern "C" size_t km_jacobian_stats_workspace_bytes(int N) {
+  return (size_t)KM_RED_BLOCKS * N * 3 * sizeof(double);
+}
+
+extern "C" int km_jacobian_stats(const float* field, long long stride_n, long long stride_c,
+                                 long long stride_z, long long stride_y, long long stride_x, double* out,
+                                 void* workspace, int N, int D, int H, int W, km_stream_t stream) {
+  KM_CHECK_ARG(field && out && workspace && N > 0, "km_jacobian_stats: bad arguments");
+  KM_CHECK_ARG(D > 4 && H > 4 && W > 4, "km_jacobian_stats: the field must be larger than the 2-voxel crop (got %dx%dx%d)", D, H, W);
+  double* part = reinterpret_cast<double*>(workspace);
+  jacobian_stats_kernel<<<dim3(KM_RED_BLOCKS, N), 256, 0, km_cs(stream)>>>(field, stride_n, stride_c, stride_z,
+                                                                           stride_y, stride_x, part, N, D, H, W);
+  KM_LAUNCH_OK("jacobian_stats_kernel");
+  const double count = (double)(D - 4) * (H - 4) * (W - 4);
+  jacobian_finalize_kernel<<<N, 32, 0, km_cs(stream)>>>(part, KM_RED_BLOCKS, count, out, N);
+  KM_LAUNCH_OK("jacobian_finalize_kernel");
   return KM_OK;
 }
 

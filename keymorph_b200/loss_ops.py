@@ -42,3 +42,22 @@ class DiceLoss(torch.nn.Module):
         n, c = target.shape[0], target.shape[1]
         sums = ops.pair_stats(pred.reshape(n, c, -1), target.reshape(n, c, -1), hard=self.hard)
         return dice_from_sums(sums, ign_first_ch, self.return_regions)
+
+
+def _as_field(disp):
+    if not isinstance(disp, torch.Tensor):
+        disp = torch.as_tensor(disp)
+    if not disp.is_cuda:
+        raise ops._lib.KMError("keymorph_b200.loss_ops.jdstd / jdlessthan0 run on CUDA tensors only")
+    return disp
+
+
+def jdstd(disp):
+    """keymorph/loss_ops.py:237-240: std of the Jacobian determinant of a (1,3,D,H,W) field."""
+    return ops.jacobian_stats(_as_field(disp))[0, 0]
+
+
+def jdlessthan0(disp, as_percentage=False):
+    """keymorph/loss_ops.py:243-248: number (or fraction) of interior voxels with det(J) <= 0."""
+    st = ops.jacobian_stats(_as_field(disp))[0]
+    return st[1] / st[3] if as_percentage else st[1]

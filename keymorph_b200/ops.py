@@ -170,6 +170,23 @@ def warp_labels_dice(labels_m, labels_f, num_classes, *, mat34=None, grid=None, 
     return (soft, hard, lout) if want_labels else (soft, hard)
 
 
+def jacobian_stats(field):
+    """field: fp32 (N,3,D,H,W) -- any strides, e.g. grid.permute(0,4,1,2,3) -- -> (N,4) fp64
+    [std, count(det <= 0), mean, #interior voxels] of the Jacobian determinant (loss_ops.py:161-247)."""
+    _need_cuda(field)
+    if field.dtype != torch.float32:
+        field = field.float()
+    N, Cc, D, H, W = field.shape
+    assert Cc == 3
+    out = torch.empty((N, 4), dtype=torch.float64, device=field.device)
+    ws = _ws(_lib.query("km_jacobian_stats_workspace_bytes", N), field.device)
+    sn, sc, sz, sy, sx = field.stride()
+    with torch.cuda.device(field.device):
+        _lib.call("km_jacobian_stats", _ptr(field), sn, sc, sz, sy, sx, _ptr(out), _ptr(ws), N, D, H, W,
+                  _stream())
+    return out
+
+
 def pair_stats(pred, target, hard=False):
     """sums (N,C,4) fp64 = [sum (p-t)^2, sum p*t, sum p*p, sum t*t] over the flattened spatial dims;
     hard=True replaces pred by one_hot(argmax_c pred)."""

@@ -60,9 +60,33 @@ def save(name, **arrays):
     print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB, keys {sorted(conv)}")
 
 
+def gen_jacobian():
+    """Jacobian-determinant metrics (keymorph/loss_ops.py:161-247) of an affine grid and of a folded
+    (non-diffeomorphic) field, computed by the reference functions themselves."""
+    from keymorph import loss_ops
+    from keymorph.keypoint_aligners import TPS
+    g = torch.Generator().manual_seed(7)
+    pts_f = torch.rand(1, 24, 3, generator=g) * 1.6 - 0.8
+    pts_m = pts_f + 0.15 * torch.randn(1, 24, 3, generator=g)
+    grid = TPS(pts_m, pts_f, torch.tensor([0.0])).get_flow_field((1, 1, 14, 12, 16))     # (1,14,12,16,3)
+    disp = grid.permute(0, 4, 1, 2, 3).contiguous()
+    # the reference is handed the NORMALISED grid (pairwise_register_eval.py:337-338); a second case in
+    # voxel units exercises determinants <= 0
+    disp_vox = disp * torch.tensor([8.0, 6.0, 7.0]).view(1, 3, 1, 1, 1) * torch.randn(1, 3, 14, 12, 16, generator=g).sign()
+    out = {"disp": disp, "disp_vox": disp_vox}
+    for tag, d in (("norm", disp), ("vox", disp_vox)):
+        out[f"jdstd_{tag}"] = np.float64(loss_ops.jdstd(d.numpy()))
+        out[f"jdneg_{tag}"] = np.int64(loss_ops.jdlessthan0(d.numpy()))
+        out[f"jd_{tag}"] = loss_ops._jacobian_determinant(d.numpy())
+    save("jacobian", **out)
+
+
 def main():
     import_reference()
     sys.path.insert(0, ROOT)
+    if "--only-jacobian" in sys.argv:
+        gen_jacobian()
+        return
     from keymorph import layers, loss_ops, utils
     from keymorph.augmentation import affine_augment
     from keymorph.keypoint_aligners import TPS, AffineKeypointAligner, RigidKeypointAligner
@@ -225,6 +249,7 @@ def main():
             for i in range(4):
                 out[f"{t}_grid_{i}"] = np.load(os.path.join(sd, f"{t}_grid_{i:03}.npy"))[:, ::2, ::2, ::2]
         save("groupwise32", **out)
+    gen_jacobian()
 
 
 if __name__ == "__main__":

@@ -105,6 +105,47 @@ def weight_by_power(feat1, feat2):
     return w / w.sum(dim=1)
 
 
+def jacobian_determinant(disp):
+    """keymorph/loss_ops.py:161-234 without scipy: central differences (-0.5, 0, 0.5) of the three
+    components of a (1,3,D,H,W) fp32 field along z, y, x (each rounded to fp32 as
+    scipy.ndimage.correlate does for a float32 input), + identity in fp64, cofactor determinant,
+    2-voxel crop.  Returns the float64 (D-4,H-4,W-4) array."""
+    import numpy as np
+    d = np.asarray(disp.detach().cpu().numpy() if isinstance(disp, torch.Tensor) else disp)[0].astype(np.float32)
+
+    def grad(a, axis):
+        a = a.astype(np.float64)
+        g = np.zeros_like(a)
+        hi = [slice(None)] * 3
+        lo = [slice(None)] * 3
+        mid = [slice(None)] * 3
+        hi[axis], lo[axis], mid[axis] = slice(2, None), slice(None, -2), slice(1, -1)
+        g[tuple(mid)] = 0.5 * a[tuple(hi)] - 0.5 * a[tuple(lo)]
+        return g.astype(np.float32).astype(np.float64)
+
+    J = np.zeros((3, 3) + d.shape[1:], dtype=np.float64)
+    for a in range(3):
+        for b in range(3):
+            J[a, b] = grad(d[b], a)
+        J[a, a] += 1.0
+    J = J[:, :, 2:-2, 2:-2, 2:-2]
+    return (J[0, 0] * (J[1, 1] * J[2, 2] - J[1, 2] * J[2, 1]) - J[1, 0] * (J[0, 1] * J[2, 2] - J[0, 2] * J[2, 1])
+            + J[2, 0] * (J[0, 1] * J[1, 2] - J[0, 2] * J[1, 1]))
+
+
+def jdstd(disp):
+    """keymorph/loss_ops.py:237-240."""
+    return float(jacobian_determinant(disp).std())
+
+
+def jdlessthan0(disp, as_percentage=False):
+    """keymorph/loss_ops.py:243-248."""
+    import numpy as np
+    jd = jacobian_determinant(disp)
+    n = int(np.count_nonzero(jd <= 0))
+    return n / jd.size if as_percentage else n
+
+
 # --------------------------------------------------------------------------------------------
 # closed-form aligners
 

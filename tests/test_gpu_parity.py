@@ -157,6 +157,27 @@ def test_label_map_dice_fast_path_vs_one_hot_and_oracle(shape, C):
     assert_close(kb.loss_ops.dice_from_sums(hard2), kb.loss_ops.dice_from_sums(hard), rtol=0, atol=2e-3)
 
 
+def test_jacobian_stats_golden_and_strided(golden):
+    """km_jacobian_stats (loss_ops.jdstd / jdlessthan0 on the device) against the reference's outputs,
+    on the contiguous (1,3,D,H,W) field and in place on the permuted view of an (N,D,H,W,3) grid."""
+    g = golden("jacobian")
+    for tag, key in (("norm", "disp"), ("vox", "disp_vox")):
+        d = cu(g[key])
+        assert abs(float(kb.loss_ops.jdstd(d)) - float(g[f"jdstd_{tag}"])) < 1e-9
+        assert int(kb.loss_ops.jdlessthan0(d)) == int(g[f"jdneg_{tag}"])
+        grid_like = d.permute(0, 2, 3, 4, 1).contiguous()          # (1,D,H,W,3)
+        st = ops.jacobian_stats(grid_like.permute(0, 4, 1, 2, 3))    # the view run_eval builds
+        assert abs(float(st[0, 0]) - float(g[f"jdstd_{tag}"])) < 1e-9 and int(st[0, 1]) == int(g[f"jdneg_{tag}"])
+    # batch of two + oracle on a larger random field
+    gen = torch.Generator().manual_seed(5)
+    f = torch.randn(2, 3, 19, 23, 21, generator=gen)
+    st = ops.jacobian_stats(cu(f)).cpu()
+    for i in range(2):
+        assert abs(float(st[i, 0]) - O.jdstd(f[i:i + 1])) < 1e-9
+        assert int(st[i, 1]) == O.jdlessthan0(f[i:i + 1])
+        assert int(st[i, 3]) == 15 * 19 * 17
+
+
 # ------------------------------------------------------------------------------------ CoM
 def _blob(shape, at, sigma=5):
     img = np.zeros(shape)

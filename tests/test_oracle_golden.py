@@ -208,3 +208,16 @@ def test_golden_groupwise(golden):
         for i in range(len(subj)):
             grid = O.register_points(mean, pts[i:i + 1], t, subj.shape[2:], None, False)["grid"]
             assert_close(grid[:, ::2, ::2, ::2], g[f"{t}_grid_{i}"], rtol=2e-4, atol=2e-4)
+
+
+def test_golden_jacobian(golden):
+    """Oracle restatement of loss_ops._jacobian_determinant / jdstd / jdlessthan0 (no scipy) against the
+    reference's own outputs: the determinant field must agree to fp64 rounding."""
+    import numpy as np
+    g = golden("jacobian")
+    for tag, key in (("norm", "disp"), ("vox", "disp_vox")):
+        jd = O.jacobian_determinant(g[key])
+        np.testing.assert_allclose(jd, g[f"jd_{tag}"].numpy(), rtol=1e-12, atol=1e-12)
+        assert abs(O.jdstd(g[key]) - float(g[f"jdstd_{tag}"])) < 1e-12
+        assert O.jdlessthan0(g[key]) == int(g[f"jdneg_{tag}"])
+    assert int(g["jdneg_vox"]) > 0      # the folded field really has non-positive determinants
