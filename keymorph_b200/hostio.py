@@ -35,3 +35,97 @@ def prefetch_to_device(items, device):
         for t in cur:
             t.record_stream(compute)
         yield cur
+
+
+# --------------------------------------------------------------------------------------------
+# NIfTI-1 input without nibabel / torchio (scripts/register.py:40-118 goes through torchio's
+# ScalarImage / LabelMap, hyperparameters.py:4-11 TRANSFORM = ToCanonical, Mask, Resize(128),
+# rescale_intensity).  Host-side Python/numpy only: file parsing is not on the GPU hot path.
+_NIFTI_DTYPES = {2: "u1", 4: "i2", 8: "i4", 16: "f4", 64: "f8", 256: "i1", 512: "u2", 768: "u4"}
+
+
+def read_nifti(path):
+    """Read a NIfTI-1 single-file image (.nii or .nii.gz).  Returns (array (X,Y,Z[,T]) in file
+    orientation with scl_slope / scl_inter applied when set, affine (4,4) float64 from the sform,
+    or the pixdim-scaled identity when sform_code == 0)."""
+    import gzip
+    import struct
+
+    import numpy as np
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rb") as f:
+        raw = f.read()
+    for end in ("<", ">"):
+        if struct.unpack(end + "i", raw[:4])[0] == 348:
+            break
+    else:
+        raise ValueError(f"{path}: not a NIfTI-1 file (sizeof_hdr != 348)")
+    if raw[344:347] not in (b"n+1", b"ni1"):
+        raise ValueError(f"{path}: bad NIfTI magic {raw[344:348]!r}")
+    dim = struct.unpack(end + "8h", raw[40:56])
+    datatype = struct.unpack(end + "h", raw[70:72])[0]
+    if datatype not in _NIFTI_DTYPES:
+        raise ValueError(f"{path}: unsupported NIfTI datatype {datatype}")
+    pixdim = struct.unpack(end + "8f", raw[76:108])
+    vox_offset = int(struct.unpack(end + "f", raw[108:112])[0])
+    slope, inter = struct.unpack(end + "2f", raw[112:120])
+    sform_code = struct.unpack(end + "h", raw[254:256])[0]
+    shape = tuple(int(d) for d in dim[1:1 + dim[0]])
+    dt = np.dtype(end + _NIFTI_DTYPES[datatype])
+    count = int(np.prod(shape))
+    data = np.frombuffer(raw, dtype=dt, count=count, offset=vox_offset).reshape(shape, order="F")
+    if slope not in (0.0, 1.0) or (slope != 0.0 and inter != 0.0):
+        data = data.astype(np.float64) * slope + inter
+    affine = np.eye(4)
+    if sform_code > 0:
+        affine[:3, :] = np.array(struct.unpack(end + "12f", raw[280:328]), dtype=np.float64).reshape(3, 4)
+    else:
+        affine[:3, :3] = np.diag(pixdim[1:4])
+    return data, affine
+
+
+def to_canonical(data, affine):
+    """torchio.ToCanonical / nibabel.as_closest_canonical for (near) axis-aligned affines: permute
+    and flip the voxel axes so that they run left->Right, posterior->Anterior, inferior->Superior."""
+    import numpy as np
+    R = affine[:3, :3]
+    perm = [int(np.argmax(np.abs(R[i, :]))) for i in range(3)]   # voxel axis that drives world axis i
+    if sorted(perm) != [0, 1, 2]:
+        raise ValueError("to_canonical: oblique affine; resample first")
+    data = np.transpose(data, perm + list(range(3, data.ndim)))
+    aff = affine[:, perm + [3]].copy()
+    for i in range(3):
+        if aff[i, i] < 0:
+            data = np.flip(data, axis=i)
+            aff[:3, 3] += aff[:3, i] * (data.shape[i] - 1)
+            aff[:3, i] = -aff[:3, i]
+    return np.ascontiguousarray(data), aff
+
+
+def load_volume(path, size=None, labels=False):
+    """One subject as the reference's loaders deliver it to the model: canonical orientation, resized
+    to `size`^3 when the volume is an integer multiple of it (block mean for images, strided pick
+    for label maps -- a deterministic stand-in for torchio.Resize), intensities
+    rescaled to [0, 1] (keymorph/utils.py:78-94).  Returns (tensor (1,1,D,H,W) float32 | uint8, affine)."""
+    import numpy as np
+    data, affine = to_canonical(*read_nifti(path))
+    if data.ndim == 4:
+        data = data[..., 0]
+    if size is not None and data.shape != (size,) * 3:
+        f = [s // size for s in data.shape]
+        if any(s != size * k or k < 1 for s, k in zip(data.shape, f)):
+            raise ValueError(f"load_volume: {data.shape} is not an integer multiple of {size}")
+        if labels:
+            data = data[::f[0], ::f[1], ::f[2]]
+        else:
+            data = data.astype(np.float32).reshape(size, f[0], size, f[1], size, f[2]).mean(axis=(1, 3, 5))
+        affine = affine.copy()
+        affine[:3, :3] = affine[:3, :3] * np.array(f, dtype=np.float64)[None, :]
+    if labels:
+        t = torch.from_numpy(np.ascontiguousarray(data).astype(np.uint8))
+    else:
+        a = np.ascontiguousarray(data).astype(np.float32)
+        lo, hi = float(a.min()), float(a.max())
+        a = (a - lo) / (hi - lo) if hi > lo else np.zeros_like(a)
+        t = torch.from_numpy(a)
+    return t[None, None], affine

@@ -81,11 +81,60 @@ def gen_jacobian():
     save("jacobian", **out)
 
 
+def gen_example_pair():
+    """BASELINE config 1 at fixture size: the bundled example_data_half pair (real T1 anatomy + 14-label
+    segmentations, read with keymorph_b200.hostio -- no nibabel / torchio here), block-averaged to 64^3
+    and quantised to uint8 so that the fixture is small and every consumer sees identical floats,
+    through the REFERENCE model (seeded TruncatedUNet3D, K = 32) and the reference's align_img /
+    MSELoss / DiceLoss / jdstd."""
+    sys.path.insert(0, ROOT)
+    from keymorph import loss_ops, utils
+    from keymorph.model import KeyMorph
+    from keymorph.unet3d.model import TruncatedUNet3D
+    from keymorph_b200 import hostio
+    d = os.path.join(REF, "example_data_half")
+    f_img, _ = hostio.load_volume(os.path.join(d, "img_m", "IXI_001_128x128x128.nii.gz"), size=64)
+    m_img, _ = hostio.load_volume(os.path.join(d, "img_m", "IXI_002_128x128x128.nii.gz"), size=64)
+    f_seg, _ = hostio.load_volume(os.path.join(d, "seg_m", "IXI_001_128x128x128.nii.gz"), size=64, labels=True)
+    m_seg, _ = hostio.load_volume(os.path.join(d, "seg_m", "IXI_002_128x128x128.nii.gz"), size=64, labels=True)
+    f_u8 = (f_img * 255).round().to(torch.uint8)
+    m_u8 = (m_img * 255).round().to(torch.uint8)
+    img_f, img_m = f_u8.float() / 255, m_u8.float() / 255
+    C = int(max(f_seg.max(), m_seg.max())) + 1
+    oh = lambda lab: torch.nn.functional.one_hot(lab[:, 0].long(), C).permute(0, 4, 1, 2, 3).float()  # noqa: E731
+    seg_f, seg_m = oh(f_seg), oh(m_seg)
+    torch.manual_seed(23)
+    net = TruncatedUNet3D(1, 32, 1, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8,
+                          num_levels=4, is_segmentation=False, conv_padding=1)
+    model = KeyMorph(torch.nn.DataParallel(net), 32, 3).eval()
+    types = ["rigid", "affine", "tps_1"]
+    with torch.no_grad():
+        res = model(img_f, img_m, transform_type=types, return_aligned_points=True)
+    out = {"img_f_u8": f_u8, "img_m_u8": m_u8, "lab_f": f_seg, "lab_m": m_seg, "num_classes": np.int64(C)}
+    for t in types:
+        r = res[t]
+        img_a = utils.align_img(r["grid"], img_m)
+        seg_a = utils.align_img(r["grid"], seg_m)
+        out[f"{t}_points_f"], out[f"{t}_points_m"] = r["points_f"], r["points_m"]
+        out[f"{t}_grid"] = r["grid"][:, ::4, ::4, ::4]
+        if "matrix" in r:
+            out[f"{t}_matrix"] = r["matrix"]
+        out[f"{t}_mse"] = loss_ops.MSELoss()(img_a, img_f)
+        out[f"{t}_softdice"] = loss_ops.DiceLoss()(seg_a, seg_f)
+        out[f"{t}_harddice"] = loss_ops.DiceLoss(hard=True)(seg_a, seg_f)
+        out[f"{t}_jdstd"] = np.float64(loss_ops.jdstd(r["grid"].permute(0, 4, 1, 2, 3).numpy()))
+        out[f"{t}_jdneg"] = np.int64(loss_ops.jdlessthan0(r["grid"].permute(0, 4, 1, 2, 3).numpy()))
+    save("example_pair64", **out)
+
+
 def main():
     import_reference()
     sys.path.insert(0, ROOT)
     if "--only-jacobian" in sys.argv:
         gen_jacobian()
+        return
+    if "--only-example" in sys.argv:
+        gen_example_pair()
         return
     from keymorph import layers, loss_ops, utils
     from keymorph.augmentation import affine_augment
@@ -250,6 +299,7 @@ def main():
                 out[f"{t}_grid_{i}"] = np.load(os.path.join(sd, f"{t}_grid_{i:03}.npy"))[:, ::2, ::2, ::2]
         save("groupwise32", **out)
     gen_jacobian()
+    gen_example_pair()
 
 
 if __name__ == "__main__":

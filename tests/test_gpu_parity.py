@@ -599,6 +599,49 @@ def test_forward_golden(golden, power):
         assert_close(al.get_forward_transformed_points(pm).cpu(), g[f"{t}_points_a"], rtol=0, atol=tol)
 
 
+def test_example_pair_config1_vs_reference(golden):
+    """BASELINE config 1 on the GPU (bundled example pair reduced to 64^3, real anatomy + 14 labels):
+    the whole pairwise call incl. the label-map Dice fast path and the Jacobian statistics against the
+    reference's own numbers.  End to end the bf16 backbone moves the keypoints (budget 1e-2); on the
+    reference's keypoints every later stage is tight."""
+    g = golden("example_pair64")
+    C = int(g["num_classes"])
+    img_f, img_m = cu(g["img_f_u8"].float() / 255), cu(g["img_m_u8"].float() / 255)
+    lab_f, lab_m = cu(g["lab_f"]), cu(g["lab_m"])
+    model = kb.KeyMorph(torch.nn.DataParallel(_seeded("trunc", 32).to(DEV)), 32, 3, fused_warp=True).eval()
+    types = ["rigid", "affine", "tps_1"]
+    res = model(img_f, img_m, transform_type=types, return_aligned_points=True, labels_f=lab_f, labels_m=lab_m,
+                num_classes=C)
+    for t in types:
+        r = res[t]
+        e_kp = max((r["points_f"].cpu() - g[f"{t}_points_f"]).abs().max().item(),
+                   (r["points_m"].cpu() - g[f"{t}_points_m"]).abs().max().item())
+        print(f"example pair {t}: keypoints {e_kp:.2e}  mse {r['mse'].item():.5f} (ref {g[f'{t}_mse'].item():.5f})  "
+              f"softdice {r['softdice'].item():.4f} (ref {g[f'{t}_softdice'].item():.4f})  "
+              f"harddice {r['harddice'].item():.4f} (ref {g[f'{t}_harddice'].item():.4f})")
+        assert e_kp < 1e-2
+        # end to end: the metrics move with the keypoints; they must stay close to the reference's
+        assert abs(r["mse"].item() - g[f"{t}_mse"].item()) < 0.1 * g[f"{t}_mse"].item() + 1e-4
+        assert abs(r["softdice"].item() - g[f"{t}_softdice"].item()) < 3e-2
+        assert abs(r["harddice"].item() - g[f"{t}_harddice"].item()) < 3e-2
+        # identical inputs: the reference's keypoints through our aligner / warp / Dice / Jacobian kernels
+        pf, pm = cu(g[f"{t}_points_f"]), cu(g[f"{t}_points_m"])
+        kind, lam = O.parse_transform(t)
+        al = kb.TPS(pm, pf, torch.tensor([lam], device=DEV)) if kind == "tps" else \
+            (kb.RigidKeypointAligner if kind == "rigid" else kb.AffineKeypointAligner)(pm, pf)
+        grid = al.get_flow_field(img_f.shape)
+        assert_close(grid.cpu()[:, ::4, ::4, ::4], g[f"{t}_grid"], rtol=0, atol=2e-4)
+        if kind != "tps":
+            assert_close(al.transform_matrix.cpu(), g[f"{t}_matrix"], rtol=1e-4, atol=1e-4)
+        img_a, sums = ops.warp_loss(img_m, img_f, grid=grid)
+        assert_close((sums[..., 0].sum() / img_f.numel()).float().cpu(), g[f"{t}_mse"], rtol=2e-3, atol=1e-6)
+        soft, hard = ops.warp_labels_dice(lab_m, lab_f, C, grid=grid)
+        assert_close(kb.loss_ops.dice_from_sums(soft).cpu(), g[f"{t}_softdice"], rtol=2e-3, atol=1e-4)
+        assert_close(kb.loss_ops.dice_from_sums(hard).cpu(), g[f"{t}_harddice"], rtol=5e-3, atol=5e-4)
+        assert abs(float(kb.loss_ops.jdstd(grid.permute(0, 4, 1, 2, 3))) - float(g[f"{t}_jdstd"])) < 1e-5
+        assert int(kb.loss_ops.jdlessthan0(grid.permute(0, 4, 1, 2, 3))) == int(g[f"{t}_jdneg"])
+
+
 def test_forward_fused_warp_outputs():
     net = _seeded("trunc").to(DEV)
     model = kb.KeyMorph(net, 16, 3, fused_warp=True).eval()

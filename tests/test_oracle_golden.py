@@ -221,3 +221,54 @@ def test_golden_jacobian(golden):
         assert abs(O.jdstd(g[key]) - float(g[f"jdstd_{tag}"])) < 1e-12
         assert O.jdlessthan0(g[key]) == int(g[f"jdneg_{tag}"])
     assert int(g["jdneg_vox"]) > 0      # the folded field really has non-positive determinants
+
+
+def _example_inputs(g):
+    C = int(g["num_classes"])
+    img_f, img_m = g["img_f_u8"].float() / 255, g["img_m_u8"].float() / 255
+    oh = lambda lab: torch.nn.functional.one_hot(lab[:, 0].long(), C).permute(0, 4, 1, 2, 3).float()  # noqa: E731
+    return img_f, img_m, oh(g["lab_f"]), oh(g["lab_m"]), C
+
+
+def test_golden_example_pair_config1(golden):
+    """BASELINE config 1 (bundled example_data_half pair, reduced to 64^3): the oracle pipeline on real
+    anatomy against the reference's own forward / align_img / MSELoss / DiceLoss / jdstd outputs."""
+    import keymorph_b200 as kb
+    g = golden("example_pair64")
+    img_f, img_m, seg_f, seg_m, _ = _example_inputs(g)
+    torch.manual_seed(23)
+    net = kb.TruncatedUNet3D(1, 32, 1, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8,
+                             num_levels=4, is_segmentation=False, conv_padding=1)
+    types = ["rigid", "affine", "tps_1"]
+    res = O.keymorph_forward("truncatedunet", net.state_dict(), img_f, img_m, types)
+    for t in types:
+        r = res[t]
+        assert_close(r["points_f"], g[f"{t}_points_f"], rtol=1e-5, atol=1e-5)
+        assert_close(r["points_m"], g[f"{t}_points_m"], rtol=1e-5, atol=1e-5)
+        assert_close(r["grid"][:, ::4, ::4, ::4], g[f"{t}_grid"], rtol=1e-4, atol=1e-4)
+        img_a, seg_a = O.align_img(r["grid"], img_m), O.align_img(r["grid"], seg_m)
+        assert_close(O.mse_loss(img_a, img_f), g[f"{t}_mse"], rtol=1e-3, atol=1e-6)
+        assert_close(O.dice_loss(seg_a, seg_f), g[f"{t}_softdice"], rtol=1e-3, atol=1e-5)
+        assert_close(O.dice_loss(seg_a, seg_f, hard=True), g[f"{t}_harddice"], rtol=2e-3, atol=1e-4)
+        assert abs(O.jdstd(r["grid"].permute(0, 4, 1, 2, 3)) - float(g[f"{t}_jdstd"])) < 1e-6
+
+
+def test_nifti_reader_reproduces_the_fixture(golden):
+    """keymorph_b200.hostio.load_volume (NIfTI-1 + canonical orientation + block resize + rescale, no
+    nibabel / torchio) on the reference's bundled files; skipped where /root/reference is absent."""
+    import os
+    import pytest
+    from keymorph_b200 import hostio
+    d = "/root/reference/example_data_half"
+    if not os.path.isdir(d):
+        pytest.skip("reference example data not available on this machine")
+    g = golden("example_pair64")
+    img, aff = hostio.load_volume(os.path.join(d, "img_m", "IXI_001_128x128x128.nii.gz"), size=64)
+    lab, _ = hostio.load_volume(os.path.join(d, "seg_m", "IXI_001_128x128x128.nii.gz"), size=64, labels=True)
+    assert img.shape == (1, 1, 64, 64, 64) and float(img.min()) == 0.0 and float(img.max()) == 1.0
+    assert torch.equal((img * 255).round().to(torch.uint8), g["img_f_u8"])
+    assert torch.equal(lab, g["lab_f"]) and int(lab.max()) == 13
+    # canonical (RAS+) orientation: the file's sform diag(-1,-1,1) is flipped on axes 0 and 1
+    assert aff[0, 0] > 0 and aff[1, 1] > 0 and aff[2, 2] > 0
+    raw, a0 = hostio.read_nifti(os.path.join(d, "img_m", "IXI_001_128x128x128.nii.gz"))
+    assert raw.shape == (256, 256, 256) and a0[0, 0] == -1.0 and a0[1, 1] == -1.0
