@@ -190,6 +190,11 @@ flow_affine_kernel(const float* __restrict__ mat, float* __restrict__ grid, int 
   }
 }
 
+// Dense TPS field.  MUFU / FP32-issue bound (K radial-basis terms per voxel, 2 MUFU + ~13 FP32
+// instructions each), not memory bound: a thread evaluates FOUR voxels per control point so that
+// the two broadcast shared-memory loads and the loop overhead are amortised over four terms and
+// the four independent FMA chains hide the MUFU latency.  A warp owns 128 consecutive voxels
+// (lane i: voxels i, i+32, i+64, i+96), so the 12-byte stores of a warp stay contiguous.
 template <bool FAST>
 __global__ void __launch_bounds__(256)
 flow_tps_kernel(const float* __restrict__ ctrl, const float* __restrict__ theta,
@@ -202,15 +207,45 @@ flow_tps_kernel(const float* __restrict__ ctrl, const float* __restrict__ theta,
   load_tps_smem(ctrl + (size_t)n * K * 3, theta + (size_t)n * (K + 4) * 3, K, c4, w4, aff);
   const long long nvox = (long long)D * H * W;
   float* gn = grid + (size_t)n * nvox * 3;
-  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvox;
-       v += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(v % W), y = (int)((v / W) % H), z = (int)(v / ((long long)W * H));
-    float oz, oy, ox;
-    tps_eval<FAST>(c4, w4, aff, K, km_linspace(-1.f, 1.f, D, z), km_linspace(-1.f, 1.f, H, y),
-                   km_linspace(-1.f, 1.f, W, x), oz, oy, ox);
-    gn[v * 3 + 0] = ox;
-    gn[v * 3 + 1] = oy;
-    gn[v * 3 + 2] = oz;
+  const int lane = threadIdx.x & 31;
+  const long long nchunks = (nvox + 127) / 128;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long chunk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks;
+       chunk += warps) {
+    float pz[4], py[4], px[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      long long v = chunk * 128 + lane + 32 * k;
+      if (v >= nvox) v = nvox - 1;
+      const int x = (int)(v % W), y = (int)((v / W) % H), z = (int)(v / ((long long)W * H));
+      pz[k] = km_linspace(-1.f, 1.f, D, z);
+      py[k] = km_linspace(-1.f, 1.f, H, y);
+      px[k] = km_linspace(-1.f, 1.f, W, x);
+    }
+    float az[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int t = 0; t < K; ++t) {
+      const float4 c = c4[t];
+      const float4 w = w4[t];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float dz = pz[k] - c.x, dy = py[k] - c.y, dx = px[k] - c.z;
+        const float u = tps_u<FAST>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        az[k] = fmaf(u, w.x, az[k]);
+        ay[k] = fmaf(u, w.y, ay[k]);
+        ax[k] = fmaf(u, w.z, ax[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long v = chunk * 128 + lane + 32 * k;
+      if (v < nvox) {
+        // z = [1, p] . affine  (keymorph/keypoint_aligners.py:427-433), out = z + b
+        gn[v * 3 + 0] = (aff[2] + aff[5] * pz[k] + aff[8] * py[k] + aff[11] * px[k]) + ax[k];
+        gn[v * 3 + 1] = (aff[1] + aff[4] * pz[k] + aff[7] * py[k] + aff[10] * px[k]) + ay[k];
+        gn[v * 3 + 2] = (aff[0] + aff[3] * pz[k] + aff[6] * py[k] + aff[9] * px[k]) + az[k];
+      }
+    }
   }
 }
 

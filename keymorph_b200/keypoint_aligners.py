@@ -97,7 +97,7 @@ class TPS(nn.Module):
 
     def __init__(self, points_m, points_f, lmbda, w=None, dim=3, num_subgrids=4,
                  use_checkpoint=False, align_in_real_world_coords=False, aff_m=None, aff_f=None,
-                 shape_m=None, shape_f=None):
+                 shape_m=None, shape_f=None, fit_forward=False):
         super().__init__()
         if dim != 3:
             raise NotImplementedError("keymorph_b200 implements the 3-D path only")
@@ -115,8 +115,18 @@ class TPS(nn.Module):
             self.points_m = convert_points_norm2real(self.points_m, aff_m, shape_m)
             self.points_f = convert_points_norm2real(self.points_f, aff_f, shape_f)
         # note the flipped order: theta maps FIXED -> MOVING (keymorph/keypoint_aligners.py:268-274)
-        self.inverse_theta = self.fit(self.points_f, self.points_m, lmbda, weights=w)
-        self.theta = None
+        if fit_forward:
+            # both directions (the reference fits the forward one lazily in
+            # get_forward_transformed_points, :451-465) as ONE batched device solve
+            nb = self.points_f.shape[0]
+            lam = torch.as_tensor(lmbda).reshape(-1)
+            both = self.fit(torch.cat([self.points_f, self.points_m]), torch.cat([self.points_m, self.points_f]),
+                            torch.cat([lam, lam]) if lam.numel() == nb else lam,
+                            weights=None if w is None else torch.cat([w, w]))
+            self.inverse_theta, self.theta = both[:nb], both[nb:]
+        else:
+            self.inverse_theta = self.fit(self.points_f, self.points_m, lmbda, weights=w)
+            self.theta = None
 
     def fit(self, c_src, c_dst, lmbda, weights=None):
         """keymorph/keypoint_aligners.py:341-363: theta (bs, T+4, 3)."""

@@ -87,7 +87,7 @@ class KeyMorph(nn.Module):
         return s in ["affine", "rigid"] or bool(re.match(r"^tps_.*$", s))
 
     def _make_aligner(self, align_type, points_m, points_f, weights, tps_lmbda, aff_f=None,
-                      aff_m=None, shape_f=None, shape_m=None, real_world=False):
+                      aff_m=None, shape_f=None, shape_m=None, real_world=False, fit_forward=False):
         common = dict(points_m=points_m, points_f=points_f, w=weights, aff_f=aff_f, aff_m=aff_m,
                       shape_f=shape_f, shape_m=shape_m, dim=self.dim,
                       align_in_real_world_coords=real_world)
@@ -95,7 +95,7 @@ class KeyMorph(nn.Module):
             return RigidKeypointAligner(**common)
         if align_type == "affine":
             return AffineKeypointAligner(**common)
-        return TPS(lmbda=tps_lmbda, use_checkpoint=self.use_checkpoint, **common)
+        return TPS(lmbda=tps_lmbda, use_checkpoint=self.use_checkpoint, fit_forward=fit_forward, **common)
 
     # ------------------------------------------------------------------ pairwise
     @torch.no_grad()
@@ -146,7 +146,8 @@ class KeyMorph(nn.Module):
                 align_type, tps_lmbda = align_type_str, None
             aligner = self._make_aligner(align_type, points_m, points_f, weights, tps_lmbda, aff_f,
                                          aff_m, shape_f, shape_m,
-                                         self.align_keypoints_in_real_world_coords)
+                                         self.align_keypoints_in_real_world_coords,
+                                         fit_forward=bool(return_aligned_points))
             fused = None
             if self.fused_warp and align_type in ("rigid", "affine") and img_m.shape == img_f.shape:
                 # one pass generates the flow field, warps the moving image and takes the loss sums
