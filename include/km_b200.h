@@ -282,6 +282,15 @@ int km_pack_weights_zfold(const float* w, void* packed, int Cout, int Cin, km_st
 int km_conv3d_zfold(const void* x, const void* wz, void* out, void* pooled, float* stats, int N, int Cin,
                     int Cout, int D, int H, int W, int flags, km_stream_t stream);
 
+/* 2-CTA (cta_group::2) variant of km_conv3d_tc for the 3x3x3 layers with Cout in {64, 128} and
+ * Cin % 32 == 0 (csrc/conv_tc2.cu): two SMs execute one M = 256 MMA, each supplying its own 128
+ * activation rows and half of the weight rows, which halves the weight bytes read from shared
+ * memory per SM (the bound of these layers).  Same tensors, weights (km_pack_weights, taps = 27),
+ * flags (KM_CONV_RELU | KM_CONV_STATS) and statistics layout as km_conv3d_tc, no bias. */
+int km_conv3d_tc_pair_supported(int Cin, int Cout, int D, int H, int W);
+int km_conv3d_tc_pair(const void* x, const void* wp, void* out, float* stats, int N, int Cin, int Cout,
+                      int D, int H, int W, int flags, km_stream_t stream);
+
 /* Final 1x1x1 convolution fused with ReLU + centre of mass, transposed tcgen05 formulation
  * (keymorph/unet3d/model.py:99,389 final_conv + keymorph/layers.py:92-134 + keymorph/model.py:95-109):
  * heat^T[channel, voxel] = W . X^T, one epilogue thread per keypoint channel, sums in registers; the

@@ -109,6 +109,10 @@ class UNetEngine(_EngineBase):
             # first tensor-core layer (16 -> 32 at full resolution): dz taps folded into MMA N
             out, stats = ops.conv3d_zfold(x_norm, self.weights.get(key + ".zf", w, zfold=True),
                                           relu=True, want_stats=True)
+        elif ops.USE_PAIR_CONV and D * H * W >= 64 ** 3 and ops.pair_supported(Cin, w.shape[0], D, H, W):
+            # Cout in {64, 128}: two SMs per M = 256 MMA, half of the weight rows per SM (measured faster
+            # from 64^3 up; below that there are too few brick groups per CTA pair)
+            out, stats = ops.conv3d_tc_pair(x_norm, self.weights.get(key, w), relu=True, want_stats=True)
         else:
             out, stats, _ = ops.conv3d_tc(x_norm, self.weights.get(key, w), relu=True, want_stats=True)
         self._dbg(key, out)

@@ -325,6 +325,31 @@ def conv3d_tc(x, wp, bias=None, relu=False, want_stats=False, want_com=False, st
     return out, stats, com
 
 
+USE_PAIR_CONV = True      # engine switch: 2-CTA kernel for the Cout in {64,128} layers (A/B testing)
+
+
+def pair_supported(Cin, Cout, D, H, W):
+    return bool(_lib.query("km_conv3d_tc_pair_supported", Cin, Cout, D, H, W))
+
+
+def conv3d_tc_pair(x, wp, relu=False, want_stats=False):
+    """2-CTA (cta_group::2) tcgen05 conv, 3x3x3, Cout in {64,128}.  Same arguments as conv3d_tc."""
+    _need_cuda(x, wp)
+    assert x.dtype == torch.bfloat16 and wp.dtype == torch.bfloat16
+    x, wp = x.contiguous(), wp.contiguous()
+    N, D, H, W, Cin = x.shape
+    taps, Cout, Cin2 = wp.shape
+    assert taps == 27 and Cin2 == Cin
+    flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
+    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x.device) \
+        if want_stats else None
+    with torch.cuda.device(x.device):
+        _lib.call("km_conv3d_tc_pair", _ptr(x), _ptr(wp), _ptr(out), _ptr(stats), N, Cin, Cout, D, H, W,
+                  flags, _stream())
+    return out, stats
+
+
 def zfold_supported(Cin, Cout, D, H, W):
     return bool(_lib.query("km_conv3d_zfold_supported", Cin, Cout, D, H, W))
 

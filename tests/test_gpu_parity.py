@@ -244,6 +244,23 @@ def test_conv3d_zfold_vs_general_kernel_and_fp32(shape):
         assert_close(stp.double().sum(0).cpu(), sp_ref, rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("cfg", [(1, 64, 64, 8, 32, 32), (2, 192, 64, 5, 40, 24), (1, 32, 64, 3, 70, 17),
+                                 (1, 128, 128, 4, 32, 16), (1, 384, 128, 3, 33, 9)])
+def test_conv3d_tc_pair_vs_single_cta_kernel(cfg):
+    """km_conv3d_tc_pair (cta_group::2: one M=256 MMA over two SMs, each holding half of the weight
+    rows) must reproduce km_conv3d_tc: same bf16 operands, same fp32 accumulation order per output
+    -> identical stored values; statistics equal up to the order of the partial sums."""
+    N, Cin, Cout, D, H, W = cfg
+    assert ops.pair_supported(Cin, Cout, D, H, W)
+    g = torch.Generator().manual_seed(sum(cfg))
+    xb = ops.ncdhw_to_ndhwc(cu(torch.randn(N, Cin, D, H, W, generator=g)))
+    wp = ops.pack_weights(cu(torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5))
+    ref, st_ref, _ = ops.conv3d_tc(xb, wp, relu=True, want_stats=True)
+    out, st = ops.conv3d_tc_pair(xb, wp, relu=True, want_stats=True)
+    assert torch.equal(out, ref)
+    assert_close(st.double().sum(0), st_ref.double().sum(0), rtol=1e-5, atol=1e-3)
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 200, 32, 32, 32), (1, 32, 130, 5, 6, 20), (1, 16, 70, 3, 9, 48),
                                    (2, 128, 512, 8, 16, 16), (1, 64, 256, 64, 64, 64)])
 def test_conv1x1_com_transposed_vs_fp32(shape):

@@ -51,3 +51,21 @@ e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / 5 * 1e3
 print(f"enc0.c2 z-folded: {us:8.1f} us  {2.0 * 27 * 16 * 32 * S ** 3 * N / us / 1e6:7.1f} TFLOP/s")
+# the 2-CTA (cta_group::2) kernel on the layers it supports
+for name, cin, cout, e in LAYERS:
+    if not ops.pair_supported(cin, cout, e, e, e):
+        continue
+    x = torch.randn(N, e, e, e, cin, device="cuda").bfloat16()
+    wp = (torch.randn(27, cout, cin, device="cuda") / (27 * cin) ** 0.5).bfloat16()
+    for _ in range(2):
+        ops.conv3d_tc_pair(x, wp, relu=True, want_stats=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.conv3d_tc_pair(x, wp, relu=True, want_stats=True)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 5 * 1e3
+    print(f"{name:8s} {cin:4d}->{cout:4d} @{e:3d}^3 x{N} 2-CTA: {us:8.1f} us  {2.0 * 27 * cin * cout * e ** 3 * N / us / 1e6:7.1f} TFLOP/s", flush=True)
+    del x
