@@ -14,6 +14,7 @@ from . import ops
 from .engine import backbone_engine
 from .keypoint_aligners import TPS, AffineKeypointAligner, RigidKeypointAligner
 from .layers import CenterOfMass3d
+from .transformations import deferred_singular_checks
 from .loss_ops import dice_from_sums
 from .utils import str_or_float
 
@@ -136,6 +137,13 @@ class KeyMorph(nn.Module):
         keypoint_extract_time = time.time() - start_time
 
         result_dict = {}
+        with deferred_singular_checks():   # one read of the status flags, after the last launch
+            self._align_all(result_dict, transform_type, img_f, img_m, points_f, points_m, weights, aff_f,
+                            aff_m, shape_f, shape_m, return_aligned_points, keypoint_extract_time, kwargs)
+        return result_dict
+
+    def _align_all(self, result_dict, transform_type, img_f, img_m, points_f, points_m, weights, aff_f, aff_m,
+                   shape_f, shape_m, return_aligned_points, keypoint_extract_time, kwargs):
         for align_type_str in transform_type:
             start_time = time.time()
             if align_type_str.startswith("tps"):
@@ -176,7 +184,6 @@ class KeyMorph(nn.Module):
             if self.fused_warp:
                 self._fused_outputs(res, grid, img_f, img_m, kwargs, fused)
             result_dict[align_type_str] = res
-        return result_dict
 
     def _fused_outputs(self, res, grid, img_f, img_m, kwargs, fused=None):
         """Warped image / segmentation and loss sums in the same pass that reads (or, for rigid /

@@ -12,9 +12,42 @@ from . import ops
 CHECK_SINGULAR = True
 
 
+_DEFERRED = None     # list of (status tensor, name) while a caller batches the checks
+
+
 def raise_if_singular(status, what):
-    if CHECK_SINGULAR and bool(status.any().item()):
+    """LinAlgError like the reference's torch.inverse / torch.linalg.solve.  The status flag lives on
+    the device: reading it synchronises, so KeyMorph.forward collects the flags of a whole call
+    (`deferred_singular_checks`) and reads them once, after everything has been enqueued."""
+    if not CHECK_SINGULAR:
+        return
+    if _DEFERRED is not None:
+        _DEFERRED.append((status, what))
+        return
+    if bool(status.any().item()):
         raise torch.linalg.LinAlgError(f"{what}: the matrix is singular (status={status.tolist()})")
+
+
+class deferred_singular_checks:
+    """Context manager: singular-matrix flags raised inside are checked on exit with one device
+    synchronisation instead of one per fit (the kernels are safe on singular input; their outputs
+    are simply not returned)."""
+
+    def __enter__(self):
+        global _DEFERRED
+        self._outer = _DEFERRED
+        _DEFERRED = []
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        global _DEFERRED
+        pending, _DEFERRED = _DEFERRED, self._outer
+        if exc_type is None and pending:
+            flags = torch.stack([st.reshape(-1).any() for st, _ in pending]).cpu()
+            for bad, (st, what) in zip(flags.tolist(), pending):
+                if bad:
+                    raise torch.linalg.LinAlgError(f"{what}: the matrix is singular (status={st.tolist()})")
+        return False
 
 
 def norm2voxel_matrix(sizes, device):
