@@ -209,7 +209,7 @@ def test_com_golden_and_empty_channels(golden):
     assert_close(kb.CenterOfMass3d("ij")(cu(neg)).cpu(), O.center_of_mass3d(neg))
 
 
-@pytest.mark.parametrize("shape", [(1, 32, 32, 32), (2, 70, 40, 24), (1, 5, 16, 8), (1, 130, 17, 9)])
+@pytest.mark.parametrize("shape", [(1, 32, 32, 32), (2, 70, 40, 24), (1, 5, 16, 8), (1, 130, 17, 9), (3, 66, 33, 12)])
 def test_conv3d_zfold_vs_general_kernel_and_fp32(shape):
     """km_conv3d_zfold (dz taps folded into MMA N, output planes as a TMEM ring along z) against
     km_conv3d_tc and the fp32 conv of the same bf16-rounded operands.  Shapes cover two z segments
@@ -245,7 +245,9 @@ def test_conv3d_zfold_vs_general_kernel_and_fp32(shape):
 
 
 @pytest.mark.parametrize("cfg", [(1, 64, 64, 8, 32, 32), (2, 192, 64, 5, 40, 24), (1, 32, 64, 3, 70, 17),
-                                 (1, 128, 128, 4, 32, 16), (1, 384, 128, 3, 33, 9)])
+                                 (1, 128, 128, 4, 32, 16), (1, 384, 128, 3, 33, 9),
+                                 (1, 64, 64, 3, 32, 8),        # 3 brick groups: the last CTA pair is half empty
+                                 (3, 64, 128, 5, 48, 20)])     # odd batch, pairs straddle images
 def test_conv3d_tc_pair_vs_single_cta_kernel(cfg):
     """km_conv3d_tc_pair (cta_group::2: one M=256 MMA over two SMs, each holding half of the weight
     rows) must reproduce km_conv3d_tc: same bf16 operands, same fp32 accumulation order per output
