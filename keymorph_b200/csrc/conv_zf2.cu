@@ -1,0 +1,563 @@
+// z-folded AND 2-CTA tcgen05 implicit-GEMM 3x3x3 convolution for the Cout = 64 layers
+// (keymorph/unet3d/buildingblocks.py:50-52; in the bench network 32->64 and 64->64 at 128^3, 64->64 at
+// 64^3 and the 192->64 first decoder conv at 128^3, together 60 % of the backbone's FLOPs).
+//
+// It combines the two ideas that are measured separately in conv_zf.cu and conv_tc2.cu:
+//   * dz folded into N (conv_zf.cu): one input plane z' feeds, with 9 (dx, dy) taps instead of 27,
+//     the three output planes z'+1, z', z'-1, which live as a rotating ring of three 64-column blocks
+//     in TMEM while the CTA walks along z.  N = 192 per MMA instead of 64: a third of the MMA
+//     instructions and a third of the activation bytes read from shared memory per output.
+//   * CTA pairs (conv_tc2.cu): N = 192 weight rows would cost 6 KB of shared-memory reads per MMA and
+//     24 KB of TMA per tap and Cin chunk; with cta_group::2 each SM holds and reads only 96 of them
+//     (A 4 KB + B 3 KB per MMA), and the weights are streamed (3 ring rotations x 27 taps do not fit).
+// Work unit = a column of ONE 8(x) x 16(y) brick x a z segment of up to 64 planes (+2 halo planes);
+// the two CTAs of a pair take x-adjacent bricks and step through the planes in lockstep (they share
+// every weight tile, hence the ring rotation).  A pair interleaves two unit pairs (TMEM sets 0 / 1).
+// Barrier protocol: exactly conv_tc2.cu (leader-side full / tempty, multicast empty / tfull).
+#include <algorithm>
+#include <type_traits>
+#include "km_common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace kmtc;
+
+namespace {
+
+constexpr int kThreads = 320;           // warp 0 TMA, warp 1 MMA (leader), warps 2..9 epilogue
+constexpr int kEpiThreads = 256;
+constexpr int kKC = 64;                 // Cin chunk (128-byte rows, SWIZZLE_128B)
+constexpr int kCout = 64;
+constexpr int kN3 = 3 * kCout;          // MMA N
+constexpr int kHalfRows = kN3 / 2;      // weight rows held by each CTA
+constexpr int kRowBytes = kKC * 2;
+constexpr int kSteps = kKC / 16;
+constexpr int kBoxRows = 8 * 18;        // 8 x-voxels by 16 + 2 y-rows
+constexpr uint32_t kASub = kBoxRows * kRowBytes;               // 18432 B (multiple of 1 KB)
+constexpr uint32_t kBTile = kHalfRows * kRowBytes;             // 12288 B, one dy slice of this CTA's rows
+constexpr uint32_t kBSub = 3 * kBTile;                         // dy = 0, 1, 2
+constexpr uint32_t kStage = kASub + kBSub;                     // one (dx, chunk) sub-iteration: 55296 B
+constexpr int kStages = 4;
+
+struct Zf2Geom {
+  int N, D, H, W, chunks;
+  int xpairs, tiles_y, zsegs, lz, punits;   // punits = N * zsegs * tiles_y * xpairs (unit pairs), lz planes each
+  int flags;
+  uint32_t off_scratch, off_stats, off_bars;
+};
+
+struct Unit {
+  int n, x0, y0, zs, planes;
+  bool valid;   // this CTA's brick lies inside the volume (odd tiles_x: the last pair is half empty)
+};
+
+__device__ __forceinline__ Unit decode_unit(const Zf2Geom& g, int pu, uint32_t rank) {
+  Unit r;
+  const int xp = pu % g.xpairs;
+  pu /= g.xpairs;
+  r.x0 = (2 * xp + (int)rank) * 8;
+  r.y0 = (pu % g.tiles_y) * 16;
+  pu /= g.tiles_y;
+  r.zs = (pu % g.zsegs) * g.lz;
+  r.n = pu / g.zsegs;
+  r.planes = min(g.lz, g.D - r.zs) + 2;
+  r.valid = r.x0 < g.W;
+  return r;
+}
+
+// tile sequence of a CTA pair (identical for all roles of both CTAs): unit pairs pair + k * npairs,
+// two at a time, interleaved plane by plane; images never mix inside one interleave group
+template <typename F>
+__device__ __forceinline__ void for_each_tile(const Zf2Geom& g, uint32_t rank, F&& fn) {
+  uint32_t cnt[2] = {0u, 0u};
+  const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
+  const int upi = g.punits / g.N;
+  for (int n = 0; n < g.N; ++n) {
+    for (int ua = pair; ua < upi; ua += 2 * npairs) {
+      const int ub = ua + npairs;
+      const Unit a = decode_unit(g, n * upi + ua, rank);
+      Unit b = a;
+      b.planes = 0;
+      if (ub < upi) b = decode_unit(g, n * upi + ub, rank);
+      const int pmax = max(a.planes, b.planes);
+      for (int p = 0; p < pmax; ++p) {
+        if (p < a.planes) fn(std::integral_constant<uint32_t, 0u>{}, a, p, cnt[0]++);
+        if (p < b.planes) fn(std::integral_constant<uint32_t, 1u>{}, b, p, cnt[1]++);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0,
+                                             int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0,
+                                             int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_pred(uint32_t d_tmem, uint32_t adesc_lo, uint32_t bdesc_lo,
+                                                uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
+                                                uint32_t issue) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "setp.ne.b32 q, %6, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(adesc_lo), "r"(bdesc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_pred(uint32_t bar, uint32_t issue) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      ".reg .b16 m;\n"
+      "setp.ne.b32 q, %1, 0;\n"
+      "mov.b16 m, 3;\n"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+      "}\n" ::"r"(bar),
+      "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const Zf2Geom g, __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
+  constexpr uint32_t kLayout = 2u;                 // SWIZZLE_128B
+  constexpr uint32_t kSbo = 8u * kRowBytes;        // 1024 B between 8-row groups
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_u32);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  const uint32_t bars = base + g.off_bars;   // full[S], empty[S], tfull[2], tempty[2]
+  auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(kStages + s); };
+  auto tfull_bar = [&](uint32_t a) { return bars + 8u * (uint32_t)(2 * kStages + a); };
+  auto tempty_bar = [&](uint32_t a) { return bars + 8u * (uint32_t)(2 * kStages + 2 + a); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + g.off_bars + 8u * (2 * kStages + 5));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 2);            // both CTAs' producers
+      mbar_init(empty_bar(s), 1);
+    }
+    for (uint32_t a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * kEpiThreads);   // both CTAs' epilogues
+    }
+    fence_mbar_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc2(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish2();
+  }
+  {
+    float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);
+    if (g.flags & KM_CONV_STATS)
+      for (int i = threadIdx.x; i < g.N * kCout * 2; i += kThreads) s_stats[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int subs = 3 * g.chunks;   // (dx, chunk) sub-iterations per plane, one pipeline stage each
+
+  if (warp == 0) {
+    // =============================== TMA producer (both CTAs) ====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for_each_tile(g, rank, [&](auto, const Unit& u, int p, uint32_t) {
+        const int z = u.zs - 1 + p;   // input plane; outside [0, D) -> TMA zero fill
+        const int rot = p % 3;
+        for (int dx = 0; dx < 3; ++dx) {
+          for (int ch = 0; ch < g.chunks; ++ch) {
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t lead_full = mapa_u32(full_bar(s), 0);
+            mbar_arrive_expect_tx_cluster(lead_full, kStage);
+            const uint32_t dst = base + (uint32_t)s * kStage;
+            tma2_load_5d(dst, &tmA, lead_full, ch * kKC, u.x0 + dx - 1, u.y0 - 1, z, u.n);
+            // weights (Cin, 3*Cout rows, dy, dx, rot): this CTA's 96 rows of all three dy slices
+            tma2_load_5d(dst + kASub, &tmB, lead_full, ch * kKC, (int)rank * kHalfRows, 0, dx, rot);
+            if (++s == kStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      });
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA only) ===============
+    if (rank == 0) {
+      const uint32_t issue = elect_one();
+      constexpr uint32_t desc_hi = (kSbo >> 4) | (1u << 14) | (kLayout << 29);
+      const uint32_t lo_flag = 1u << 16;
+      const uint32_t base16 = ((base & 0x3FFFFu) >> 4) | lo_flag;
+      const uint32_t idesc = umma_idesc_bf16(256, kN3);
+      int s = 0;
+      uint32_t ph = 0;
+      for_each_tile(g, rank, [&](auto set_c, const Unit&, int p, uint32_t cnt) {
+        constexpr uint32_t set = decltype(set_c)::value;
+        mbar_wait(tempty_bar(set), (cnt & 1u) ^ 1u);   // both CTAs drained + zeroed the previous plane
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + set * 256u;
+        uint32_t accum = p == 0 ? 0u : 1u;   // a unit's first plane overwrites the whole ring
+        for (int si = 0; si < subs; ++si) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a16 = base16 + (uint32_t)s * (kStage >> 4);
+          const uint32_t b16 = a16 + (kASub >> 4);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+            for (int kk = 0; kk < kSteps; ++kk) {
+              umma2_bf16_pred(d_tmem, a16 + (uint32_t)dy * (kSbo >> 4) + 2u * kk,
+                              b16 + (uint32_t)dy * (kBTile >> 4) + 2u * kk, desc_hi, idesc, accum, issue);
+              accum = 1u;
+            }
+          }
+          umma2_commit_pred(empty_bar(s), issue);   // frees the stage in both CTAs
+          if (++s == kStages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        umma2_commit_pred(tfull_bar(set), issue);
+      });
+    }
+  } else {
+    // =============================== epilogue (8 warps, both CTAs) ===============
+    // A thread owns one voxel row of the brick (TMEM lane) and 32 of the 64 output channels; the
+    // bf16 row piece goes straight to global memory (two 256-bit stores), the GroupNorm statistics
+    // stay in registers until the image changes.
+    const int q = warp & 3;
+    const int row = q * 32 + lane;        // tx = row & 7, ty = row >> 3
+    const int half = (warp - 2) >> 2;     // column half [32 half, 32 half + 32)
+    const int et = half * 128 + row;
+    float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);     // [N][Cout][2]
+    float* s_wred = reinterpret_cast<float*>(sm + g.off_scratch);    // [8 warps][64] flush scratch
+    const bool do_relu = (g.flags & KM_CONV_RELU) != 0;
+    const bool do_stats = (g.flags & KM_CONV_STATS) != 0;
+    auto all_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    const int tx = row & 7, ty = row >> 3;
+    float ssum[32], ssq[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ssum[j] = ssq[j] = 0.f;
+    int n_cur = -1;
+    auto flush_stats = [&](int n) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float a = km_warp_sum(ssum[j]), b = km_warp_sum(ssq[j]);
+        if (lane == 0) {
+          s_wred[(warp - 2) * 64 + 2 * j] = a;
+          s_wred[(warp - 2) * 64 + 2 * j + 1] = b;
+        }
+        ssum[j] = ssq[j] = 0.f;
+      }
+      all_bar();
+      if (et < 128) {   // thread -> (column half h, column j, sum | sumsq)
+        const int h = et >> 6, i = et & 63;
+        float a = 0.f;
+        for (int w4 = 0; w4 < 4; ++w4) a += s_wred[(h * 4 + w4) * 64 + i];
+        s_stats[((size_t)n * kCout + h * 32 + (i >> 1)) * 2 + (i & 1)] += a;
+      }
+      all_bar();
+    };
+
+    for_each_tile(g, rank, [&](auto set_c, const Unit& u, int p, uint32_t cnt) {
+      constexpr uint32_t set = decltype(set_c)::value;
+      const int zo = u.zs - 2 + p;
+      const bool store = p >= 2 && zo < g.D;
+      const uint32_t slot = (uint32_t)((p + 2) % 3);
+      if (do_stats && u.n != n_cur) {
+        if (n_cur >= 0) flush_stats(n_cur);
+        n_cur = u.n;
+      }
+      const uint32_t lead_tempty = mapa_u32(tempty_bar(set), 0);
+      mbar_wait(tfull_bar(set), cnt & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256u + slot * kCout +
+                             (uint32_t)half * 32u;
+      const int x2 = u.x0 + tx, y2 = u.y0 + ty;
+      if (store) {   // warp-uniform: tcgen05.ld is a warp-collective operation
+        uint32_t r0[16], r1[16];
+        tmem_ld16(taddr, r0);
+        tmem_ld16(taddr + 16u, r1);
+        tmem_ld_wait();
+        tmem_st16_zero(taddr);          // the drained block becomes the fresh output plane z' + 2
+        tmem_st16_zero(taddr + 16u);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_cluster(lead_tempty);
+        if (u.valid && x2 < g.W && y2 < g.H) {
+          const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
+          __nv_bfloat16* dst = out + vox * kCout + half * 32;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a = __uint_as_float(hh ? r1[2 * j] : r0[2 * j]);
+              float b = __uint_as_float(hh ? r1[2 * j + 1] : r0[2 * j + 1]);
+              if (do_relu) {
+                a = fmaxf(a, 0.f);
+                b = fmaxf(b, 0.f);
+              }
+              pk[j] = pack_bf16(a, b);
+              if (do_stats) {   // statistics of the values actually stored (bf16-rounded)
+                const float ar = __uint_as_float(pk[j] << 16), br = __uint_as_float(pk[j] & 0xffff0000u);
+                ssum[16 * hh + 2 * j] += ar;
+                ssq[16 * hh + 2 * j] = fmaf(ar, ar, ssq[16 * hh + 2 * j]);
+                ssum[16 * hh + 2 * j + 1] += br;
+                ssq[16 * hh + 2 * j + 1] = fmaf(br, br, ssq[16 * hh + 2 * j + 1]);
+              }
+            }
+            st_global_v8(dst + 16 * hh, pk);
+          }
+        }
+      } else {
+        tmem_st16_zero(taddr);
+        tmem_st16_zero(taddr + 16u);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_cluster(lead_tempty);
+      }
+    });
+
+    if (do_stats) {
+      if (n_cur >= 0) flush_stats(n_cur);
+      float* dst = stats + (size_t)blockIdx.x * g.N * kCout * 2;
+      for (int i = et; i < g.N * kCout * 2; i += kEpiThreads) dst[i] = s_stats[i];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// fp32 (Cout, Cin, 3, 3, 3) -> bf16 [rot][dx][dy][j*Cout + cout][Cin], dz(j, rot) = (rot + 1 - j) mod 3
+__global__ void pack_weights_zf2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int Cout,
+                                        int Cin) {
+  const long long total = 27ll * 3 * Cout * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int ci = (int)(t % Cin);
+    t /= Cin;
+    const int co = (int)(t % Cout);
+    t /= Cout;
+    const int j = (int)(t % 3);
+    t /= 3;
+    const int dy = (int)(t % 3);
+    t /= 3;
+    const int dx = (int)(t % 3);
+    const int r = (int)(t / 3);
+    const int dz = (r + 1 - j + 3) % 3;
+    p[i] = __float2bfloat16_rn(w[((size_t)co * Cin + ci) * 27 + dz * 9 + dy * 3 + dx]);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled zf2_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+}  // namespace
+
+extern "C" int km_sm_count(void);
+
+extern "C" int km_conv3d_zfold_pair_supported(int Cin, int Cout, int D, int H, int W) {
+  return (Cin >= kKC && Cin % kKC == 0 && Cout == kCout && W >= 8 && H >= 16 && D >= 1) ? 1 : 0;
+}
+
+extern "C" int km_pack_weights_zfold_pair(const float* w, void* packed, int Cout, int Cin, km_stream_t stream) {
+  KM_CHECK_ARG(w && packed && Cout == kCout && Cin % kKC == 0 && Cin > 0,
+               "km_pack_weights_zfold_pair: needs Cout=%d, Cin %% %d == 0", kCout, kKC);
+  pack_weights_zf2_kernel<<<128, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
+  KM_LAUNCH_OK("pack_weights_zf2_kernel");
+  return KM_OK;
+}
+
+extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, float* stats, int N, int Cin,
+                                    int Cout, int D, int H, int W, int flags, km_stream_t stream) {
+  KM_CHECK_ARG(x && wz && out, "km_conv3d_zfold_pair: null argument");
+  KM_CHECK_ARG(km_conv3d_zfold_pair_supported(Cin, Cout, D, H, W),
+               "km_conv3d_zfold_pair: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
+  KM_CHECK_ARG(N > 0, "km_conv3d_zfold_pair: bad batch");
+  KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "km_conv3d_zfold_pair: KM_CONV_STATS needs stats");
+  KM_CHECK_ARG(!(flags & KM_CONV_COM), "km_conv3d_zfold_pair: KM_CONV_COM is not supported");
+  KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wz & 15) == 0 && ((uintptr_t)out & 31) == 0,
+               "km_conv3d_zfold_pair: pointers must be 16-byte (output: 32-byte) aligned");
+  Zf2Geom g;
+  memset(&g, 0, sizeof(g));
+  g.N = N; g.D = D; g.H = H; g.W = W;
+  g.chunks = Cin / kKC;
+  g.flags = flags;
+  const int tiles_x = (W + 7) / 8;
+  g.xpairs = (tiles_x + 1) / 2;
+  g.tiles_y = (H + 15) / 16;
+  // z segment length: longer segments amortise the two halo planes, shorter ones balance the unit
+  // pairs over the CTA pairs; pick the cheaper of 64 / 32 / 16 planes for this shape
+  const int npairs_hw = km_sm_count() / 2;
+  double best = 1e30;
+  for (int lz = 64; lz >= 16; lz /= 2) {
+    const long long zs = (D + lz - 1) / lz;
+    const long long upi = zs * g.tiles_y * g.xpairs;
+    const long long rounds = (upi + npairs_hw - 1) / npairs_hw;
+    const double cost = (double)rounds * (double)(std::min(lz, D) + 2);   // planes walked by the busiest pair
+    if (cost < best) {
+      best = cost;
+      g.lz = lz;
+    }
+  }
+  g.zsegs = (D + g.lz - 1) / g.lz;
+  const long long punits = (long long)N * g.zsegs * g.tiles_y * g.xpairs;
+  KM_CHECK_ARG(punits < (1ll << 30), "km_conv3d_zfold_pair: too many units");
+  g.punits = (int)punits;
+  const uint32_t stats_bytes = (flags & KM_CONV_STATS) ? (uint32_t)N * kCout * 2u * 4u : 0u;
+  uint32_t off = (uint32_t)kStages * kStage;
+  g.off_scratch = off; off += 8u * 64u * 4u;
+  g.off_stats = off; off += stats_bytes;
+  off = (off + 7u) & ~7u;
+  g.off_bars = off; off += 8u * (2u * kStages + 6u) + 16u;
+  const uint32_t smem_bytes = off + 1024;
+  KM_CHECK_ARG(smem_bytes <= 232448, "km_conv3d_zfold_pair: shared memory overflow (%u; batch too large)", smem_bytes);
+
+  PFN_encodeTiled encode = zf2_encode_fn();
+  if (!encode) {
+    km_set_error("km_conv3d_zfold_pair: cuTensorMapEncodeTiled unavailable");
+    return KM_ECUDA;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
+                             (cuuint64_t)D * H * W * Cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)kKC, 8, 18, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      km_set_error("km_conv3d_zfold_pair: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+      return KM_ECUDA;
+    }
+  }
+  {
+    // packed weights [rot][dx][dy][192 rows][Cin] viewed as (Cin, rows, dy, dx, rot): one box = the
+    // three dy slices of one (rot, dx) for half of the rows
+    const cuuint64_t tile = (cuuint64_t)kN3 * Cin * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)kN3, 3, 3, 3};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, tile, 3 * tile, 9 * tile};
+    cuuint32_t box[5] = {(cuuint32_t)kKC, (cuuint32_t)kHalfRows, 3, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(wz), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      km_set_error("km_conv3d_zfold_pair: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+      return KM_ECUDA;
+    }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  const int nsm = km_sm_count();
+  const int upi = g.punits / N;
+  int grid = nsm & ~1;
+  if (grid / 2 > upi) grid = 2 * upi;
+  if ((flags & KM_CONV_STATS) && grid < nsm)
+    KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * kCout * 2 * sizeof(float), km_cs(stream)));
+  conv_zf2_kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                stats);
+  KM_LAUNCH_OK("conv_zf2_kernel");
+  return KM_OK;
+}

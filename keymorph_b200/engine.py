@@ -59,7 +59,8 @@ class _WeightCache:
         if pad_out_to is not None and w.shape[0] % pad_out_to:
             extra = pad_out_to - w.shape[0] % pad_out_to
             w = torch.cat([w, w.new_zeros((extra,) + tuple(w.shape[1:]))], 0)
-        packed = ops.pack_weights_zfold(w) if zfold else ops.pack_weights(w)
+        packed = ops.pack_weights_zfold_pair(w) if zfold == "pair" else \
+            (ops.pack_weights_zfold(w) if zfold else ops.pack_weights(w))
         self._packed[key] = (sig, packed)
         return packed
 
@@ -109,6 +110,10 @@ class UNetEngine(_EngineBase):
             # first tensor-core layer (16 -> 32 at full resolution): dz taps folded into MMA N
             out, stats = ops.conv3d_zfold(x_norm, self.weights.get(key + ".zf", w, zfold=True),
                                           relu=True, want_stats=True)
+        elif ops.USE_ZFOLD_PAIR and D * H * W >= 96 ** 3 and ops.zfold_pair_supported(Cin, w.shape[0], D, H, W):
+            # Cout = 64 at 128^3: dz folded into N = 192 AND the weight rows split over a CTA pair
+            out, stats = ops.conv3d_zfold_pair(x_norm, self.weights.get(key + ".zf2", w, zfold="pair"),
+                                               relu=True, want_stats=True)
         elif ops.USE_PAIR_CONV and D * H * W >= 64 ** 3 and ops.pair_supported(Cin, w.shape[0], D, H, W):
             # Cout in {64, 128}: two SMs per M = 256 MMA, half of the weight rows per SM (measured faster
             # from 64^3 up; below that there are too few brick groups per CTA pair)

@@ -350,6 +350,41 @@ def conv3d_tc_pair(x, wp, relu=False, want_stats=False):
     return out, stats
 
 
+USE_ZFOLD_PAIR = True     # engine switch: z-folded 2-CTA kernel for the Cout = 64 layers (A/B testing)
+
+
+def zfold_pair_supported(Cin, Cout, D, H, W):
+    return bool(_lib.query("km_conv3d_zfold_pair_supported", Cin, Cout, D, H, W))
+
+
+def pack_weights_zfold_pair(w):
+    """fp32 (64,Cin,3,3,3) -> bf16 (3 rotations, 3 dx, 3 dy, 192, Cin) for conv3d_zfold_pair."""
+    _need_cuda(w)
+    w = _f32c(w)
+    Cout, Cin = w.shape[0], w.shape[1]
+    out = torch.empty((3, 3, 3, 3 * Cout, Cin), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.call("km_pack_weights_zfold_pair", _ptr(w), _ptr(out), Cout, Cin, _stream())
+    return out
+
+
+def conv3d_zfold_pair(x, wz, relu=False, want_stats=False):
+    """z-folded 2-CTA tcgen05 conv (Cin % 64 == 0 -> 64, 3x3x3, pad 1).  x: bf16 (N,D,H,W,Cin)."""
+    _need_cuda(x, wz)
+    assert x.dtype == torch.bfloat16 and wz.dtype == torch.bfloat16
+    x, wz = x.contiguous(), wz.contiguous()
+    N, D, H, W, Cin = x.shape
+    Cout = wz.shape[3] // 3
+    flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
+    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x.device) \
+        if want_stats else None
+    with torch.cuda.device(x.device):
+        _lib.call("km_conv3d_zfold_pair", _ptr(x), _ptr(wz), _ptr(out), _ptr(stats), N, Cin, Cout, D, H, W,
+                  flags, _stream())
+    return out, stats
+
+
 def zfold_supported(Cin, Cout, D, H, W):
     return bool(_lib.query("km_conv3d_zfold_supported", Cin, Cout, D, H, W))
 

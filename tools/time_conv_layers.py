@@ -69,3 +69,21 @@ for name, cin, cout, e in LAYERS:
     us = e0.elapsed_time(e1) / 5 * 1e3
     print(f"{name:8s} {cin:4d}->{cout:4d} @{e:3d}^3 x{N} 2-CTA: {us:8.1f} us  {2.0 * 27 * cin * cout * e ** 3 * N / us / 1e6:7.1f} TFLOP/s", flush=True)
     del x
+# the z-folded 2-CTA kernel on the Cout = 64 layers
+for name, cin, cout, e in LAYERS:
+    if not ops.zfold_pair_supported(cin, cout, e, e, e):
+        continue
+    x = torch.randn(N, e, e, e, cin, device="cuda").bfloat16()
+    wz = ops.pack_weights_zfold_pair(torch.randn(cout, cin, 3, 3, 3, device="cuda") / (27 * cin) ** 0.5)
+    for _ in range(2):
+        ops.conv3d_zfold_pair(x, wz, relu=True, want_stats=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.conv3d_zfold_pair(x, wz, relu=True, want_stats=True)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 5 * 1e3
+    print(f"{name:8s} {cin:4d}->{cout:4d} @{e:3d}^3 x{N} z-fold + 2-CTA: {us:8.1f} us  {2.0 * 27 * cin * cout * e ** 3 * N / us / 1e6:7.1f} TFLOP/s", flush=True)
+    del x
