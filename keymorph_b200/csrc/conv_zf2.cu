@@ -25,24 +25,30 @@ namespace {
 
 constexpr int kThreads = 320;           // warp 0 TMA, warp 1 MMA (leader), warps 2..9 epilogue
 constexpr int kEpiThreads = 256;
-constexpr int kKC = 64;                 // Cin chunk (128-byte rows, SWIZZLE_128B)
-constexpr int kCout = 64;
-constexpr int kN3 = 3 * kCout;          // MMA N
-constexpr int kHalfRows = kN3 / 2;      // weight rows held by each CTA
-constexpr int kRowBytes = kKC * 2;
-constexpr int kSteps = kKC / 16;
 constexpr int kBoxRows = 8 * 18;        // 8 x-voxels by 16 + 2 y-rows
-constexpr uint32_t kASub = kBoxRows * kRowBytes;               // 18432 B (multiple of 1 KB)
-constexpr uint32_t kBTile = kHalfRows * kRowBytes;             // 12288 B, one dy slice of this CTA's rows
-constexpr uint32_t kBSub = 3 * kBTile;                         // dy = 0, 1, 2
-constexpr uint32_t kStage = kASub + kBSub;                     // one (dx, chunk) sub-iteration: 55296 B
-constexpr int kStages = 4;
+constexpr int kStagesMax = 12;
+
+// compile-time shape of one instantiation: COUT output channels, KC input channels per chunk
+template <int COUT, int KC>
+struct Cfg {
+  static constexpr int kCout = COUT;
+  static constexpr int kKC = KC;
+  static constexpr int kN3 = 3 * COUT;                 // MMA N
+  static constexpr int kHalfRows = kN3 / 2;            // weight rows held by each CTA
+  static constexpr int kRowBytes = KC * 2;             // 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B)
+  static constexpr int kSteps = KC / 16;
+  static constexpr uint32_t kASub = kBoxRows * kRowBytes;                                  // multiple of 1 KB
+  static constexpr uint32_t kBTile = kHalfRows * kRowBytes;                                // one dy slice
+  static constexpr uint32_t kStage = kASub + 3 * kBTile;                                   // one (dx, chunk)
+  static constexpr int kCols = COUT / 2;               // output channels per epilogue thread
+};
 
 struct Zf2Geom {
   int N, D, H, W, chunks;
   int xpairs, tiles_y, zsegs, lz, punits;   // punits = N * zsegs * tiles_y * xpairs (unit pairs), lz planes each
   int flags;
   uint32_t off_scratch, off_stats, off_bars;
+  int stages;
 };
 
 struct Unit {
@@ -182,11 +188,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+template <int COUT, int KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const Zf2Geom g, __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
-  constexpr uint32_t kLayout = 2u;                 // SWIZZLE_128B
-  constexpr uint32_t kSbo = 8u * kRowBytes;        // 1024 B between 8-row groups
+  using C = Cfg<COUT, KC>;
+  constexpr int kCout = C::kCout, kKC = C::kKC, kN3 = C::kN3, kHalfRows = C::kHalfRows;
+  constexpr int kRowBytes = C::kRowBytes, kSteps = C::kSteps, kCols = C::kCols;
+  constexpr uint32_t kASub = C::kASub, kBTile = C::kBTile, kStage = C::kStage;
+  constexpr uint32_t kLayout = kRowBytes == 128 ? 2u : 4u;   // SWIZZLE_128B / SWIZZLE_64B
+  constexpr uint32_t kSbo = 8u * kRowBytes;                  // bytes between 8-row groups
+  const int kStages = g.stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -302,34 +314,34 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // stay in registers until the image changes.
     const int q = warp & 3;
     const int row = q * 32 + lane;        // tx = row & 7, ty = row >> 3
-    const int half = (warp - 2) >> 2;     // column half [32 half, 32 half + 32)
+    const int half = (warp - 2) >> 2;     // column half [kCols half, kCols half + kCols)
     const int et = half * 128 + row;
     float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);     // [N][Cout][2]
-    float* s_wred = reinterpret_cast<float*>(sm + g.off_scratch);    // [8 warps][64] flush scratch
+    float* s_wred = reinterpret_cast<float*>(sm + g.off_scratch);    // [8 warps][2 kCols] flush scratch
     const bool do_relu = (g.flags & KM_CONV_RELU) != 0;
     const bool do_stats = (g.flags & KM_CONV_STATS) != 0;
     auto all_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     const int tx = row & 7, ty = row >> 3;
-    float ssum[32], ssq[32];
+    float ssum[kCols], ssq[kCols];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) ssum[j] = ssq[j] = 0.f;
+    for (int j = 0; j < kCols; ++j) ssum[j] = ssq[j] = 0.f;
     int n_cur = -1;
     auto flush_stats = [&](int n) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < kCols; ++j) {
         const float a = km_warp_sum(ssum[j]), b = km_warp_sum(ssq[j]);
         if (lane == 0) {
-          s_wred[(warp - 2) * 64 + 2 * j] = a;
-          s_wred[(warp - 2) * 64 + 2 * j + 1] = b;
+          s_wred[(warp - 2) * 2 * kCols + 2 * j] = a;
+          s_wred[(warp - 2) * 2 * kCols + 2 * j + 1] = b;
         }
         ssum[j] = ssq[j] = 0.f;
       }
       all_bar();
-      if (et < 128) {   // thread -> (column half h, column j, sum | sumsq)
-        const int h = et >> 6, i = et & 63;
+      if (et < 4 * kCols) {   // thread -> (column half h, column, sum | sumsq)
+        const int h = et / (2 * kCols), i = et % (2 * kCols);
         float a = 0.f;
-        for (int w4 = 0; w4 < 4; ++w4) a += s_wred[(h * 4 + w4) * 64 + i];
-        s_stats[((size_t)n * kCout + h * 32 + (i >> 1)) * 2 + (i & 1)] += a;
+        for (int w4 = 0; w4 < 4; ++w4) a += s_wred[(h * 4 + w4) * 2 * kCols + i];
+        s_stats[((size_t)n * kCout + h * kCols + (i >> 1)) * 2 + (i & 1)] += a;
       }
       all_bar();
     };
@@ -347,28 +359,28 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull_bar(set), cnt & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256u + slot * kCout +
-                             (uint32_t)half * 32u;
+                             (uint32_t)(half * kCols);
       const int x2 = u.x0 + tx, y2 = u.y0 + ty;
       if (store) {   // warp-uniform: tcgen05.ld is a warp-collective operation
-        uint32_t r0[16], r1[16];
-        tmem_ld16(taddr, r0);
-        tmem_ld16(taddr + 16u, r1);
+        uint32_t r[kCols / 16][16];
+#pragma unroll
+        for (int b = 0; b < kCols / 16; ++b) tmem_ld16(taddr + 16u * b, r[b]);
         tmem_ld_wait();
-        tmem_st16_zero(taddr);          // the drained block becomes the fresh output plane z' + 2
-        tmem_st16_zero(taddr + 16u);
+#pragma unroll
+        for (int b = 0; b < kCols / 16; ++b) tmem_st16_zero(taddr + 16u * b);   // fresh output plane z' + 2
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive_cluster(lead_tempty);
         if (u.valid && x2 < g.W && y2 < g.H) {
           const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
-          __nv_bfloat16* dst = out + vox * kCout + half * 32;
+          __nv_bfloat16* dst = out + vox * kCout + half * kCols;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
+          for (int hh = 0; hh < kCols / 16; ++hh) {
             uint32_t pk[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float a = __uint_as_float(hh ? r1[2 * j] : r0[2 * j]);
-              float b = __uint_as_float(hh ? r1[2 * j + 1] : r0[2 * j + 1]);
+              float a = __uint_as_float(r[hh][2 * j]);
+              float b = __uint_as_float(r[hh][2 * j + 1]);
               if (do_relu) {
                 a = fmaxf(a, 0.f);
                 b = fmaxf(b, 0.f);
@@ -386,8 +398,8 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       } else {
-        tmem_st16_zero(taddr);
-        tmem_st16_zero(taddr + 16u);
+#pragma unroll
+        for (int b = 0; b < kCols / 16; ++b) tmem_st16_zero(taddr + 16u * b);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive_cluster(lead_tempty);
@@ -453,31 +465,27 @@ PFN_encodeTiled zf2_encode_fn() {
 extern "C" int km_sm_count(void);
 
 extern "C" int km_conv3d_zfold_pair_supported(int Cin, int Cout, int D, int H, int W) {
-  return (Cin >= kKC && Cin % kKC == 0 && Cout == kCout && W >= 8 && H >= 16 && D >= 1) ? 1 : 0;
+  const bool shape = (Cout == 64 && Cin % 32 == 0) || (Cout == 32 && Cin % 32 == 0);
+  return (shape && Cin >= 32 && Cin <= 512 && W >= 8 && H >= 16 && D >= 1) ? 1 : 0;
 }
 
 extern "C" int km_pack_weights_zfold_pair(const float* w, void* packed, int Cout, int Cin, km_stream_t stream) {
-  KM_CHECK_ARG(w && packed && Cout == kCout && Cin % kKC == 0 && Cin > 0,
-               "km_pack_weights_zfold_pair: needs Cout=%d, Cin %% %d == 0", kCout, kKC);
+  KM_CHECK_ARG(w && packed && (Cout == 64 || Cout == 32) && Cin % 32 == 0 && Cin > 0,
+               "km_pack_weights_zfold_pair: needs Cout in {32, 64}, Cin %% 32 == 0");
   pack_weights_zf2_kernel<<<128, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
   KM_LAUNCH_OK("pack_weights_zf2_kernel");
   return KM_OK;
 }
 
-extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, float* stats, int N, int Cin,
-                                    int Cout, int D, int H, int W, int flags, km_stream_t stream) {
-  KM_CHECK_ARG(x && wz && out, "km_conv3d_zfold_pair: null argument");
-  KM_CHECK_ARG(km_conv3d_zfold_pair_supported(Cin, Cout, D, H, W),
-               "km_conv3d_zfold_pair: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
-  KM_CHECK_ARG(N > 0, "km_conv3d_zfold_pair: bad batch");
-  KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "km_conv3d_zfold_pair: KM_CONV_STATS needs stats");
-  KM_CHECK_ARG(!(flags & KM_CONV_COM), "km_conv3d_zfold_pair: KM_CONV_COM is not supported");
-  KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wz & 15) == 0 && ((uintptr_t)out & 31) == 0,
-               "km_conv3d_zfold_pair: pointers must be 16-byte (output: 32-byte) aligned");
+namespace {
+template <int COUT, int KC>
+int launch_zf2(const void* x, const void* wz, void* out, float* stats, int N, int Cin, int D, int H, int W,
+               int flags, cudaStream_t st) {
+  using C = Cfg<COUT, KC>;
   Zf2Geom g;
   memset(&g, 0, sizeof(g));
   g.N = N; g.D = D; g.H = H; g.W = W;
-  g.chunks = Cin / kKC;
+  g.chunks = Cin / KC;
   g.flags = flags;
   const int tiles_x = (W + 7) / 8;
   g.xpairs = (tiles_x + 1) / 2;
@@ -500,54 +508,61 @@ extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, fl
   const long long punits = (long long)N * g.zsegs * g.tiles_y * g.xpairs;
   KM_CHECK_ARG(punits < (1ll << 30), "km_conv3d_zfold_pair: too many units");
   g.punits = (int)punits;
-  const uint32_t stats_bytes = (flags & KM_CONV_STATS) ? (uint32_t)N * kCout * 2u * 4u : 0u;
-  uint32_t off = (uint32_t)kStages * kStage;
-  g.off_scratch = off; off += 8u * 64u * 4u;
+  const uint32_t stats_bytes = (flags & KM_CONV_STATS) ? (uint32_t)N * COUT * 2u * 4u : 0u;
+  const uint32_t fixed = 8u * 2u * C::kCols * 4u + stats_bytes + 8u * (2u * kStagesMax + 6u) + 16u + 64u;
+  const uint32_t kSmemMax = 232448 - 1024;
+  int stages = (int)((kSmemMax - fixed) / C::kStage);
+  if (stages > kStagesMax) stages = kStagesMax;
+  KM_CHECK_ARG(stages >= 2, "km_conv3d_zfold_pair: shared memory budget exceeded (batch too large)");
+  g.stages = stages;
+  uint32_t off = (uint32_t)stages * C::kStage;
+  g.off_scratch = off; off += 8u * 2u * C::kCols * 4u;
   g.off_stats = off; off += stats_bytes;
   off = (off + 7u) & ~7u;
-  g.off_bars = off; off += 8u * (2u * kStages + 6u) + 16u;
+  g.off_bars = off; off += 8u * (2u * kStagesMax + 6u) + 16u;
   const uint32_t smem_bytes = off + 1024;
-  KM_CHECK_ARG(smem_bytes <= 232448, "km_conv3d_zfold_pair: shared memory overflow (%u; batch too large)", smem_bytes);
+  KM_CHECK_ARG(smem_bytes <= 232448, "km_conv3d_zfold_pair: shared memory overflow (%u)", smem_bytes);
 
   PFN_encodeTiled encode = zf2_encode_fn();
   if (!encode) {
     km_set_error("km_conv3d_zfold_pair: cuTensorMapEncodeTiled unavailable");
     return KM_ECUDA;
   }
+  const CUtensorMapSwizzle swz = C::kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
                              (cuuint64_t)D * H * W * Cin * 2};
-    cuuint32_t box[5] = {(cuuint32_t)kKC, 8, 18, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)KC, 8, 18, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box,
-                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       km_set_error("km_conv3d_zfold_pair: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
       return KM_ECUDA;
     }
   }
   {
-    // packed weights [rot][dx][dy][192 rows][Cin] viewed as (Cin, rows, dy, dx, rot): one box = the
+    // packed weights [rot][dx][dy][3*Cout rows][Cin] viewed as (Cin, rows, dy, dx, rot): one box = the
     // three dy slices of one (rot, dx) for half of the rows
-    const cuuint64_t tile = (cuuint64_t)kN3 * Cin * 2;
-    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)kN3, 3, 3, 3};
+    const cuuint64_t tile = (cuuint64_t)C::kN3 * Cin * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)C::kN3, 3, 3, 3};
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, tile, 3 * tile, 9 * tile};
-    cuuint32_t box[5] = {(cuuint32_t)kKC, (cuuint32_t)kHalfRows, 3, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)C::kHalfRows, 3, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(wz), dims, strides, box,
-                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       km_set_error("km_conv3d_zfold_pair: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
       return KM_ECUDA;
     }
   }
-  static bool attr_set = false;
+  static bool attr_set = false;   // one flag per instantiation
   if (!attr_set) {
-    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel<COUT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const int nsm = km_sm_count();
@@ -555,9 +570,28 @@ extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, fl
   int grid = nsm & ~1;
   if (grid / 2 > upi) grid = 2 * upi;
   if ((flags & KM_CONV_STATS) && grid < nsm)
-    KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * kCout * 2 * sizeof(float), km_cs(stream)));
-  conv_zf2_kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
-                                                                stats);
+    KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * COUT * 2 * sizeof(float), st));
+  conv_zf2_kernel<COUT, KC><<<grid, kThreads, smem_bytes, st>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
+                                                               stats);
   KM_LAUNCH_OK("conv_zf2_kernel");
   return KM_OK;
+}
+}  // namespace
+
+extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, float* stats, int N, int Cin,
+                                    int Cout, int D, int H, int W, int flags, km_stream_t stream) {
+  KM_CHECK_ARG(x && wz && out, "km_conv3d_zfold_pair: null argument");
+  KM_CHECK_ARG(km_conv3d_zfold_pair_supported(Cin, Cout, D, H, W),
+               "km_conv3d_zfold_pair: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
+  KM_CHECK_ARG(N > 0, "km_conv3d_zfold_pair: bad batch");
+  KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "km_conv3d_zfold_pair: KM_CONV_STATS needs stats");
+  KM_CHECK_ARG(!(flags & KM_CONV_COM), "km_conv3d_zfold_pair: KM_CONV_COM is not supported");
+  KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wz & 15) == 0 && ((uintptr_t)out & 31) == 0,
+               "km_conv3d_zfold_pair: pointers must be 16-byte (output: 32-byte) aligned");
+  cudaStream_t st = km_cs(stream);
+  const bool k64 = Cin % 64 == 0;
+  if (Cout == 64) return k64 ? launch_zf2<64, 64>(x, wz, out, stats, N, Cin, D, H, W, flags, st)
+                             : launch_zf2<64, 32>(x, wz, out, stats, N, Cin, D, H, W, flags, st);
+  return k64 ? launch_zf2<32, 64>(x, wz, out, stats, N, Cin, D, H, W, flags, st)
+             : launch_zf2<32, 32>(x, wz, out, stats, N, Cin, D, H, W, flags, st);
 }

@@ -110,8 +110,10 @@ class UNetEngine(_EngineBase):
             # first tensor-core layer (16 -> 32 at full resolution): dz taps folded into MMA N
             out, stats = ops.conv3d_zfold(x_norm, self.weights.get(key + ".zf", w, zfold=True),
                                           relu=True, want_stats=True)
-        elif ops.USE_ZFOLD_PAIR and D * H * W >= 96 ** 3 and ops.zfold_pair_supported(Cin, w.shape[0], D, H, W):
-            # Cout = 64 at 128^3: dz folded into N = 192 AND the weight rows split over a CTA pair
+        elif ops.USE_ZFOLD_PAIR and D * H * W >= 96 ** 3 and (w.shape[0] == 32 or Cin % 64 == 0) \
+                and ops.zfold_pair_supported(Cin, w.shape[0], D, H, W):
+            # 32 -> 32, 64 -> 64 and 192 -> 64 at 128^3: dz folded into N = 3 Cout AND the weight rows split
+            # over a CTA pair (32 -> 64 measures the same as the plain pair kernel and stays there)
             out, stats = ops.conv3d_zfold_pair(x_norm, self.weights.get(key + ".zf2", w, zfold="pair"),
                                                relu=True, want_stats=True)
         elif ops.USE_PAIR_CONV and D * H * W >= 64 ** 3 and ops.pair_supported(Cin, w.shape[0], D, H, W):

@@ -244,18 +244,19 @@ def test_conv3d_zfold_vs_general_kernel_and_fp32(shape):
         assert_close(stp.double().sum(0).cpu(), sp_ref, rtol=1e-4, atol=1e-2)
 
 
-@pytest.mark.parametrize("cfg", [(1, 64, 8, 32, 32), (2, 192, 70, 40, 24), (1, 64, 3, 16, 8), (3, 128, 5, 33, 20),
-                                 (1, 64, 130, 17, 9)])
+@pytest.mark.parametrize("cfg", [(1, 64, 64, 8, 32, 32), (2, 192, 64, 70, 40, 24), (1, 64, 64, 3, 16, 8),
+                                 (3, 128, 64, 5, 33, 20), (1, 64, 64, 130, 17, 9), (2, 32, 32, 9, 32, 24),
+                                 (1, 32, 64, 20, 48, 40), (1, 64, 32, 6, 16, 16), (1, 96, 32, 4, 20, 12)])
 def test_conv3d_zfold_pair_vs_single_cta_kernel(cfg):
-    """km_conv3d_zfold_pair (dz folded into N = 192, weight rows split over a CTA pair) against
+    """km_conv3d_zfold_pair (dz folded into N = 3*Cout, weight rows split over a CTA pair) against
     km_conv3d_tc: same bf16 operands; the fp32 accumulation order differs, so values agree to the
-    bf16 rounding of the stored result.  Shapes: two z segments, odd brick counts in x (half-empty
-    pairs), partial bricks, 1-3 Cin chunks, odd batch."""
-    N, Cin, D, H, W = cfg
-    assert ops.zfold_pair_supported(Cin, 64, D, H, W)
+    bf16 rounding of the stored result.  Shapes: all four (Cout, Cin chunk) instantiations, two z
+    segments, odd brick counts in x (half-empty pairs), partial bricks, 1-3 Cin chunks, odd batch."""
+    N, Cin, Cout, D, H, W = cfg
+    assert ops.zfold_pair_supported(Cin, Cout, D, H, W)
     g = torch.Generator().manual_seed(sum(cfg))
     xb = ops.ncdhw_to_ndhwc(cu(torch.randn(N, Cin, D, H, W, generator=g)))
-    w = cu(torch.randn(64, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5)
+    w = cu(torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5)
     ref, st_ref, _ = ops.conv3d_tc(xb, ops.pack_weights(w), relu=True, want_stats=True)
     out, st = ops.conv3d_zfold_pair(xb, ops.pack_weights_zfold_pair(w), relu=True, want_stats=True)
     a, b = out.float(), ref.float()
