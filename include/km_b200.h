@@ -295,11 +295,13 @@ int km_conv3d_tc_pair(const void* x, const void* wp, void* out, float* stats, in
  * taps are folded into N = 192 (TMEM ring of output planes as in km_conv3d_zfold) and the 192 weight
  * rows are split between the two CTAs of a pair (as in km_conv3d_tc_pair), weights streamed by TMA.
  * wz: km_pack_weights_zfold_pair (fp32 (Cout,Cin,3,3,3) -> bf16 [rotation][dx][dy][3*Cout][Cin],
- * 81*Cout*Cin*2 bytes).  Same tensors / flags / statistics as km_conv3d_tc (KM_CONV_RELU | KM_CONV_STATS). */
+ * 81*Cout*Cin*2 bytes).  Same tensors / flags / statistics as km_conv3d_tc (KM_CONV_RELU | KM_CONV_STATS);
+ * `pooled` (may be NULL) as in km_conv3d_zfold: fused MaxPool3d(2), statistics of the pooled tensor,
+ * `out` may then be NULL.  Shapes: Cout 64 with Cin % 32 == 0, Cout 32 with Cin % 32 == 0 or Cin == 16. */
 int km_conv3d_zfold_pair_supported(int Cin, int Cout, int D, int H, int W);
 int km_pack_weights_zfold_pair(const float* w, void* packed, int Cout, int Cin, km_stream_t stream);
-int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, float* stats, int N, int Cin, int Cout,
-                         int D, int H, int W, int flags, km_stream_t stream);
+int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, void* pooled, float* stats, int N, int Cin,
+                         int Cout, int D, int H, int W, int flags, km_stream_t stream);
 
 /* Final 1x1x1 convolution fused with ReLU + centre of mass, transposed tcgen05 formulation
  * (keymorph/unet3d/model.py:99,389 final_conv + keymorph/layers.py:92-134 + keymorph/model.py:95-109):

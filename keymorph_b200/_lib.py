@@ -61,7 +61,7 @@ SIGNATURES = {
     "km_conv3d_tc_pair": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "km_conv3d_zfold_pair_supported": (_i, [_i, _i, _i, _i, _i]),
     "km_pack_weights_zfold_pair": (_i, [_p, _p, _i, _i, _p]),
-    "km_conv3d_zfold_pair": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "km_conv3d_zfold_pair": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "km_conv1x1_com_nparts": (_i, []),
     "km_conv1x1_com": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "km_conv3d_stem": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

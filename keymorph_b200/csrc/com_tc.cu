@@ -318,8 +318,6 @@ PFN_encodeTiled encode_fn() {
   return fn;
 }
 
-inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
-
 typedef void (*ComKernel)(const CUtensorMap, const CUtensorMap, const ComGeom, const float*, float*);
 
 }  // namespace

@@ -121,14 +121,6 @@ __device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* tm
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
-__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0,
-                                             int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
                : "memory");
@@ -183,20 +175,26 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) 
                "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a),
+                                   *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int COUT, int KC>
+template <int COUT, int KC, bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const Zf2Geom g, __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
+                const Zf2Geom g, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
+                float* __restrict__ stats) {
   using C = Cfg<COUT, KC>;
   constexpr int kCout = C::kCout, kKC = C::kKC, kN3 = C::kN3, kHalfRows = C::kHalfRows;
   constexpr int kRowBytes = C::kRowBytes, kSteps = C::kSteps, kCols = C::kCols;
   constexpr uint32_t kASub = C::kASub, kBTile = C::kBTile, kStage = C::kStage;
-  constexpr uint32_t kLayout = kRowBytes == 128 ? 2u : 4u;   // SWIZZLE_128B / SWIZZLE_64B
+  constexpr uint32_t kLayout = kRowBytes == 128 ? 2u : (kRowBytes == 64 ? 4u : 6u);   // SWIZZLE_128B / 64B / 32B
   constexpr uint32_t kSbo = 8u * kRowBytes;                  // bytes between 8-row groups
   const int kStages = g.stages;
   extern __shared__ uint8_t smem_raw[];
@@ -325,6 +323,13 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float ssum[kCols], ssq[kCols];
 #pragma unroll
     for (int j = 0; j < kCols; ++j) ssum[j] = ssq[j] = 0.f;
+    uint32_t zprev[POOL ? 2 : 1][kCols / 16][8];   // xy-pooled even plane of each unit in flight (pool mode)
+#pragma unroll
+    for (int a = 0; a < (POOL ? 2 : 1); ++a)
+#pragma unroll
+      for (int b = 0; b < kCols / 16; ++b)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zprev[a][b][j] = 0u;
     int n_cur = -1;
     auto flush_stats = [&](int n) {
 #pragma unroll
@@ -371,30 +376,54 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive_cluster(lead_tempty);
-        if (u.valid && x2 < g.W && y2 < g.H) {
-          const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
-          __nv_bfloat16* dst = out + vox * kCout + half * kCols;
+        const bool inside = u.valid && x2 < g.W && y2 < g.H;
+        const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
 #pragma unroll
-          for (int hh = 0; hh < kCols / 16; ++hh) {
-            uint32_t pk[8];
+        for (int hh = 0; hh < kCols / 16; ++hh) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a = __uint_as_float(r[hh][2 * j]);
+            float b = __uint_as_float(r[hh][2 * j + 1]);
+            if (do_relu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            }
+            pk[j] = pack_bf16(a, b);
+          }
+          if (out && inside) st_global_v8(out + vox * kCout + half * kCols + 16 * hh, pk);
+          bool acc_stats = inside && !(POOL && pooled);
+          if (POOL && pooled) {
+            // MaxPool3d(2) in registers (see conv_zf.cu): x / y neighbours are lanes ^1 / ^8, the z
+            // neighbour is the previous plane of this unit; max commutes with the bf16 rounding
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float a = __uint_as_float(r[hh][2 * j]);
-              float b = __uint_as_float(r[hh][2 * j + 1]);
-              if (do_relu) {
-                a = fmaxf(a, 0.f);
-                b = fmaxf(b, 0.f);
-              }
-              pk[j] = pack_bf16(a, b);
-              if (do_stats) {   // statistics of the values actually stored (bf16-rounded)
-                const float ar = __uint_as_float(pk[j] << 16), br = __uint_as_float(pk[j] & 0xffff0000u);
-                ssum[16 * hh + 2 * j] += ar;
-                ssq[16 * hh + 2 * j] = fmaf(ar, ar, ssq[16 * hh + 2 * j]);
-                ssum[16 * hh + 2 * j + 1] += br;
-                ssq[16 * hh + 2 * j + 1] = fmaf(br, br, ssq[16 * hh + 2 * j + 1]);
+              pk[j] = hmax2_u32(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
+              pk[j] = hmax2_u32(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 8));
+            }
+            if ((zo & 1) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) zprev[POOL ? set : 0][hh][j] = pk[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pk[j] = hmax2_u32(pk[j], zprev[POOL ? set : 0][hh][j]);
+              const int xp = x2 >> 1, yp = y2 >> 1, zp = zo >> 1;
+              if (u.valid && ((tx | ty) & 1) == 0 && xp < (g.W >> 1) && yp < (g.H >> 1)) {
+                const size_t pv = (((size_t)u.n * (g.D >> 1) + zp) * (g.H >> 1) + yp) * (g.W >> 1) + xp;
+                st_global_v8(pooled + pv * kCout + half * kCols + 16 * hh, pk);
+                acc_stats = true;   // statistics of the pooled map
               }
             }
-            st_global_v8(dst + 16 * hh, pk);
+          }
+          if (do_stats && acc_stats) {   // statistics of the values actually stored (bf16-rounded)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float ar = __uint_as_float(pk[j] << 16), br = __uint_as_float(pk[j] & 0xffff0000u);
+              ssum[16 * hh + 2 * j] += ar;
+              ssq[16 * hh + 2 * j] = fmaf(ar, ar, ssq[16 * hh + 2 * j]);
+              ssum[16 * hh + 2 * j + 1] += br;
+              ssq[16 * hh + 2 * j + 1] = fmaf(br, br, ssq[16 * hh + 2 * j + 1]);
+            }
           }
         }
       } else {
@@ -465,23 +494,24 @@ PFN_encodeTiled zf2_encode_fn() {
 extern "C" int km_sm_count(void);
 
 extern "C" int km_conv3d_zfold_pair_supported(int Cin, int Cout, int D, int H, int W) {
-  const bool shape = (Cout == 64 && Cin % 32 == 0) || (Cout == 32 && Cin % 32 == 0);
-  return (shape && Cin >= 32 && Cin <= 512 && W >= 8 && H >= 16 && D >= 1) ? 1 : 0;
+  const bool shape = (Cout == 64 && Cin % 32 == 0) || (Cout == 32 && (Cin % 32 == 0 || Cin == 16));
+  return (shape && Cin >= 16 && Cin <= 512 && W >= 8 && H >= 16 && D >= 1) ? 1 : 0;
 }
 
 extern "C" int km_pack_weights_zfold_pair(const float* w, void* packed, int Cout, int Cin, km_stream_t stream) {
-  KM_CHECK_ARG(w && packed && (Cout == 64 || Cout == 32) && Cin % 32 == 0 && Cin > 0,
-               "km_pack_weights_zfold_pair: needs Cout in {32, 64}, Cin %% 32 == 0");
+  KM_CHECK_ARG(w && packed && (Cout == 64 || Cout == 32) && Cin % 16 == 0 && Cin > 0,
+               "km_pack_weights_zfold_pair: needs Cout in {32, 64}, Cin %% 16 == 0");
   pack_weights_zf2_kernel<<<128, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
   KM_LAUNCH_OK("pack_weights_zf2_kernel");
   return KM_OK;
 }
 
 namespace {
-template <int COUT, int KC>
-int launch_zf2(const void* x, const void* wz, void* out, float* stats, int N, int Cin, int D, int H, int W,
-               int flags, cudaStream_t st) {
+template <int COUT, int KC, bool POOL>
+int launch_zf2(const void* x, const void* wz, void* out, void* pooled, float* stats, int N, int Cin, int D,
+               int H, int W, int flags, cudaStream_t st) {
   using C = Cfg<COUT, KC>;
+  KM_CHECK_ARG(POOL || !pooled, "km_conv3d_zfold_pair: fused pooling is built for Cout = 32 only");
   Zf2Geom g;
   memset(&g, 0, sizeof(g));
   g.N = N; g.D = D; g.H = H; g.W = W;
@@ -528,7 +558,8 @@ int launch_zf2(const void* x, const void* wz, void* out, float* stats, int N, in
     km_set_error("km_conv3d_zfold_pair: cuTensorMapEncodeTiled unavailable");
     return KM_ECUDA;
   }
-  const CUtensorMapSwizzle swz = C::kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle swz = C::kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : C::kRowBytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
@@ -562,7 +593,7 @@ int launch_zf2(const void* x, const void* wz, void* out, float* stats, int N, in
   }
   static bool attr_set = false;   // one flag per instantiation
   if (!attr_set) {
-    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel<COUT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel<COUT, KC, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const int nsm = km_sm_count();
@@ -571,27 +602,31 @@ int launch_zf2(const void* x, const void* wz, void* out, float* stats, int N, in
   if (grid / 2 > upi) grid = 2 * upi;
   if ((flags & KM_CONV_STATS) && grid < nsm)
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * COUT * 2 * sizeof(float), st));
-  conv_zf2_kernel<COUT, KC><<<grid, kThreads, smem_bytes, st>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
-                                                               stats);
+  conv_zf2_kernel<COUT, KC, POOL><<<grid, kThreads, smem_bytes, st>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
+                                                               reinterpret_cast<__nv_bfloat16*>(pooled), stats);
   KM_LAUNCH_OK("conv_zf2_kernel");
   return KM_OK;
 }
 }  // namespace
 
-extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, float* stats, int N, int Cin,
-                                    int Cout, int D, int H, int W, int flags, km_stream_t stream) {
-  KM_CHECK_ARG(x && wz && out, "km_conv3d_zfold_pair: null argument");
+extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, void* pooled, float* stats,
+                                    int N, int Cin, int Cout, int D, int H, int W, int flags,
+                                    km_stream_t stream) {
+  KM_CHECK_ARG(x && wz && (out || pooled), "km_conv3d_zfold_pair: null argument");
   KM_CHECK_ARG(km_conv3d_zfold_pair_supported(Cin, Cout, D, H, W),
                "km_conv3d_zfold_pair: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
   KM_CHECK_ARG(N > 0, "km_conv3d_zfold_pair: bad batch");
+  KM_CHECK_ARG(!pooled || (D >= 2 && H >= 2 && W >= 2), "km_conv3d_zfold_pair: volume too small to pool");
   KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "km_conv3d_zfold_pair: KM_CONV_STATS needs stats");
   KM_CHECK_ARG(!(flags & KM_CONV_COM), "km_conv3d_zfold_pair: KM_CONV_COM is not supported");
-  KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wz & 15) == 0 && ((uintptr_t)out & 31) == 0,
-               "km_conv3d_zfold_pair: pointers must be 16-byte (output: 32-byte) aligned");
+  KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wz & 15) == 0 && ((uintptr_t)out & 31) == 0 &&
+                   ((uintptr_t)pooled & 31) == 0,
+               "km_conv3d_zfold_pair: pointers must be 16-byte (outputs: 32-byte) aligned");
   cudaStream_t st = km_cs(stream);
+  if (Cin == 16) return launch_zf2<32, 16, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
   const bool k64 = Cin % 64 == 0;
-  if (Cout == 64) return k64 ? launch_zf2<64, 64>(x, wz, out, stats, N, Cin, D, H, W, flags, st)
-                             : launch_zf2<64, 32>(x, wz, out, stats, N, Cin, D, H, W, flags, st);
-  return k64 ? launch_zf2<32, 64>(x, wz, out, stats, N, Cin, D, H, W, flags, st)
-             : launch_zf2<32, 32>(x, wz, out, stats, N, Cin, D, H, W, flags, st);
+  if (Cout == 64) return k64 ? launch_zf2<64, 64, false>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st)
+                             : launch_zf2<64, 32, false>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  return k64 ? launch_zf2<32, 64, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st)
+             : launch_zf2<32, 32, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
 }

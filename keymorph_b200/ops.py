@@ -368,21 +368,24 @@ def pack_weights_zfold_pair(w):
     return out
 
 
-def conv3d_zfold_pair(x, wz, relu=False, want_stats=False):
-    """z-folded 2-CTA tcgen05 conv (Cin % 64 == 0 -> 64, 3x3x3, pad 1).  x: bf16 (N,D,H,W,Cin)."""
+def conv3d_zfold_pair(x, wz, relu=False, want_stats=False, pool=False, store=True):
+    """z-folded 2-CTA tcgen05 conv (3x3x3, pad 1; Cout 64 or 32).  x: bf16 (N,D,H,W,Cin).  Returns
+    (out | None, stats | None) or, with pool=True, (out | None, pooled, stats | None) like conv3d_zfold."""
     _need_cuda(x, wz)
     assert x.dtype == torch.bfloat16 and wz.dtype == torch.bfloat16
     x, wz = x.contiguous(), wz.contiguous()
     N, D, H, W, Cin = x.shape
     Cout = wz.shape[3] // 3
     flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
-    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device) if store else None
+    pooled = torch.empty((N, D // 2, H // 2, W // 2, Cout), dtype=torch.bfloat16, device=x.device) \
+        if pool else None
     stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x.device) \
         if want_stats else None
     with torch.cuda.device(x.device):
-        _lib.call("km_conv3d_zfold_pair", _ptr(x), _ptr(wz), _ptr(out), _ptr(stats), N, Cin, Cout, D, H, W,
-                  flags, _stream())
-    return out, stats
+        _lib.call("km_conv3d_zfold_pair", _ptr(x), _ptr(wz), _ptr(out), _ptr(pooled), _ptr(stats), N, Cin,
+                  Cout, D, H, W, flags, _stream())
+    return (out, pooled, stats) if pool else (out, stats)
 
 
 def zfold_supported(Cin, Cout, D, H, W):

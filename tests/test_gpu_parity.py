@@ -242,6 +242,14 @@ def test_conv3d_zfold_vs_general_kernel_and_fp32(shape):
         assert torch.equal(ops.ndhwc_to_ncdhw(pooled).cpu(), pref)
         sp_ref = torch.stack([pref.double().flatten(2).sum(-1), (pref.double() ** 2).flatten(2).sum(-1)], -1)
         assert_close(stp.double().sum(0).cpu(), sp_ref, rtol=1e-4, atol=1e-2)
+        # the 2-CTA z-folded kernel on the same layer (Cin = 16 instantiation, fused pooling)
+        wz2 = ops.pack_weights_zfold_pair(cu(w))
+        full2, pooled3, stp2 = ops.conv3d_zfold_pair(xb, wz2, relu=True, want_stats=True, pool=True)
+        assert_close(ops.ndhwc_to_ncdhw(full2).cpu(), a, rtol=1e-2, atol=1e-2)
+        assert torch.equal(ops.ndhwc_to_ncdhw(pooled3).cpu(), F.max_pool3d(ops.ndhwc_to_ncdhw(full2).cpu(), 2))
+        p3 = ops.ndhwc_to_ncdhw(pooled3).cpu().double()
+        assert_close(stp2.double().sum(0).cpu(), torch.stack([p3.flatten(2).sum(-1), (p3 ** 2).flatten(2).sum(-1)], -1),
+                     rtol=1e-4, atol=1e-2)
 
 
 @pytest.mark.parametrize("cfg", [(1, 64, 64, 8, 32, 32), (2, 192, 64, 70, 40, 24), (1, 64, 64, 3, 16, 8),

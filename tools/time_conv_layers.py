@@ -87,3 +87,21 @@ for name, cin, cout, e in LAYERS:
     us = e0.elapsed_time(e1) / 5 * 1e3
     print(f"{name:8s} {cin:4d}->{cout:4d} @{e:3d}^3 x{N} z-fold + 2-CTA: {us:8.1f} us  {2.0 * 27 * cin * cout * e ** 3 * N / us / 1e6:7.1f} TFLOP/s", flush=True)
     del x
+# first layer through the 2-CTA z-folded kernel (Cin = 16), with and without the fused pool
+x = torch.randn(N, S, S, S, 16, device="cuda").bfloat16()
+wz2 = ops.pack_weights_zfold_pair(torch.randn(32, 16, 3, 3, 3, device="cuda") / (27 * 16) ** 0.5)
+wz1 = ops.pack_weights_zfold(torch.randn(32, 16, 3, 3, 3, device="cuda") / (27 * 16) ** 0.5)
+for label, fn in (("zfold  1-CTA, full store", lambda: ops.conv3d_zfold(x, wz1, relu=True, want_stats=True)),
+                  ("zfold  1-CTA, pooled only", lambda: ops.conv3d_zfold(x, wz1, relu=True, want_stats=True, pool=True, store=False)),
+                  ("zfold  2-CTA, full store", lambda: ops.conv3d_zfold_pair(x, wz2, relu=True, want_stats=True)),
+                  ("zfold  2-CTA, pooled only", lambda: ops.conv3d_zfold_pair(x, wz2, relu=True, want_stats=True, pool=True, store=False))):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"enc0.c2 16->32 @256^3 x{N} {label}: {e0.elapsed_time(e1) / 5 * 1e3:8.1f} us", flush=True)
