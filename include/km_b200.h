@@ -65,6 +65,10 @@ int km_sm_count(void);
 /* key KM_OPT_CONV_TWO_ISSUERS (default 128): layers whose output-channel block is at most this wide
  * split the bricks of a group between two MMA issuer warps (0 = always one issuer; A/B testing). */
 #define KM_OPT_CONV_TWO_ISSUERS 9
+/* key KM_OPT_ZF2_TWO_BRICKS (default 0): km_conv3d_zfold_pair processes two y-adjacent bricks per unit
+ * for the 64 -> 64 shapes (half the weight traffic, but only one TMEM set: measured slower) instead of
+ * one (A/B testing). */
+#define KM_OPT_ZF2_TWO_BRICKS 10
 int km_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------ *

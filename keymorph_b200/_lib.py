@@ -83,6 +83,8 @@ KM_OPT_CONV_NO_EPILOGUE_BATCH = 5
 KM_OPT_CONV_HALO_AXIS = 6
 KM_OPT_TPS_SINGLE_CTA = 7
 KM_OPT_CONV_INTERLEAVE_BRICKS = 8
+KM_OPT_CONV_TWO_ISSUERS = 9
+KM_OPT_ZF2_TWO_BRICKS = 10
 
 _lib = None
 

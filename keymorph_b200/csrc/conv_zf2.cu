@@ -25,12 +25,15 @@ namespace {
 
 constexpr int kThreads = 320;           // warp 0 TMA, warp 1 MMA (leader), warps 2..9 epilogue
 constexpr int kEpiThreads = 256;
-constexpr int kBoxRows = 8 * 18;        // 8 x-voxels by 16 + 2 y-rows
 constexpr int kStagesMax = 12;
 
 // compile-time shape of one instantiation: COUT output channels, KC input channels per chunk
-template <int COUT, int KC>
+template <int COUT, int KC, int MT>
 struct Cfg {
+  static constexpr int kMT = MT;                       // y-adjacent bricks per unit sharing every weight tile
+  static constexpr int kBoxRows = 8 * (16 * MT + 2);   // 8 x-voxels by 16 MT + 2 y-rows
+  static constexpr int kSets = (2 * MT * 3 * COUT <= 512) ? 2 : 1;   // TMEM accumulator sets (units in flight)
+  static constexpr uint32_t kSetStride = kSets == 2 ? 256u : 0u;
   static constexpr int kCout = COUT;
   static constexpr int kKC = KC;
   static constexpr int kN3 = 3 * COUT;                 // MMA N
@@ -45,6 +48,7 @@ struct Cfg {
 
 struct Zf2Geom {
   int N, D, H, W, chunks;
+  int mt, sets;
   int xpairs, tiles_y, zsegs, lz, punits;   // punits = N * zsegs * tiles_y * xpairs (unit pairs), lz planes each
   int flags;
   uint32_t off_scratch, off_stats, off_bars;
@@ -61,7 +65,7 @@ __device__ __forceinline__ Unit decode_unit(const Zf2Geom& g, int pu, uint32_t r
   const int xp = pu % g.xpairs;
   pu /= g.xpairs;
   r.x0 = (2 * xp + (int)rank) * 8;
-  r.y0 = (pu % g.tiles_y) * 16;
+  r.y0 = (pu % g.tiles_y) * (16 * g.mt);
   pu /= g.tiles_y;
   r.zs = (pu % g.zsegs) * g.lz;
   r.n = pu / g.zsegs;
@@ -78,6 +82,13 @@ __device__ __forceinline__ void for_each_tile(const Zf2Geom& g, uint32_t rank, F
   const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
   const int upi = g.punits / g.N;
   for (int n = 0; n < g.N; ++n) {
+    if (g.sets == 1) {   // one TMEM set: the unit pairs of this CTA pair one after the other
+      for (int ua = pair; ua < upi; ua += npairs) {
+        const Unit a = decode_unit(g, n * upi + ua, rank);
+        for (int p = 0; p < a.planes; ++p) fn(std::integral_constant<uint32_t, 0u>{}, a, p, cnt[0]++);
+      }
+      continue;
+    }
     for (int ua = pair; ua < upi; ua += 2 * npairs) {
       const int ub = ua + npairs;
       const Unit a = decode_unit(g, n * upi + ua, rank);
@@ -185,12 +196,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int COUT, int KC, bool POOL>
+template <int COUT, int KC, int MT, bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const Zf2Geom g, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
                 float* __restrict__ stats) {
-  using C = Cfg<COUT, KC>;
+  using C = Cfg<COUT, KC, MT>;
+  constexpr int kMT = C::kMT;
+  constexpr uint32_t kSetStride = C::kSetStride;
   constexpr int kCout = C::kCout, kKC = C::kKC, kN3 = C::kN3, kHalfRows = C::kHalfRows;
   constexpr int kRowBytes = C::kRowBytes, kSteps = C::kSteps, kCols = C::kCols;
   constexpr uint32_t kASub = C::kASub, kBTile = C::kBTile, kStage = C::kStage;
@@ -280,7 +293,7 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         constexpr uint32_t set = decltype(set_c)::value;
         mbar_wait(tempty_bar(set), (cnt & 1u) ^ 1u);   // both CTAs drained + zeroed the previous plane
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + set * 256u;
+        const uint32_t d_tmem = tmem_base + set * kSetStride;
         uint32_t accum = p == 0 ? 0u : 1u;   // a unit's first plane overwrites the whole ring
         for (int si = 0; si < subs; ++si) {
           mbar_wait(full_bar(s), ph);
@@ -291,8 +304,10 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
             for (int kk = 0; kk < kSteps; ++kk) {
-              umma2_bf16_pred(d_tmem, a16 + (uint32_t)dy * (kSbo >> 4) + 2u * kk,
-                              b16 + (uint32_t)dy * (kBTile >> 4) + 2u * kk, desc_hi, idesc, accum, issue);
+#pragma unroll
+              for (int m = 0; m < kMT; ++m)   // bricks sharing this weight tile
+                umma2_bf16_pred(d_tmem + (uint32_t)(m * kN3), a16 + (uint32_t)(16 * m + dy) * (kSbo >> 4) + 2u * kk,
+                                b16 + (uint32_t)dy * (kBTile >> 4) + 2u * kk, desc_hi, idesc, accum, issue);
               accum = 1u;
             }
           }
@@ -323,13 +338,15 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float ssum[kCols], ssq[kCols];
 #pragma unroll
     for (int j = 0; j < kCols; ++j) ssum[j] = ssq[j] = 0.f;
-    uint32_t zprev[POOL ? 2 : 1][kCols / 16][8];   // xy-pooled even plane of each unit in flight (pool mode)
+    uint32_t zprev[POOL ? 2 : 1][POOL ? kMT : 1][kCols / 16][8];   // xy-pooled even planes in flight (pool mode)
 #pragma unroll
     for (int a = 0; a < (POOL ? 2 : 1); ++a)
 #pragma unroll
-      for (int b = 0; b < kCols / 16; ++b)
+      for (int m = 0; m < (POOL ? kMT : 1); ++m)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) zprev[a][b][j] = 0u;
+        for (int b = 0; b < kCols / 16; ++b)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) zprev[a][m][b][j] = 0u;
     int n_cur = -1;
     auto flush_stats = [&](int n) {
 #pragma unroll
@@ -363,9 +380,11 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t lead_tempty = mapa_u32(tempty_bar(set), 0);
       mbar_wait(tfull_bar(set), cnt & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256u + slot * kCout +
-                             (uint32_t)(half * kCols);
-      const int x2 = u.x0 + tx, y2 = u.y0 + ty;
+#pragma unroll
+      for (int m = 0; m < kMT; ++m) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * kSetStride + (uint32_t)(m * kN3) +
+                             slot * kCout + (uint32_t)(half * kCols);
+      const int x2 = u.x0 + tx, y2 = u.y0 + 16 * m + ty;
       if (store) {   // warp-uniform: tcgen05.ld is a warp-collective operation
         uint32_t r[kCols / 16][16];
 #pragma unroll
@@ -373,9 +392,11 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld_wait();
 #pragma unroll
         for (int b = 0; b < kCols / 16; ++b) tmem_st16_zero(taddr + 16u * b);   // fresh output plane z' + 2
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive_cluster(lead_tempty);
+        if (m == kMT - 1) {   // last brick drained: the set goes back to the issuer before the arithmetic
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive_cluster(lead_tempty);
+        }
         const bool inside = u.valid && x2 < g.W && y2 < g.H;
         const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
 #pragma unroll
@@ -403,10 +424,10 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             if ((zo & 1) == 0) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) zprev[POOL ? set : 0][hh][j] = pk[j];
+              for (int j = 0; j < 8; ++j) zprev[POOL ? set : 0][POOL ? m : 0][hh][j] = pk[j];
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) pk[j] = hmax2_u32(pk[j], zprev[POOL ? set : 0][hh][j]);
+              for (int j = 0; j < 8; ++j) pk[j] = hmax2_u32(pk[j], zprev[POOL ? set : 0][POOL ? m : 0][hh][j]);
               const int xp = x2 >> 1, yp = y2 >> 1, zp = zo >> 1;
               if (u.valid && ((tx | ty) & 1) == 0 && xp < (g.W >> 1) && yp < (g.H >> 1)) {
                 const size_t pv = (((size_t)u.n * (g.D >> 1) + zp) * (g.H >> 1) + yp) * (g.W >> 1) + xp;
@@ -429,9 +450,12 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       } else {
 #pragma unroll
         for (int b = 0; b < kCols / 16; ++b) tmem_st16_zero(taddr + 16u * b);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive_cluster(lead_tempty);
+        if (m == kMT - 1) {
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive_cluster(lead_tempty);
+        }
+      }
       }
     });
 
@@ -507,10 +531,11 @@ extern "C" int km_pack_weights_zfold_pair(const float* w, void* packed, int Cout
 }
 
 namespace {
-template <int COUT, int KC, bool POOL>
+int g_zf2_mt2 = 0;   // km_set_option(KM_OPT_ZF2_TWO_BRICKS)
+template <int COUT, int KC, int MT, bool POOL>
 int launch_zf2(const void* x, const void* wz, void* out, void* pooled, float* stats, int N, int Cin, int D,
                int H, int W, int flags, cudaStream_t st) {
-  using C = Cfg<COUT, KC>;
+  using C = Cfg<COUT, KC, MT>;
   KM_CHECK_ARG(POOL || !pooled, "km_conv3d_zfold_pair: fused pooling is built for Cout = 32 only");
   Zf2Geom g;
   memset(&g, 0, sizeof(g));
@@ -519,7 +544,9 @@ int launch_zf2(const void* x, const void* wz, void* out, void* pooled, float* st
   g.flags = flags;
   const int tiles_x = (W + 7) / 8;
   g.xpairs = (tiles_x + 1) / 2;
-  g.tiles_y = (H + 15) / 16;
+  g.mt = MT;
+  g.sets = C::kSets;
+  g.tiles_y = (H + 16 * MT - 1) / (16 * MT);
   // z segment length: longer segments amortise the two halo planes, shorter ones balance the unit
   // pairs over the CTA pairs; pick the cheaper of 64 / 32 / 16 planes for this shape
   const int npairs_hw = km_sm_count() / 2;
@@ -565,7 +592,7 @@ int launch_zf2(const void* x, const void* wz, void* out, void* pooled, float* st
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
                              (cuuint64_t)D * H * W * Cin * 2};
-    cuuint32_t box[5] = {(cuuint32_t)KC, 8, 18, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)KC, 8, (cuuint32_t)(16 * MT + 2), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -593,7 +620,7 @@ int launch_zf2(const void* x, const void* wz, void* out, void* pooled, float* st
   }
   static bool attr_set = false;   // one flag per instantiation
   if (!attr_set) {
-    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel<COUT, KC, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel<COUT, KC, MT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const int nsm = km_sm_count();
@@ -602,12 +629,14 @@ int launch_zf2(const void* x, const void* wz, void* out, void* pooled, float* st
   if (grid / 2 > upi) grid = 2 * upi;
   if ((flags & KM_CONV_STATS) && grid < nsm)
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * COUT * 2 * sizeof(float), st));
-  conv_zf2_kernel<COUT, KC, POOL><<<grid, kThreads, smem_bytes, st>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
+  conv_zf2_kernel<COUT, KC, MT, POOL><<<grid, kThreads, smem_bytes, st>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
                                                                reinterpret_cast<__nv_bfloat16*>(pooled), stats);
   KM_LAUNCH_OK("conv_zf2_kernel");
   return KM_OK;
 }
 }  // namespace
+
+void km_zf2_set_two_bricks(int v) { g_zf2_mt2 = v ? 1 : 0; }
 
 extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, void* pooled, float* stats,
                                     int N, int Cin, int Cout, int D, int H, int W, int flags,
@@ -623,10 +652,16 @@ extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, vo
                    ((uintptr_t)pooled & 31) == 0,
                "km_conv3d_zfold_pair: pointers must be 16-byte (outputs: 32-byte) aligned");
   cudaStream_t st = km_cs(stream);
-  if (Cin == 16) return launch_zf2<32, 16, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  if (Cin == 16) return launch_zf2<32, 16, 1, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
   const bool k64 = Cin % 64 == 0;
-  if (Cout == 64) return k64 ? launch_zf2<64, 64, false>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st)
-                             : launch_zf2<64, 32, false>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
-  return k64 ? launch_zf2<32, 64, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st)
-             : launch_zf2<32, 32, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  if (Cout == 64 && k64) {
+    // two bricks per unit halve the weight bytes per output (the kernel is bound by L2 -> SM traffic)
+    // at the price of a single TMEM set; needs two brick rows
+    if (H >= 32 && g_zf2_mt2)
+      return launch_zf2<64, 64, 2, false>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
+    return launch_zf2<64, 64, 1, false>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  }
+  if (Cout == 64) return launch_zf2<64, 32, 1, false>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  return k64 ? launch_zf2<32, 64, 1, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st)
+             : launch_zf2<32, 32, 1, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
 }

@@ -22,6 +22,7 @@ void km_conv_set_no_epi_batch(int v);
 void km_conv_set_halo_axis(int v);
 void km_conv_set_interleave(int v);
 void km_conv_set_two_issuers(int v);
+void km_zf2_set_two_bricks(int v);
 void km_tps_set_single_cta(int v);
 namespace {
 
@@ -866,6 +867,10 @@ extern "C" int km_set_option(int key, int value) {
   }
   if (key == KM_OPT_CONV_TWO_ISSUERS) {
     km_conv_set_two_issuers(value);
+    return KM_OK;
+  }
+  if (key == KM_OPT_ZF2_TWO_BRICKS) {
+    km_zf2_set_two_bricks(value);
     return KM_OK;
   }
   if (key == KM_OPT_TPS_SINGLE_CTA) {
