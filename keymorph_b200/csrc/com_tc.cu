@@ -301,22 +301,6 @@ com_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   }
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_encodeTiled encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<PFN_encodeTiled>(p);
-  return fn;
-}
 
 typedef void (*ComKernel)(const CUtensorMap, const CUtensorMap, const ComGeom, const float*, float*);
 
@@ -371,7 +355,7 @@ extern "C" int km_conv1x1_com(const void* x, const void* wp, const float* bias, 
   g.off_bars = off; off += bars_bytes;
   const uint32_t smem_bytes = off + 1024;
 
-  PFN_encodeTiled encode = encode_fn();
+  PFN_encodeTiled encode = tensor_map_encoder();
   if (!encode) {
     km_set_error("km_conv1x1_com: cuTensorMapEncodeTiled unavailable");
     return KM_ECUDA;

@@ -649,23 +649,6 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
-          cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<PFN_encodeTiled>(p);
-  return fn;
-}
 
 int g_sm_count = 0;
 int sm_count() {
@@ -866,7 +849,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   const uint32_t smem_bytes = off + 1024;
   KM_CHECK_ARG(smem_bytes <= 232448, "km_conv3d_tc: shared memory overflow (%u)", smem_bytes);
 
-  PFN_encodeTiled encode = get_encode_fn();
+  PFN_encodeTiled encode = tensor_map_encoder();
   if (!encode) {
     km_set_error("km_conv3d_tc: cuTensorMapEncodeTiled unavailable");
     return KM_ECUDA;

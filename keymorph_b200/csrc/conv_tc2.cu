@@ -49,74 +49,6 @@ struct PairGeom {
   int total_tiles;
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
-}
-__device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0,
-                                             int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish2() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma2_bf16_pred(uint32_t d_tmem, uint32_t adesc_lo, uint32_t bdesc_lo,
-                                                uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
-                                                uint32_t issue) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, q;\n"
-      ".reg .b64 da, db;\n"
-      "setp.ne.b32 p, %5, 0;\n"
-      "setp.ne.b32 q, %6, 0;\n"
-      "mov.b64 da, {%1, %3};\n"
-      "mov.b64 db, {%2, %3};\n"
-      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(adesc_lo), "r"(bdesc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
-}
-// arrives on the barrier at this offset in BOTH CTAs when all previously issued MMAs have completed
-__device__ __forceinline__ void umma2_commit_pred(uint32_t bar, uint32_t issue) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      ".reg .b16 m;\n"
-      "setp.ne.b32 q, %1, 0;\n"
-      "mov.b16 m, 3;\n"
-      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
-      "}\n" ::"r"(bar),
-      "r"(issue)
-      : "memory");
-}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -435,21 +367,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_encodeTiled pair_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<PFN_encodeTiled>(p);
-  return fn;
-}
 inline uint32_t pair_round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 typedef void (*PairKernel)(const CUtensorMap, const CUtensorMap, const PairGeom, __nv_bfloat16*, float*);
@@ -527,7 +444,7 @@ extern "C" int km_conv3d_tc_pair(const void* x, const void* wp, void* out, float
   const uint32_t smem_bytes = off + 1024;
   KM_CHECK_ARG(smem_bytes <= 232448, "km_conv3d_tc_pair: shared memory overflow (%u)", smem_bytes);
 
-  PFN_encodeTiled encode = pair_encode_fn();
+  PFN_encodeTiled encode = tensor_map_encoder();
   if (!encode) {
     km_set_error("km_conv3d_tc_pair: cuTensorMapEncodeTiled unavailable");
     return KM_ECUDA;

@@ -93,22 +93,6 @@ __device__ __forceinline__ void for_each_tile(const ZfGeom& g, F&& fn) {
   }
 }
 
-__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
-  const uint32_t z = 0u;
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
-      "r"(z)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() {
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]),
-               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
   const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a),
                                    *reinterpret_cast<const __nv_bfloat162*>(&b));
@@ -394,21 +378,6 @@ __global__ void pack_weights_zf_kernel(const float* __restrict__ w, __nv_bfloat1
   }
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_encodeTiled zf_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<PFN_encodeTiled>(p);
-  return fn;
-}
 inline uint32_t zf_round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
@@ -464,7 +433,7 @@ extern "C" int km_conv3d_zfold(const void* x, const void* wz, void* out, void* p
   const uint32_t smem_bytes = off + 1024;
   KM_CHECK_ARG(smem_bytes <= 232448, "km_conv3d_zfold: shared memory overflow (%u; batch too large)", smem_bytes);
 
-  PFN_encodeTiled encode = zf_encode_fn();
+  PFN_encodeTiled encode = tensor_map_encoder();
   if (!encode) {
     km_set_error("km_conv3d_zfold: cuTensorMapEncodeTiled unavailable");
     return KM_ECUDA;
