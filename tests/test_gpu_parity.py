@@ -690,6 +690,23 @@ def test_example_pair_config1_vs_reference(golden):
         assert int(kb.loss_ops.jdlessthan0(grid.permute(0, 4, 1, 2, 3))) == int(g[f"{t}_jdneg"])
 
 
+def test_prefetch_to_device_ring_keeps_items_intact():
+    """hostio.prefetch_to_device: persistent double-buffered staging; every item must arrive intact
+    although the copy of item k+1 overlaps the (deliberately long) work on item k."""
+    from keymorph_b200.hostio import prefetch_to_device
+    items = [(torch.full((64, 64, 64), float(i)).pin_memory(), torch.arange(4096).float().add(i).pin_memory())
+             for i in range(7)]
+    sums = []
+    for a, b in prefetch_to_device(items, DEV):
+        x = a
+        for _ in range(20):          # keep the compute stream busy while the next copy is in flight
+            x = x * 1.0000001
+        sums.append((a.sum(), b[0] + 0, x.mean()))
+    torch.cuda.synchronize()
+    for i, (sa, b0, _) in enumerate(sums):
+        assert float(sa) == float(i) * 64 ** 3 and float(b0) == float(i)
+
+
 def test_forward_fused_warp_outputs():
     net = _seeded("trunc").to(DEV)
     model = kb.KeyMorph(net, 16, 3, fused_warp=True).eval()

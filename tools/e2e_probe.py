@@ -11,7 +11,8 @@ from keymorph_b200.hostio import prefetch_to_device  # noqa: E402
 from oracle import keymorph_oracle as O  # noqa: E402
 
 S, K, steps = 256, 256, int(sys.argv[1]) if len(sys.argv) > 1 else 10
-dev = torch.device("cuda", 0)
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
 torch.manual_seed(23)
 net = kb.TruncatedUNet3D(1, K, 1, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8,
                          num_levels=4, is_segmentation=False, conv_padding=1).eval().to(dev)
@@ -79,6 +80,12 @@ def host_only(n):
     print(f"   host enqueue time per step: {(time.perf_counter() - t0) * 1e3 / n:.2f} ms")
 
 
+def h2d_only(n):
+    for a, b in prefetch_to_device([(fh, mh)] * n, dev):
+        pass
+
+
+run("H pinned H2D copies alone (2 x 64 MB per step)", h2d_only)
 run("A device-resident, async (bench 'value')", resident_async)
 run("B device-resident, .item() every step", resident_item)
 run("C pinned H2D prefetch + .item() every step (bench 'e2e')", h2d_item)
