@@ -127,9 +127,13 @@ template <bool FAST>
 __device__ __forceinline__ float tps_u(float d2) {
   const float s = d2 + 1e-6f;
   if (FAST) {
-    // log(r + e) = 0.5*log(s) + log1p(e/r) ~= 0.5*ln2*lg2(s) + e*rsqrt(s)   (e/r <= 1e-3)
-    const float l = fmaf(0.34657359028f, __log2f(s), 1e-6f * rsqrtf(s));
-    return s * l;
+    // r^2 log(r + e) = s * (0.5 log s + log1p(e/r)) ~= 0.5 ln2 * s * lg2(s) + e * r      (e/r <= 1e-3)
+    // The second term is at most 3.5e-6, so r = sqrt(s) only needs ~1e-2 relative accuracy: the
+    // exponent-halving bit trick (max error 3.5 %) replaces the second MUFU op of every term; the
+    // resulting absolute error (< 1.3e-7 per unit weight) is a fifth of the fp32 rounding of the
+    // first term.
+    const float r = __int_as_float((__float_as_int(s) >> 1) + 0x1fbd1df5);
+    return fmaf(0.34657359028f * s, __log2f(s), 1e-6f * r);
   } else {
     const float r = sqrtf(s);
     return (r * r) * logf(r + 1e-6f);
