@@ -147,6 +147,20 @@ int km_jacobian_stats(const float* field, long long stride_n, long long stride_c
                       long long stride_y, long long stride_x, double* out, void* workspace, int N,
                       int D, int H, int W, km_stream_t stream);
 
+/* keymorph/loss_ops.py:120-157 (_surfd, hausdorff_distance): symmetric Hausdorff
+ * distance between the surfaces of two binary volumes (voxel != 0), surface = volume minus its
+ * 6-connected binary erosion (array border counts as background), exact anisotropic Euclidean
+ * distance transform with voxel sizes (sz, sy, sx) along (D, H, W).  The reference calls it on channel 0
+ * of two (N,C,D,H,W) one-hot tensors with sampling (1.25, 1.25, 10): pass the channel-0 pointers and the
+ * batch strides in elements.
+ *   out (N,2) fp64 = [distance, empty] -- empty = 1 (distance = -1) when either surface has no voxel,
+ *   a case in which scipy's transform is undefined and the reference returns garbage.
+ * workspace: km_hausdorff_workspace_bytes(D, H, W) = 10 bytes per voxel. */
+size_t km_hausdorff_workspace_bytes(int D, int H, int W);
+int km_hausdorff(const float* a, const float* b, long long stride_a, long long stride_b, int N, int D,
+                 int H, int W, float sz, float sy, float sx, double* out, void* workspace,
+                 km_stream_t stream);
+
 /* keymorph/loss_ops.py:9-13 and :16-63.  Elementwise-pair statistics of two (N,C,M) fp32 tensors:
  * sums[n,c,:] = [sum (p-t)^2, sum p*t, sum p*p, sum t*t] (fp64).  With hard != 0 pred is replaced
  * by one_hot(argmax_c pred) (first maximum wins, like torch.argmax) before the products.

@@ -2,10 +2,12 @@
 
 The names below mirror the reference modules on the registration hot path
 (keymorph.model / keypoint_aligners / transformations / layers / net / unet3d.model / utils /
-loss_ops); everything they compute runs in hand-written CUDA kernels reached through the C ABI of
+loss_ops / augmentation); everything they compute runs in hand-written CUDA kernels reached through the C ABI of
 libkm_b200.so (include/km_b200.h).  There is no CPU path.
 """
 from . import ops  # noqa: F401
+from .augmentation import (AffineDeformation3d, affine_augment, random_affine_augment,  # noqa: F401
+                           random_affine_augment_pair)
 from .keypoint_aligners import (TPS, AffineKeypointAligner, RigidKeypointAligner,  # noqa: F401
                                 grid_from_points)
 from .layers import CenterOfMass3d, ConvBlock  # noqa: F401

@@ -187,6 +187,26 @@ def jacobian_stats(field):
     return out
 
 
+def hausdorff(a, b, sampling=(1.25, 1.25, 10.0)):
+    """a, b: fp32 (N,D,H,W) binary volumes (voxel != 0), dense in (D,H,W), any batch stride -- e.g.
+    seg[:, 0] -> (N,2) fp64 [symmetric surface Hausdorff distance, empty flag] (loss_ops.py:120-157)."""
+    _need_cuda(a, b)
+    assert a.dim() == 4 and a.shape == b.shape and a.dtype == torch.float32 and b.dtype == torch.float32
+    N, D, H, W = a.shape
+    dense = (H * W, W, 1)
+    if a.stride()[1:] != dense:
+        a = a.contiguous()
+    if b.stride()[1:] != dense:
+        b = b.contiguous()
+    out = torch.empty((N, 2), dtype=torch.float64, device=a.device)
+    ws = _ws(_lib.query("km_hausdorff_workspace_bytes", D, H, W), a.device)
+    sz, sy, sx = (float(v) for v in sampling)
+    with torch.cuda.device(a.device):
+        _lib.call("km_hausdorff", _ptr(a), _ptr(b), a.stride(0), b.stride(0), N, D, H, W, sz, sy, sx,
+                  _ptr(out), _ptr(ws), _stream())
+    return out
+
+
 def pair_stats(pred, target, hard=False):
     """sums (N,C,4) fp64 = [sum (p-t)^2, sum p*t, sum p*p, sum t*t] over the flattened spatial dims;
     hard=True replaces pred by one_hot(argmax_c pred)."""

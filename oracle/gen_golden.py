@@ -127,9 +127,79 @@ def gen_example_pair():
     save("example_pair64", **out)
 
 
+def gen_augment_aniso():
+    """Anisotropic augmentation (keymorph/augmentation.py:81-178) through the reference's own
+    AffineDeformation3d on the CPU: matrix, moved points, bilinear image and nearest segmentation for
+    one volume (the reference's affine_grid supports batch size 1 only)."""
+    from keymorph.augmentation import AffineDeformation3d
+    g = torch.Generator().manual_seed(5)
+    scale = torch.empty(1, 3).uniform_(0.8, 1.2, generator=g)
+    offset = torch.empty(1, 3).uniform_(-0.2, 0.2, generator=g)
+    theta = torch.empty(1, 3).uniform_(-3.1416, 3.1416, generator=g)
+    shear = torch.empty(1, 6).uniform_(-0.1, 0.1, generator=g)
+    params = (scale, offset, theta, shear)
+    img = torch.rand(1, 2, 12, 16, 20, generator=g)
+    seg = torch.randint(0, 5, (1, 1, 12, 16, 20), generator=g).float()
+    pts = torch.rand(1, 9, 3, generator=g) * 2 - 1
+    aug = AffineDeformation3d(device="cpu")
+    save("augment_aniso", scale=scale, offset=offset, theta=theta, shear=shear, img=img, seg=seg, points=pts,
+         matrix=aug.build_affine_matrix(1, params), img_aug=aug(img, params=params, interp_mode="bilinear"),
+         seg_aug=aug(seg, params=params, interp_mode="nearest"), points_aug=aug.deform_points(pts, params))
+
+
+def gen_group_metrics():
+    """Evaluation metrics of SURVEY.md 8f-3 computed by the reference itself (keymorph/loss_ops.py):
+    hausdorff_distance / fast_dice on a pair of soft 4-class maps, and the O(G^2) group metrics
+    (MSEPairwiseLoss, MultipleAvgSegPairwiseMetric, MultipleAvgGridMetric) on a group of three."""
+    from keymorph import loss_ops
+    from keymorph.keypoint_aligners import TPS
+    g = torch.Generator().manual_seed(31)
+    G, C, shape = 3, 4, (12, 14, 16)
+    zz, yy, xx = torch.meshgrid(*[torch.linspace(-1, 1, n) for n in shape], indexing="ij")
+    segs, imgs, grids = [], [], []
+    for i in range(G):
+        c = torch.rand(C, 3, generator=g) * 1.2 - 0.6
+        r = torch.rand(C, generator=g) * 0.4 + 0.3
+        logits = torch.stack([-(((zz - c[k, 0]) ** 2 + (yy - c[k, 1]) ** 2 + (xx - c[k, 2]) ** 2) / r[k] ** 2)
+                              for k in range(C)])
+        logits[0] = -1.0                                   # channel 0 = background shell around the blobs
+        segs.append(torch.softmax(4 * logits, 0))
+        imgs.append(torch.rand(1, *shape, generator=g))
+        pf = torch.rand(1, 12, 3, generator=g) * 1.6 - 0.8
+        pm = pf + 0.1 * torch.randn(1, 12, 3, generator=g)
+        grids.append(TPS(pm, pf, torch.tensor([0.0])).get_flow_field((1, 1) + shape)[0])
+    segs, imgs, grids = torch.stack(segs), torch.stack(imgs), torch.stack(grids)
+    hard = torch.nn.functional.one_hot(segs.argmax(1), C).permute(0, 4, 1, 2, 3).float()
+    names = ["dice", "harddice", "harddiceroi", "softdice", "hausd"]
+    seg_m = loss_ops.MultipleAvgSegPairwiseMetric()(hard, names)
+    grid_m = loss_ops.MultipleAvgGridMetric()(grids, ["jdstd", "jdlessthan0"])
+    out = {"segs": segs, "imgs": imgs, "grids": grids,
+           "hausd_01": np.float64(loss_ops.hausdorff_distance(hard[0:1], hard[1:2])),
+           "hausd_batch": np.float64(loss_ops.hausdorff_distance(hard[0:2], hard[1:3])),
+           "hausd_blobs": np.array([loss_ops.hausdorff_distance(hard[i:i + 1, k:], hard[j:j + 1, k:])
+                                    for (i, j) in ((0, 1), (0, 2), (1, 2)) for k in (1, 2, 3)]),
+           "fast_dice_01": np.float64(loss_ops.fast_dice(segs[0:1].numpy(), segs[1:2].numpy())),
+           "mse_pairwise": loss_ops.MSEPairwiseLoss()(imgs),
+           "softdice_pairwise": loss_ops.SoftDicePairwiseLoss()(segs),
+           "harddice_pairwise": loss_ops.HardDicePairwiseLoss()(segs),
+           "avg_jdstd": np.float64(loss_ops.AvgJDStd()(grids)),
+           "avg_jdneg": np.float64(loss_ops.AvgJDLessThan0()(grids))}
+    for k, v in seg_m.items():
+        out[f"multi_{k}"] = v if isinstance(v, torch.Tensor) else np.float64(v)
+    for k, v in grid_m.items():
+        out[f"multi_{k}"] = np.float64(v)
+    save("group_metrics", **out)
+
+
 def main():
     import_reference()
     sys.path.insert(0, ROOT)
+    if "--only-group-metrics" in sys.argv:
+        gen_group_metrics()
+        return
+    if "--only-augment" in sys.argv:
+        gen_augment_aniso()
+        return
     if "--only-jacobian" in sys.argv:
         gen_jacobian()
         return

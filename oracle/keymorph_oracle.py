@@ -147,6 +147,71 @@ def jdlessthan0(disp, as_percentage=False):
 
 
 # --------------------------------------------------------------------------------------------
+# surface Hausdorff distance and the pairwise group metrics (keymorph/loss_ops.py:66-157, 405-551)
+
+
+def surface_mask(vol):
+    """keymorph/loss_ops.py:121-129: A minus binary_erosion(A) with the 6-connected element and
+    border_value 0 (scipy.ndimage default): a set voxel is on the surface when one of its six
+    neighbours is clear or lies outside the array."""
+    import numpy as np
+    a = np.asarray(vol).astype(bool)
+    p = np.pad(a, 1, constant_values=False)
+    er = (p[1:-1, 1:-1, 1:-1] & p[:-2, 1:-1, 1:-1] & p[2:, 1:-1, 1:-1] & p[1:-1, :-2, 1:-1] & p[1:-1, 2:, 1:-1]
+          & p[1:-1, 1:-1, :-2] & p[1:-1, 1:-1, 2:])
+    return a & ~er
+
+
+def surface_distances(vol1, vol2, sampling=(1.25, 1.25, 10.0), chunk=2048):
+    """keymorph/loss_ops.py:121-141 (_surfd) with scipy's distance_transform_edt replaced by its
+    definition: for every surface voxel of one volume the Euclidean distance (voxel sizes
+    `sampling`) to the nearest surface voxel of the other, both directions concatenated."""
+    import numpy as np
+    s1, s2 = surface_mask(vol1), surface_mask(vol2)
+    c1 = np.argwhere(s1) * np.asarray(sampling, dtype=np.float64)
+    c2 = np.argwhere(s2) * np.asarray(sampling, dtype=np.float64)
+
+    def nearest(src, dst):
+        out = np.empty(len(src))
+        for i in range(0, len(src), chunk):
+            d = src[i:i + chunk, None, :] - dst[None, :, :]
+            out[i:i + chunk] = np.sqrt((d * d).sum(-1).min(1))
+        return out
+
+    return np.concatenate([nearest(c2, c1), nearest(c1, c2)])
+
+
+def hausdorff_distance(test_seg, gt_seg, sampling=(1.25, 1.25, 10.0)):
+    """keymorph/loss_ops.py:144-157: mean over the batch of the maximum surface distance of channel 0."""
+    a = test_seg.detach().cpu().numpy() if isinstance(test_seg, torch.Tensor) else test_seg
+    b = gt_seg.detach().cpu().numpy() if isinstance(gt_seg, torch.Tensor) else gt_seg
+    return sum(surface_distances(a[i, 0], b[i, 0], sampling).max() for i in range(len(a))) / len(a)
+
+
+def fast_dice(x, y):
+    """keymorph/loss_ops.py:66-106 without the histogram detour: Dice of argmax label maps per label
+    present in either input, eps 1e-5 in the denominator, averaged; 1 for a single label."""
+    import numpy as np
+    x = np.asarray(x).argmax(1)
+    y = np.asarray(y).argmax(1)
+    labels = np.unique(np.concatenate([np.unique(x), np.unique(y)]))
+    if len(labels) <= 1:
+        return 1.0
+    return float(np.mean([2 * np.sum((x == l) & (y == l)) / (np.sum(x == l) + np.sum(y == l) + 1e-5)
+                          for l in labels]))
+
+
+def avg_pairwise(batch, fn):
+    """keymorph/loss_ops.py:414-435 / 499-527: mean of fn over the unordered pairs of a (G, ...) batch."""
+    tot, num = 0, 0
+    for i in range(len(batch)):
+        for j in range(i + 1, len(batch)):
+            tot = tot + fn(batch[i:i + 1], batch[j:j + 1])
+            num += 1
+    return tot / num
+
+
+# --------------------------------------------------------------------------------------------
 # closed-form aligners
 
 
@@ -481,6 +546,40 @@ def affine_matrix_3d(scale, offset, angle, shear, dtype=torch.float32):
     Mz[0, 1] = Mz[0, 2] = Mz[1, 0] = Mz[1, 2] = Mz[2, 0] = Mz[2, 1] = z
     M = Mz @ Ms @ Mt @ (R3 @ R2 @ R1)
     return M.to(dtype)[None]
+
+
+def affine_matrix_3d_params(scale, offset, theta, shear, dtype=torch.float32):
+    """keymorph/augmentation.py:85-158 for per-axis parameters: scale (3,), offset (3,), theta (3,)
+    (rotations about axis 0, 1, 2, applied in that order), shear (6,) filling the off-diagonal of Mz
+    row by row.  Returns (1,4,4)."""
+    scale, offset, theta, shear = (torch.as_tensor(v, dtype=torch.float64).reshape(-1) for v in
+                                   (scale, offset, theta, shear))
+    Ms = torch.diag(torch.cat([scale, torch.ones(1, dtype=torch.float64)]))
+    Mt = torch.eye(4, dtype=torch.float64)
+    Mt[:3, 3] = offset
+    c, sn = torch.cos(theta), torch.sin(theta)
+    R1, R2, R3 = (torch.eye(4, dtype=torch.float64) for _ in range(3))
+    R1[1, 1], R1[1, 2], R1[2, 1], R1[2, 2] = c[0], -sn[0], sn[0], c[0]
+    R2[0, 0], R2[0, 2], R2[2, 0], R2[2, 2] = c[1], sn[1], -sn[1], c[1]
+    R3[0, 0], R3[0, 1], R3[1, 0], R3[1, 1] = c[2], -sn[2], sn[2], c[2]
+    Mz = torch.eye(4, dtype=torch.float64)
+    Mz[0, 1], Mz[0, 2], Mz[1, 0], Mz[1, 2], Mz[2, 0], Mz[2, 1] = shear
+    return (Mz @ Ms @ Mt @ (R3 @ R2 @ R1)).to(dtype)[None]
+
+
+def deform(M, img=None, seg=None, points=None):
+    """keymorph/augmentation.py:160-167: bilinear image / nearest segmentation through
+    AffineTransform(matrix=M).get_flow_field, points through the forward matrix."""
+    res = ()
+    if img is not None:
+        grid = affine_flow_field(torch.inverse(M), img.shape[2:])
+        res += (align_img(grid, img),)
+    if seg is not None:
+        grid = affine_flow_field(torch.inverse(M), seg.shape[2:])
+        res += (align_img(grid, seg, mode="nearest"),)
+    if points is not None:
+        res += (transform_points(M, points),)
+    return res[0] if len(res) == 1 else res
 
 
 def affine_augment(img, params, seg=None):

@@ -707,6 +707,113 @@ def test_prefetch_to_device_ring_keeps_items_intact():
         assert float(sa) == float(i) * 64 ** 3 and float(b0) == float(i)
 
 
+def test_augmentation_golden(golden):
+    """keymorph/augmentation.py through the fused affine warp (no flow field in memory)."""
+    from keymorph_b200 import augmentation as A
+    g = golden("augment_aniso")
+    params = (g["scale"], g["offset"], g["theta"], g["shear"])
+    aug = A.AffineDeformation3d(device=DEV)
+    assert_close(aug.build_affine_matrix(1, params).cpu(), g["matrix"], rtol=1e-6, atol=1e-6)
+    img = aug(cu(g["img"]), params=params, interp_mode="bilinear")
+    assert_close(img.cpu(), g["img_aug"], rtol=1e-5, atol=2e-5)
+    seg = aug(cu(g["seg"]), params=params, interp_mode="nearest")
+    assert (seg.cpu() != g["seg_aug"]).float().mean() < 5e-3
+    assert_close(aug.deform_points(cu(g["points"]), params).cpu(), g["points_aug"], rtol=1e-5, atol=1e-6)
+    # batched: every sample gets the same draw (the reference is limited to batch size 1)
+    imgs = cu(torch.cat([g["img"], g["img"].flip(2)], 0))
+    out = aug.deform_img(imgs, params)
+    assert torch.equal(out[0], img[0])
+    # isotropic convenience wrapper against the first fixture; random wrapper against its own matrix
+    g0 = golden("augment")
+    p0 = tuple(float(v) for v in g0["params"])
+    i0, s0 = A.affine_augment(cu(g0["img"]), p0, seg=cu(g0["seg"]))
+    assert_close(i0.cpu(), g0["img_aug"], rtol=1e-5, atol=2e-5)
+    assert (s0.cpu() != g0["seg_aug"]).float().mean() < 1e-3
+    gen = torch.Generator().manual_seed(3)
+    i1, s1, p1, M = A.random_affine_augment(cu(g["img"]), seg=cu(g["seg"]), points=cu(g["points"]),
+                                            return_affine_matrix=True, generator=gen)
+    ri, rs, rp = O.deform(M.cpu(), g["img"], g["seg"], g["points"])
+    assert_close(i1.cpu(), ri, rtol=1e-5, atol=2e-5)
+    assert (s1.cpu() != rs).float().mean() < 5e-3
+    assert_close(p1.cpu(), rp, rtol=1e-5, atol=1e-6)
+    a, b = A.random_affine_augment_pair(cu(g["img"]), cu(g["img"]), generator=gen)
+    assert torch.equal(a, b)
+    with pytest.raises(NotImplementedError):
+        A.affine_augment(cu(g["img"][0]), p0)
+
+
+def _scipy_hausdorff(a, b, sampling):
+    """the reference's _surfd (keymorph/loss_ops.py:121-141) on its own dependency, scipy.ndimage"""
+    conn = ndimage.generate_binary_structure(3, 1)
+    a, b = a.astype(bool), b.astype(bool)
+    sa, sb = a & ~ndimage.binary_erosion(a, conn), b & ~ndimage.binary_erosion(b, conn)
+    dta, dtb = ndimage.distance_transform_edt(~sa, sampling), ndimage.distance_transform_edt(~sb, sampling)
+    return max(dta[sb].max(), dtb[sa].max())
+
+
+def test_hausdorff_and_group_metrics_golden(golden, tmp_path):
+    from keymorph_b200 import loss_ops as L
+    g = golden("group_metrics")
+    segs, C = cu(g["segs"]), g["segs"].shape[1]
+    hard = torch.nn.functional.one_hot(segs.argmax(1), C).permute(0, 4, 1, 2, 3).float()
+    assert L.hausdorff_distance(hard[0:1], hard[1:2]) == float(g["hausd_01"])
+    assert L.hausdorff_distance(hard[0:2], hard[1:3]) == float(g["hausd_batch"])
+    blobs = [L.hausdorff_distance(hard[i:i + 1, k:], hard[j:j + 1, k:])
+             for (i, j) in ((0, 1), (0, 2), (1, 2)) for k in (1, 2, 3)]
+    np.testing.assert_allclose(blobs, g["hausd_blobs"].numpy(), rtol=1e-12)    # exact: dyadic sampling
+    assert abs(L.fast_dice(segs[0:1], segs[1:2]) - float(g["fast_dice_01"])) < 1e-7
+    assert_close(L.MSEPairwiseLoss()(cu(g["imgs"])).cpu(), g["mse_pairwise"], rtol=1e-5, atol=0)
+    assert_close(L.SoftDicePairwiseLoss()(segs).cpu(), g["softdice_pairwise"], rtol=1e-5, atol=0)
+    assert_close(L.HardDicePairwiseLoss()(segs).cpu(), g["harddice_pairwise"], rtol=1e-5, atol=0)
+    assert abs(float(L.AvgJDStd()(cu(g["grids"]))) - float(g["avg_jdstd"])) < 1e-6
+    assert float(L.AvgJDLessThan0()(cu(g["grids"]))) == float(g["avg_jdneg"])
+    # file-backed group (.npy, the layout groupwise_register_eval.py:407-431 writes): each file is read once
+    paths = []
+    for i in range(3):
+        paths.append(str(tmp_path / f"seg_{i}.npy"))
+        np.save(paths[-1], hard[i:i + 1].cpu().numpy())
+    names = ["dice", "harddice", "harddiceroi", "softdice", "hausd"]
+    res = L.MultipleAvgSegPairwiseMetric()(paths, names)
+    for n in names:
+        got = res[n].cpu() if isinstance(res[n], torch.Tensor) else torch.tensor(res[n], dtype=torch.float64)
+        assert_close(got.double(), g[f"multi_{n}"].double(), rtol=1e-5, atol=1e-7)
+    gpaths = []
+    for i in range(3):
+        gpaths.append(str(tmp_path / f"grid_{i}.npy"))
+        np.save(gpaths[-1], g["grids"][i:i + 1].numpy())
+    gres = L.MultipleAvgGridMetric()(gpaths, ["jdstd", "jdlessthan0"])
+    assert abs(float(gres["jdstd"]) - float(g["multi_jdstd"])) < 1e-6
+    assert float(gres["jdlessthan0"]) == float(g["multi_jdlessthan0"])
+
+
+@pytest.mark.parametrize("shape,sampling", [((24, 20, 28), (1.25, 1.25, 10.0)), ((40, 33, 70), (1.0, 1.0, 1.0)),
+                                            ((96, 80, 100), (1.25, 1.25, 10.0)), ((17, 300, 9), (0.7, 1.3, 2.1))])
+def test_hausdorff_vs_oracle_and_scipy(shape, sampling):
+    """ragged sizes (W not a multiple of 32, lines longer than one sweep), blobs touching the border,
+    non-dyadic voxel sizes"""
+    gen = torch.Generator().manual_seed(sum(shape))
+    vols = []
+    for _ in range(2):
+        v = torch.rand(1, 1, *[max(2, s // 6) for s in shape], generator=gen)
+        v = torch.nn.functional.interpolate(v, size=shape, mode="trilinear")[0, 0]
+        vols.append((v > 0.55).float())
+    a, b = vols
+    ref = _scipy_hausdorff(a.numpy(), b.numpy(), sampling)
+    got = float(ops.hausdorff(cu(a)[None], cu(b)[None], sampling)[0, 0])
+    exact = sampling == (1.25, 1.25, 10.0) or sampling == (1.0, 1.0, 1.0)
+    assert got == ref if exact else abs(got - ref) <= 1e-6 * ref
+    if a.numel() <= 24 * 20 * 28:
+        assert abs(O.hausdorff_distance(a[None, None], b[None, None], sampling) - ref) < 1e-9
+    # strided batch view (channel 0 of a 3-channel tensor), batch of two, and the empty-surface flag
+    t = cu(torch.stack([torch.stack([a, b, a]), torch.stack([b, a, b])]))
+    r = ops.hausdorff(t[:, 0], t[:, 1], sampling)
+    assert float(r[0, 0]) == got and float(r[1, 0]) == got and float(r[:, 1].sum()) == 0
+    e = ops.hausdorff(cu(a)[None], torch.zeros_like(cu(a))[None], sampling)
+    assert float(e[0, 1]) == 1 and float(e[0, 0]) == -1
+    with pytest.raises(kb.ops._lib.KMError):
+        kb.loss_ops.hausdorff_distance(cu(a)[None, None], torch.zeros_like(cu(a))[None, None])
+
+
 def test_forward_fused_warp_outputs():
     net = _seeded("trunc").to(DEV)
     model = kb.KeyMorph(net, 16, 3, fused_warp=True).eval()

@@ -141,6 +141,45 @@ def test_golden_augment(golden):
     assert (seg != g["seg_aug"]).float().mean() < 1e-3   # nearest: a coordinate may sit on a tie
 
 
+def test_golden_augment_anisotropic(golden):
+    """oracle AND the product's host-side matrix builder against the reference's AffineDeformation3d."""
+    from keymorph_b200.augmentation import AffineDeformation3d
+    g = golden("augment_aniso")
+    M = O.affine_matrix_3d_params(g["scale"], g["offset"], g["theta"], g["shear"])
+    assert_close(M, g["matrix"], rtol=1e-6, atol=1e-6)
+    params = (g["scale"], g["offset"], g["theta"], g["shear"])
+    Mp = AffineDeformation3d(device="cpu").build_affine_matrix(1, params)
+    assert_close(Mp, g["matrix"], rtol=1e-6, atol=1e-6)
+    Mb = AffineDeformation3d(device="cpu").build_affine_matrix(3, params)
+    assert Mb.shape == (3, 4, 4) and torch.equal(Mb[2], Mp[0])
+    img, seg, pts = O.deform(g["matrix"], g["img"], g["seg"], g["points"])
+    assert_close(img, g["img_aug"], rtol=1e-5, atol=1e-5)
+    assert (seg != g["seg_aug"]).float().mean() < 5e-3   # nearest: a coordinate may sit on a tie
+    assert_close(pts, g["points_aug"], rtol=1e-5, atol=1e-6)
+
+
+def test_golden_group_metrics(golden):
+    """Hausdorff / fast_dice / pairwise group metrics of the oracle against the reference's own values
+    (which come from scipy.ndimage's erosion and exact EDT)."""
+    g = golden("group_metrics")
+    segs, C = g["segs"], g["segs"].shape[1]
+    hard = torch.nn.functional.one_hot(segs.argmax(1), C).permute(0, 4, 1, 2, 3).float()
+    assert abs(O.hausdorff_distance(hard[0:1], hard[1:2]) - float(g["hausd_01"])) < 1e-9
+    assert abs(O.hausdorff_distance(hard[0:2], hard[1:3]) - float(g["hausd_batch"])) < 1e-9
+    blobs = [O.hausdorff_distance(hard[i:i + 1, k:], hard[j:j + 1, k:])
+             for (i, j) in ((0, 1), (0, 2), (1, 2)) for k in (1, 2, 3)]
+    np.testing.assert_allclose(blobs, g["hausd_blobs"].numpy(), rtol=1e-12)
+    assert abs(O.fast_dice(segs[0:1].numpy(), segs[1:2].numpy()) - float(g["fast_dice_01"])) < 1e-9
+    assert_close(O.avg_pairwise(g["imgs"], O.mse_loss), g["mse_pairwise"], rtol=1e-6, atol=0)
+    assert_close(O.avg_pairwise(segs, O.dice_loss), g["softdice_pairwise"], rtol=1e-6, atol=0)
+    assert_close(O.avg_pairwise(segs, lambda a, b: O.dice_loss(a, b, hard=True)), g["harddice_pairwise"],
+                 rtol=1e-6, atol=0)
+    assert abs(O.avg_pairwise(hard, O.hausdorff_distance) - float(g["multi_hausd"])) < 1e-9
+    assert abs(O.avg_pairwise(hard.numpy(), O.fast_dice) - float(g["multi_dice"])) < 1e-9
+    jd = np.mean([O.jdstd(g["grids"][i:i + 1].permute(0, 4, 1, 2, 3)) for i in range(3)])
+    assert abs(jd - float(g["avg_jdstd"])) < 1e-7
+
+
 def _seeded(cls_name, **kw):
     import keymorph_b200 as kb
     torch.manual_seed(23)
