@@ -200,7 +200,7 @@ def run_engine(args):
 
     # tracer: CUDA events around the kernels whose rooflines are reported
     traced = {"km_conv3d_tc": [], "km_conv3d_tc_pair": [], "km_conv3d_zfold_pair": [], "km_conv3d_zfold": [],
-              "km_conv1x1_com": [],
+              "km_conv3d_zfold_gn": [], "km_conv1x1_com": [],
               "km_conv3d_stem": [], "km_warp_loss": []}
     stream = torch.cuda.current_stream()
     pending = {}
@@ -243,7 +243,8 @@ def run_engine(args):
 
     # conv_tc_kernel (one SM per MMA) and conv_tc2_kernel (cta_group::2) are the same implicit GEMM
     conv_ms = per_step_ms("km_conv3d_tc") + per_step_ms("km_conv3d_tc_pair") + per_step_ms("km_conv3d_zfold_pair")
-    zf_ms, com_ms = per_step_ms("km_conv3d_zfold"), per_step_ms("km_conv1x1_com")
+    zf_ms = per_step_ms("km_conv3d_zfold") + per_step_ms("km_conv3d_zfold_gn")
+    com_ms = per_step_ms("km_conv1x1_com")
     stem_ms, warp_ms = per_step_ms("km_conv3d_stem"), per_step_ms("km_warp_loss")
     layers = {l[0]: l[5] for l in conv_layers(S, K, 2)}
     zf_flops = layers["enc0.c2"] if zf_ms > 0 else 0.0
@@ -262,7 +263,7 @@ def run_engine(args):
     all_flops = sum(layers.values())
     roofline_other = []
     if zf_ms > 0:
-        roofline_other.append({"bound": "tensor", "kernel": "conv_zf_kernel (16->32 @256^3, dz folded into N, pool fused)",
+        roofline_other.append({"bound": "tensor", "kernel": "conv_zf_kernel (16->32 @256^3, dz folded into N, GroupNorm folded in, pool fused)",
                                "achieved": zf_flops / (zf_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
                                "frac": zf_flops / (zf_ms * 1e-3) / 1e12 / tc_peak, "kernel_ms_per_step": zf_ms,
                                "traffic": NCU_TRAFFIC.get("conv_zf_kernel")})
@@ -272,7 +273,7 @@ def run_engine(args):
                                "frac": com_flops / (com_ms * 1e-3) / 1e12 / tc_peak, "kernel_ms_per_step": com_ms,
                                "hbm_gbs": 2 * (S // 2) ** 3 * 64 * 2 / (com_ms * 1e-3) / 1e9,
                                "traffic": NCU_TRAFFIC.get("com_tc_kernel")})
-    roofline_other.append({"bound": "tensor", "kernel": "whole backbone (stem x2 + conv_zf + conv_tc + com_tc)",
+    roofline_other.append({"bound": "tensor", "kernel": "whole backbone (stem + conv_zf + conv_tc + com_tc)",
                            "achieved": all_flops / (backbone_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
                            "frac": all_flops / (backbone_ms * 1e-3) / 1e12 / tc_peak,
                            "kernel_ms_per_step": backbone_ms})

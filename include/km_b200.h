@@ -300,6 +300,19 @@ int km_pack_weights_zfold(const float* w, void* packed, int Cout, int Cin, km_st
 int km_conv3d_zfold(const void* x, const void* wz, void* out, void* pooled, float* stats, int N, int Cin,
                     int Cout, int D, int H, int W, int flags, km_stream_t stream);
 
+/* The same layer with the preceding GroupNorm folded in (buildingblocks.py:50-52, order "gcr": nothing
+ * non-linear sits between the norm and the conv).  x is the RAW bf16 activation; w the fp32
+ * (Cout,Cin,3,3,3) weights; scale / shift (N,Cin) the per-sample GroupNorm coefficients of
+ * km_norm_finalize.  conv(scale x + shift) with zero padding of the normalised input is evaluated as
+ * conv_{w scale}(x) + bias[class(voxel)][cout], class = which taps fall outside the volume: a fold
+ * kernel writes per-sample bf16 weights and the 36 x Cout bias table into the workspace, then the
+ * z-folded kernel runs once per sample.  Removes the normalisation pass over the activation (for the
+ * stem: its second run).  workspace: km_conv3d_zfold_gn_workspace_bytes(N), 16-byte aligned. */
+size_t km_conv3d_zfold_gn_workspace_bytes(int N);
+int km_conv3d_zfold_gn(const void* x, const float* w, const float* scale, const float* shift, void* out,
+                       void* pooled, float* stats, void* workspace, int N, int Cin, int Cout, int D, int H,
+                       int W, int flags, km_stream_t stream);
+
 /* 2-CTA (cta_group::2) variant of km_conv3d_tc for the 3x3x3 layers with Cout in {64, 128} and
  * Cin % 32 == 0 (csrc/conv_tc2.cu): two SMs execute one M = 256 MMA, each supplying its own 128
  * activation rows and half of the weight rows, which halves the weight bytes read from shared

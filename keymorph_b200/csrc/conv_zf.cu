@@ -50,11 +50,14 @@ constexpr int kLZ = 64;                 // z planes per unit
 
 struct ZfGeom {
   int N, D, H, W;
+  int n_base, n_count;          // samples handled by this launch (the GN-folded path launches per sample)
   int tiles_x, tiles_y, zsegs, units;
   int flags;
-  uint32_t off_b, off_staging, off_stats, off_bars;
+  uint32_t off_b, off_staging, off_stats, off_bias, off_bars;
   int stat_parts;
 };
+
+constexpr int kBiasClasses = 36;        // z code (0..3) x y code (0..2) x x code (0..2)
 
 struct Unit {
   int n, x0, y0, zs, planes;   // planes = segment length + 2
@@ -67,7 +70,7 @@ __device__ __forceinline__ Unit decode_unit(const ZfGeom& g, int u) {
   r.y0 = (u % g.tiles_y) * (16 * kMT);
   u /= g.tiles_y;
   r.zs = (u % g.zsegs) * kLZ;
-  r.n = u / g.zsegs;
+  r.n = g.n_base + u / g.zsegs;
   r.planes = min(kLZ, g.D - r.zs) + 2;
   return r;
 }
@@ -103,10 +106,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// BIAS: the input is the RAW (un-normalised) activation and tmB holds weights pre-multiplied by the
+// sample's GroupNorm scale; the GroupNorm shift enters as bias_tab[class][cout], class = which of the
+// 27 taps fall outside the volume for this voxel (zero padding applies to the NORMALISED input).
+template <bool BIAS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ZfGeom g, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
-               float* __restrict__ stats) {
+               float* __restrict__ stats, const float* __restrict__ bias_tab) {
   constexpr uint32_t kLayout = 6u;                 // SWIZZLE_32B
   constexpr uint32_t kSbo = 8u * kRowBytes;        // 256 B between 8-row groups
   extern __shared__ uint8_t smem_raw[];
@@ -146,6 +153,10 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* s_stats = reinterpret_cast<float*>(sm + g.off_stats);
     if (g.flags & KM_CONV_STATS)
       for (int i = threadIdx.x; i < g.N * kCout * 2; i += kThreads) s_stats[i] = 0.f;
+    if (BIAS) {
+      float* s_bias = reinterpret_cast<float*>(sm + g.off_bias);
+      for (int i = threadIdx.x; i < kBiasClasses * kCout; i += kThreads) s_bias[i] = bias_tab[i];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -268,6 +279,7 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int zo = u.zs - 2 + p;                   // the output plane completed by this tile
       const bool store = p >= 2 && zo < g.D;         // (zo >= zs by construction)
       const uint32_t slot = (uint32_t)((p + 2) % 3);
+      const int zcode = (zo == 0 ? 1 : 0) | (zo == g.D - 1 ? 2 : 0);
       if (do_stats && u.n != n_cur) {                // CTA-uniform: the tile sequence is shared
         if (n_cur >= 0) flush_stats(n_cur);
         n_cur = u.n;
@@ -283,6 +295,19 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t r[16];
           tmem_ld16(taddr, r);
           tmem_ld_wait();
+          if (BIAS) {
+            const int cls = zcode * 9 + (y2 == 0 ? 1 : (y2 == g.H - 1 ? 2 : 0)) * 3 +
+                            (x2 == 0 ? 1 : (x2 == g.W - 1 ? 2 : 0));
+            const float4* bp = reinterpret_cast<const float4*>(sm + g.off_bias) + cls * (kCout / 4) + half * 4;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bv = bp[j4];
+              r[4 * j4 + 0] = __float_as_uint(__uint_as_float(r[4 * j4 + 0]) + bv.x);
+              r[4 * j4 + 1] = __float_as_uint(__uint_as_float(r[4 * j4 + 1]) + bv.y);
+              r[4 * j4 + 2] = __float_as_uint(__uint_as_float(r[4 * j4 + 2]) + bv.z);
+              r[4 * j4 + 3] = __float_as_uint(__uint_as_float(r[4 * j4 + 3]) + bv.w);
+            }
+          }
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -345,7 +370,8 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (do_stats) {
       if (n_cur >= 0) flush_stats(n_cur);
       float* dst = stats + (size_t)blockIdx.x * g.N * kCout * 2;
-      for (int i = et; i < g.N * kCout * 2; i += kEpiThreads) dst[i] = s_stats[i];
+      for (int i = g.n_base * kCout * 2 + et; i < (g.n_base + g.n_count) * kCout * 2; i += kEpiThreads)
+        dst[i] = s_stats[i];
     }
   }
 
@@ -378,6 +404,56 @@ __global__ void pack_weights_zf_kernel(const float* __restrict__ w, __nv_bfloat1
   }
 }
 
+// GroupNorm folded into the conv (keymorph/unet3d/buildingblocks.py:50-52, order "gcr": GN -> conv -> ReLU
+// with nothing non-linear between GN and the conv): conv(scale x + shift) with zero padding of the
+// normalised input = conv_{w scale}(x) + sum over the IN-BOUNDS taps of w . shift.  Per sample n
+// (blockIdx.y): packed[n] = bf16(w * scale[n]) in the layout of pack_weights_zf_kernel, and
+// bias[n][class][cout], class = zcode * 9 + ycode * 3 + xcode, code bit 0 = voxel on the low border of
+// that axis (tap offset -1 outside), bit 1 = on the high border (tap offset +1 outside).
+__global__ void fold_gn_zf_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, __nv_bfloat16* __restrict__ packed,
+                                  float* __restrict__ bias, int Cout, int Cin) {
+  const int n = blockIdx.y;
+  const int total = 27 * 3 * Cout * Cin;
+  __nv_bfloat16* p = packed + (size_t)n * total;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t = i;
+    const int ci = t % Cin;
+    t /= Cin;
+    const int co = t % Cout;
+    t /= Cout;
+    const int j = t % 3;
+    t /= 3;
+    const int dy = t % 3;
+    t /= 3;
+    const int dx = t % 3;
+    const int r = t / 3;
+    const int dz = (r + 1 - j + 3) % 3;
+    p[i] = __float2bfloat16_rn(w[((size_t)co * Cin + ci) * 27 + dz * 9 + dy * 3 + dx] * scale[n * Cin + ci]);
+  }
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kBiasClasses * Cout; e += gridDim.x * blockDim.x) {
+    const int co = e % Cout, cls = e / Cout;
+    const int xc = cls % 3, yc = (cls / 3) % 3, zc = cls / 9;
+    float acc = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* wk = w + ((size_t)co * Cin + ci) * 27;
+      float ws = 0.f;
+      for (int dz = 0; dz < 3; ++dz) {
+        if ((dz == 0 && (zc & 1)) || (dz == 2 && (zc & 2))) continue;
+        for (int dy = 0; dy < 3; ++dy) {
+          if ((dy == 0 && (yc & 1)) || (dy == 2 && (yc & 2))) continue;
+          for (int dx = 0; dx < 3; ++dx) {
+            if ((dx == 0 && (xc & 1)) || (dx == 2 && (xc & 2))) continue;
+            ws += wk[dz * 9 + dy * 3 + dx];
+          }
+        }
+      }
+      acc = fmaf(ws, shift[n * Cin + ci], acc);
+    }
+    bias[(size_t)n * kBiasClasses * Cout + e] = acc;
+  }
+}
+
 inline uint32_t zf_round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
@@ -399,27 +475,20 @@ extern "C" int km_pack_weights_zfold(const float* w, void* packed, int Cout, int
   return KM_OK;
 }
 
-extern "C" int km_conv3d_zfold(const void* x, const void* wz, void* out, void* pooled, float* stats,
-                               int N, int Cin, int Cout, int D, int H, int W, int flags,
-                               km_stream_t stream) {
-  KM_CHECK_ARG(x && wz && (out || pooled), "km_conv3d_zfold: null argument");
-  KM_CHECK_ARG(!pooled || (D >= 2 && H >= 2 && W >= 2), "km_conv3d_zfold: volume too small to pool");
-  KM_CHECK_ARG(((uintptr_t)pooled & 31) == 0 && ((uintptr_t)out & 31) == 0,
-               "km_conv3d_zfold: outputs must be 32-byte aligned");
-  KM_CHECK_ARG(km_conv3d_zfold_supported(Cin, Cout, D, H, W), "km_conv3d_zfold: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
-  KM_CHECK_ARG(N > 0, "km_conv3d_zfold: bad batch");
-  KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "km_conv3d_zfold: KM_CONV_STATS needs stats");
-  KM_CHECK_ARG(!(flags & KM_CONV_COM), "km_conv3d_zfold: KM_CONV_COM is not supported");
-  KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wz & 15) == 0 && ((uintptr_t)out & 15) == 0,
-               "km_conv3d_zfold: pointers must be 16-byte aligned");
+namespace {
+
+// one launch over samples [n_base, n_base + n_count) of an N-sample tensor
+int launch_zf(const void* x, const void* wz, const float* bias_tab, void* out, void* pooled, float* stats, int N,
+              int n_base, int n_count, int Cin, int D, int H, int W, int flags, km_stream_t stream) {
   ZfGeom g;
   memset(&g, 0, sizeof(g));
   g.N = N; g.D = D; g.H = H; g.W = W;
+  g.n_base = n_base; g.n_count = n_count;
   g.flags = flags;
   g.tiles_x = (W + 7) / 8;
   g.tiles_y = (H + 16 * kMT - 1) / (16 * kMT);
   g.zsegs = (D + kLZ - 1) / kLZ;
-  const long long units = (long long)N * g.zsegs * g.tiles_y * g.tiles_x;
+  const long long units = (long long)n_count * g.zsegs * g.tiles_y * g.tiles_x;
   KM_CHECK_ARG(units < (1ll << 30), "km_conv3d_zfold: too many units");
   g.units = (int)units;
   g.stat_parts = 1;
@@ -427,6 +496,7 @@ extern "C" int km_conv3d_zfold(const void* x, const void* wz, void* out, void* p
   uint32_t off = (uint32_t)kStages * kAStage;
   g.off_b = off; off += kBBytes;
   g.off_staging = off; off += 8u * 32u * 4u;   // per-warp scratch of the statistics flush
+  g.off_bias = off; off += bias_tab ? (uint32_t)kBiasClasses * kCout * 4u : 0u;
   g.off_stats = off; off += stats_bytes;
   off = zf_round_up(off, 8);
   g.off_bars = off; off += 8u * (2u * kStages + 6u) + 16u;
@@ -466,17 +536,68 @@ extern "C" int km_conv3d_zfold(const void* x, const void* wz, void* out, void* p
       return KM_ECUDA;
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
-  }
+  KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   const int nsm = km_sm_count();
   const int grid = g.units < nsm ? g.units : nsm;
-  if (grid < nsm && (flags & KM_CONV_STATS))
+  if (grid < nsm && (flags & KM_CONV_STATS) && n_base == 0)   // partial slots of the CTAs that do not run
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * kCout * 2 * sizeof(float), km_cs(stream)));
-  conv_zf_kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
-                                                               reinterpret_cast<__nv_bfloat16*>(pooled), stats);
+  if (bias_tab)
+    conv_zf_kernel<true><<<grid, kThreads, smem_bytes, km_cs(stream)>>>(
+        tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<__nv_bfloat16*>(pooled), stats, bias_tab);
+  else
+    conv_zf_kernel<false><<<grid, kThreads, smem_bytes, km_cs(stream)>>>(
+        tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<__nv_bfloat16*>(pooled), stats, nullptr);
   KM_LAUNCH_OK("conv_zf_kernel");
+  return KM_OK;
+}
+
+int check_zf_args(const char* who, const void* x, const void* w, void* out, void* pooled, float* stats, int N,
+                  int Cin, int Cout, int D, int H, int W, int flags) {
+  KM_CHECK_ARG(x && w && (out || pooled), "%s: null argument", who);
+  KM_CHECK_ARG(!pooled || (D >= 2 && H >= 2 && W >= 2), "%s: volume too small to pool", who);
+  KM_CHECK_ARG(((uintptr_t)pooled & 31) == 0 && ((uintptr_t)out & 31) == 0, "%s: outputs must be 32-byte aligned", who);
+  KM_CHECK_ARG(km_conv3d_zfold_supported(Cin, Cout, D, H, W), "%s: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", who,
+               Cin, Cout, H, W);
+  KM_CHECK_ARG(N > 0, "%s: bad batch", who);
+  KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "%s: KM_CONV_STATS needs stats", who);
+  KM_CHECK_ARG(!(flags & KM_CONV_COM), "%s: KM_CONV_COM is not supported", who);
+  KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, "%s: pointers must be 16-byte aligned", who);
+  return KM_OK;
+}
+
+}  // namespace
+
+extern "C" int km_conv3d_zfold(const void* x, const void* wz, void* out, void* pooled, float* stats,
+                               int N, int Cin, int Cout, int D, int H, int W, int flags,
+                               km_stream_t stream) {
+  const int rc = check_zf_args("km_conv3d_zfold", x, wz, out, pooled, stats, N, Cin, Cout, D, H, W, flags);
+  if (rc != KM_OK) return rc;
+  return launch_zf(x, wz, nullptr, out, pooled, stats, N, 0, N, Cin, D, H, W, flags, stream);
+}
+
+extern "C" size_t km_conv3d_zfold_gn_workspace_bytes(int N) {
+  return (size_t)N * (27 * 3 * kCout * kKC * 2 + kBiasClasses * kCout * 4);
+}
+
+extern "C" int km_conv3d_zfold_gn(const void* x, const float* w, const float* scale, const float* shift,
+                                  void* out, void* pooled, float* stats, void* workspace, int N, int Cin,
+                                  int Cout, int D, int H, int W, int flags, km_stream_t stream) {
+  const int rc = check_zf_args("km_conv3d_zfold_gn", x, w, out, pooled, stats, N, Cin, Cout, D, H, W, flags);
+  if (rc != KM_OK) return rc;
+  KM_CHECK_ARG(scale && shift && workspace && ((uintptr_t)workspace & 15) == 0, "km_conv3d_zfold_gn: null / unaligned argument");
+  const size_t wbytes = (size_t)27 * 3 * kCout * kKC * 2;
+  __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(workspace);
+  float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (size_t)N * wbytes);
+  fold_gn_zf_kernel<<<dim3(16, N), 256, 0, km_cs(stream)>>>(w, scale, shift, packed, bias, Cout, Cin);
+  KM_LAUNCH_OK("fold_gn_zf_kernel");
+  const size_t vox = (size_t)D * H * W;
+  (void)vox;
+  for (int n = 0; n < N; ++n) {
+    const int r2 = launch_zf(x, static_cast<const char*>(workspace) + (size_t)n * wbytes,
+                             bias + (size_t)n * kBiasClasses * kCout, out, pooled, stats, N, n, 1, Cin, D, H, W, flags,
+                             stream);
+    if (r2 != KM_OK) return r2;
+  }
   return KM_OK;
 }

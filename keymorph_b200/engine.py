@@ -140,26 +140,43 @@ class UNetEngine(_EngineBase):
         st = ops.volume_stats(x)
         scale, shift = ops.norm_finalize(st, D * H * W, sc0.groupnorm.weight, sc0.groupnorm.bias,
                                          sc0.groupnorm.num_groups, sc0.groupnorm.eps)
-        # the stem runs twice: a statistics pass, then a store pass with the next GroupNorm folded in
         w0 = sc0.conv.weight.detach()
         in_sc, in_sh = scale.reshape(-1), shift.reshape(-1)
-        _, st = ops.conv3d_stem(x, w0, None, in_sc, in_sh, relu_pre=True, store=False)
         sc1 = enc[0].basic_module.SingleConv2
-        scale, shift = ops.norm_finalize(st, D * H * W, sc1.groupnorm.weight, sc1.groupnorm.bias,
-                                         sc1.groupnorm.num_groups, sc1.groupnorm.eps)
-        if self.debug is not None:
-            self._dbg("enc0.c1", ops.conv3d_stem(x, w0, None, in_sc, in_sh, relu_pre=True,
-                                                 want_stats=False)[0])
-        a, _ = ops.conv3d_stem(x, w0, None, in_sc, in_sh, scale, shift, relu_pre=True,
-                               want_stats=False)
+        g1 = sc1.groupnorm
+        w1 = sc1.conv.weight
+        zf = ops.zfold_supported(w0.shape[0], w1.shape[0], D, H, W)
+        fold = ops.USE_GN_FOLD and zf and self.debug is None
+        if fold:
+            # ONE stem pass stores the raw ReLU'd map and its statistics; the next GroupNorm is folded into
+            # the z-folded conv (per-sample scaled weights + border-class bias), so the map is never normalised
+            # in memory and the stem is not run a second time
+            a, st = ops.conv3d_stem(x, w0, None, in_sc, in_sh, relu_pre=True)
+            scale, shift = ops.norm_finalize(st, D * H * W, g1.weight, g1.bias, g1.num_groups, g1.eps)
+        else:
+            # the stem runs twice: a statistics pass, then a store pass with the next GroupNorm folded in
+            _, st = ops.conv3d_stem(x, w0, None, in_sc, in_sh, relu_pre=True, store=False)
+            scale, shift = ops.norm_finalize(st, D * H * W, g1.weight, g1.bias, g1.num_groups, g1.eps)
+            if self.debug is not None:
+                self._dbg("enc0.c1", ops.conv3d_stem(x, w0, None, in_sc, in_sh, relu_pre=True,
+                                                     want_stats=False)[0])
+            a, _ = ops.conv3d_stem(x, w0, None, in_sc, in_sh, scale, shift, relu_pre=True,
+                                   want_stats=False)
         # the truncated net never consumes the first encoder's full-resolution output as a skip:
         # then the z-folded kernel pools in its epilogue and the 32-channel full-resolution map
         # (2.1 GB for a 256^3 pair) is never written
         need_full0 = len(m.decoders) >= len(enc) - 1 or self.debug is not None or len(enc) < 2
         pooled0 = None
-        w1 = sc1.conv.weight
-        if not need_full0 and ops.zfold_supported(a.shape[-1], w1.shape[0], D, H, W) \
-                and min(D, H, W) >= 2:
+        pool0 = not need_full0 and zf and min(D, H, W) >= 2
+        if fold:
+            r = ops.conv3d_zfold_gn(a, w1.detach(), scale, shift, relu=True, want_stats=True, pool=pool0,
+                                    store=not pool0)
+            if pool0:
+                pooled0 = (r[1], r[2])
+                cur = cur_st = None
+            else:
+                cur, cur_st = r
+        elif pool0:
             _, p0, st0 = ops.conv3d_zfold(a, self.weights.get("enc0.c2.zf", w1, zfold=True), relu=True,
                                           want_stats=True, pool=True, store=False)
             pooled0 = (p0, st0)

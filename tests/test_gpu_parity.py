@@ -252,6 +252,49 @@ def test_conv3d_zfold_vs_general_kernel_and_fp32(shape):
                      rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("shape", [(1, 32, 32, 32), (2, 70, 40, 24), (1, 1, 16, 8), (1, 2, 17, 9), (3, 66, 33, 12)])
+def test_conv3d_zfold_groupnorm_folded(shape):
+    """km_conv3d_zfold_gn: GroupNorm folded into the conv (per-sample scaled weights + border-class bias
+    table) against the fp64 conv of the explicitly normalised, zero-padded input.  Post-ReLU-like raw
+    activations with a non-zero mean make the shift term matter on every face, edge and corner; D = 1 and
+    D = 2 exercise voxels that sit on both z borders / the two-plane classes."""
+    import torch.nn.functional as F
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    raw = F.relu(torch.randn(N, 16, D, H, W, generator=g) * 1.5 + 0.7)
+    w = torch.randn(32, 16, 3, 3, 3, generator=g) / (27 * 16) ** 0.5
+    scale = torch.rand(N, 16, generator=g) + 0.5
+    shift = torch.randn(N, 16, generator=g)
+    xb = ops.ncdhw_to_ndhwc(cu(raw))
+    rawb = ops.ndhwc_to_ncdhw(xb).cpu().double()
+    xn = rawb * scale.double()[:, :, None, None, None] + shift.double()[:, :, None, None, None]
+    ref = F.relu(F.conv3d(xn, w.double(), padding=1)).float()
+    out, st = ops.conv3d_zfold_gn(xb, cu(w), cu(scale), cu(shift), relu=True, want_stats=True)
+    a = ops.ndhwc_to_ncdhw(out).cpu()
+    # operand rounding: bf16(w * scale) (2^-9 relative per weight) over 432 products + bf16 result
+    assert_close(a, ref, rtol=1e-2, atol=2e-2)
+    assert (a - ref).abs().mean().item() < 5e-3
+    # the border classes specifically: compare against the un-folded device path on the same raw data
+    xnb = ops.ncdhw_to_ndhwc(cu(xn.float()))
+    unf, _ = ops.conv3d_zfold(xnb, ops.pack_weights_zfold(cu(w)), relu=True, want_stats=True)
+    u = ops.ndhwc_to_ncdhw(unf).cpu()
+    border = torch.zeros(D, H, W, dtype=torch.bool)
+    border[0], border[-1], border[:, 0], border[:, -1], border[:, :, 0], border[:, :, -1] = (True,) * 6
+    eb = (a - ref).abs()[:, :, border].mean().item()
+    ei = (a - ref).abs()[:, :, ~border].mean().item() if (~border).any() else eb
+    ub = (u - ref).abs()[:, :, border].mean().item()
+    assert eb < 2.0 * max(ei, ub) + 1e-4, (eb, ei, ub)      # no systematic error on faces / edges / corners
+    s_ref = torch.stack([a.double().flatten(2).sum(-1), (a.double() ** 2).flatten(2).sum(-1)], -1)
+    assert_close(st.double().sum(0).cpu(), s_ref, rtol=1e-4, atol=1e-2)
+    if min(D, H, W) >= 2:
+        none, pooled, stp = ops.conv3d_zfold_gn(xb, cu(w), cu(scale), cu(shift), relu=True, want_stats=True,
+                                                pool=True, store=False)
+        pref = F.max_pool3d(a, 2)
+        assert none is None and torch.equal(ops.ndhwc_to_ncdhw(pooled).cpu(), pref)
+        sp_ref = torch.stack([pref.double().flatten(2).sum(-1), (pref.double() ** 2).flatten(2).sum(-1)], -1)
+        assert_close(stp.double().sum(0).cpu(), sp_ref, rtol=1e-4, atol=1e-2)
+
+
 @pytest.mark.parametrize("cfg", [(1, 64, 64, 8, 32, 32), (2, 192, 64, 70, 40, 24), (1, 64, 64, 3, 16, 8),
                                  (3, 128, 64, 5, 33, 20), (1, 64, 64, 130, 17, 9), (2, 32, 32, 9, 32, 24),
                                  (1, 32, 64, 20, 48, 40), (1, 64, 32, 6, 16, 16), (1, 96, 32, 4, 20, 12)])
