@@ -200,7 +200,7 @@ def run_engine(args):
 
     # tracer: CUDA events around the kernels whose rooflines are reported
     traced = {"km_conv3d_tc": [], "km_conv3d_tc_pair": [], "km_conv3d_zfold_pair": [], "km_conv3d_zfold": [],
-              "km_conv3d_zfold_gn": [], "km_conv1x1_com": [],
+              "km_conv3d_zfold_gn": [], "km_conv3d_zfold_pair_gn": [], "km_conv1x1_com": [],
               "km_conv3d_stem": [], "km_warp_loss": []}
     stream = torch.cuda.current_stream()
     pending = {}
@@ -242,7 +242,8 @@ def run_engine(args):
         return sum(a.elapsed_time(b) for a, b in traced[name]) / args.steps
 
     # conv_tc_kernel (one SM per MMA) and conv_tc2_kernel (cta_group::2) are the same implicit GEMM
-    conv_ms = per_step_ms("km_conv3d_tc") + per_step_ms("km_conv3d_tc_pair") + per_step_ms("km_conv3d_zfold_pair")
+    conv_names = ("km_conv3d_tc", "km_conv3d_tc_pair", "km_conv3d_zfold_pair", "km_conv3d_zfold_pair_gn")
+    conv_ms = sum(per_step_ms(k) for k in conv_names)
     zf_ms = per_step_ms("km_conv3d_zfold") + per_step_ms("km_conv3d_zfold_gn")
     com_ms = per_step_ms("km_conv1x1_com")
     stem_ms, warp_ms = per_step_ms("km_conv3d_stem"), per_step_ms("km_warp_loss")
@@ -251,8 +252,7 @@ def run_engine(args):
     com_flops = layers["final"] if com_ms > 0 else 0.0
     tc_flops = sum(v for k, v in layers.items() if k != "enc0.c1") - zf_flops - com_flops
     achieved = tc_flops / (conv_ms * 1e-3) / 1e12
-    n_conv = (len(traced["km_conv3d_tc"]) + len(traced["km_conv3d_tc_pair"]) +
-              len(traced["km_conv3d_zfold_pair"])) // args.steps
+    n_conv = sum(len(traced[k]) for k in conv_names) // args.steps
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel / conv_zf2_kernel (cta_group::2)", "achieved": achieved, "peak": tc_peak,
                 "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": NCU_TRAFFIC.get("conv_tc_kernel"),
                 "flops_per_step": tc_flops, "launches_per_step": n_conv, "kernel_ms_per_step": conv_ms,

@@ -306,7 +306,8 @@ int km_conv3d_zfold(const void* x, const void* wz, void* out, void* pooled, floa
  * km_norm_finalize.  conv(scale x + shift) with zero padding of the normalised input is evaluated as
  * conv_{w scale}(x) + bias[class(voxel)][cout], class = which taps fall outside the volume: a fold
  * kernel writes per-sample bf16 weights and the 36 x Cout bias table into the workspace, then the
- * z-folded kernel runs once per sample.  Removes the normalisation pass over the activation (for the
+ * z-folded kernel runs with its CTAs split evenly between the samples, each keeping its sample's weights
+ * resident.  Removes the normalisation pass over the activation (for the
  * stem: its second run).  workspace: km_conv3d_zfold_gn_workspace_bytes(N), 16-byte aligned. */
 size_t km_conv3d_zfold_gn_workspace_bytes(int N);
 int km_conv3d_zfold_gn(const void* x, const float* w, const float* scale, const float* shift, void* out,
@@ -333,6 +334,16 @@ int km_conv3d_zfold_pair_supported(int Cin, int Cout, int D, int H, int W);
 int km_pack_weights_zfold_pair(const float* w, void* packed, int Cout, int Cin, km_stream_t stream);
 int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, void* pooled, float* stats, int N, int Cin,
                          int Cout, int D, int H, int W, int flags, km_stream_t stream);
+
+/* km_conv3d_zfold_pair with the preceding GroupNorm folded in, exactly as km_conv3d_zfold_gn: x is the
+ * RAW bf16 activation, w the fp32 (Cout,Cin,3,3,3) weights, scale / shift (N,Cin).  The per-sample
+ * weight sets are the last dimension of the weight tensor map (rotation + 3 n); the epilogue adds
+ * bias[n][border class][cout] after it has handed the TMEM block back to the MMA issuer.
+ * workspace: km_conv3d_zfold_pair_gn_workspace_bytes(N, Cin, Cout), 256-byte aligned. */
+size_t km_conv3d_zfold_pair_gn_workspace_bytes(int N, int Cin, int Cout);
+int km_conv3d_zfold_pair_gn(const void* x, const float* w, const float* scale, const float* shift, void* out,
+                            void* pooled, float* stats, void* workspace, int N, int Cin, int Cout, int D,
+                            int H, int W, int flags, km_stream_t stream);
 
 /* Final 1x1x1 convolution fused with ReLU + centre of mass, transposed tcgen05 formulation
  * (keymorph/unet3d/model.py:99,389 final_conv + keymorph/layers.py:92-134 + keymorph/model.py:95-109):

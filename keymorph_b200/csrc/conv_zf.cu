@@ -50,7 +50,8 @@ constexpr int kLZ = 64;                 // z planes per unit
 
 struct ZfGeom {
   int N, D, H, W;
-  int n_base, n_count;          // samples handled by this launch (the GN-folded path launches per sample)
+  int n_base, n_count;          // samples handled by this launch
+  int cta_per_sample;           // > 0 (GN-folded path): CTAs [k cps, (k+1) cps) own sample k and its weights
   int tiles_x, tiles_y, zsegs, units;
   int flags;
   uint32_t off_b, off_staging, off_stats, off_bias, off_bars;
@@ -81,13 +82,19 @@ __device__ __forceinline__ Unit decode_unit(const ZfGeom& g, int u) {
 template <typename F>
 __device__ __forceinline__ void for_each_tile(const ZfGeom& g, F&& fn) {
   uint32_t cnt[2] = {0u, 0u};
-  const int G = (int)gridDim.x;
-  for (int ua = (int)blockIdx.x; ua < g.units; ua += 2 * G) {
+  int G = (int)gridDim.x, first = (int)blockIdx.x, end = g.units;
+  if (g.cta_per_sample > 0) {
+    const int ups = g.zsegs * g.tiles_y * g.tiles_x, ns = (int)blockIdx.x / g.cta_per_sample;
+    G = g.cta_per_sample;
+    first = ns * ups + (int)blockIdx.x % g.cta_per_sample;
+    end = (ns + 1) * ups;
+  }
+  for (int ua = first; ua < end; ua += 2 * G) {
     const int ub = ua + G;
     const Unit a = decode_unit(g, ua);
     Unit b = a;
     b.planes = 0;
-    if (ub < g.units) b = decode_unit(g, ub);
+    if (ub < end) b = decode_unit(g, ub);
     const int pmax = max(a.planes, b.planes);
     for (int p = 0; p < pmax; ++p) {
       if (p < a.planes) fn(std::integral_constant<uint32_t, 0u>{}, a, p, cnt[0]++);
@@ -155,7 +162,8 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = threadIdx.x; i < g.N * kCout * 2; i += kThreads) s_stats[i] = 0.f;
     if (BIAS) {
       float* s_bias = reinterpret_cast<float*>(sm + g.off_bias);
-      for (int i = threadIdx.x; i < kBiasClasses * kCout; i += kThreads) s_bias[i] = bias_tab[i];
+      const float* src = bias_tab + (g.cta_per_sample > 0 ? (size_t)(blockIdx.x / g.cta_per_sample) * kBiasClasses * kCout : 0);
+      for (int i = threadIdx.x; i < kBiasClasses * kCout; i += kThreads) s_bias[i] = src[i];
     }
   }
   tc_fence_before();
@@ -167,7 +175,8 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =============================== TMA producer ===============================
     if (lane == 0) {
       mbar_arrive_expect_tx(w_bar, kBBytes);
-      for (int t = 0; t < 27; ++t) tma_load_3d(base + g.off_b + (uint32_t)t * kBTile, &tmB, w_bar, 0, 0, t);
+      const int t0 = g.cta_per_sample > 0 ? 27 * ((int)blockIdx.x / g.cta_per_sample) : 0;   // this sample's weights
+      for (int t = 0; t < 27; ++t) tma_load_3d(base + g.off_b + (uint32_t)t * kBTile, &tmB, w_bar, 0, 0, t0 + t);
       int s = 0;
       uint32_t ph = 0;
       for_each_tile(g, [&](auto, const Unit& u, int p, uint32_t) {
@@ -478,8 +487,10 @@ extern "C" int km_pack_weights_zfold(const float* w, void* packed, int Cout, int
 namespace {
 
 // one launch over samples [n_base, n_base + n_count) of an N-sample tensor
+// (per_sample: wz / bias_tab hold n_count consecutive weight sets / tables and the CTAs are partitioned by sample)
 int launch_zf(const void* x, const void* wz, const float* bias_tab, void* out, void* pooled, float* stats, int N,
-              int n_base, int n_count, int Cin, int D, int H, int W, int flags, km_stream_t stream) {
+              int n_base, int n_count, int Cin, int D, int H, int W, int flags, bool per_sample,
+              km_stream_t stream) {
   ZfGeom g;
   memset(&g, 0, sizeof(g));
   g.N = N; g.D = D; g.H = H; g.W = W;
@@ -524,7 +535,7 @@ int launch_zf(const void* x, const void* wz, const float* bias_tab, void* out, v
     }
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)kN3, 27};
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)kN3, (cuuint64_t)(per_sample ? 27 * n_count : 27)};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)kN3 * Cin * 2};
     cuuint32_t box[3] = {(cuuint32_t)kKC, (cuuint32_t)kN3, 1};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -539,7 +550,12 @@ int launch_zf(const void* x, const void* wz, const float* bias_tab, void* out, v
   KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   const int nsm = km_sm_count();
-  const int grid = g.units < nsm ? g.units : nsm;
+  int grid = g.units < nsm ? g.units : nsm;
+  if (per_sample) {
+    const int ups = g.units / n_count;
+    g.cta_per_sample = nsm / n_count < ups ? nsm / n_count : ups;
+    grid = g.cta_per_sample * n_count;
+  }
   if (grid < nsm && (flags & KM_CONV_STATS) && n_base == 0)   // partial slots of the CTAs that do not run
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * kCout * 2 * sizeof(float), km_cs(stream)));
   if (bias_tab)
@@ -573,7 +589,7 @@ extern "C" int km_conv3d_zfold(const void* x, const void* wz, void* out, void* p
                                km_stream_t stream) {
   const int rc = check_zf_args("km_conv3d_zfold", x, wz, out, pooled, stats, N, Cin, Cout, D, H, W, flags);
   if (rc != KM_OK) return rc;
-  return launch_zf(x, wz, nullptr, out, pooled, stats, N, 0, N, Cin, D, H, W, flags, stream);
+  return launch_zf(x, wz, nullptr, out, pooled, stats, N, 0, N, Cin, D, H, W, flags, false, stream);
 }
 
 extern "C" size_t km_conv3d_zfold_gn_workspace_bytes(int N) {
@@ -591,12 +607,14 @@ extern "C" int km_conv3d_zfold_gn(const void* x, const float* w, const float* sc
   float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (size_t)N * wbytes);
   fold_gn_zf_kernel<<<dim3(16, N), 256, 0, km_cs(stream)>>>(w, scale, shift, packed, bias, Cout, Cin);
   KM_LAUNCH_OK("fold_gn_zf_kernel");
-  const size_t vox = (size_t)D * H * W;
-  (void)vox;
+  // one launch, the CTAs split evenly between the samples (each keeps its sample's weights resident);
+  // batches larger than half the SM count fall back to one launch per sample
+  if (2 * N <= km_sm_count())
+    return launch_zf(x, workspace, bias, out, pooled, stats, N, 0, N, Cin, D, H, W, flags, true, stream);
   for (int n = 0; n < N; ++n) {
     const int r2 = launch_zf(x, static_cast<const char*>(workspace) + (size_t)n * wbytes,
                              bias + (size_t)n * kBiasClasses * kCout, out, pooled, stats, N, n, 1, Cin, D, H, W, flags,
-                             stream);
+                             false, stream);
     if (r2 != KM_OK) return r2;
   }
   return KM_OK;

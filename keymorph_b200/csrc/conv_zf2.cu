@@ -53,7 +53,10 @@ struct Zf2Geom {
   int flags;
   uint32_t off_scratch, off_stats, off_bars;
   int stages;
+  int w_per_sample;   // GN-folded path: one packed weight set per sample (tmB's last dimension is 3 N)
 };
+
+constexpr int kBiasClasses = 36;   // z code (0..3) x y code (0..2) x x code (0..2), see conv_zf.cu
 
 struct Unit {
   int n, x0, y0, zs, planes;
@@ -118,7 +121,7 @@ template <int COUT, int KC, int MT, bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const Zf2Geom g, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
-                float* __restrict__ stats) {
+                float* __restrict__ stats, const float* __restrict__ bias_tab) {
   using C = Cfg<COUT, KC, MT>;
   constexpr int kMT = C::kMT;
   constexpr uint32_t kSetStride = C::kSetStride;
@@ -179,7 +182,7 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t ph = 0;
       for_each_tile(g, rank, [&](auto, const Unit& u, int p, uint32_t) {
         const int z = u.zs - 1 + p;   // input plane; outside [0, D) -> TMA zero fill
-        const int rot = p % 3;
+        const int rot = p % 3 + (g.w_per_sample ? 3 * u.n : 0);
         for (int dx = 0; dx < 3; ++dx) {
           for (int ch = 0; ch < g.chunks; ++ch) {
             mbar_wait(empty_bar(s), ph ^ 1u);
@@ -317,6 +320,22 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         const bool inside = u.valid && x2 < g.W && y2 < g.H;
         const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
+        if (bias_tab) {   // GroupNorm shift of the folded norm: bias[sample][border class][cout] (L1-resident)
+          const int cls = ((zo == 0 ? 1 : 0) | (zo == g.D - 1 ? 2 : 0)) * 9 +
+                          (y2 == 0 ? 1 : (y2 == g.H - 1 ? 2 : 0)) * 3 + (x2 == 0 ? 1 : (x2 == g.W - 1 ? 2 : 0));
+          const float4* bp = reinterpret_cast<const float4*>(bias_tab + ((size_t)u.n * kBiasClasses + cls) * kCout +
+                                                             half * kCols);
+#pragma unroll
+          for (int hh = 0; hh < kCols / 16; ++hh)
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bv = __ldg(bp + hh * 4 + j4);
+              r[hh][4 * j4 + 0] = __float_as_uint(__uint_as_float(r[hh][4 * j4 + 0]) + bv.x);
+              r[hh][4 * j4 + 1] = __float_as_uint(__uint_as_float(r[hh][4 * j4 + 1]) + bv.y);
+              r[hh][4 * j4 + 2] = __float_as_uint(__uint_as_float(r[hh][4 * j4 + 2]) + bv.z);
+              r[hh][4 * j4 + 3] = __float_as_uint(__uint_as_float(r[hh][4 * j4 + 3]) + bv.w);
+            }
+        }
 #pragma unroll
         for (int hh = 0; hh < kCols / 16; ++hh) {
           uint32_t pk[8];
@@ -415,6 +434,56 @@ __global__ void pack_weights_zf2_kernel(const float* __restrict__ w, __nv_bfloat
   }
 }
 
+// GroupNorm folded into the conv (see fold_gn_zf_kernel in conv_zf.cu): per sample n = blockIdx.y the
+// packed bf16 weights w * scale[n] and the bias table [36 classes][Cout] of the shift term; one warp per
+// table entry, lanes over the input channels.
+__global__ void fold_gn_zf2_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, __nv_bfloat16* __restrict__ packed,
+                                   float* __restrict__ bias, int Cout, int Cin) {
+  const int n = blockIdx.y;
+  const long long total = 27ll * 3 * Cout * Cin;
+  __nv_bfloat16* p = packed + (size_t)n * total;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int ci = (int)(t % Cin);
+    t /= Cin;
+    const int co = (int)(t % Cout);
+    t /= Cout;
+    const int j = (int)(t % 3);
+    t /= 3;
+    const int dy = (int)(t % 3);
+    t /= 3;
+    const int dx = (int)(t % 3);
+    const int r = (int)(t / 3);
+    const int dz = (r + 1 - j + 3) % 3;
+    p[i] = __float2bfloat16_rn(w[((size_t)co * Cin + ci) * 27 + dz * 9 + dy * 3 + dx] * scale[n * Cin + ci]);
+  }
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < kBiasClasses * Cout; e += nwarps) {
+    const int co = e % Cout, cls = e / Cout;
+    const int xc = cls % 3, yc = (cls / 3) % 3, zc = cls / 9;
+    float acc = 0.f;
+    for (int ci = lane; ci < Cin; ci += 32) {
+      const float* wk = w + ((size_t)co * Cin + ci) * 27;
+      float ws = 0.f;
+      for (int dz = 0; dz < 3; ++dz) {
+        if ((dz == 0 && (zc & 1)) || (dz == 2 && (zc & 2))) continue;
+        for (int dy = 0; dy < 3; ++dy) {
+          if ((dy == 0 && (yc & 1)) || (dy == 2 && (yc & 2))) continue;
+          for (int dx = 0; dx < 3; ++dx) {
+            if ((dx == 0 && (xc & 1)) || (dx == 2 && (xc & 2))) continue;
+            ws += wk[dz * 9 + dy * 3 + dx];
+          }
+        }
+      }
+      acc = fmaf(ws, shift[n * Cin + ci], acc);
+    }
+    acc = km_warp_sum(acc);
+    if (lane == 0) bias[(size_t)n * kBiasClasses * Cout + e] = acc;
+  }
+}
 
 }  // namespace
 
@@ -436,8 +505,8 @@ extern "C" int km_pack_weights_zfold_pair(const float* w, void* packed, int Cout
 namespace {
 int g_zf2_mt2 = 0;   // km_set_option(KM_OPT_ZF2_TWO_BRICKS)
 template <int COUT, int KC, int MT, bool POOL>
-int launch_zf2(const void* x, const void* wz, void* out, void* pooled, float* stats, int N, int Cin, int D,
-               int H, int W, int flags, cudaStream_t st) {
+int launch_zf2(const void* x, const void* wz, const float* bias_tab, void* out, void* pooled, float* stats, int N,
+               int Cin, int D, int H, int W, int flags, cudaStream_t st) {
   using C = Cfg<COUT, KC, MT>;
   KM_CHECK_ARG(POOL || !pooled, "km_conv3d_zfold_pair: fused pooling is built for Cout = 32 only");
   Zf2Geom g;
@@ -445,6 +514,7 @@ int launch_zf2(const void* x, const void* wz, void* out, void* pooled, float* st
   g.N = N; g.D = D; g.H = H; g.W = W;
   g.chunks = Cin / KC;
   g.flags = flags;
+  g.w_per_sample = bias_tab ? 1 : 0;
   const int tiles_x = (W + 7) / 8;
   g.xpairs = (tiles_x + 1) / 2;
   g.mt = MT;
@@ -509,7 +579,7 @@ int launch_zf2(const void* x, const void* wz, void* out, void* pooled, float* st
     // packed weights [rot][dx][dy][3*Cout rows][Cin] viewed as (Cin, rows, dy, dx, rot): one box = the
     // three dy slices of one (rot, dx) for half of the rows
     const cuuint64_t tile = (cuuint64_t)C::kN3 * Cin * 2;
-    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)C::kN3, 3, 3, 3};
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)C::kN3, 3, 3, (cuuint64_t)(bias_tab ? 3 * N : 3)};
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, tile, 3 * tile, 9 * tile};
     cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)C::kHalfRows, 3, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -533,7 +603,7 @@ int launch_zf2(const void* x, const void* wz, void* out, void* pooled, float* st
   if ((flags & KM_CONV_STATS) && grid < nsm)
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * COUT * 2 * sizeof(float), st));
   conv_zf2_kernel<COUT, KC, MT, POOL><<<grid, kThreads, smem_bytes, st>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
-                                                               reinterpret_cast<__nv_bfloat16*>(pooled), stats);
+                                                               reinterpret_cast<__nv_bfloat16*>(pooled), stats, bias_tab);
   KM_LAUNCH_OK("conv_zf2_kernel");
   return KM_OK;
 }
@@ -541,30 +611,60 @@ int launch_zf2(const void* x, const void* wz, void* out, void* pooled, float* st
 
 void km_zf2_set_two_bricks(int v) { g_zf2_mt2 = v ? 1 : 0; }
 
-extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, void* pooled, float* stats,
-                                    int N, int Cin, int Cout, int D, int H, int W, int flags,
-                                    km_stream_t stream) {
-  KM_CHECK_ARG(x && wz && (out || pooled), "km_conv3d_zfold_pair: null argument");
-  KM_CHECK_ARG(km_conv3d_zfold_pair_supported(Cin, Cout, D, H, W),
-               "km_conv3d_zfold_pair: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
-  KM_CHECK_ARG(N > 0, "km_conv3d_zfold_pair: bad batch");
-  KM_CHECK_ARG(!pooled || (D >= 2 && H >= 2 && W >= 2), "km_conv3d_zfold_pair: volume too small to pool");
-  KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "km_conv3d_zfold_pair: KM_CONV_STATS needs stats");
-  KM_CHECK_ARG(!(flags & KM_CONV_COM), "km_conv3d_zfold_pair: KM_CONV_COM is not supported");
+namespace {
+int dispatch_zf2(const char* who, const void* x, const void* wz, const float* bias_tab, void* out, void* pooled,
+                 float* stats, int N, int Cin, int Cout, int D, int H, int W, int flags, km_stream_t stream) {
+  KM_CHECK_ARG(x && wz && (out || pooled), "%s: null argument", who);
+  KM_CHECK_ARG(km_conv3d_zfold_pair_supported(Cin, Cout, D, H, W), "%s: unsupported shape (Cin=%d Cout=%d H=%d W=%d)",
+               who, Cin, Cout, H, W);
+  KM_CHECK_ARG(N > 0, "%s: bad batch", who);
+  KM_CHECK_ARG(!pooled || (D >= 2 && H >= 2 && W >= 2), "%s: volume too small to pool", who);
+  KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "%s: KM_CONV_STATS needs stats", who);
+  KM_CHECK_ARG(!(flags & KM_CONV_COM), "%s: KM_CONV_COM is not supported", who);
   KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wz & 15) == 0 && ((uintptr_t)out & 31) == 0 &&
                    ((uintptr_t)pooled & 31) == 0,
-               "km_conv3d_zfold_pair: pointers must be 16-byte (outputs: 32-byte) aligned");
+               "%s: pointers must be 16-byte (outputs: 32-byte) aligned", who);
   cudaStream_t st = km_cs(stream);
-  if (Cin == 16) return launch_zf2<32, 16, 1, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  if (Cin == 16) return launch_zf2<32, 16, 1, true>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
   const bool k64 = Cin % 64 == 0;
   if (Cout == 64 && k64) {
     // two bricks per unit halve the weight bytes per output (the kernel is bound by L2 -> SM traffic)
     // at the price of a single TMEM set; needs two brick rows
     if (H >= 32 && g_zf2_mt2)
-      return launch_zf2<64, 64, 2, false>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
-    return launch_zf2<64, 64, 1, false>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
+      return launch_zf2<64, 64, 2, false>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
+    return launch_zf2<64, 64, 1, false>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
   }
-  if (Cout == 64) return launch_zf2<64, 32, 1, false>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
-  return k64 ? launch_zf2<32, 64, 1, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st)
-             : launch_zf2<32, 32, 1, true>(x, wz, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  if (Cout == 64) return launch_zf2<64, 32, 1, false>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  return k64 ? launch_zf2<32, 64, 1, true>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st)
+             : launch_zf2<32, 32, 1, true>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
+}
+}  // namespace
+
+extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, void* pooled, float* stats,
+                                    int N, int Cin, int Cout, int D, int H, int W, int flags,
+                                    km_stream_t stream) {
+  return dispatch_zf2("km_conv3d_zfold_pair", x, wz, nullptr, out, pooled, stats, N, Cin, Cout, D, H, W, flags, stream);
+}
+
+extern "C" size_t km_conv3d_zfold_pair_gn_workspace_bytes(int N, int Cin, int Cout) {
+  const size_t wbytes = ((size_t)27 * 3 * Cout * Cin * 2 + 255) & ~(size_t)255;
+  return (size_t)N * wbytes + (size_t)N * kBiasClasses * Cout * 4;
+}
+
+extern "C" int km_conv3d_zfold_pair_gn(const void* x, const float* w, const float* scale, const float* shift,
+                                       void* out, void* pooled, float* stats, void* workspace, int N, int Cin,
+                                       int Cout, int D, int H, int W, int flags, km_stream_t stream) {
+  KM_CHECK_ARG(w && scale && shift && workspace && ((uintptr_t)workspace & 255) == 0,
+               "km_conv3d_zfold_pair_gn: null / unaligned (256 B) argument");
+  KM_CHECK_ARG(km_conv3d_zfold_pair_supported(Cin, Cout, D, H, W),
+               "km_conv3d_zfold_pair_gn: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
+  KM_CHECK_ARG(N > 0 && N <= 1024, "km_conv3d_zfold_pair_gn: bad batch");
+  // the per-sample weight sets must be contiguous for the 5-D tensor map: (27 * 3 * Cout * Cin * 2) bytes each
+  const size_t wbytes = (size_t)27 * 3 * Cout * Cin * 2;
+  __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(workspace);
+  float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)N * wbytes + 255) & ~(size_t)255));
+  fold_gn_zf2_kernel<<<dim3(64, N), 256, 0, km_cs(stream)>>>(w, scale, shift, packed, bias, Cout, Cin);
+  KM_LAUNCH_OK("fold_gn_zf2_kernel");
+  return dispatch_zf2("km_conv3d_zfold_pair_gn", x, workspace, bias, out, pooled, stats, N, Cin, Cout, D, H, W, flags,
+                      stream);
 }

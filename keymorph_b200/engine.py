@@ -103,15 +103,27 @@ class _EngineBase:
 
 
 class UNetEngine(_EngineBase):
-    def _single_conv(self, key, sc_mod, x_norm):
+    def _single_conv(self, key, sc_mod, x, scale=None, shift=None):
+        """GN -> conv -> ReLU of one SingleConv.  With scale / shift, x is the RAW activation: the norm is
+        folded into the z-folded pair kernel where that kernel takes the layer, otherwise applied in place
+        first.  Without them x is already normalised."""
         w = sc_mod.conv.weight
-        _, D, H, W, Cin = x_norm.shape
+        _, D, H, W, Cin = x.shape
+        use_zf2 = ops.USE_ZFOLD_PAIR and D * H * W >= 96 ** 3 and (w.shape[0] == 32 or Cin % 64 == 0) \
+            and ops.zfold_pair_supported(Cin, w.shape[0], D, H, W) \
+            and not ops.zfold_supported(Cin, w.shape[0], D, H, W)
+        if scale is not None:
+            if use_zf2 and ops.USE_GN_FOLD:
+                out, stats = ops.conv3d_zfold_pair_gn(x, w.detach(), scale, shift, relu=True, want_stats=True)
+                self._dbg(key, out)
+                return out, stats
+            x = ops.norm_apply(x, scale, shift, out=x)
+        x_norm = x
         if ops.zfold_supported(Cin, w.shape[0], D, H, W):
             # first tensor-core layer (16 -> 32 at full resolution): dz taps folded into MMA N
             out, stats = ops.conv3d_zfold(x_norm, self.weights.get(key + ".zf", w, zfold=True),
                                           relu=True, want_stats=True)
-        elif ops.USE_ZFOLD_PAIR and D * H * W >= 96 ** 3 and (w.shape[0] == 32 or Cin % 64 == 0) \
-                and ops.zfold_pair_supported(Cin, w.shape[0], D, H, W):
+        elif use_zf2:
             # 32 -> 32, 64 -> 64 and 192 -> 64 at 128^3: dz folded into N = 3 Cout AND the weight rows split
             # over a CTA pair (32 -> 64 measures the same as the plain pair kernel and stays there)
             out, stats = ops.conv3d_zfold_pair(x_norm, self.weights.get(key + ".zf2", w, zfold="pair"),
@@ -194,13 +206,11 @@ class UNetEngine(_EngineBase):
                 p, st = ops.maxpool2_stats(cur)
             g = dc.SingleConv1.groupnorm
             scale, shift = ops.norm_finalize(st, nvox(p), g.weight, g.bias, g.num_groups, g.eps)
-            p = ops.norm_apply(p, scale, shift, out=p)
-            c1, st = self._single_conv(f"enc{i}.c1", dc.SingleConv1, p)
+            c1, st = self._single_conv(f"enc{i}.c1", dc.SingleConv1, p, scale, shift)
             del p
             g = dc.SingleConv2.groupnorm
             scale, shift = ops.norm_finalize(st, nvox(c1), g.weight, g.bias, g.num_groups, g.eps)
-            c1 = ops.norm_apply(c1, scale, shift, out=c1)
-            cur, cur_st = self._single_conv(f"enc{i}.c2", dc.SingleConv2, c1)
+            cur, cur_st = self._single_conv(f"enc{i}.c2", dc.SingleConv2, c1, scale, shift)
             del c1
             feats.append((cur, cur_st))
         # the truncated net never consumes the first encoder's full-resolution output as a skip
@@ -230,8 +240,7 @@ class UNetEngine(_EngineBase):
             del cat
             g = dc.SingleConv2.groupnorm
             scale, shift = ops.norm_finalize(st, nvox(c1), g.weight, g.bias, g.num_groups, g.eps)
-            c1 = ops.norm_apply(c1, scale, shift, out=c1)
-            cur, cur_st = self._single_conv(f"dec{j}.c2", dc.SingleConv2, c1)
+            cur, cur_st = self._single_conv(f"dec{j}.c2", dc.SingleConv2, c1, scale, shift)
             del c1
         # ---- final 1x1x1 conv (+bias) fused with ReLU + centre of mass
         K = m.final_conv.out_channels
