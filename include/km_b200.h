@@ -323,6 +323,14 @@ int km_conv3d_tc_pair_supported(int Cin, int Cout, int D, int H, int W);
 int km_conv3d_tc_pair(const void* x, const void* wp, void* out, float* stats, int N, int Cin, int Cout,
                       int D, int H, int W, int flags, km_stream_t stream);
 
+/* km_conv3d_tc_pair with the preceding GroupNorm folded in (see km_conv3d_zfold_gn): RAW bf16 input,
+ * fp32 (Cout,Cin,3,3,3) weights, scale / shift (N,Cin).  workspace:
+ * km_conv3d_tc_pair_gn_workspace_bytes(N, Cin, Cout), 256-byte aligned. */
+size_t km_conv3d_tc_pair_gn_workspace_bytes(int N, int Cin, int Cout);
+int km_conv3d_tc_pair_gn(const void* x, const float* w, const float* scale, const float* shift, void* out,
+                         float* stats, void* workspace, int N, int Cin, int Cout, int D, int H, int W,
+                         int flags, km_stream_t stream);
+
 /* z-folded AND 2-CTA convolution for the Cout = 64, Cin % 64 == 0 layers (csrc/conv_zf2.cu): the dz
  * taps are folded into N = 192 (TMEM ring of output planes as in km_conv3d_zfold) and the 192 weight
  * rows are split between the two CTAs of a pair (as in km_conv3d_tc_pair), weights streamed by TMA.

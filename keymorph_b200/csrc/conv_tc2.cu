@@ -47,7 +47,10 @@ struct PairGeom {
   uint32_t staging_pitch;
   uint32_t idesc;
   int total_tiles;
+  int w_per_sample;    // GN-folded path: one packed weight set per sample (tmB's last dimension is 3 N)
 };
+
+constexpr int kBiasClasses = 36;   // z code (0..3) x y code (0..2) x x code (0..2), see conv_zf.cu
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -71,7 +74,8 @@ __device__ __forceinline__ TileCoord decode_tile(const PairGeom& g, int t) {
 template <int KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const PairGeom g, __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
+                const PairGeom g, __nv_bfloat16* __restrict__ out, float* __restrict__ stats,
+                const float* __restrict__ bias_tab) {
   constexpr int kRowBytes = KC * 2;
   constexpr int kSteps = KC / 16;
   constexpr uint32_t kLayout = kRowBytes == 128 ? 2u : (kRowBytes == 64 ? 4u : 6u);
@@ -151,7 +155,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // activations: dims (C, W, H, D, N), box 8 x-voxels by 16*mt+2 y-rows
             tma2_load_5d(a_dst, &tmA, lead_full, ch * KC, tc.x0 + dx, tc.y0 - 1, tc.z0 + dz, tc.n);
             // weights: (Cin, Cout, dx, dy, dz) map, this CTA's half of the rows, all three dy slices
-            tma2_load_5d(b_dst, &tmB, lead_full, ch * KC, (int)rank * hbn, dx + 1, 0, dz + 1);
+            tma2_load_5d(b_dst, &tmB, lead_full, ch * KC, (int)rank * hbn, dx + 1, 0,
+                         dz + 1 + (g.w_per_sample ? 3 * tc.n : 0));
             a_dst += g.a_sub_stride;
             b_dst += g.b_sub_stride;
             if (++ch == g.chunks) {
@@ -284,11 +289,32 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const bool vrow = ((vmask >> mb) & 1u) != 0;
             const uint32_t taddr_b = taddr + (uint32_t)(mb * BN);
             uint8_t* srow = staging + (size_t)(mb * kTileM + row) * pitch;
+            const float4* brow = nullptr;
+            if (bias_tab) {   // GroupNorm shift of the folded norm: bias[sample][border class][cout] (L1-resident)
+              const int x2 = tc0.x0 + tx, y2 = y0 + 16 * mb + ty, z2 = tc0.z0;
+              const int cls = ((z2 == 0 ? 1 : 0) | (z2 == g.D - 1 ? 2 : 0)) * 9 +
+                              (y2 == 0 ? 1 : (y2 == g.H - 1 ? 2 : 0)) * 3 + (x2 == 0 ? 1 : (x2 == g.W - 1 ? 2 : 0));
+              brow = reinterpret_cast<const float4*>(bias_tab + ((size_t)tc0.n * kBiasClasses + cls) * g.Cout);
+            }
             for (int blk = b_lo; blk < b_hi; ++blk) {
               const int c0 = blk * 16;
               uint32_t r[16];
               tmem_ld16(taddr_b + (uint32_t)c0, r);
+              float4 bv[4];
+              if (brow) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) bv[j4] = __ldg(brow + blk * 4 + j4);
+              }
               tmem_ld_wait();
+              if (brow) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  r[4 * j4 + 0] = __float_as_uint(__uint_as_float(r[4 * j4 + 0]) + bv[j4].x);
+                  r[4 * j4 + 1] = __float_as_uint(__uint_as_float(r[4 * j4 + 1]) + bv[j4].y);
+                  r[4 * j4 + 2] = __float_as_uint(__uint_as_float(r[4 * j4 + 2]) + bv[j4].z);
+                  r[4 * j4 + 3] = __float_as_uint(__uint_as_float(r[4 * j4 + 3]) + bv[j4].w);
+                }
+              }
               uint32_t pk[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -369,7 +395,50 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 inline uint32_t pair_round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-typedef void (*PairKernel)(const CUtensorMap, const CUtensorMap, const PairGeom, __nv_bfloat16*, float*);
+typedef void (*PairKernel)(const CUtensorMap, const CUtensorMap, const PairGeom, __nv_bfloat16*, float*,
+                           const float*);
+
+// GroupNorm folded into the conv (see fold_gn_zf_kernel in conv_zf.cu): per sample n = blockIdx.y the
+// packed bf16 weights [tap][Cout][Cin] of w * scale[n] and the bias table [36 classes][Cout] of the shift
+// term; one warp per table entry, lanes over the input channels.
+__global__ void fold_gn_tc_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, __nv_bfloat16* __restrict__ packed,
+                                  float* __restrict__ bias, int Cout, int Cin) {
+  const int n = blockIdx.y;
+  const long long total = 27ll * Cout * Cin;
+  __nv_bfloat16* p = packed + (size_t)n * total;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int co = (int)((i / Cin) % Cout);
+    const int tap = (int)(i / ((long long)Cin * Cout));
+    p[i] = __float2bfloat16_rn(w[((long long)co * Cin + ci) * 27 + tap] * scale[n * Cin + ci]);
+  }
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < kBiasClasses * Cout; e += nwarps) {
+    const int co = e % Cout, cls = e / Cout;
+    const int xc = cls % 3, yc = (cls / 3) % 3, zc = cls / 9;
+    float acc = 0.f;
+    for (int ci = lane; ci < Cin; ci += 32) {
+      const float* wk = w + ((size_t)co * Cin + ci) * 27;
+      float ws = 0.f;
+      for (int dz = 0; dz < 3; ++dz) {
+        if ((dz == 0 && (zc & 1)) || (dz == 2 && (zc & 2))) continue;
+        for (int dy = 0; dy < 3; ++dy) {
+          if ((dy == 0 && (yc & 1)) || (dy == 2 && (yc & 2))) continue;
+          for (int dx = 0; dx < 3; ++dx) {
+            if ((dx == 0 && (xc & 1)) || (dx == 2 && (xc & 2))) continue;
+            ws += wk[dz * 9 + dy * 3 + dx];
+          }
+        }
+      }
+      acc = fmaf(ws, shift[n * Cin + ci], acc);
+    }
+    acc = km_warp_sum(acc);
+    if (lane == 0) bias[(size_t)n * kBiasClasses * Cout + e] = acc;
+  }
+}
 
 }  // namespace
 
@@ -380,8 +449,39 @@ extern "C" int km_conv3d_tc_pair_supported(int Cin, int Cout, int D, int H, int 
   return (cin_ok && (Cout == 64 || Cout == 128) && W >= 8 && H >= 32 && D >= 1) ? 1 : 0;
 }
 
+namespace {
+int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out, float* stats, int N, int Cin,
+                int Cout, int D, int H, int W, int flags, km_stream_t stream);
+}
+
 extern "C" int km_conv3d_tc_pair(const void* x, const void* wp, void* out, float* stats, int N, int Cin,
                                  int Cout, int D, int H, int W, int flags, km_stream_t stream) {
+  return launch_pair(x, wp, nullptr, out, stats, N, Cin, Cout, D, H, W, flags, stream);
+}
+
+extern "C" size_t km_conv3d_tc_pair_gn_workspace_bytes(int N, int Cin, int Cout) {
+  return (((size_t)N * 27 * Cout * Cin * 2 + 255) & ~(size_t)255) + (size_t)N * kBiasClasses * Cout * 4;
+}
+
+extern "C" int km_conv3d_tc_pair_gn(const void* x, const float* w, const float* scale, const float* shift,
+                                    void* out, float* stats, void* workspace, int N, int Cin, int Cout, int D,
+                                    int H, int W, int flags, km_stream_t stream) {
+  KM_CHECK_ARG(w && scale && shift && workspace && ((uintptr_t)workspace & 255) == 0,
+               "km_conv3d_tc_pair_gn: null / unaligned (256 B) argument");
+  KM_CHECK_ARG(km_conv3d_tc_pair_supported(Cin, Cout, D, H, W),
+               "km_conv3d_tc_pair_gn: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
+  KM_CHECK_ARG(N > 0 && N <= 1024, "km_conv3d_tc_pair_gn: bad batch");
+  const size_t wbytes = (size_t)27 * Cout * Cin * 2;
+  __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(workspace);
+  float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)N * wbytes + 255) & ~(size_t)255));
+  fold_gn_tc_kernel<<<dim3(64, N), 256, 0, km_cs(stream)>>>(w, scale, shift, packed, bias, Cout, Cin);
+  KM_LAUNCH_OK("fold_gn_tc_kernel");
+  return launch_pair(x, workspace, bias, out, stats, N, Cin, Cout, D, H, W, flags, stream);
+}
+
+namespace {
+int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out, float* stats, int N, int Cin,
+                int Cout, int D, int H, int W, int flags, km_stream_t stream) {
   KM_CHECK_ARG(x && wp && out, "km_conv3d_tc_pair: null argument");
   KM_CHECK_ARG(km_conv3d_tc_pair_supported(Cin, Cout, D, H, W),
                "km_conv3d_tc_pair: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
@@ -394,6 +494,7 @@ extern "C" int km_conv3d_tc_pair(const void* x, const void* wp, void* out, float
   memset(&g, 0, sizeof(g));
   g.N = N; g.D = D; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
   g.flags = flags;
+  g.w_per_sample = bias_tab ? 1 : 0;
   const int kc = (Cin % 64 == 0) ? 64 : 32;
   g.chunks = Cin / kc;
   const int row_bytes = kc * 2;
@@ -469,7 +570,7 @@ extern "C" int km_conv3d_tc_pair(const void* x, const void* wp, void* out, float
     // [tap = dz*9 + dy*3 + dx][Cout][Cin] viewed as (Cin, Cout, dx, dy, dz): one box = the three dy
     // slices of a (dz, dx) group for HALF of the output channels, landing as three [BN/2 x kc] tiles
     const cuuint64_t slice = (cuuint64_t)Cout * Cin * 2;
-    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 3, 3, 3};
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 3, 3, (cuuint64_t)(bias_tab ? 3 * N : 3)};
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, slice, 3 * slice, 9 * slice};
     cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(g.BN / 2), 1, 3, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -493,7 +594,9 @@ extern "C" int km_conv3d_tc_pair(const void* x, const void* wp, void* out, float
   if (grid / 2 > pairs_needed) grid = 2 * pairs_needed;
   if ((flags & KM_CONV_STATS) && grid < nsm)
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * Cout * 2 * sizeof(float), km_cs(stream)));
-  kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out), stats);
+  kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out), stats,
+                                                        bias_tab);
   KM_LAUNCH_OK("conv_tc2_kernel");
   return KM_OK;
 }
+}  // namespace

@@ -112,9 +112,12 @@ class UNetEngine(_EngineBase):
         use_zf2 = ops.USE_ZFOLD_PAIR and D * H * W >= 96 ** 3 and (w.shape[0] == 32 or Cin % 64 == 0) \
             and ops.zfold_pair_supported(Cin, w.shape[0], D, H, W) \
             and not ops.zfold_supported(Cin, w.shape[0], D, H, W)
+        use_pair = not use_zf2 and not ops.zfold_supported(Cin, w.shape[0], D, H, W) and ops.USE_PAIR_CONV \
+            and D * H * W >= 64 ** 3 and ops.pair_supported(Cin, w.shape[0], D, H, W)
         if scale is not None:
-            if use_zf2 and ops.USE_GN_FOLD:
-                out, stats = ops.conv3d_zfold_pair_gn(x, w.detach(), scale, shift, relu=True, want_stats=True)
+            if ops.USE_GN_FOLD and (use_zf2 or (use_pair and ops.USE_GN_FOLD_TC_PAIR)):
+                fn = ops.conv3d_zfold_pair_gn if use_zf2 else ops.conv3d_tc_pair_gn
+                out, stats = fn(x, w.detach(), scale, shift, relu=True, want_stats=True)
                 self._dbg(key, out)
                 return out, stats
             x = ops.norm_apply(x, scale, shift, out=x)
@@ -128,7 +131,7 @@ class UNetEngine(_EngineBase):
             # over a CTA pair (32 -> 64 measures the same as the plain pair kernel and stays there)
             out, stats = ops.conv3d_zfold_pair(x_norm, self.weights.get(key + ".zf2", w, zfold="pair"),
                                                relu=True, want_stats=True)
-        elif ops.USE_PAIR_CONV and D * H * W >= 64 ** 3 and ops.pair_supported(Cin, w.shape[0], D, H, W):
+        elif use_pair:
             # Cout in {64, 128}: two SMs per M = 256 MMA, half of the weight rows per SM (measured faster
             # from 64^3 up; below that there are too few brick groups per CTA pair)
             out, stats = ops.conv3d_tc_pair(x_norm, self.weights.get(key, w), relu=True, want_stats=True)

@@ -445,6 +445,11 @@ def conv3d_zfold(x, wz, relu=False, want_stats=False, pool=False, store=True):
 
 
 USE_GN_FOLD = True
+# The fold is also built for the plain CTA-pair kernel (conv3d_tc_pair_gn, parity-tested) but stays off
+# in the engine: its staged epilogue is on the critical path, the bias loads cost more (+0.3 ms over the
+# four layers) than the four in-place normalisation passes they replace (0.2 ms), and at 256^3 the extra
+# un-centred bf16 roundings push the mean keypoint error over torch's own autocast drift.
+USE_GN_FOLD_TC_PAIR = False
 
 
 def conv3d_zfold_gn(x_raw, w, scale, shift, relu=False, want_stats=False, pool=False, store=True):
@@ -489,6 +494,25 @@ def conv3d_zfold_pair_gn(x_raw, w, scale, shift, relu=False, want_stats=False, p
         _lib.call("km_conv3d_zfold_pair_gn", _ptr(x_raw), _ptr(w), _ptr(scale), _ptr(shift), _ptr(out),
                   _ptr(pooled), _ptr(stats), _ptr(ws), N, Cin, Cout, D, H, W, flags, _stream())
     return (out, pooled, stats) if pool else (out, stats)
+
+
+def conv3d_tc_pair_gn(x_raw, w, scale, shift, relu=False, want_stats=False):
+    """conv3d_tc_pair of GroupNorm(x_raw) without the normalisation pass (see conv3d_zfold_gn)."""
+    _need_cuda(x_raw, w, scale, shift)
+    assert x_raw.dtype == torch.bfloat16
+    x_raw, w, scale, shift = x_raw.contiguous(), _f32c(w), _f32c(scale), _f32c(shift)
+    N, D, H, W, Cin = x_raw.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == Cin and scale.numel() == N * Cin and shift.numel() == N * Cin
+    flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
+    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x_raw.device)
+    stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x_raw.device) \
+        if want_stats else None
+    ws = _ws(_lib.query("km_conv3d_tc_pair_gn_workspace_bytes", N, Cin, Cout), x_raw.device)
+    with torch.cuda.device(x_raw.device):
+        _lib.call("km_conv3d_tc_pair_gn", _ptr(x_raw), _ptr(w), _ptr(scale), _ptr(shift), _ptr(out), _ptr(stats),
+                  _ptr(ws), N, Cin, Cout, D, H, W, flags, _stream())
+    return out, stats
 
 
 def conv1x1_com(x, wp, bias=None):

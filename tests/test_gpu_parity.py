@@ -329,6 +329,38 @@ def test_conv3d_zfold_pair_groupnorm_folded(cfg):
     assert_close(st.double().sum(0).cpu(), s_ref, rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("cfg", [(1, 64, 64, 8, 32, 32), (2, 32, 64, 3, 70, 17), (2, 128, 128, 4, 32, 16),
+                                 (3, 64, 128, 1, 48, 20), (2, 64, 64, 2, 32, 8)])
+def test_conv3d_tc_pair_groupnorm_folded(cfg):
+    """km_conv3d_tc_pair_gn against the fp64 conv of the explicitly normalised, zero-padded input and the
+    un-folded pair kernel (same checks as the z-folded variants)."""
+    import torch.nn.functional as F
+    N, Cin, Cout, D, H, W = cfg
+    g = torch.Generator().manual_seed(sum(cfg) + 3)
+    raw = F.relu(torch.randn(N, Cin, D, H, W, generator=g) * 1.5 + 0.7)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5
+    scale = torch.rand(N, Cin, generator=g) + 0.5
+    shift = torch.randn(N, Cin, generator=g)
+    xb = ops.ncdhw_to_ndhwc(cu(raw))
+    rawb = ops.ndhwc_to_ncdhw(xb).cpu().double()
+    xn = rawb * scale.double()[:, :, None, None, None] + shift.double()[:, :, None, None, None]
+    ref = F.relu(F.conv3d(xn, w.double(), padding=1)).float()
+    out, st = ops.conv3d_tc_pair_gn(xb, cu(w), cu(scale), cu(shift), relu=True, want_stats=True)
+    a = out.float().permute(0, 4, 1, 2, 3).cpu()
+    assert_close(a, ref, rtol=1e-2, atol=2e-2)
+    assert (a - ref).abs().mean().item() < 5e-3
+    unf, _ = ops.conv3d_tc_pair(ops.ncdhw_to_ndhwc(cu(xn.float())), ops.pack_weights(cu(w)), relu=True, want_stats=True)
+    u = unf.float().permute(0, 4, 1, 2, 3).cpu()
+    border = torch.zeros(D, H, W, dtype=torch.bool)
+    border[0], border[-1], border[:, 0], border[:, -1], border[:, :, 0], border[:, :, -1] = (True,) * 6
+    eb = (a - ref).abs()[:, :, border].mean().item()
+    ei = (a - ref).abs()[:, :, ~border].mean().item() if (~border).any() else eb
+    ub = (u - ref).abs()[:, :, border].mean().item()
+    assert eb < 2.0 * max(ei, ub) + 1e-4, (eb, ei, ub)
+    s_ref = torch.stack([a.double().flatten(2).sum(-1), (a.double() ** 2).flatten(2).sum(-1)], -1)
+    assert_close(st.double().sum(0).cpu(), s_ref, rtol=1e-4, atol=1e-2)
+
+
 @pytest.mark.parametrize("cfg", [(1, 64, 64, 8, 32, 32), (2, 192, 64, 70, 40, 24), (1, 64, 64, 3, 16, 8),
                                  (3, 128, 64, 5, 33, 20), (1, 64, 64, 130, 17, 9), (2, 32, 32, 9, 32, 24),
                                  (1, 32, 64, 20, 48, 40), (1, 64, 32, 6, 16, 16), (1, 96, 32, 4, 20, 12)])
