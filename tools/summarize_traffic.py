@@ -1,11 +1,13 @@
 """Per-kernel totals (time, DRAM read/write bytes) of the LAST step in an ncu csv log taken with
 --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum.
-Usage: summarize_traffic.py file.csv [nsteps]"""
+Usage: summarize_traffic.py file.csv [nsteps | first-kernel-of-a-step]
+With a kernel name (e.g. volume_stats_kernel) the step is the launches between its last two occurrences."""
 import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
-nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+arg = sys.argv[2] if len(sys.argv) > 2 else "2"
+nsteps = int(arg) if arg.isdigit() else 0
 for i, r in enumerate(rows):
     if r and r[0] == "ID":
         hdr, start = r, i + 1
@@ -21,7 +23,11 @@ for r in rows[start:]:
     scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1, "us": 1e3, "ms": 1e6, "nsecond": 1, "usecond": 1e3, "msecond": 1e6}.get(u, 1)
     d[r[mi]] = v * scale
 ids = sorted(launches)
-step = ids[len(ids) - len(ids) // nsteps:]
+if nsteps:
+    step = ids[len(ids) - len(ids) // nsteps:]
+else:
+    marks = [i for i in ids if arg in launches[i]["name"]]
+    step = [i for i in ids if marks[-2] <= i < marks[-1]]
 agg = {}
 for i in step:
     d = launches[i]
