@@ -200,7 +200,7 @@ def run_engine(args):
 
     # tracer: CUDA events around the kernels whose rooflines are reported
     traced = {"km_conv3d_tc": [], "km_conv3d_tc_pair": [], "km_conv3d_zfold_pair": [], "km_conv3d_zfold": [],
-              "km_conv3d_zfold_gn": [], "km_conv3d_zfold_pair_gn": [], "km_conv3d_tc_pair_gn": [], "km_conv1x1_com": [],
+              "km_conv3d_zfold_gn": [], "km_conv3d_zfold_pair_gn": [], "km_conv3d_zfold_pair_gn_cat": [], "km_conv3d_tc_pair_gn": [], "km_conv1x1_com": [],
               "km_conv3d_stem": [], "km_warp_loss": []}
     stream = torch.cuda.current_stream()
     pending = {}
@@ -243,7 +243,7 @@ def run_engine(args):
 
     # conv_tc_kernel (one SM per MMA) and conv_tc2_kernel (cta_group::2) are the same implicit GEMM
     conv_names = ("km_conv3d_tc", "km_conv3d_tc_pair", "km_conv3d_zfold_pair", "km_conv3d_zfold_pair_gn",
-                  "km_conv3d_tc_pair_gn")
+                  "km_conv3d_zfold_pair_gn_cat", "km_conv3d_tc_pair_gn")
     conv_ms = sum(per_step_ms(k) for k in conv_names)
     zf_ms = per_step_ms("km_conv3d_zfold") + per_step_ms("km_conv3d_zfold_gn")
     com_ms = per_step_ms("km_conv1x1_com")

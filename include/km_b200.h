@@ -353,6 +353,19 @@ int km_conv3d_zfold_pair_gn(const void* x, const float* w, const float* scale, c
                             void* pooled, float* stats, void* workspace, int N, int Cin, int Cout, int D,
                             int H, int W, int flags, km_stream_t stream);
 
+/* The same for a channel-concatenated input that is never materialised (decoder: cat(skip, upsampled x),
+ * keymorph/unet3d/buildingblocks.py:409-445): input channels [0, Cin0) are read from x0 (N,D,H,W,Cin0) and
+ * [Cin0, Cin0 + Cin1) from x1 (N,D,H,W,Cin1) through two tensor maps; w / scale / shift cover all
+ * Cin0 + Cin1 channels.  Cin0 and Cin1 must be multiples of the K chunk (64 when both are, else 32). */
+int km_conv3d_zfold_pair_gn_cat(const void* x0, const void* x1, int Cin0, int Cin1, const float* w,
+                                const float* scale, const float* shift, void* out, void* pooled, float* stats,
+                                void* workspace, int N, int Cout, int D, int H, int W, int flags,
+                                km_stream_t stream);
+
+/* Nearest-neighbour x2 upsampling of a bf16 NDHWC tensor (F.interpolate in the decoders,
+ * buildingblocks.py:409-445): (N,Dc,Hc,Wc,C) -> (N,2Dc,2Hc,2Wc,C), C % 8 == 0. */
+int km_upsample2_ndhwc(const void* src, void* dst, int N, int C, int Dc, int Hc, int Wc, km_stream_t stream);
+
 /* Final 1x1x1 convolution fused with ReLU + centre of mass, transposed tcgen05 formulation
  * (keymorph/unet3d/model.py:99,389 final_conv + keymorph/layers.py:92-134 + keymorph/model.py:95-109):
  * heat^T[channel, voxel] = W . X^T, one epilogue thread per keypoint channel, sums in registers; the

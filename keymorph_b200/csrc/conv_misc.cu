@@ -436,6 +436,47 @@ extern "C" int km_maxpool2_stats(const void* src, void* out, float* stats, int N
   return KM_OK;
 }
 
+// nearest-neighbour x2 upsampling of a bf16 NDHWC tensor (F.interpolate(scale 2, 'nearest') in the
+// decoders, keymorph/unet3d/buildingblocks.py:409-445): every 16-byte chunk of a coarse voxel is read
+// once and written to its 2x2x2 fine voxels
+__global__ void __launch_bounds__(256)
+upsample2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long chunks, int cpv, int Dc,
+                 int Hc, int Wc) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < chunks; i += 256ll * gridDim.x) {
+    const int c = (int)(i % cpv);
+    long long v = i / cpv;
+    const int x = (int)(v % Wc);
+    v /= Wc;
+    const int y = (int)(v % Hc);
+    v /= Hc;
+    const int z = (int)(v % Dc);
+    const long long n = v / Dc;
+    const uint4 val = src[i];
+    const long long W2 = 2ll * Wc, H2 = 2ll * Hc;
+    const long long base = (((n * 2 * Dc + 2 * z) * H2 + 2 * y) * W2 + 2 * x) * cpv + c;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        uint4* o = dst + base + ((long long)dz * H2 + dy) * W2 * cpv;
+        o[0] = val;
+        o[cpv] = val;
+      }
+  }
+}
+
+extern "C" int km_upsample2_ndhwc(const void* src, void* dst, int N, int C, int Dc, int Hc, int Wc,
+                                  km_stream_t stream) {
+  KM_CHECK_ARG(src && dst && N > 0 && C > 0 && C % 8 == 0 && Dc > 0 && Hc > 0 && Wc > 0,
+               "km_upsample2_ndhwc: bad arguments (C must be a multiple of 8)");
+  KM_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "km_upsample2_ndhwc: pointers must be 16-byte aligned");
+  const long long chunks = (long long)N * Dc * Hc * Wc * (C / 8);
+  upsample2_kernel<<<blocks_for(chunks, 256), 256, 0, km_cs(stream)>>>(
+      reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), chunks, C / 8, Dc, Hc, Wc);
+  KM_LAUNCH_OK("upsample2_kernel");
+  return KM_OK;
+}
+
 extern "C" int km_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int N, int C, int D, int H,
                                           int W, km_stream_t stream) {
   KM_CHECK_ARG(src && dst && N > 0 && C > 0, "km_ndhwc_bf16_to_ncdhw_f32: bad arguments");

@@ -54,6 +54,7 @@ struct Zf2Geom {
   uint32_t off_scratch, off_stats, off_bars;
   int stages;
   int w_per_sample;   // GN-folded path: one packed weight set per sample (tmB's last dimension is 3 N)
+  int chunks0;        // K chunks [0, chunks0) come from tmA, the rest from tmA1 (un-materialised concat)
 };
 
 constexpr int kBiasClasses = 36;   // z code (0..3) x y code (0..2) x x code (0..2), see conv_zf.cu
@@ -119,8 +120,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 template <int COUT, int KC, int MT, bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const Zf2Geom g, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
+conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmB, const Zf2Geom g, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
                 float* __restrict__ stats, const float* __restrict__ bias_tab) {
   using C = Cfg<COUT, KC, MT>;
   constexpr int kMT = C::kMT;
@@ -156,6 +157,7 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     fence_mbar_init();
     prefetch_tmap(&tmA);
+    prefetch_tmap(&tmA1);
     prefetch_tmap(&tmB);
   }
   __syncwarp();
@@ -189,7 +191,11 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t lead_full = mapa_u32(full_bar(s), 0);
             mbar_arrive_expect_tx_cluster(lead_full, kStage);
             const uint32_t dst = base + (uint32_t)s * kStage;
-            tma2_load_5d(dst, &tmA, lead_full, ch * kKC, u.x0 + dx - 1, u.y0 - 1, z, u.n);
+            // channel-concatenated input read in place: the first chunks0 chunks from tmA, the rest from tmA1
+            if (ch < g.chunks0)
+              tma2_load_5d(dst, &tmA, lead_full, ch * kKC, u.x0 + dx - 1, u.y0 - 1, z, u.n);
+            else
+              tma2_load_5d(dst, &tmA1, lead_full, (ch - g.chunks0) * kKC, u.x0 + dx - 1, u.y0 - 1, z, u.n);
             // weights (Cin, 3*Cout rows, dy, dx, rot): this CTA's 96 rows of all three dy slices
             tma2_load_5d(dst + kASub, &tmB, lead_full, ch * kKC, (int)rank * kHalfRows, 0, dx, rot);
             if (++s == kStages) {
@@ -505,8 +511,8 @@ extern "C" int km_pack_weights_zfold_pair(const float* w, void* packed, int Cout
 namespace {
 int g_zf2_mt2 = 0;   // km_set_option(KM_OPT_ZF2_TWO_BRICKS)
 template <int COUT, int KC, int MT, bool POOL>
-int launch_zf2(const void* x, const void* wz, const float* bias_tab, void* out, void* pooled, float* stats, int N,
-               int Cin, int D, int H, int W, int flags, cudaStream_t st) {
+int launch_zf2(const void* x, const void* x1, int Cin0, const void* wz, const float* bias_tab, void* out, void* pooled,
+               float* stats, int N, int Cin, int D, int H, int W, int flags, cudaStream_t st) {
   using C = Cfg<COUT, KC, MT>;
   KM_CHECK_ARG(POOL || !pooled, "km_conv3d_zfold_pair: fused pooling is built for Cout = 32 only");
   Zf2Geom g;
@@ -515,6 +521,11 @@ int launch_zf2(const void* x, const void* wz, const float* bias_tab, void* out, 
   g.chunks = Cin / KC;
   g.flags = flags;
   g.w_per_sample = bias_tab ? 1 : 0;
+  if (!x1) Cin0 = Cin;
+  KM_CHECK_ARG(Cin0 > 0 && Cin0 <= Cin && Cin0 % KC == 0 && (Cin - Cin0) % KC == 0,
+               "km_conv3d_zfold_pair: the two inputs must split the channels at a multiple of %d (got %d + %d)", KC,
+               Cin0, Cin - Cin0);
+  g.chunks0 = Cin0 / KC;
   const int tiles_x = (W + 7) / 8;
   g.xpairs = (tiles_x + 1) / 2;
   g.mt = MT;
@@ -560,18 +571,20 @@ int launch_zf2(const void* x, const void* wz, const float* bias_tab, void* out, 
   }
   const CUtensorMapSwizzle swz = C::kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : C::kRowBytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-  CUtensorMap tmA, tmB;
-  {
-    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
-    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
-                             (cuuint64_t)D * H * W * Cin * 2};
+  CUtensorMap tmA, tmA1, tmB;
+  for (int which = 0; which < 2; ++which) {
+    const int Cc = which == 0 ? Cin0 : (x1 ? Cin - Cin0 : Cin0);
+    const void* ptr = which == 0 ? x : (x1 ? x1 : x);
+    cuuint64_t dims[5] = {(cuuint64_t)Cc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cc * 2, (cuuint64_t)W * Cc * 2, (cuuint64_t)H * W * Cc * 2,
+                             (cuuint64_t)D * H * W * Cc * 2};
     cuuint32_t box[5] = {(cuuint32_t)KC, 8, (cuuint32_t)(16 * MT + 2), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box,
-                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = encode(which == 0 ? &tmA : &tmA1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      km_set_error("km_conv3d_zfold_pair: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+      km_set_error("km_conv3d_zfold_pair: cuTensorMapEncodeTiled(A%d) failed with %d", which, (int)r);
       return KM_ECUDA;
     }
   }
@@ -602,7 +615,7 @@ int launch_zf2(const void* x, const void* wz, const float* bias_tab, void* out, 
   if (grid / 2 > upi) grid = 2 * upi;
   if ((flags & KM_CONV_STATS) && grid < nsm)
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * COUT * 2 * sizeof(float), st));
-  conv_zf2_kernel<COUT, KC, MT, POOL><<<grid, kThreads, smem_bytes, st>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
+  conv_zf2_kernel<COUT, KC, MT, POOL><<<grid, kThreads, smem_bytes, st>>>(tmA, tmA1, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
                                                                reinterpret_cast<__nv_bfloat16*>(pooled), stats, bias_tab);
   KM_LAUNCH_OK("conv_zf2_kernel");
   return KM_OK;
@@ -612,8 +625,9 @@ int launch_zf2(const void* x, const void* wz, const float* bias_tab, void* out, 
 void km_zf2_set_two_bricks(int v) { g_zf2_mt2 = v ? 1 : 0; }
 
 namespace {
-int dispatch_zf2(const char* who, const void* x, const void* wz, const float* bias_tab, void* out, void* pooled,
-                 float* stats, int N, int Cin, int Cout, int D, int H, int W, int flags, km_stream_t stream) {
+int dispatch_zf2(const char* who, const void* x, const void* x1, int Cin0, const void* wz, const float* bias_tab,
+                 void* out, void* pooled, float* stats, int N, int Cin, int Cout, int D, int H, int W, int flags,
+                 km_stream_t stream) {
   KM_CHECK_ARG(x && wz && (out || pooled), "%s: null argument", who);
   KM_CHECK_ARG(km_conv3d_zfold_pair_supported(Cin, Cout, D, H, W), "%s: unsupported shape (Cin=%d Cout=%d H=%d W=%d)",
                who, Cin, Cout, H, W);
@@ -621,29 +635,30 @@ int dispatch_zf2(const char* who, const void* x, const void* wz, const float* bi
   KM_CHECK_ARG(!pooled || (D >= 2 && H >= 2 && W >= 2), "%s: volume too small to pool", who);
   KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "%s: KM_CONV_STATS needs stats", who);
   KM_CHECK_ARG(!(flags & KM_CONV_COM), "%s: KM_CONV_COM is not supported", who);
-  KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wz & 15) == 0 && ((uintptr_t)out & 31) == 0 &&
-                   ((uintptr_t)pooled & 31) == 0,
+  KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)x1 & 15) == 0 && ((uintptr_t)wz & 15) == 0 &&
+                   ((uintptr_t)out & 31) == 0 && ((uintptr_t)pooled & 31) == 0,
                "%s: pointers must be 16-byte (outputs: 32-byte) aligned", who);
   cudaStream_t st = km_cs(stream);
-  if (Cin == 16) return launch_zf2<32, 16, 1, true>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
-  const bool k64 = Cin % 64 == 0;
+  if (Cin == 16) return launch_zf2<32, 16, 1, true>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  const bool k64 = Cin % 64 == 0 && (!x1 || Cin0 % 64 == 0);
   if (Cout == 64 && k64) {
     // two bricks per unit halve the weight bytes per output (the kernel is bound by L2 -> SM traffic)
     // at the price of a single TMEM set; needs two brick rows
     if (H >= 32 && g_zf2_mt2)
-      return launch_zf2<64, 64, 2, false>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
-    return launch_zf2<64, 64, 1, false>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
+      return launch_zf2<64, 64, 2, false>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
+    return launch_zf2<64, 64, 1, false>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
   }
-  if (Cout == 64) return launch_zf2<64, 32, 1, false>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
-  return k64 ? launch_zf2<32, 64, 1, true>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st)
-             : launch_zf2<32, 32, 1, true>(x, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  if (Cout == 64) return launch_zf2<64, 32, 1, false>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  return k64 ? launch_zf2<32, 64, 1, true>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st)
+             : launch_zf2<32, 32, 1, true>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
 }
 }  // namespace
 
 extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, void* pooled, float* stats,
                                     int N, int Cin, int Cout, int D, int H, int W, int flags,
                                     km_stream_t stream) {
-  return dispatch_zf2("km_conv3d_zfold_pair", x, wz, nullptr, out, pooled, stats, N, Cin, Cout, D, H, W, flags, stream);
+  return dispatch_zf2("km_conv3d_zfold_pair", x, nullptr, Cin, wz, nullptr, out, pooled, stats, N, Cin, Cout, D, H, W,
+                      flags, stream);
 }
 
 extern "C" size_t km_conv3d_zfold_pair_gn_workspace_bytes(int N, int Cin, int Cout) {
@@ -651,9 +666,11 @@ extern "C" size_t km_conv3d_zfold_pair_gn_workspace_bytes(int N, int Cin, int Co
   return (size_t)N * wbytes + (size_t)N * kBiasClasses * Cout * 4;
 }
 
-extern "C" int km_conv3d_zfold_pair_gn(const void* x, const float* w, const float* scale, const float* shift,
-                                       void* out, void* pooled, float* stats, void* workspace, int N, int Cin,
-                                       int Cout, int D, int H, int W, int flags, km_stream_t stream) {
+extern "C" int km_conv3d_zfold_pair_gn_cat(const void* x0, const void* x1, int Cin0, int Cin1, const float* w,
+                                           const float* scale, const float* shift, void* out, void* pooled,
+                                           float* stats, void* workspace, int N, int Cout, int D, int H, int W,
+                                           int flags, km_stream_t stream) {
+  const int Cin = Cin0 + (x1 ? Cin1 : 0);
   KM_CHECK_ARG(w && scale && shift && workspace && ((uintptr_t)workspace & 255) == 0,
                "km_conv3d_zfold_pair_gn: null / unaligned (256 B) argument");
   KM_CHECK_ARG(km_conv3d_zfold_pair_supported(Cin, Cout, D, H, W),
@@ -665,6 +682,13 @@ extern "C" int km_conv3d_zfold_pair_gn(const void* x, const float* w, const floa
   float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)N * wbytes + 255) & ~(size_t)255));
   fold_gn_zf2_kernel<<<dim3(64, N), 256, 0, km_cs(stream)>>>(w, scale, shift, packed, bias, Cout, Cin);
   KM_LAUNCH_OK("fold_gn_zf2_kernel");
-  return dispatch_zf2("km_conv3d_zfold_pair_gn", x, workspace, bias, out, pooled, stats, N, Cin, Cout, D, H, W, flags,
-                      stream);
+  return dispatch_zf2("km_conv3d_zfold_pair_gn", x0, x1, Cin0, workspace, bias, out, pooled, stats, N, Cin, Cout, D, H,
+                      W, flags, stream);
+}
+
+extern "C" int km_conv3d_zfold_pair_gn(const void* x, const float* w, const float* scale, const float* shift,
+                                       void* out, void* pooled, float* stats, void* workspace, int N, int Cin,
+                                       int Cout, int D, int H, int W, int flags, km_stream_t stream) {
+  return km_conv3d_zfold_pair_gn_cat(x, nullptr, Cin, 0, w, scale, shift, out, pooled, stats, workspace, N, Cout, D,
+                                     H, W, flags, stream);
 }

@@ -229,6 +229,25 @@ class UNetEngine(_EngineBase):
                 scale, shift = ops.norm_finalize(skip_st, nvox(skip), g.weight, g.bias,
                                                  g.num_groups, g.eps, stats1=cur_st,
                                                  count1=nvox(cur), rep1=8.0)
+                w1 = dc.SingleConv1.conv.weight
+                Cs, Cu = skip.shape[-1], cur.shape[-1]
+                sd = skip.shape[1:4]
+                if ops.USE_GN_FOLD and ops.USE_ZFOLD_PAIR and sd[0] * sd[1] * sd[2] >= 96 ** 3 \
+                        and (w1.shape[0] == 32 or (Cs % 64 == 0 and Cu % 64 == 0)) and Cs % 32 == 0 and Cu % 32 == 0 \
+                        and ops.zfold_pair_supported(Cs + Cu, w1.shape[0], *sd):
+                    # the concat is never materialised: the skip is read raw through its own tensor map, only
+                    # the upsampled half is written (also raw); the joint GroupNorm is folded into the conv
+                    up = ops.upsample2(cur)
+                    c1, st = ops.conv3d_zfold_pair_gn(skip, w1.detach(), scale, shift, relu=True, want_stats=True,
+                                                      x1=up)
+                    self._dbg(f"dec{j}.c1", c1)
+                    del up
+                    skips[j] = None
+                    g = dc.SingleConv2.groupnorm
+                    scale, shift = ops.norm_finalize(st, nvox(c1), g.weight, g.bias, g.num_groups, g.eps)
+                    cur, cur_st = self._single_conv(f"dec{j}.c2", dc.SingleConv2, c1, scale, shift)
+                    del c1
+                    continue
                 cat = ops.norm_apply(skip, scale, shift, src1=cur)
             else:
                 C = skip.shape[-1] + cur.shape[-1]

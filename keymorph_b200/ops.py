@@ -475,12 +475,31 @@ def conv3d_zfold_gn(x_raw, w, scale, shift, relu=False, want_stats=False, pool=F
     return (out, pooled, stats) if pool else (out, stats)
 
 
-def conv3d_zfold_pair_gn(x_raw, w, scale, shift, relu=False, want_stats=False, pool=False, store=True):
-    """conv3d_zfold_pair of GroupNorm(x_raw) without the normalisation pass (see conv3d_zfold_gn)."""
-    _need_cuda(x_raw, w, scale, shift)
+def upsample2(x):
+    """bf16 (N,Dc,Hc,Wc,C) -> (N,2Dc,2Hc,2Wc,C), nearest neighbour."""
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16
+    x = x.contiguous()
+    N, Dc, Hc, Wc, Cc = x.shape
+    out = torch.empty((N, 2 * Dc, 2 * Hc, 2 * Wc, Cc), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("km_upsample2_ndhwc", _ptr(x), _ptr(out), N, Cc, Dc, Hc, Wc, _stream())
+    return out
+
+
+def conv3d_zfold_pair_gn(x_raw, w, scale, shift, relu=False, want_stats=False, pool=False, store=True, x1=None):
+    """conv3d_zfold_pair of GroupNorm(x_raw) without the normalisation pass (see conv3d_zfold_gn).  With
+    x1 the input is cat(x_raw, x1) along the channels, read in place through two tensor maps."""
+    _need_cuda(x_raw, w, scale, shift, x1)
     assert x_raw.dtype == torch.bfloat16
     x_raw, w, scale, shift = x_raw.contiguous(), _f32c(w), _f32c(scale), _f32c(shift)
-    N, D, H, W, Cin = x_raw.shape
+    N, D, H, W, Cin0 = x_raw.shape
+    Cin1 = 0
+    if x1 is not None:
+        assert x1.dtype == torch.bfloat16 and x1.shape[:4] == x_raw.shape[:4]
+        x1 = x1.contiguous()
+        Cin1 = x1.shape[4]
+    Cin = Cin0 + Cin1
     Cout = w.shape[0]
     assert w.shape[1] == Cin and scale.numel() == N * Cin and shift.numel() == N * Cin
     flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
@@ -491,8 +510,8 @@ def conv3d_zfold_pair_gn(x_raw, w, scale, shift, relu=False, want_stats=False, p
         if want_stats else None
     ws = _ws(_lib.query("km_conv3d_zfold_pair_gn_workspace_bytes", N, Cin, Cout), x_raw.device)
     with torch.cuda.device(x_raw.device):
-        _lib.call("km_conv3d_zfold_pair_gn", _ptr(x_raw), _ptr(w), _ptr(scale), _ptr(shift), _ptr(out),
-                  _ptr(pooled), _ptr(stats), _ptr(ws), N, Cin, Cout, D, H, W, flags, _stream())
+        _lib.call("km_conv3d_zfold_pair_gn_cat", _ptr(x_raw), _ptr(x1), Cin0, Cin1, _ptr(w), _ptr(scale),
+                  _ptr(shift), _ptr(out), _ptr(pooled), _ptr(stats), _ptr(ws), N, Cout, D, H, W, flags, _stream())
     return (out, pooled, stats) if pool else (out, stats)
 
 
