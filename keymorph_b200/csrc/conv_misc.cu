@@ -436,6 +436,102 @@ extern "C" int km_maxpool2_stats(const void* src, void* out, float* stats, int N
   return KM_OK;
 }
 
+// GroupNorm folded into the consumer conv (keymorph/unet3d/buildingblocks.py:50-52, order "gcr": GN -> conv
+// -> ReLU with nothing non-linear between GN and the conv): conv(scale x + shift) with zero padding of the
+// normalised input = conv_{w scale}(x) + sum over the IN-BOUNDS taps of w . shift.  For every sample n:
+//   packed[n] = bf16(w * scale[n]) in the layout the conv kernel streams
+//               (layout 0: [tap][Cout][Cin]; layout 1, z-folded: [rot][dx][dy][j][Cout][Cin], dz = (rot+1-j) mod 3)
+//   bias[n][class][cout], class = zcode * 9 + ycode * 3 + xcode; code bit 0 = voxel on the low border of that
+//               axis (tap offset -1 outside), bit 1 = on the high border (tap offset +1 outside)
+// Blocks [0, pack_blocks) pack; the others build the tables, one warp per output channel with the lanes
+// over the input channels: the 36 class sums of a 3x3x3 kernel come from three separable reductions.
+__global__ void __launch_bounds__(256)
+fold_gn_kernel(const float* __restrict__ w, const float* __restrict__ scale, const float* __restrict__ shift,
+               bf16* __restrict__ packed, float* __restrict__ bias, int N, int Cout, int Cin, int layout,
+               int pack_blocks) {
+  if ((int)blockIdx.x < pack_blocks) {
+    const long long total = 27ll * (layout ? 3 : 1) * Cout * Cin;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * pack_blocks) {
+      long long t = i;
+      const int ci = (int)(t % Cin);
+      t /= Cin;
+      const int co = (int)(t % Cout);
+      t /= Cout;
+      int tap;
+      if (layout) {
+        const int j = (int)(t % 3);
+        t /= 3;
+        const int dy = (int)(t % 3);
+        t /= 3;
+        const int dx = (int)(t % 3);
+        const int r = (int)(t / 3);
+        tap = ((r + 1 - j + 3) % 3) * 9 + dy * 3 + dx;
+      } else {
+        tap = (int)t;
+      }
+      const float wv = w[((size_t)co * Cin + ci) * 27 + tap];
+      for (int n = 0; n < N; ++n) packed[(size_t)n * total + i] = __float2bfloat16_rn(wv * scale[n * Cin + ci]);
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int co = ((int)blockIdx.x - pack_blocks) * 8 + (threadIdx.x >> 5);
+  if (co >= Cout) return;
+  for (int n = 0; n < N; ++n) {
+    float acc[36];
+#pragma unroll
+    for (int c = 0; c < 36; ++c) acc[c] = 0.f;
+    for (int ci = lane; ci < Cin; ci += 32) {
+      const float* wk = w + ((size_t)co * Cin + ci) * 27;
+      const float sh = shift[n * Cin + ci];
+      float xs[3][3][3];   // [dz][dy][x code]: mid = all three dx, low border = dx 1..2, high border = dx 0..1
+#pragma unroll
+      for (int d = 0; d < 9; ++d) {
+        const float w0 = wk[d * 3], w1 = wk[d * 3 + 1], w2 = wk[d * 3 + 2];
+        xs[d / 3][d % 3][0] = w0 + w1 + w2;
+        xs[d / 3][d % 3][1] = w1 + w2;
+        xs[d / 3][d % 3][2] = w0 + w1;
+      }
+#pragma unroll
+      for (int xc = 0; xc < 3; ++xc) {
+        float ys[3][3];    // [dz][y code]
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz) {
+          const float a0 = xs[dz][0][xc], a1 = xs[dz][1][xc], a2 = xs[dz][2][xc];
+          ys[dz][0] = a0 + a1 + a2;
+          ys[dz][1] = a1 + a2;
+          ys[dz][2] = a0 + a1;
+        }
+#pragma unroll
+        for (int yc = 0; yc < 3; ++yc) {
+          const float b0 = ys[0][yc], b1 = ys[1][yc], b2 = ys[2][yc];
+          acc[(0 * 3 + yc) * 3 + xc] = fmaf(b0 + b1 + b2, sh, acc[(0 * 3 + yc) * 3 + xc]);
+          acc[(1 * 3 + yc) * 3 + xc] = fmaf(b1 + b2, sh, acc[(1 * 3 + yc) * 3 + xc]);
+          acc[(2 * 3 + yc) * 3 + xc] = fmaf(b0 + b1, sh, acc[(2 * 3 + yc) * 3 + xc]);
+          acc[(3 * 3 + yc) * 3 + xc] = fmaf(b1, sh, acc[(3 * 3 + yc) * 3 + xc]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 36; ++c) {
+      const float v = km_warp_sum(acc[c]);
+      if (lane == 0) bias[((size_t)n * 36 + c) * Cout + co] = v;
+    }
+  }
+}
+
+int km_fold_gn(const float* w, const float* scale, const float* shift, void* packed, float* bias, int N, int Cout,
+               int Cin, int layout, km_stream_t stream) {
+  const long long total = 27ll * (layout ? 3 : 1) * Cout * Cin;
+  long long pb = (total + 1023) / 1024;
+  const int pack_blocks = (int)(pb < 1 ? 1 : (pb > 1184 ? 1184 : pb));
+  const int bias_blocks = (Cout + 7) / 8;
+  fold_gn_kernel<<<pack_blocks + bias_blocks, 256, 0, km_cs(stream)>>>(w, scale, shift, reinterpret_cast<bf16*>(packed),
+                                                                       bias, N, Cout, Cin, layout, pack_blocks);
+  KM_LAUNCH_OK("fold_gn_kernel");
+  return KM_OK;
+}
+
 // nearest-neighbour x2 upsampling of a bf16 NDHWC tensor (F.interpolate(scale 2, 'nearest') in the
 // decoders, keymorph/unet3d/buildingblocks.py:409-445): every 16-byte chunk of a coarse voxel is read
 // once and written to its 2x2x2 fine voxels

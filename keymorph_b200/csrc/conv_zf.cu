@@ -413,55 +413,6 @@ __global__ void pack_weights_zf_kernel(const float* __restrict__ w, __nv_bfloat1
   }
 }
 
-// GroupNorm folded into the conv (keymorph/unet3d/buildingblocks.py:50-52, order "gcr": GN -> conv -> ReLU
-// with nothing non-linear between GN and the conv): conv(scale x + shift) with zero padding of the
-// normalised input = conv_{w scale}(x) + sum over the IN-BOUNDS taps of w . shift.  Per sample n
-// (blockIdx.y): packed[n] = bf16(w * scale[n]) in the layout of pack_weights_zf_kernel, and
-// bias[n][class][cout], class = zcode * 9 + ycode * 3 + xcode, code bit 0 = voxel on the low border of
-// that axis (tap offset -1 outside), bit 1 = on the high border (tap offset +1 outside).
-__global__ void fold_gn_zf_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                  const float* __restrict__ shift, __nv_bfloat16* __restrict__ packed,
-                                  float* __restrict__ bias, int Cout, int Cin) {
-  const int n = blockIdx.y;
-  const int total = 27 * 3 * Cout * Cin;
-  __nv_bfloat16* p = packed + (size_t)n * total;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int t = i;
-    const int ci = t % Cin;
-    t /= Cin;
-    const int co = t % Cout;
-    t /= Cout;
-    const int j = t % 3;
-    t /= 3;
-    const int dy = t % 3;
-    t /= 3;
-    const int dx = t % 3;
-    const int r = t / 3;
-    const int dz = (r + 1 - j + 3) % 3;
-    p[i] = __float2bfloat16_rn(w[((size_t)co * Cin + ci) * 27 + dz * 9 + dy * 3 + dx] * scale[n * Cin + ci]);
-  }
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kBiasClasses * Cout; e += gridDim.x * blockDim.x) {
-    const int co = e % Cout, cls = e / Cout;
-    const int xc = cls % 3, yc = (cls / 3) % 3, zc = cls / 9;
-    float acc = 0.f;
-    for (int ci = 0; ci < Cin; ++ci) {
-      const float* wk = w + ((size_t)co * Cin + ci) * 27;
-      float ws = 0.f;
-      for (int dz = 0; dz < 3; ++dz) {
-        if ((dz == 0 && (zc & 1)) || (dz == 2 && (zc & 2))) continue;
-        for (int dy = 0; dy < 3; ++dy) {
-          if ((dy == 0 && (yc & 1)) || (dy == 2 && (yc & 2))) continue;
-          for (int dx = 0; dx < 3; ++dx) {
-            if ((dx == 0 && (xc & 1)) || (dx == 2 && (xc & 2))) continue;
-            ws += wk[dz * 9 + dy * 3 + dx];
-          }
-        }
-      }
-      acc = fmaf(ws, shift[n * Cin + ci], acc);
-    }
-    bias[(size_t)n * kBiasClasses * Cout + e] = acc;
-  }
-}
 
 inline uint32_t zf_round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
@@ -605,8 +556,8 @@ extern "C" int km_conv3d_zfold_gn(const void* x, const float* w, const float* sc
   const size_t wbytes = (size_t)27 * 3 * kCout * kKC * 2;
   __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(workspace);
   float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (size_t)N * wbytes);
-  fold_gn_zf_kernel<<<dim3(16, N), 256, 0, km_cs(stream)>>>(w, scale, shift, packed, bias, Cout, Cin);
-  KM_LAUNCH_OK("fold_gn_zf_kernel");
+  const int rf = km_fold_gn(w, scale, shift, packed, bias, N, Cout, Cin, 1, stream);
+  if (rf != KM_OK) return rf;
   // one launch, the CTAs split evenly between the samples (each keeps its sample's weights resident);
   // batches larger than half the SM count fall back to one launch per sample
   if (2 * N <= km_sm_count())

@@ -440,56 +440,6 @@ __global__ void pack_weights_zf2_kernel(const float* __restrict__ w, __nv_bfloat
   }
 }
 
-// GroupNorm folded into the conv (see fold_gn_zf_kernel in conv_zf.cu): per sample n = blockIdx.y the
-// packed bf16 weights w * scale[n] and the bias table [36 classes][Cout] of the shift term; one warp per
-// table entry, lanes over the input channels.
-__global__ void fold_gn_zf2_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                   const float* __restrict__ shift, __nv_bfloat16* __restrict__ packed,
-                                   float* __restrict__ bias, int Cout, int Cin) {
-  const int n = blockIdx.y;
-  const long long total = 27ll * 3 * Cout * Cin;
-  __nv_bfloat16* p = packed + (size_t)n * total;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    const int ci = (int)(t % Cin);
-    t /= Cin;
-    const int co = (int)(t % Cout);
-    t /= Cout;
-    const int j = (int)(t % 3);
-    t /= 3;
-    const int dy = (int)(t % 3);
-    t /= 3;
-    const int dx = (int)(t % 3);
-    const int r = (int)(t / 3);
-    const int dz = (r + 1 - j + 3) % 3;
-    p[i] = __float2bfloat16_rn(w[((size_t)co * Cin + ci) * 27 + dz * 9 + dy * 3 + dx] * scale[n * Cin + ci]);
-  }
-  const int lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < kBiasClasses * Cout; e += nwarps) {
-    const int co = e % Cout, cls = e / Cout;
-    const int xc = cls % 3, yc = (cls / 3) % 3, zc = cls / 9;
-    float acc = 0.f;
-    for (int ci = lane; ci < Cin; ci += 32) {
-      const float* wk = w + ((size_t)co * Cin + ci) * 27;
-      float ws = 0.f;
-      for (int dz = 0; dz < 3; ++dz) {
-        if ((dz == 0 && (zc & 1)) || (dz == 2 && (zc & 2))) continue;
-        for (int dy = 0; dy < 3; ++dy) {
-          if ((dy == 0 && (yc & 1)) || (dy == 2 && (yc & 2))) continue;
-          for (int dx = 0; dx < 3; ++dx) {
-            if ((dx == 0 && (xc & 1)) || (dx == 2 && (xc & 2))) continue;
-            ws += wk[dz * 9 + dy * 3 + dx];
-          }
-        }
-      }
-      acc = fmaf(ws, shift[n * Cin + ci], acc);
-    }
-    acc = km_warp_sum(acc);
-    if (lane == 0) bias[(size_t)n * kBiasClasses * Cout + e] = acc;
-  }
-}
 
 }  // namespace
 
@@ -680,8 +630,8 @@ extern "C" int km_conv3d_zfold_pair_gn_cat(const void* x0, const void* x1, int C
   const size_t wbytes = (size_t)27 * 3 * Cout * Cin * 2;
   __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(workspace);
   float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)N * wbytes + 255) & ~(size_t)255));
-  fold_gn_zf2_kernel<<<dim3(64, N), 256, 0, km_cs(stream)>>>(w, scale, shift, packed, bias, Cout, Cin);
-  KM_LAUNCH_OK("fold_gn_zf2_kernel");
+  const int rf = km_fold_gn(w, scale, shift, packed, bias, N, Cout, Cin, 1, stream);
+  if (rf != KM_OK) return rf;
   return dispatch_zf2("km_conv3d_zfold_pair_gn", x0, x1, Cin0, workspace, bias, out, pooled, stats, N, Cin, Cout, D, H,
                       W, flags, stream);
 }

@@ -39,6 +39,11 @@ void km_set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
+// conv_misc.cu: per-sample bf16 weights w * scale[n] (layout 0: [tap][Cout][Cin], 1: z-folded) and the
+// [N][36 border classes][Cout] bias tables of a GroupNorm folded into its consumer conv
+int km_fold_gn(const float* w, const float* scale, const float* shift, void* packed, float* bias, int N, int Cout,
+               int Cin, int layout, km_stream_t stream);
+
 static inline cudaStream_t km_cs(km_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Number of partial-sum slots written by the grid-stride reduction kernels (one per block).
