@@ -1074,9 +1074,18 @@ def test_full_size_256_backbone_and_registration_vs_oracle():
     print(f"256^3 keypoints vs fp32 oracle: max err {err:.3e} mean {mean_err:.3e}; "
           f"torch bf16-autocast drift on the same input: max {drift:.3e} mean {drift_mean:.3e}")
     # the MEAN error must not exceed torch's own bf16-autocast drift; the max over the K keypoints is
-    # one worst, weakly localised blob in either run, so it only has to stay within 2x of it
-    assert mean_err < max(1e-3, 1.1 * drift_mean)
-    assert err < max(1e-2, 2.0 * drift)
+    # one worst, weakly localised blob in either run, so it gets 25 % of slack (measured: 1.36e-2 vs 1.41e-2
+    # max, 1.15e-3 vs 1.53e-3 mean)
+    assert mean_err < max(1e-3, 1.0 * drift_mean)
+    assert err < max(1e-2, 1.25 * drift)
+    # the optional stem fold (ops.USE_GN_FOLD_STEM) trades accuracy for 5 % speed: it has to stay inside 2x
+    ops.USE_GN_FOLD_STEM = True
+    try:
+        pts2 = model(f, m, transform_type="affine", return_aligned_points=False)["affine"]["points_f"].cpu()
+    finally:
+        ops.USE_GN_FOLD_STEM = False
+    assert (pts2 - ref_pts).abs().mean().item() < max(1e-3, 1.1 * drift_mean)
+    assert (pts2 - ref_pts).abs().max().item() < max(1e-2, 2.0 * drift)
     for t in ("rigid", "affine"):
         ref = O.register_points(r[t]["points_f"].cpu(), r[t]["points_m"].cpu(), t, (S, S, S))
         assert_close(r[t]["matrix"].cpu(), ref["matrix"], rtol=1e-4, atol=1e-4)
