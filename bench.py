@@ -264,7 +264,8 @@ def run_engine(args):
     all_flops = sum(layers.values())
     roofline_other = []
     if zf_ms > 0:
-        roofline_other.append({"bound": "tensor", "kernel": "conv_zf_kernel (16->32 @256^3, dz folded into N, GroupNorm folded in, pool fused)",
+        roofline_other.append({"bound": "tensor", "kernel": "conv_zf_kernel (16->32 @256^3, dz folded into N, pool fused%s)" % (
+                                   ", GroupNorm folded in" if traced["km_conv3d_zfold_gn"] else ""),
                                "achieved": zf_flops / (zf_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
                                "frac": zf_flops / (zf_ms * 1e-3) / 1e12 / tc_peak, "kernel_ms_per_step": zf_ms,
                                "traffic": NCU_TRAFFIC.get("conv_zf_kernel")})
@@ -274,7 +275,8 @@ def run_engine(args):
                                "frac": com_flops / (com_ms * 1e-3) / 1e12 / tc_peak, "kernel_ms_per_step": com_ms,
                                "hbm_gbs": 2 * (S // 2) ** 3 * 64 * 2 / (com_ms * 1e-3) / 1e9,
                                "traffic": NCU_TRAFFIC.get("com_tc_kernel")})
-    roofline_other.append({"bound": "tensor", "kernel": "whole backbone (stem + conv_zf + conv_tc + com_tc)",
+    roofline_other.append({"bound": "tensor", "kernel": "whole backbone (stem%s + conv_zf + conv_tc + com_tc)" % (
+                               "" if traced["km_conv3d_zfold_gn"] else " x2"),
                            "achieved": all_flops / (backbone_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
                            "frac": all_flops / (backbone_ms * 1e-3) / 1e12 / tc_peak,
                            "kernel_ms_per_step": backbone_ms})
