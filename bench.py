@@ -33,9 +33,9 @@ METRIC = "pairwise 256^3 registrations/sec"
 UNIT = "registrations/s"
 CPU_SLAB = 64      # the CPU arm times a 64x256x256 slab of each volume and scales by 256/64
 # dram__bytes_read.sum + dram__bytes_write.sum per step from the ncu capture of this workload
-# (profiles/r01_s3_ncu_launches_dram_traffic_gn_fold.txt); filled in by hand after each profiling pass
-NCU_TRAFFIC = {"conv_tc_kernel": 5.615e9,    # 11 launches: 3.594 GB read + 2.022 GB written
-               "conv_zf_kernel": 1.374e9,    # 1.118 GB read + 0.256 GB written (pooled output only)
+# (profiles/r01_s3_ncu_launches_dram_traffic_default.txt); filled in by hand after each profiling pass
+NCU_TRAFFIC = {"conv_tc_kernel": 5.639e9,    # 10 launches: 3.617 GB read + 2.023 GB written
+               "conv_zf_kernel": 1.351e9,    # 1.100 GB read + 0.251 GB written (pooled output only)
                "com_tc_kernel": 0.540e9}     # 0.537 GB read
 
 
