@@ -5,7 +5,7 @@ The names below mirror the reference modules on the registration hot path
 loss_ops / augmentation); everything they compute runs in hand-written CUDA kernels reached through the C ABI of
 libkm_b200.so (include/km_b200.h).  There is no CPU path.
 """
-from . import ops  # noqa: F401
+from . import evaluation, loss_ops, ops  # noqa: F401
 from .augmentation import (AffineDeformation3d, affine_augment, random_affine_augment,  # noqa: F401
                            random_affine_augment_pair)
 from .keypoint_aligners import (TPS, AffineKeypointAligner, RigidKeypointAligner,  # noqa: F401

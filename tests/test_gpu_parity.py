@@ -10,6 +10,8 @@ Tolerances (also listed in DESIGN.md):
   * backbone (bf16 operands, fp32 accumulation): keypoints within 1e-2 normalised units of the fp32
     oracle = the reference's own fp32 <-> autocast drift budget (hard part 3).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -826,6 +828,43 @@ def test_example_pair_config1_vs_reference(golden):
         assert_close(kb.loss_ops.dice_from_sums(hard).cpu(), g[f"{t}_harddice"], rtol=5e-3, atol=5e-4)
         assert abs(float(kb.loss_ops.jdstd(grid.permute(0, 4, 1, 2, 3))) - float(g[f"{t}_jdstd"])) < 1e-5
         assert int(kb.loss_ops.jdlessthan0(grid.permute(0, 4, 1, 2, 3))) == int(g[f"{t}_jdneg"])
+
+
+def test_evaluation_metrics_and_layout_on_example_pair(golden, tmp_path):
+    """evaluation.pair_metrics (scripts/pairwise_register_eval.py:303-345) on the reference's own grid of the
+    example pair: every metric against the reference's value; then the file layout with device tensors and
+    the groupwise img_a / seg_a files feeding the pairwise group metrics."""
+    from keymorph_b200 import evaluation as E
+    g = golden("example_pair64")
+    C = int(g["num_classes"])
+    img_f, img_m = cu(g["img_f_u8"].float() / 255), cu(g["img_m_u8"].float() / 255)
+    oh = lambda lab: torch.nn.functional.one_hot(lab[:, 0].long(), C).permute(0, 4, 1, 2, 3).float()  # noqa: E731
+    seg_f, seg_m = cu(oh(g["lab_f"])), cu(oh(g["lab_m"]))
+    pf, pm = cu(g["affine_points_f"]), cu(g["affine_points_m"])
+    grid = kb.AffineKeypointAligner(pm, pf).get_flow_field(img_f.shape)
+    img_a, seg_a = kb.align_img(grid, img_m), kb.align_img(grid, seg_m)
+    names = ["mse", "softdice", "harddice", "harddiceroi", "hausd", "jdstd", "jdlessthan0"]
+    met = E.pair_metrics(names, img_f, img_a, seg_f, seg_a, grid)
+    assert abs(met["mse"] - float(g["affine_mse"])) < 2e-3 * float(g["affine_mse"]) + 1e-6
+    assert abs(met["softdiceloss"] - float(g["affine_softdice"])) < 2e-3
+    # the script's hard Dice ignores the background channel; the fixture holds the all-channel value
+    hd_all = 1 - kb.DiceLoss(hard=True)(seg_a, seg_f).item()
+    assert abs((1 - hd_all) - float(g["affine_harddice"])) < 5e-3
+    assert len(met["harddiceroi"]) == C - 1 and abs(np.mean(met["harddiceroi"]) - met["harddice"]) < 1e-6
+    assert abs(met["jdstd"] - float(g["affine_jdstd"])) < 1e-5 and met["jdlessthan0"] == float(g["affine_jdneg"])
+    assert abs(met["hausd"] - O.hausdorff_distance(seg_a.cpu(), seg_f.cpu())) < 1e-9
+    w = E.save_pair_outputs(tmp_path, 0, "T1", "T1", "rot0", "affine", met, img_f, img_m, img_a, grid=grid,
+                            seg_f=seg_f, seg_m=seg_m, seg_a=seg_a, points_f=pf, points_m=pm, points_a=pf)
+    assert len(w) == 11
+    lab = np.load(tmp_path / "seg_a_0-T1-T1-rot0-affine.npy")
+    assert lab.dtype == np.int64 and np.array_equal(lab, seg_a.cpu().numpy().argmax(1))
+    ip, sp = E.save_group_aligned(tmp_path / "img", "affine", [grid, grid], [img_m, img_f], tmp_path / "seg",
+                                  [seg_m, seg_f])
+    assert [os.path.basename(p) for p in ip] == ["img_a_affine_000.npy", "img_a_affine_001.npy"]
+    gm = kb.loss_ops.MultipleAvgSegPairwiseMetric()(sp, ["harddice", "softdice"])
+    assert_close(gm["softdice"].cpu(), kb.DiceLoss()(seg_a, kb.align_img(grid, seg_f)).cpu(), rtol=1e-5, atol=1e-6)
+    assert_close(kb.loss_ops.MSEPairwiseLoss()(ip).cpu(), kb.MSELoss()(img_a, kb.align_img(grid, img_f)).cpu(),
+                 rtol=1e-5, atol=1e-7)
 
 
 def test_prefetch_to_device_ring_keeps_items_intact():

@@ -1,6 +1,8 @@
 """The CPU oracle (oracle/keymorph_oracle.py) against (a) the reference's own known-answer tests
 (test/test.py, restated here) and (b) golden vectors produced by the reference itself
 (oracle/gen_golden.py).  No GPU involved."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -178,6 +180,38 @@ def test_golden_group_metrics(golden):
     assert abs(O.avg_pairwise(hard.numpy(), O.fast_dice) - float(g["multi_dice"])) < 1e-9
     jd = np.mean([O.jdstd(g["grids"][i:i + 1].permute(0, 4, 1, 2, 3)) for i in range(3)])
     assert abs(jd - float(g["avg_jdstd"])) < 1e-7
+
+
+def test_eval_output_layout(tmp_path):
+    """File names, dtypes and write-once behaviour of scripts/pairwise_register_eval.py:368-458 (host side)."""
+    import json
+    from keymorph_b200 import evaluation as E
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(1, 1, 4, 5, 6, generator=g)
+    seg = torch.rand(1, 3, 4, 5, 6, generator=g)
+    grid = torch.rand(1, 4, 5, 6, 3, generator=g)
+    pts = torch.rand(1, 7, 3, generator=g)
+    metrics = {"mse": 0.5, "harddiceroi": [0.1, 0.2]}
+    w = E.save_pair_outputs(tmp_path, 3, "T1", "T2", "rot0", "affine", metrics, img, img * 2, img * 3, grid=grid,
+                            seg_f=seg, seg_m=seg, seg_a=seg, points_f=pts, points_m=pts, points_a=pts,
+                            points_weights=pts[..., 0])
+    names = sorted(os.path.basename(p) for p in w)
+    assert names == sorted([
+        "metrics-rot0-affine.json", "img_f_3-T1.npy", "img_m_3-T2-rot0.npy", "img_a_3-T1-T2-rot0-affine.npy",
+        "grid_3-T1-T2-rot0-affine.npy", "seg_f_3-T1.npy", "seg_m_3-T2-rot0.npy", "seg_a_3-T1-T2-rot0-affine.npy",
+        "points_f_3-T1.npy", "points_m_3-T2-rot0.npy", "points_a_3-T1-T2-rot0-affine.npy",
+        "points_weights_3-T1-T2-rot0-affine.npy"])
+    assert json.load(open(tmp_path / "metrics-rot0-affine.json")) == metrics
+    assert np.load(tmp_path / "img_a_3-T1-T2-rot0-affine.npy").shape == (1, 4, 5, 6)
+    lab = np.load(tmp_path / "seg_a_3-T1-T2-rot0-affine.npy")
+    assert lab.shape == (1, 4, 5, 6) and lab.dtype == np.int64
+    assert np.array_equal(lab, seg.numpy().argmax(1))
+    assert np.load(tmp_path / "grid_3-T1-T2-rot0-affine.npy").shape == (4, 5, 6, 3)
+    assert np.load(tmp_path / "points_weights_3-T1-T2-rot0-affine.npy").shape == (7,)
+    # a second alignment type of the same pair re-uses the fixed / moving files
+    w2 = E.save_pair_outputs(tmp_path, 3, "T1", "T2", "rot0", "tps_0", metrics, img * 9, img, img, grid=None)
+    assert sorted(os.path.basename(p) for p in w2) == ["img_a_3-T1-T2-rot0-tps_0.npy", "metrics-rot0-tps_0.json"]
+    assert np.array_equal(np.load(tmp_path / "img_f_3-T1.npy"), img[0].numpy())
 
 
 def _seeded(cls_name, **kw):
