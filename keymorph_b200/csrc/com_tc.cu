@@ -392,12 +392,10 @@ extern "C" int km_conv1x1_com(const void* x, const void* wp, const float* bias, 
     }
   }
   ComKernel kernel = kc == 64 ? com_tc_kernel<64> : (kc == 32 ? com_tc_kernel<32> : com_tc_kernel<16>);
-  static bool attr_set[3] = {false, false, false};
+  static unsigned long long attr_set[3] = {0, 0, 0};
   const int ki = kc == 64 ? 2 : (kc == 32 ? 1 : 0);
-  if (!attr_set[ki]) {
+  if (km_first_use_on_device(&attr_set[ki]))
     KM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set[ki] = true;
-  }
   const int nsm = km_sm_count();
   const int grid = g.total_tiles < nsm ? g.total_tiles : nsm;
   // a CTA only writes the (image, channel) slots of the images it worked on

@@ -910,12 +910,10 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   }
 
   ConvKernel kernel = pick_kernel(kc, mode);
-  static bool attr_set[3][3] = {{false, false, false}, {false, false, false}, {false, false, false}};
+  static unsigned long long attr_set[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   const int ki = kc == 64 ? 2 : (kc == 32 ? 1 : 0);
-  if (!attr_set[mode][ki]) {
+  if (km_first_use_on_device(&attr_set[mode][ki]))
     KM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set[mode][ki] = true;
-  }
   const int nsm = sm_count();
   const int grid = g.total_tiles < nsm ? g.total_tiles : nsm;
   // partial slots of CTAs that are not launched must still be defined

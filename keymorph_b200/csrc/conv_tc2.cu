@@ -542,11 +542,9 @@ int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out,
     }
   }
   PairKernel kernel = kc == 64 ? conv_tc2_kernel<64> : conv_tc2_kernel<32>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[kc == 64]) {
+  static unsigned long long attr_set[2] = {0, 0};
+  if (km_first_use_on_device(&attr_set[kc == 64]))
     KM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set[kc == 64] = true;
-  }
   const int nsm = km_sm_count();
   int grid = nsm & ~1;
   const int pairs_needed = (g.total_tiles + 1) / 2;

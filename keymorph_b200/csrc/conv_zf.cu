@@ -498,8 +498,11 @@ int launch_zf(const void* x, const void* wz, const float* bias_tab, void* out, v
       return KM_ECUDA;
     }
   }
-  KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  static unsigned long long attr_set = 0;
+  if (km_first_use_on_device(&attr_set)) {
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  }
   const int nsm = km_sm_count();
   int grid = g.units < nsm ? g.units : nsm;
   if (per_sample) {

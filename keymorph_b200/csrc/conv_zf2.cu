@@ -554,11 +554,9 @@ int launch_zf2(const void* x, const void* x1, int Cin0, const void* wz, const fl
       return KM_ECUDA;
     }
   }
-  static bool attr_set = false;   // one flag per instantiation
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;   // one mask per instantiation
+  if (km_first_use_on_device(&attr_set))
     KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel<COUT, KC, MT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
-  }
   const int nsm = km_sm_count();
   const int upi = g.punits / N;
   int grid = nsm & ~1;

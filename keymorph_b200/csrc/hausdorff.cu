@@ -164,8 +164,11 @@ extern "C" int km_hausdorff(const float* a, const float* b, long long stride_a, 
   const size_t tile_bytes = (size_t)Lmax * 32 * sizeof(float);
   KM_CHECK_ARG(tile_bytes <= 200 * 1024, "km_hausdorff: D and H must be <= 1600 (got %d, %d)", D, H);
   KM_CHECK_ARG((size_t)W * 8 <= 200 * 1024, "km_hausdorff: W must be <= 25600 (got %d)", W);
-  KM_CUDA_OK(cudaFuncSetAttribute(edt_line_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  KM_CUDA_OK(cudaFuncSetAttribute(edt_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  static unsigned long long attr_set = 0;
+  if (km_first_use_on_device(&attr_set)) {
+    KM_CUDA_OK(cudaFuncSetAttribute(edt_line_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    KM_CUDA_OK(cudaFuncSetAttribute(edt_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
   cudaStream_t st = km_cs(stream);
   const size_t M = (size_t)D * H * W;
   Ws w;

@@ -44,6 +44,17 @@ void km_set_error(const char* fmt, ...);
 int km_fold_gn(const float* w, const float* scale, const float* shift, void* packed, float* bias, int N, int Cout,
                int Cin, int layout, km_stream_t stream);
 
+// cudaFuncSetAttribute (opt-in shared memory) is per device: one bit per device ordinal in a per-kernel mask,
+// so that a process driving several GPUs sets it on each of them once
+static inline bool km_first_use_on_device(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
 static inline cudaStream_t km_cs(km_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Number of partial-sum slots written by the grid-stride reduction kernels (one per block).
