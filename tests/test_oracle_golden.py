@@ -182,6 +182,26 @@ def test_golden_group_metrics(golden):
     assert abs(jd - float(g["avg_jdstd"])) < 1e-7
 
 
+@pytest.mark.parametrize("shape,sampling", [((10, 12, 14), (1.25, 1.25, 10.0)), ((7, 20, 9), (1.0, 2.0, 0.5)),
+                                            ((16, 16, 16), (1.0, 1.0, 1.0))])
+def test_oracle_hausdorff_vs_scipy_and_properties(shape, sampling):
+    """The scipy-free restatement against the reference's own recipe on its dependency (binary_erosion +
+    distance_transform_edt, keymorph/loss_ops.py:121-141), plus symmetry and d(A, A) = 0."""
+    gen = torch.Generator().manual_seed(sum(shape))
+    a = (torch.rand(shape, generator=gen) > 0.6).numpy()
+    b = (torch.rand(shape, generator=gen) > 0.7).numpy()
+    a[0, 0, 0] = b[-1, -1, -1] = True                      # never empty; corners exercise the border rule
+    conn = ndimage.generate_binary_structure(3, 1)
+    sa, sb = a & ~ndimage.binary_erosion(a, conn), b & ~ndimage.binary_erosion(b, conn)
+    assert np.array_equal(O.surface_mask(a), sa) and np.array_equal(O.surface_mask(b), sb)
+    dta, dtb = ndimage.distance_transform_edt(~sa, sampling), ndimage.distance_transform_edt(~sb, sampling)
+    ref = max(dta[sb].max(), dtb[sa].max())
+    got = O.hausdorff_distance(a[None, None], b[None, None], sampling)
+    assert abs(got - ref) < 1e-9
+    assert abs(O.hausdorff_distance(b[None, None], a[None, None], sampling) - got) < 1e-12
+    assert O.hausdorff_distance(a[None, None], a[None, None], sampling) == 0.0
+
+
 def test_eval_output_layout(tmp_path):
     """File names, dtypes and write-once behaviour of scripts/pairwise_register_eval.py:368-458 (host side)."""
     import json
