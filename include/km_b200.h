@@ -69,6 +69,11 @@ int km_sm_count(void);
  * for the 64 -> 64 shapes (half the weight traffic, but only one TMEM set: measured slower) instead of
  * one (A/B testing). */
 #define KM_OPT_ZF2_TWO_BRICKS 10
+/* key KM_OPT_TPS_PACKED (default 1): the dense TPS field issues its per-term FP32 arithmetic as packed
+ * f32x2 instructions on voxel pairs (A/B switch; results are bit-identical to the scalar path). */
+#define KM_OPT_TPS_PACKED 11
+/* key KM_OPT_TPS_VPT (default 0 = chosen from W): voxels per thread of the dense TPS field (2, 4 or 8). */
+#define KM_OPT_TPS_VPT 12
 int km_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------ *

@@ -95,6 +95,8 @@ KM_OPT_TPS_SINGLE_CTA = 7
 KM_OPT_CONV_INTERLEAVE_BRICKS = 8
 KM_OPT_CONV_TWO_ISSUERS = 9
 KM_OPT_ZF2_TWO_BRICKS = 10
+KM_OPT_TPS_PACKED = 11
+KM_OPT_TPS_VPT = 12
 
 _lib = None
 

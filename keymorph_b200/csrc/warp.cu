@@ -24,6 +24,9 @@ void km_conv_set_interleave(int v);
 void km_conv_set_two_issuers(int v);
 void km_zf2_set_two_bricks(int v);
 void km_tps_set_single_cta(int v);
+void km_tps_set_packed(int v);
+void km_tps_set_vpt(int v);
+int km_tps_fast_enabled() { return g_tps_fast; }
 namespace {
 
 // ---- ATen grid_sampler_3d source-index arithmetic (align_corners=False, padding "border"),
@@ -192,65 +195,6 @@ flow_affine_kernel(const float* __restrict__ mat, float* __restrict__ grid, int 
     gn[v * 3 + 0] = gx;
     gn[v * 3 + 1] = gy;
     gn[v * 3 + 2] = gz;
-  }
-}
-
-// Dense TPS field.  MUFU / FP32-issue bound (K radial-basis terms per voxel, 2 MUFU + ~13 FP32
-// instructions each), not memory bound: a thread evaluates FOUR voxels per control point so that
-// the two broadcast shared-memory loads and the loop overhead are amortised over four terms and
-// the four independent FMA chains hide the MUFU latency.  A warp owns 128 consecutive voxels
-// (lane i: voxels i, i+32, i+64, i+96), so the 12-byte stores of a warp stay contiguous.
-template <bool FAST>
-__global__ void __launch_bounds__(256)
-flow_tps_kernel(const float* __restrict__ ctrl, const float* __restrict__ theta,
-                float* __restrict__ grid, int K, int D, int H, int W) {
-  extern __shared__ float4 s4[];
-  float4* c4 = s4;
-  float4* w4 = s4 + K;
-  float* aff = reinterpret_cast<float*>(s4 + 2 * K);
-  const int n = blockIdx.y;
-  load_tps_smem(ctrl + (size_t)n * K * 3, theta + (size_t)n * (K + 4) * 3, K, c4, w4, aff);
-  const long long nvox = (long long)D * H * W;
-  float* gn = grid + (size_t)n * nvox * 3;
-  const int lane = threadIdx.x & 31;
-  const long long nchunks = (nvox + 127) / 128;
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long chunk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks;
-       chunk += warps) {
-    float pz[4], py[4], px[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      long long v = chunk * 128 + lane + 32 * k;
-      if (v >= nvox) v = nvox - 1;
-      const int x = (int)(v % W), y = (int)((v / W) % H), z = (int)(v / ((long long)W * H));
-      pz[k] = km_linspace(-1.f, 1.f, D, z);
-      py[k] = km_linspace(-1.f, 1.f, H, y);
-      px[k] = km_linspace(-1.f, 1.f, W, x);
-    }
-    float az[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-    for (int t = 0; t < K; ++t) {
-      const float4 c = c4[t];
-      const float4 w = w4[t];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float dz = pz[k] - c.x, dy = py[k] - c.y, dx = px[k] - c.z;
-        const float u = tps_u<FAST>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-        az[k] = fmaf(u, w.x, az[k]);
-        ay[k] = fmaf(u, w.y, ay[k]);
-        ax[k] = fmaf(u, w.z, ax[k]);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long v = chunk * 128 + lane + 32 * k;
-      if (v < nvox) {
-        // z = [1, p] . affine  (keymorph/keypoint_aligners.py:427-433), out = z + b
-        gn[v * 3 + 0] = (aff[2] + aff[5] * pz[k] + aff[8] * py[k] + aff[11] * px[k]) + ax[k];
-        gn[v * 3 + 1] = (aff[1] + aff[4] * pz[k] + aff[7] * py[k] + aff[10] * px[k]) + ay[k];
-        gn[v * 3 + 2] = (aff[0] + aff[3] * pz[k] + aff[6] * py[k] + aff[9] * px[k]) + az[k];
-      }
-    }
   }
 }
 
@@ -881,6 +825,14 @@ extern "C" int km_set_option(int key, int value) {
     km_tps_set_single_cta(value);
     return KM_OK;
   }
+  if (key == KM_OPT_TPS_PACKED) {
+    km_tps_set_packed(value);
+    return KM_OK;
+  }
+  if (key == KM_OPT_TPS_VPT) {
+    km_tps_set_vpt(value);
+    return KM_OK;
+  }
   km_set_error("km_set_option: unknown key %d", key);
   return KM_EINVAL;
 }
@@ -905,21 +857,6 @@ extern "C" int km_flow_field_affine(const float* mat, float* grid, int N, int D,
   const dim3 g(blocks_for((long long)D * H * W, 256, 148 * 8), N);
   flow_affine_kernel<<<g, 256, 0, km_cs(stream)>>>(mat, grid, D, H, W);
   KM_LAUNCH_OK("flow_affine_kernel");
-  return KM_OK;
-}
-
-extern "C" int km_flow_field_tps(const float* ctrl, const float* theta, float* grid, int N, int K,
-                                 int D, int H, int W, km_stream_t stream) {
-  KM_CHECK_ARG(ctrl && theta && grid && N > 0 && K > 0 && D > 0 && H > 0 && W > 0,
-               "km_flow_field_tps: bad arguments");
-  const size_t smem = (size_t)(2 * K + 3) * sizeof(float4);
-  KM_CHECK_ARG(smem <= 48 * 1024, "km_flow_field_tps: K=%d too large", K);
-  const dim3 g(blocks_for((long long)D * H * W, 256, 148 * 8), N);
-  if (g_tps_fast)
-    flow_tps_kernel<true><<<g, 256, smem, km_cs(stream)>>>(ctrl, theta, grid, K, D, H, W);
-  else
-    flow_tps_kernel<false><<<g, 256, smem, km_cs(stream)>>>(ctrl, theta, grid, K, D, H, W);
-  KM_LAUNCH_OK("flow_tps_kernel");
   return KM_OK;
 }
 

@@ -97,7 +97,7 @@ class TPS(nn.Module):
 
     def __init__(self, points_m, points_f, lmbda, w=None, dim=3, num_subgrids=4,
                  use_checkpoint=False, align_in_real_world_coords=False, aff_m=None, aff_f=None,
-                 shape_m=None, shape_f=None, fit_forward=False):
+                 shape_m=None, shape_f=None, fit_forward=False, fit_inverse=True):
         super().__init__()
         if dim != 3:
             raise NotImplementedError("keymorph_b200 implements the 3-D path only")
@@ -115,7 +115,13 @@ class TPS(nn.Module):
             self.points_m = convert_points_norm2real(self.points_m, aff_m, shape_m)
             self.points_f = convert_points_norm2real(self.points_f, aff_f, shape_f)
         # note the flipped order: theta maps FIXED -> MOVING (keymorph/keypoint_aligners.py:268-274)
-        if fit_forward:
+        self.inverse_theta = self.theta = None
+        if not fit_inverse:
+            # groupwise iterations only move points forward (keymorph/model.py:331-394): the inverse fit the
+            # reference's constructor always performs is deferred until a flow field is asked for
+            if fit_forward:
+                self.theta = self.fit(self.points_m, self.points_f, lmbda, weights=w)
+        elif fit_forward:
             # both directions (the reference fits the forward one lazily in
             # get_forward_transformed_points, :451-465) as ONE batched device solve
             nb = self.points_f.shape[0]
@@ -126,7 +132,11 @@ class TPS(nn.Module):
             self.inverse_theta, self.theta = both[:nb], both[nb:]
         else:
             self.inverse_theta = self.fit(self.points_f, self.points_m, lmbda, weights=w)
-            self.theta = None
+
+    def _inverse(self):
+        if self.inverse_theta is None:
+            self.inverse_theta = self.fit(self.points_f, self.points_m, self.lmbda, weights=self.weights)
+        return self.inverse_theta
 
     def fit(self, c_src, c_dst, lmbda, weights=None):
         """keymorph/keypoint_aligners.py:341-363: theta (bs, T+4, 3)."""
@@ -152,12 +162,12 @@ class TPS(nn.Module):
         """keymorph/keypoint_aligners.py:365-397: (N,D,H,W,3) in (x,y,z) order."""
         shape = tuple(int(s) for s in tuple(grid_shape)[2:])
         if not self.align_in_real_world_coords:
-            return ops.flow_field_tps(self.points_f, self.inverse_theta, shape)
+            return ops.flow_field_tps(self.points_f, self._inverse(), shape)
         # real-world variant (:441-448): fixed voxel -> real -> TPS -> moving voxel -> normalised
         dev = self.points_f.device
         pre = torch.bmm(self.aff_f.float().to(dev), norm2voxel_matrix(self.shape_f, dev))
         real = ops.flow_field_affine(pre[:, :3, :], shape).flip(-1).reshape(1, -1, 3)
-        moved = ops.points_transform_tps(self.points_f, self.inverse_theta, real)
+        moved = ops.points_transform_tps(self.points_f, self._inverse(), real)
         post = torch.bmm(voxel2norm_matrix(self.shape_m, dev),
                          torch.inverse(self.aff_m.float().to(dev)))
         out = ops.points_transform_affine(post[:, :3, :], moved)
@@ -167,7 +177,7 @@ class TPS(nn.Module):
         """keymorph/keypoint_aligners.py:435-449."""
         if self.align_in_real_world_coords:
             points = convert_points_norm2real(points, self.aff_f, self.shape_f)
-        points = self.transform_points(self.inverse_theta, self.points_f, points)
+        points = self.transform_points(self._inverse(), self.points_f, points)
         if self.align_in_real_world_coords:
             points = convert_points_real2norm(points, self.aff_m, self.shape_m)
         return points

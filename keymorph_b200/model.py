@@ -88,7 +88,8 @@ class KeyMorph(nn.Module):
         return s in ["affine", "rigid"] or bool(re.match(r"^tps_.*$", s))
 
     def _make_aligner(self, align_type, points_m, points_f, weights, tps_lmbda, aff_f=None,
-                      aff_m=None, shape_f=None, shape_m=None, real_world=False, fit_forward=False):
+                      aff_m=None, shape_f=None, shape_m=None, real_world=False, fit_forward=False,
+                      fit_inverse=True):
         common = dict(points_m=points_m, points_f=points_f, w=weights, aff_f=aff_f, aff_m=aff_m,
                       shape_f=shape_f, shape_m=shape_m, dim=self.dim,
                       align_in_real_world_coords=real_world)
@@ -96,7 +97,8 @@ class KeyMorph(nn.Module):
             return RigidKeypointAligner(**common)
         if align_type == "affine":
             return AffineKeypointAligner(**common)
-        return TPS(lmbda=tps_lmbda, use_checkpoint=self.use_checkpoint, fit_forward=fit_forward, **common)
+        return TPS(lmbda=tps_lmbda, use_checkpoint=self.use_checkpoint, fit_forward=fit_forward,
+                   fit_inverse=fit_inverse, **common)
 
     # ------------------------------------------------------------------ pairwise
     @torch.no_grad()
@@ -222,7 +224,8 @@ class KeyMorph(nn.Module):
         G = group_points.shape[0]
         fixed = mean_points.expand(G, -1, -1).contiguous()
         lam = None if lmbda is None else lmbda.reshape(-1)[:1].repeat(G)
-        aligner = self._make_aligner(align_type, group_points, fixed, None, lam)
+        aligner = self._make_aligner(align_type, group_points, fixed, None, lam, fit_forward=True,
+                                     fit_inverse=False)
         return aligner.get_forward_transformed_points(group_points)
 
     @torch.no_grad()
@@ -268,10 +271,11 @@ class KeyMorph(nn.Module):
                 align_type, tps_lmbda = align_type_str, None
             curr_points = group_points.clone()
             mean_points = None
-            for j in range(num_iters):
-                curr_points, mean_points = self._groupwise_step(curr_points, align_type, tps_lmbda)
-                if log_to_console:
-                    print(f"-> Iteration {j+1}/{num_iters}")
+            with deferred_singular_checks():     # one read of the fits' status flags per transform
+                for j in range(num_iters):
+                    curr_points, mean_points = self._groupwise_step(curr_points, align_type, tps_lmbda)
+                    if log_to_console:
+                        print(f"-> Iteration {j+1}/{num_iters}")
             res = {"time": time.time() - start_time, "grouppoints_m": group_points,
                    "grouppoints_a": curr_points}
             # grids: ORIGINAL points against the mean taken at the start of the last iteration

@@ -1,6 +1,8 @@
 """AffineTransform of keymorph/transformations.py:7-114 on the km_* kernels."""
 from __future__ import annotations
 
+import threading
+
 import torch
 import torch.nn as nn
 
@@ -12,7 +14,9 @@ from . import ops
 CHECK_SINGULAR = True
 
 
-_DEFERRED = None     # list of (status tensor, name) while a caller batches the checks
+# per-thread list of (status tensor, name) while a caller batches the checks: two threads driving
+# KeyMorph.forward concurrently (multi-GPU driver threads, a server) must not see each other's flags
+_TLS = threading.local()
 
 
 def raise_if_singular(status, what):
@@ -21,8 +25,9 @@ def raise_if_singular(status, what):
     (`deferred_singular_checks`) and reads them once, after everything has been enqueued."""
     if not CHECK_SINGULAR:
         return
-    if _DEFERRED is not None:
-        _DEFERRED.append((status, what))
+    pending = getattr(_TLS, "pending", None)
+    if pending is not None:
+        pending.append((status, what))
         return
     if bool(status.any().item()):
         raise torch.linalg.LinAlgError(f"{what}: the matrix is singular (status={status.tolist()})")
@@ -34,14 +39,12 @@ class deferred_singular_checks:
     are simply not returned)."""
 
     def __enter__(self):
-        global _DEFERRED
-        self._outer = _DEFERRED
-        _DEFERRED = []
+        self._outer = getattr(_TLS, "pending", None)
+        _TLS.pending = []
         return self
 
     def __exit__(self, exc_type, exc, tb):
-        global _DEFERRED
-        pending, _DEFERRED = _DEFERRED, self._outer
+        pending, _TLS.pending = _TLS.pending, self._outer
         if exc_type is None and pending:
             flags = torch.stack([st.reshape(-1).any() for st, _ in pending]).cpu()
             for bad, (st, what) in zip(flags.tolist(), pending):
