@@ -43,10 +43,11 @@ UNIT = "registrations/s"
 CONFIGS = {
     "affine": {"K": 256, "transform": "affine",
                "workload": "synthetic 256^3 pair, affine, 256 keypoints, TruncatedUNet3D(levels 4, truncated 1), "
-                           "bf16 operands"},
+                           "fp16 operands / fp32 accumulate (tcgen05 kind::f16; the BASELINE-named bf16 operand "
+                           "type is measured beside it in bf16_operands)"},
     "tps": {"K": 512, "transform": "tps_0",
             "workload": "synthetic 256^3 pair, TPS lambda=0, 512 keypoints, TruncatedUNet3D(levels 4, truncated 1), "
-                        "bf16 operands"},
+                        "fp16 operands / fp32 accumulate"},
 }
 GROUP_SUBJECTS, GROUP_ITERS = 32, 5
 # dram__bytes_read.sum + dram__bytes_write.sum per step, parsed from the committed ncu launch list of this
@@ -182,7 +183,7 @@ def reference_step_fn(name, device="cpu", amp=False):
         from keymorph.keypoint_aligners import TPS
         from keymorph.loss_ops import MSELoss
         from keymorph.utils import align_img
-        model = refshim.build_reference_model(cfg["K"], use_amp=amp).to(device)
+        model = refshim.build_reference_model(cfg["K"], device=device, use_amp=amp)
         mse_fn = MSELoss()
 
         def step(img_f, img_m):
@@ -198,6 +199,7 @@ def reference_step_fn(name, device="cpu", amp=False):
                     grid = model(img_f, img_m, transform_type=cfg["transform"], return_aligned_points=True)[
                         cfg["transform"]]["grid"]
                 return mse_fn(align_img(grid, img_m), img_f)
+        step.model = model
         return step, "reference"
     from oracle import keymorph_oracle as O
     sd = {k: v.clone() for k, v in seeded_backbone(cfg["K"]).state_dict().items()}
@@ -316,7 +318,7 @@ def measure_pairwise(model, name, img_f, img_m, steps, warmup, ctx):
     ctx["sync"]()
     _lib.TRACE = None
     return {"ms_step": ctx["max"](e0.elapsed_time(e1) / steps), "tr": tr, "launches": _lib.launch_count - l0,
-            "mse": float(r["mse"].item())}
+            "mse": float(r["mse"].item()), "points": torch.cat([r["points_f"], r["points_m"]]).cpu()}
 
 
 def measure_e2e(model, name, host_f, host_m, steps, ctx, with_grid=False):
@@ -423,7 +425,7 @@ def conv_rooflines(tr, name, steps, ms_step, peaks, timed_s):
     return main, other
 
 
-def gpu_baseline(dev, img_f, img_m, steps=3):
+def gpu_baseline(dev, img_f, img_m, steps=3, engine_points=None):
     """The reference ON THIS GPU through stock torch CUDA ops: fp32 and use_amp=True."""
     import torch
     out = {"impl": "unmodified reference (oracle/_ref) on cuda: cuDNN conv3d, ATen grid_sampler_3d, host LAPACK "
@@ -450,6 +452,19 @@ def gpu_baseline(dev, img_f, img_m, steps=3):
                     ms = e0.elapsed_time(e1) / steps
                     out[key] = {"value": 1e3 / ms, "ms_per_step": ms, "steps": steps, "mse": float(mse),
                                 "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+                    if engine_points and name in engine_points and hasattr(step, "model"):
+                        # accuracy of the engine's keypoints against THIS run of the reference (fp32: the
+                        # parity target; fp16 autocast: the reference's own reduced-precision mode)
+                        with torch.no_grad(), torch.amp.autocast(device_type="cuda", enabled=amp, dtype=torch.float16):
+                            rp = torch.cat([step.model.get_keypoints(img_f), step.model.get_keypoints(img_m)]).float().cpu()
+                        if not amp:
+                            out[f"{name}_reference_fp32_points"] = rp
+                        for tag, pts in engine_points[name].items():
+                            d = (pts - rp).abs()
+                            out[key][f"keypoint_err_{tag}_vs_this_run"] = {"max": float(d.max()), "mean": float(d.mean())}
+                        if amp and f"{name}_reference_fp32_points" in out:
+                            d = (rp - out[f"{name}_reference_fp32_points"]).abs()
+                            out[key]["own_drift_vs_reference_fp32"] = {"max": float(d.max()), "mean": float(d.mean())}
                 except Exception as e:  # noqa: BLE001
                     out[key] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
                 del step
@@ -457,6 +472,8 @@ def gpu_baseline(dev, img_f, img_m, steps=3):
                 torch.cuda.reset_peak_memory_stats(dev)
     except Exception as e:  # noqa: BLE001
         out["unavailable"] = f"{type(e).__name__}: {e}"[:300]
+    for k in [k for k in out if k.endswith("_reference_fp32_points")]:
+        del out[k]
     return out
 
 
@@ -582,18 +599,32 @@ def run_engine(args):
                      "bytes_per_launch": warp_bytes, "kernel_ms_per_step": warp_ms}
     e2e = measure_e2e(models["affine"], "affine", img_f_host, img_m_host, args.steps, ctx, with_grid=args.e2e_grid)
     clk = clocks.stop()
+    dtype_name = "fp16" if kb.act_dtype() == torch.float16 else "bf16"
+    engine_points = {"affine": {dtype_name: res["points"]}}
+    # the same workload with the other operand type (BASELINE configs[1] names bf16)
+    other = "bf16" if dtype_name == "fp16" else "fp16"
+    kb.set_operand_dtype(other)
+    try:
+        rb = measure_pairwise(models["affine"], "affine", img_f, img_m, args.steps, args.warmup, ctx)
+        other_block = {"value": world * 1e3 / rb["ms_step"], "unit": UNIT, "ms_per_step": rb["ms_step"], "mse": rb["mse"],
+                       "note": f"identical kernels and schedule with {other} activations / weights"}
+        engine_points["affine"][other] = rb["points"]
+    finally:
+        kb.set_operand_dtype(dtype_name)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_dict(world),
+            "vs_baseline": None, "dtype": dtype_name, "data": "synthetic", "config": config_dict(world),
             "clocks": clk, "e2e": e2e, "gpu_launches": res["launches"], "roofline": roofline,
-            "roofline_warp": roofline_warp, "roofline_other": roofline_other, "mse": res["mse"]}
+            "roofline_warp": roofline_warp, "roofline_other": roofline_other, "mse": res["mse"],
+            f"{other}_operands": other_block}
 
     # ---- configs[2], the north-star target: TPS lambda = 0, 512 keypoints
     if "tps" in models:
         c2 = ClockSampler(local)
         c2.start()
         r3 = measure_pairwise(models["tps"], "tps", img_f, img_m, args.steps, args.warmup, ctx)
+        engine_points["tps"] = {dtype_name: r3["points"]}
         tr = r3["tr"]
         flow_ms, fit_ms = tr.ms("km_flow_field_tps", per=args.steps), tr.ms("km_tps_fit", per=args.steps)
         wl_ms = tr.ms("km_warp_loss", per=args.steps)
@@ -630,7 +661,7 @@ def run_engine(args):
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
         del models
         torch.cuda.empty_cache()
-        line["gpu_baseline"] = gpu_baseline(dev, img_f, img_m)
+        line["gpu_baseline"] = gpu_baseline(dev, img_f, img_m, engine_points=engine_points)
         gb = line["gpu_baseline"]
         for name, mine in (("affine", value), ("tps", line.get("tps_config3", {}).get("value"))):
             best = max([gb[k]["value"] for k in gb if k.startswith(name) and isinstance(gb[k], dict) and "value" in gb[k]],
@@ -638,15 +669,18 @@ def run_engine(args):
             if best and mine:
                 gb[f"{name}_speedup_over_best_torch_gpu"] = mine / best
     if rank == 0 and world == 1 and not args.no_cpu:
-        step, kind = reference_step_fn("affine")
-        torch.set_num_threads(os.cpu_count() or 1)
-        f_cpu, m_cpu = img_f_host.clone(), img_m_host.clone()
-        t0 = time.perf_counter()
-        cm = float(step(f_cpu, m_cpu))
-        sec = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
-                                "sample": "ONE complete registration of the same 256^3 pair (no warm-up, no slab), "
-                                          f"torch CPU fp32, {torch.get_num_threads()} threads", "mse": cm}
+        try:
+            step, kind = reference_step_fn("affine")
+            torch.set_num_threads(os.cpu_count() or 1)
+            f_cpu, m_cpu = img_f_host.clone(), img_m_host.clone()
+            t0 = time.perf_counter()
+            cm = float(step(f_cpu, m_cpu))
+            sec = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
+                                    "sample": "ONE complete registration of the same 256^3 pair (no warm-up, no slab), "
+                                              f"torch CPU fp32, {torch.get_num_threads()} threads", "mse": cm}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -55,8 +55,9 @@ int km_sm_count(void);
 /* key KM_OPT_CONV_HALO_AXIS (default 2): axis along which the three taps share one TMA box in
  * km_conv3d_tc: 2 = y (shared-memory atoms are x-runs, contiguous in global memory), 1 = x. */
 #define KM_OPT_CONV_HALO_AXIS 6
-/* key KM_OPT_TPS_SINGLE_CTA (default 0): solve the TPS system with the un-blocked one-CTA LU instead
- * of the blocked multi-CTA Gauss-Jordan elimination (A/B testing). */
+/* key KM_OPT_TPS_SINGLE_CTA (default 0): how km_tps_fit solves the (K+4)^2 system.  0 = ONE cooperative
+ * launch (assembly + blocked Gauss-Jordan with group barriers + final division); 1 = the un-blocked one-CTA
+ * LU; 2 = the same blocked elimination as ~100 dependent launches (A/B; bit-identical to 0). */
 #define KM_OPT_TPS_SINGLE_CTA 7
 /* key KM_OPT_CONV_INTERLEAVE_BRICKS (default 0): km_conv3d_tc issues the MMAs of the bricks that
  * share a weight slice round-robin (consecutive tcgen05.mma accumulate into different TMEM tiles)
@@ -74,7 +75,15 @@ int km_sm_count(void);
 #define KM_OPT_TPS_PACKED 11
 /* key KM_OPT_TPS_VPT (default 0 = chosen from W): voxels per thread of the dense TPS field (2, 4 or 8). */
 #define KM_OPT_TPS_VPT 12
+/* key KM_OPT_OPERAND_FP16 (default 1): element type of the 16-bit activation / weight tensors of the
+ * backbone ("bf16" in the names below means "16-bit operand"): 1 = IEEE fp16, the AMP dtype of the
+ * reference (keymorph/model.py:175-177; 11-bit significand), 0 = bf16 (exponent range of fp32, 8-bit
+ * significand).  tcgen05 kind::f16 runs both at the same rate.  Tensors written under one setting must be
+ * consumed under the same setting (packed weights included). */
+#define KM_OPT_OPERAND_FP16 13
 int km_set_option(int key, int value);
+/* 1 when the 16-bit tensors of the backbone are fp16, 0 when they are bf16 (KM_OPT_OPERAND_FP16) */
+int km_operand_is_fp16(void);
 
 /* ------------------------------------------------------------------------------------------ *
  * Warp: keymorph/utils.py:14-21  align_img -> F.grid_sample(mode, padding_mode="border",

@@ -14,6 +14,7 @@ from .layers import CenterOfMass3d, ConvBlock  # noqa: F401
 from .loss_ops import DiceLoss, MSELoss  # noqa: F401
 from .model import KeyMorph  # noqa: F401
 from .net import ConvNet, ConvNet3D  # noqa: F401
+from .ops import act_dtype, set_operand_dtype  # noqa: F401
 from .transformations import AffineTransform  # noqa: F401
 from .unet3d import TruncatedUNet3D, UNet3D  # noqa: F401
 from .utils import align_img, align_moving_img, one_hot, uniform_norm_grid  # noqa: F401

@@ -24,6 +24,7 @@ SIGNATURES = {
     "km_last_error": (C.c_char_p, []),
     "km_sm_count": (_i, []),
     "km_set_option": (_i, [_i, _i]),
+    "km_operand_is_fp16": (_i, []),
     "km_grid_sample3d": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "km_flow_field_affine": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "km_flow_field_tps": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
@@ -97,6 +98,7 @@ KM_OPT_CONV_TWO_ISSUERS = 9
 KM_OPT_ZF2_TWO_BRICKS = 10
 KM_OPT_TPS_PACKED = 11
 KM_OPT_TPS_VPT = 12
+KM_OPT_OPERAND_FP16 = 13
 
 _lib = None
 
@@ -125,7 +127,7 @@ def load() -> C.CDLL:
 
 # kernels launched by one call of each entry point (bench.py's "gpu_launches" claim)
 KERNELS_PER_CALL = {
-    "km_warp_loss": 2, "km_pair_stats": 2, "km_com3d": 2, "km_tps_fit": 2, "km_warp_labels_dice": 3, "km_jacobian_stats": 2, "km_hausdorff": 13, "km_conv3d_zfold_gn": 2, "km_conv3d_zfold_pair_gn": 2, "km_conv3d_zfold_pair_gn_cat": 2, "km_conv3d_tc_pair_gn": 2,
+    "km_warp_loss": 2, "km_pair_stats": 2, "km_com3d": 2, "km_tps_fit": 1, "km_warp_labels_dice": 3, "km_jacobian_stats": 2, "km_hausdorff": 13, "km_conv3d_zfold_gn": 2, "km_conv3d_zfold_pair_gn": 2, "km_conv3d_zfold_pair_gn_cat": 2, "km_conv3d_tc_pair_gn": 2,
 }
 launch_count = 0
 # optional tracer: callable(name, phase) with phase in {"pre", "post"}; bench.py installs one that

@@ -43,6 +43,7 @@ struct ComGeom {
   int stages;
   uint32_t stage_bytes;  // chunks * 128 * KC * 2
   uint32_t off_w, off_tab, off_bars;
+  uint32_t idesc;        // kind::f16 instruction descriptor (fp16 or bf16 operands)
 };
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -153,7 +154,7 @@ com_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const uint32_t w16 = (((base + g.off_w) & 0x3FFFFu) >> 4) | lo_flag;
     const uint32_t x16_base = ((base & 0x3FFFFu) >> 4) | lo_flag;
     const uint32_t tile16 = kTileBytes >> 4;
-    const uint32_t idesc = umma_idesc_bf16(128, kBrick);
+    const uint32_t idesc = g.idesc;
     int s = 0;
     uint32_t ph = 0, ucount = 0;
     mbar_wait(w_bar, 0u);
@@ -174,7 +175,7 @@ com_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             const uint32_t b16 = x16 + (uint32_t)ch * tile16;
 #pragma unroll
             for (int kk = 0; kk < kSteps; ++kk)
-              umma_bf16_pred(d_tmem, a16 + 2u * kk, b16 + 2u * kk, desc_hi, idesc,
+              umma_16_pred(d_tmem, a16 + 2u * kk, b16 + 2u * kk, desc_hi, idesc,
                              (ch | kk) ? 1u : 0u, issue);
           }
         }
@@ -323,6 +324,7 @@ extern "C" int km_conv1x1_com(const void* x, const void* wp, const float* bias, 
   ComGeom g;
   memset(&g, 0, sizeof(g));
   g.N = N; g.D = D; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
+  g.idesc = umma_idesc_16(128, kBrick, km_operand_fp16() != 0);
   const int kc = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
   g.chunks = Cin / kc;
   const int row_bytes = kc * 2;
@@ -370,7 +372,7 @@ extern "C" int km_conv1x1_com(const void* x, const void* wp, const float* bias, 
                              (cuuint64_t)D * H * W * Cin * 2};
     cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TD, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides,
+    CUresult r = encode(&tmX, KM_TMAP_16, 5, const_cast<void*>(x), dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -383,7 +385,7 @@ extern "C" int km_conv1x1_com(const void* x, const void* wp, const float* bias, 
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
     cuuint32_t box[3] = {(cuuint32_t)kc, 128, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wp), dims, strides,
+    CUresult r = encode(&tmW, KM_TMAP_16, 3, const_cast<void*>(wp), dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

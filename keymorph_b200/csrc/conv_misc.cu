@@ -10,24 +10,35 @@
 
 namespace {
 
-typedef __nv_bfloat16 bf16;
+typedef uint16_t act16;   // one 16-bit activation / weight element: fp16 or bf16 bits (template parameter F16)
 
+int g_operand_fp16 = 1;   // km_set_option(KM_OPT_OPERAND_FP16): fp16 (default) or bf16 operands
+
+template <bool F16>
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(p[i]);
+    const float2 t = km_unpack2<F16>(p[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
 }
+template <bool F16>
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 v;
-  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&v);
+  uint32_t* p = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) p[i] = km_pack2<F16>(f[2 * i], f[2 * i + 1]);
   return v;
 }
+
+// launch KERNEL<true> or KERNEL<false> according to the operand option
+#define KM_LAUNCH_16(KERNEL, GRID, BLOCK, SMEM, STREAM, ...)                    \
+  do {                                                                          \
+    if (g_operand_fp16) KERNEL<true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__); \
+    else KERNEL<false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);               \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------
 // sum / sumsq of an fp32 volume, grid (KM_RED_BLOCKS, N)
@@ -72,8 +83,9 @@ volume_stats_kernel(const float* __restrict__ x, float* __restrict__ stats, long
 
 // ------------------------------------------------------------------------------------------
 // generic per-channel stats of a bf16 NDHWC tensor, grid (KM_RED_BLOCKS, N)
+template <bool F16>
 __global__ void __launch_bounds__(KM_RED_THREADS)
-channel_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, long long nvox, int C,
+channel_stats_kernel(const act16* __restrict__ x, float* __restrict__ stats, long long nvox, int C,
                      int N) {
   extern __shared__ float sacc[];  // [C][2]
   const int n = blockIdx.y;
@@ -86,7 +98,7 @@ channel_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, long
        i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i % cg);
     float f[8];
-    unpack8(__ldg(src + i), f);
+    unpack8<F16>(__ldg(src + i), f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       atomicAdd(&sacc[(g * 8 + k) * 2 + 0], f[k]);
@@ -165,10 +177,11 @@ norm_finalize_kernel(const float* __restrict__ stats0, int nparts0, int C0, doub
 // 16-byte channel group of one x position and walks kNormRows rows -> one 32-bit division per
 // thread, no 64-bit index arithmetic, scale/shift loaded once.
 constexpr int kNormRows = 8;
+template <bool F16>
 __global__ void __launch_bounds__(256)
-norm_apply_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict__ src1, int C1,
+norm_apply_kernel(const act16* __restrict__ src0, int C0, const act16* __restrict__ src1, int C1,
                   int D1, int H1, int W1, const float* __restrict__ scale,
-                  const float* __restrict__ shift, bf16* __restrict__ out, int N, int D, int H,
+                  const float* __restrict__ shift, act16* __restrict__ out, int N, int D, int H,
                   int W, int relu) {
   const int C = C0 + C1;
   const int cg = C / 8, cg0 = C0 / 8;
@@ -206,21 +219,22 @@ norm_apply_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict_
     const int y = y_lo + r;
     if (y < y_hi) {
       float f[8];
-      unpack8(raw[r], f);
+      unpack8<F16>(raw[r], f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         f[k] = fmaf(a[k], f[k], b[k]);
         if (relu) f[k] = fmaxf(f[k], 0.f);
       }
-      reinterpret_cast<uint4*>(out + (((size_t)blockIdx.z * H + y) * W + x) * C)[g] = pack8(f);
+      reinterpret_cast<uint4*>(out + (((size_t)blockIdx.z * H + y) * W + x) * C)[g] = pack8<F16>(f);
     }
   }
 }
 
 // normalise + activation + MaxPool3d(2) in one pass (ConvNet blocks 2/4/6/8)
+template <bool F16>
 __global__ void __launch_bounds__(256)
-norm_apply_pool_kernel(const bf16* __restrict__ src, int C, const float* __restrict__ scale,
-                       const float* __restrict__ shift, bf16* __restrict__ out, int N, int D, int H,
+norm_apply_pool_kernel(const act16* __restrict__ src, int C, const float* __restrict__ scale,
+                       const float* __restrict__ shift, act16* __restrict__ out, int N, int D, int H,
                        int W, int relu) {
   const int cg = C / 8;
   const int Do = D / 2, Ho = H / 2, Wo = W / 2;
@@ -249,7 +263,7 @@ norm_apply_pool_kernel(const bf16* __restrict__ src, int C, const float* __restr
         for (int dx = 0; dx < 2; ++dx) {
           const size_t vi = (((size_t)n * D + (2 * z + dz)) * H + (2 * y + dy)) * W + (2 * x + dx);
           float f[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(src + vi * C) + g), f);
+          unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(src + vi * C) + g), f);
 #pragma unroll
           for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], fmaf(a[k], f[k], b[k]));
         }
@@ -257,7 +271,7 @@ norm_apply_pool_kernel(const bf16* __restrict__ src, int C, const float* __restr
 #pragma unroll
       for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], 0.f);
     }
-    reinterpret_cast<uint4*>(out)[i] = pack8(m);
+    reinterpret_cast<uint4*>(out)[i] = pack8<F16>(m);
   }
 }
 
@@ -265,8 +279,9 @@ norm_apply_pool_kernel(const bf16* __restrict__ src, int C, const float* __restr
 // MaxPool3d(2) + per-channel stats of the pooled tensor, grid (KM_RED_BLOCKS, N), 256 threads.
 // Requires (gridDim.x * 256) % (C/8) == 0 and 256 % (C/8) == 0 so that a thread keeps one channel
 // group for its whole grid-stride loop (checked on the host).
+template <bool F16>
 __global__ void __launch_bounds__(256)
-maxpool2_stats_kernel(const bf16* __restrict__ src, bf16* __restrict__ out,
+maxpool2_stats_kernel(const act16* __restrict__ src, act16* __restrict__ out,
                       float* __restrict__ stats, int N, int C, int D, int H, int W) {
   __shared__ float red[256][17];
   const int n = blockIdx.y;
@@ -274,7 +289,7 @@ maxpool2_stats_kernel(const bf16* __restrict__ src, bf16* __restrict__ out,
   const int Do = D / 2, Ho = H / 2, Wo = W / 2;
   const long long nvo = (long long)Do * Ho * Wo;
   const long long total = nvo * cg;
-  const bf16* sn = src + (size_t)n * D * H * W * C;
+  const act16* sn = src + (size_t)n * D * H * W * C;
   uint4* on = reinterpret_cast<uint4*>(out + (size_t)n * nvo * C);
   float s[8], ss[8];
 #pragma unroll
@@ -295,11 +310,11 @@ maxpool2_stats_kernel(const bf16* __restrict__ src, bf16* __restrict__ out,
         for (int dx = 0; dx < 2; ++dx) {
           const size_t vi = ((size_t)(2 * z + dz) * H + (2 * y + dy)) * W + (2 * x + dx);
           float f[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(sn + vi * C) + g), f);
+          unpack8<F16>(__ldg(reinterpret_cast<const uint4*>(sn + vi * C) + g), f);
 #pragma unroll
           for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
         }
-    on[i] = pack8(m);
+    on[i] = pack8<F16>(m);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       s[k] += m[k];
@@ -327,7 +342,8 @@ maxpool2_stats_kernel(const bf16* __restrict__ src, bf16* __restrict__ out,
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int N,
+template <bool F16>
+__global__ void ndhwc_to_ncdhw_kernel(const act16* __restrict__ src, float* __restrict__ dst, int N,
                                       int C, long long nvox) {
   const long long total = (long long)N * C * nvox;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -335,10 +351,11 @@ __global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ src, float* __res
     const long long v = i % nvox;
     const int c = (int)((i / nvox) % C);
     const int n = (int)(i / (nvox * C));
-    dst[i] = __bfloat162float(src[((size_t)n * nvox + v) * C + c]);
+    dst[i] = km_to_float<F16>(src[((size_t)n * nvox + v) * C + c]);
   }
 }
-__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N,
+template <bool F16>
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, act16* __restrict__ dst, int N,
                                       int C, long long nvox) {
   const long long total = (long long)N * C * nvox;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -346,7 +363,7 @@ __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, bf16* __res
     const int c = (int)(i % C);
     const long long v = (i / C) % nvox;
     const int n = (int)(i / (nvox * C));
-    dst[i] = __float2bfloat16_rn(src[((size_t)n * C + c) * nvox + v]);
+    dst[i] = km_from_float<F16>(src[((size_t)n * C + c) * nvox + v]);
   }
 }
 
@@ -359,6 +376,9 @@ inline int blocks_for(long long work_items, int threads) {
 }
 
 }  // namespace
+
+int km_operand_fp16() { return g_operand_fp16; }
+void km_set_operand_fp16(int v) { g_operand_fp16 = v ? 1 : 0; }
 
 extern "C" int km_pool_nparts(void) { return KM_RED_BLOCKS; }
 
@@ -373,8 +393,7 @@ extern "C" int km_volume_stats(const float* x, float* stats, int N, long long M,
 extern "C" int km_channel_stats(const void* x, float* stats, int N, int C, long long nvox,
                                 km_stream_t stream) {
   KM_CHECK_ARG(x && stats && N > 0 && C % 8 == 0 && nvox > 0, "km_channel_stats: bad arguments");
-  channel_stats_kernel<<<dim3(KM_RED_BLOCKS, N), KM_RED_THREADS, 2 * C * sizeof(float),
-                         km_cs(stream)>>>(reinterpret_cast<const bf16*>(x), stats, nvox, C, N);
+  KM_LAUNCH_16(channel_stats_kernel, dim3(KM_RED_BLOCKS, N), KM_RED_THREADS, 2 * C * sizeof(float), km_cs(stream), reinterpret_cast<const act16*>(x), stats, nvox, C, N);
   KM_LAUNCH_OK("channel_stats_kernel");
   return KM_OK;
 }
@@ -408,17 +427,17 @@ extern "C" int km_norm_apply(const void* src0, int C0, const void* src1, int C1,
     KM_CHECK_ARG(C1 == 0, "km_norm_apply: pool is only supported for a single source");
     KM_CHECK_ARG(D >= 2 && H >= 2 && W >= 2, "km_norm_apply: volume too small to pool");
     const long long total = (long long)N * (D / 2) * (H / 2) * (W / 2) * (C0 / 8);
-    norm_apply_pool_kernel<<<blocks_for(total, 256), 256, 0, km_cs(stream)>>>(
-        reinterpret_cast<const bf16*>(src0), C0, scale, shift, reinterpret_cast<bf16*>(out), N, D, H,
+    KM_LAUNCH_16(norm_apply_pool_kernel, blocks_for(total, 256), 256, 0, km_cs(stream), 
+        reinterpret_cast<const act16*>(src0), C0, scale, shift, reinterpret_cast<act16*>(out), N, D, H,
         W, relu);
     KM_LAUNCH_OK("norm_apply_pool_kernel");
     return KM_OK;
   }
   KM_CHECK_ARG(H <= 65535 && (long long)N * D <= 65535, "km_norm_apply: volume too large for the grid");
   const dim3 grid((W * ((C0 + C1) / 8) + 255) / 256, (H + kNormRows - 1) / kNormRows, N * D);
-  norm_apply_kernel<<<grid, 256, 0, km_cs(stream)>>>(
-      reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1,
-      C1 ? D1 : 1, C1 ? H1 : 1, C1 ? W1 : 1, scale, shift, reinterpret_cast<bf16*>(out), N, D, H, W,
+  KM_LAUNCH_16(norm_apply_kernel, grid, 256, 0, km_cs(stream), 
+      reinterpret_cast<const act16*>(src0), C0, reinterpret_cast<const act16*>(src1), C1,
+      C1 ? D1 : 1, C1 ? H1 : 1, C1 ? W1 : 1, scale, shift, reinterpret_cast<act16*>(out), N, D, H, W,
       relu);
   KM_LAUNCH_OK("norm_apply_kernel");
   return KM_OK;
@@ -430,8 +449,8 @@ extern "C" int km_maxpool2_stats(const void* src, void* out, float* stats, int N
   KM_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0,
                "km_maxpool2_stats: C/8 must divide 256 (C=%d)", C);
   KM_CHECK_ARG(D >= 2 && H >= 2 && W >= 2, "km_maxpool2_stats: volume too small");
-  maxpool2_stats_kernel<<<dim3(KM_RED_BLOCKS, N), 256, 0, km_cs(stream)>>>(
-      reinterpret_cast<const bf16*>(src), reinterpret_cast<bf16*>(out), stats, N, C, D, H, W);
+  KM_LAUNCH_16(maxpool2_stats_kernel, dim3(KM_RED_BLOCKS, N), 256, 0, km_cs(stream), 
+      reinterpret_cast<const act16*>(src), reinterpret_cast<act16*>(out), stats, N, C, D, H, W);
   KM_LAUNCH_OK("maxpool2_stats_kernel");
   return KM_OK;
 }
@@ -445,9 +464,10 @@ extern "C" int km_maxpool2_stats(const void* src, void* out, float* stats, int N
 //               axis (tap offset -1 outside), bit 1 = on the high border (tap offset +1 outside)
 // Blocks [0, pack_blocks) pack; the others build the tables, one warp per output channel with the lanes
 // over the input channels: the 36 class sums of a 3x3x3 kernel come from three separable reductions.
+template <bool F16>
 __global__ void __launch_bounds__(256)
 fold_gn_kernel(const float* __restrict__ w, const float* __restrict__ scale, const float* __restrict__ shift,
-               bf16* __restrict__ packed, float* __restrict__ bias, int N, int Cout, int Cin, int layout,
+               act16* __restrict__ packed, float* __restrict__ bias, int N, int Cout, int Cin, int layout,
                int pack_blocks) {
   if ((int)blockIdx.x < pack_blocks) {
     const long long total = 27ll * (layout ? 3 : 1) * Cout * Cin;
@@ -470,7 +490,7 @@ fold_gn_kernel(const float* __restrict__ w, const float* __restrict__ scale, con
         tap = (int)t;
       }
       const float wv = w[((size_t)co * Cin + ci) * 27 + tap];
-      for (int n = 0; n < N; ++n) packed[(size_t)n * total + i] = __float2bfloat16_rn(wv * scale[n * Cin + ci]);
+      for (int n = 0; n < N; ++n) packed[(size_t)n * total + i] = km_from_float<F16>(wv * scale[n * Cin + ci]);
     }
     return;
   }
@@ -526,7 +546,7 @@ int km_fold_gn(const float* w, const float* scale, const float* shift, void* pac
   long long pb = (total + 1023) / 1024;
   const int pack_blocks = (int)(pb < 1 ? 1 : (pb > 1184 ? 1184 : pb));
   const int bias_blocks = (Cout + 7) / 8;
-  fold_gn_kernel<<<pack_blocks + bias_blocks, 256, 0, km_cs(stream)>>>(w, scale, shift, reinterpret_cast<bf16*>(packed),
+  KM_LAUNCH_16(fold_gn_kernel, pack_blocks + bias_blocks, 256, 0, km_cs(stream), w, scale, shift, reinterpret_cast<act16*>(packed),
                                                                        bias, N, Cout, Cin, layout, pack_blocks);
   KM_LAUNCH_OK("fold_gn_kernel");
   return KM_OK;
@@ -577,8 +597,8 @@ extern "C" int km_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int N, in
                                           int W, km_stream_t stream) {
   KM_CHECK_ARG(src && dst && N > 0 && C > 0, "km_ndhwc_bf16_to_ncdhw_f32: bad arguments");
   const long long nvox = (long long)D * H * W;
-  ndhwc_to_ncdhw_kernel<<<blocks_for((long long)N * C * nvox, 256), 256, 0, km_cs(stream)>>>(
-      reinterpret_cast<const bf16*>(src), dst, N, C, nvox);
+  KM_LAUNCH_16(ndhwc_to_ncdhw_kernel, blocks_for((long long)N * C * nvox, 256), 256, 0, km_cs(stream), 
+      reinterpret_cast<const act16*>(src), dst, N, C, nvox);
   KM_LAUNCH_OK("ndhwc_to_ncdhw_kernel");
   return KM_OK;
 }
@@ -586,8 +606,8 @@ extern "C" int km_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int N, in
                                           int W, km_stream_t stream) {
   KM_CHECK_ARG(src && dst && N > 0 && C > 0, "km_ncdhw_f32_to_ndhwc_bf16: bad arguments");
   const long long nvox = (long long)D * H * W;
-  ncdhw_to_ndhwc_kernel<<<blocks_for((long long)N * C * nvox, 256), 256, 0, km_cs(stream)>>>(
-      src, reinterpret_cast<bf16*>(dst), N, C, nvox);
+  KM_LAUNCH_16(ncdhw_to_ndhwc_kernel, blocks_for((long long)N * C * nvox, 256), 256, 0, km_cs(stream), 
+      src, reinterpret_cast<act16*>(dst), N, C, nvox);
   KM_LAUNCH_OK("ncdhw_to_ndhwc_kernel");
   return KM_OK;
 }

@@ -73,11 +73,6 @@ struct ConvGeom {
   int total_tiles;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
 // accumulator row -> offset inside the output brick
 template <int MODE>
 __device__ __forceinline__ void row_to_voxel(const ConvGeom& g, int row, int& tx, int& ty, int& tz) {
@@ -113,10 +108,10 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int t) {
   return c;
 }
 
-template <int KC, int MODE>
+template <int KC, int MODE, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const ConvGeom g, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+               const ConvGeom g, const float* __restrict__ bias, uint16_t* __restrict__ out,
                float* __restrict__ stats, float* __restrict__ com) {
   constexpr int kRowBytes = KC * 2;
   constexpr int kSteps = KC / 16;
@@ -312,7 +307,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   const uint32_t bb16 = b16 + t * b_tap16 + 2u * kk;
                   const uint32_t acc_flag = (t | kk) ? 1u : accum;
                   for (int m = 0; m < mt; ++m) {
-                    umma_bf16_pred(dm, am16, bb16, desc_hi, idesc, acc_flag, issue);
+                    umma_16_pred(dm, am16, bb16, desc_hi, idesc, acc_flag, issue);
                     am16 += 16u * a_tap16;
                     dm += bn;
                   }
@@ -325,7 +320,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int t = 0; t < kNtap; ++t) {
 #pragma unroll
                 for (int kk = 0; kk < kSteps; ++kk) {
-                  umma_bf16_pred(dm, am16 + t * a_tap16 + 2u * kk, b16 + t * b_tap16 + 2u * kk,
+                  umma_16_pred(dm, am16 + t * a_tap16 + 2u * kk, b16 + t * b_tap16 + 2u * kk,
                                  desc_hi, idesc, (t | kk) ? 1u : accum, issue);
                 }
               }
@@ -447,7 +442,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 b = fmaxf(b, 0.f);
               }
               // rows outside the volume are staged as zeros so that the statistics need no mask
-              pk[j] = vrow ? pack_bf16(a, b) : 0u;
+              pk[j] = vrow ? km_pack2<F16>(a, b) : 0u;
             }
             uint4* dst = reinterpret_cast<uint4*>(srow + (size_t)c0 * 2);
             dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -508,13 +503,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t pk[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              pk[j] = pack_bf16(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+              pk[j] = km_pack2<F16>(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
             uint4* dst = reinterpret_cast<uint4*>(staging + (size_t)row * pitch + (size_t)c0 * 2);
             dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              pk[j] = pack_bf16(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+              pk[j] = km_pack2<F16>(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
             dst[2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             dst[3] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
@@ -595,7 +590,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                (size_t)col * 2;
 #pragma unroll 8
             for (int rr = 0; rr < rows_per_part; ++rr) {
-              const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
+              const float v = km_to_float<F16>(*reinterpret_cast<const uint16_t*>(p));
               p += pitch;
               s += v;
               ss = fmaf(v, v, ss);
@@ -637,7 +632,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------
 // weight repack: fp32 (Cout, Cin, taps) -> bf16 [tap][Cout][Cin]
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p,
+template <bool F16>
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ p,
                                     int Cout, int Cin, int taps) {
   const long long total = (long long)taps * Cout * Cin;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -645,7 +641,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     const int ci = (int)(i % Cin);
     const int co = (int)((i / Cin) % Cout);
     const int tap = (int)(i / ((long long)Cin * Cout));
-    p[i] = __float2bfloat16_rn(w[((long long)co * Cin + ci) * taps + tap]);
+    p[i] = km_from_float<F16>(w[((long long)co * Cin + ci) * taps + tap]);
   }
 }
 
@@ -664,22 +660,26 @@ int sm_count() {
 inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 typedef void (*ConvKernel)(const CUtensorMap, const CUtensorMap, const ConvGeom, const float*,
-                           __nv_bfloat16*, float*, float*);
+                           uint16_t*, float*, float*);
 
-ConvKernel pick_kernel(int kc, int mode) {
+template <bool F16>
+ConvKernel pick_kernel_t(int kc, int mode) {
   if (mode == 2) {
-    if (kc == 64) return conv_tc_kernel<64, 2>;
-    if (kc == 32) return conv_tc_kernel<32, 2>;
-    return conv_tc_kernel<16, 2>;
+    if (kc == 64) return conv_tc_kernel<64, 2, F16>;
+    if (kc == 32) return conv_tc_kernel<32, 2, F16>;
+    return conv_tc_kernel<16, 2, F16>;
   }
   if (mode == 1) {
-    if (kc == 64) return conv_tc_kernel<64, 1>;
-    if (kc == 32) return conv_tc_kernel<32, 1>;
-    return conv_tc_kernel<16, 1>;
+    if (kc == 64) return conv_tc_kernel<64, 1, F16>;
+    if (kc == 32) return conv_tc_kernel<32, 1, F16>;
+    return conv_tc_kernel<16, 1, F16>;
   }
-  if (kc == 64) return conv_tc_kernel<64, 0>;
-  if (kc == 32) return conv_tc_kernel<32, 0>;
-  return conv_tc_kernel<16, 0>;
+  if (kc == 64) return conv_tc_kernel<64, 0, F16>;
+  if (kc == 32) return conv_tc_kernel<32, 0, F16>;
+  return conv_tc_kernel<16, 0, F16>;
+}
+ConvKernel pick_kernel(int kc, int mode) {
+  return km_operand_fp16() ? pick_kernel_t<true>(kc, mode) : pick_kernel_t<false>(kc, mode);
 }
 
 }  // namespace
@@ -700,8 +700,10 @@ extern "C" int km_pack_weights(const float* w, void* packed, int Cout, int Cin, 
                "km_pack_weights: bad arguments");
   const long long total = (long long)taps * Cout * Cin;
   const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-  pack_weights_kernel<<<blocks, 256, 0, km_cs(stream)>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin, taps);
+  if (km_operand_fp16())
+    pack_weights_kernel<true><<<blocks, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<uint16_t*>(packed), Cout, Cin, taps);
+  else
+    pack_weights_kernel<false><<<blocks, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<uint16_t*>(packed), Cout, Cin, taps);
   KM_LAUNCH_OK("pack_weights_kernel");
   return KM_OK;
 }
@@ -789,7 +791,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   g.total_tiles = (int)tiles;
   g.stat_parts = (g.BN <= kEpiThreads && kEpiThreads % g.BN == 0) ? kEpiThreads / g.BN : 1;
 
-  g.idesc = umma_idesc_bf16(kTileM, g.BN);
+  g.idesc = umma_idesc_16(kTileM, g.BN, km_operand_fp16() != 0);
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)(g.mt * g.BN)) cols *= 2;
   g.tmem_cols = cols;
@@ -872,7 +874,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
       box[1] = 8; box[2] = (cuuint32_t)(16 * g.mt + 2); box[3] = 1;   // natural (C, W, H, D, N) order
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims,
+    CUresult r = encode(&tmA, KM_TMAP_16, 5, const_cast<void*>(x), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -888,7 +890,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, slice, 3 * slice, 9 * slice};
     cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)g.BN, 1, 3, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(wp), dims,
+    CUresult r = encode(&tmB, KM_TMAP_16, 5, const_cast<void*>(wp), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -900,7 +902,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
     cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)g.BN, (cuuint32_t)(mode == 1 ? 3 : 1)};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wp), dims,
+    CUresult r = encode(&tmB, KM_TMAP_16, 3, const_cast<void*>(wp), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -910,9 +912,9 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
   }
 
   ConvKernel kernel = pick_kernel(kc, mode);
-  static unsigned long long attr_set[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  static unsigned long long attr_set[2][3][3] = {};   // per (operand type, mode, Cin chunk) instantiation
   const int ki = kc == 64 ? 2 : (kc == 32 ? 1 : 0);
-  if (km_first_use_on_device(&attr_set[mode][ki]))
+  if (km_first_use_on_device(&attr_set[km_operand_fp16() ? 1 : 0][mode][ki]))
     KM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   const int nsm = sm_count();
   const int grid = g.total_tiles < nsm ? g.total_tiles : nsm;
@@ -924,7 +926,7 @@ extern "C" int km_conv3d_tc(const void* x, const void* wp, const float* bias, vo
       KM_CUDA_OK(cudaMemsetAsync(com, 0, (size_t)nsm * N * Cout * 4 * sizeof(float), km_cs(stream)));
   }
   kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(
-      tmA, tmB, g, bias, reinterpret_cast<__nv_bfloat16*>(out), stats, com);
+      tmA, tmB, g, bias, reinterpret_cast<uint16_t*>(out), stats, com);
   KM_LAUNCH_OK("conv_tc_kernel");
   return KM_OK;
 }

@@ -52,11 +52,6 @@ struct PairGeom {
 
 constexpr int kBiasClasses = 36;   // z code (0..3) x y code (0..2) x x code (0..2), see conv_zf.cu
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
 struct TileCoord {
   int n, x0, y0, z0;
 };
@@ -71,10 +66,10 @@ __device__ __forceinline__ TileCoord decode_tile(const PairGeom& g, int t) {
   return c;
 }
 
-template <int KC>
+template <int KC, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const PairGeom g, __nv_bfloat16* __restrict__ out, float* __restrict__ stats,
+                const PairGeom g, uint16_t* __restrict__ out, float* __restrict__ stats,
                 const float* __restrict__ bias_tab) {
   constexpr int kRowBytes = KC * 2;
   constexpr int kSteps = KC / 16;
@@ -214,7 +209,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int t = 0; t < 3; ++t) {
 #pragma unroll
                 for (int kk = 0; kk < kSteps; ++kk) {
-                  umma2_bf16_pred(dm, am16 + t * a_tap16 + 2u * kk, b16 + t * b_tap16 + 2u * kk, desc_hi, idesc,
+                  umma2_16_pred(dm, am16 + t * a_tap16 + 2u * kk, b16 + t * b_tap16 + 2u * kk, desc_hi, idesc,
                                   (t | kk) ? 1u : accum, issue);
                 }
               }
@@ -323,7 +318,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   a = fmaxf(a, 0.f);
                   b = fmaxf(b, 0.f);
                 }
-                pk[j] = vrow ? pack_bf16(a, b) : 0u;   // rows outside the volume: zeros (stats need no mask)
+                pk[j] = vrow ? km_pack2<F16>(a, b) : 0u;   // rows outside the volume: zeros (stats need no mask)
               }
               uint4* dst = reinterpret_cast<uint4*>(srow + (size_t)c0 * 2);
               dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -357,7 +352,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const uint8_t* p = staging + (size_t)(mb * kTileM + part * rows_per_part) * pitch + (size_t)col * 2;
 #pragma unroll 8
               for (int rr = 0; rr < rows_per_part; ++rr) {
-                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
+                const float v = km_to_float<F16>(*reinterpret_cast<const uint16_t*>(p));
                 p += pitch;
                 s += v;
                 ss = fmaf(v, v, ss);
@@ -395,7 +390,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 inline uint32_t pair_round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-typedef void (*PairKernel)(const CUtensorMap, const CUtensorMap, const PairGeom, __nv_bfloat16*, float*,
+typedef void (*PairKernel)(const CUtensorMap, const CUtensorMap, const PairGeom, uint16_t*, float*,
                            const float*);
 
 
@@ -431,7 +426,7 @@ extern "C" int km_conv3d_tc_pair_gn(const void* x, const float* w, const float* 
                "km_conv3d_tc_pair_gn: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
   KM_CHECK_ARG(N > 0 && N <= 1024, "km_conv3d_tc_pair_gn: bad batch");
   const size_t wbytes = (size_t)27 * Cout * Cin * 2;
-  __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(workspace);
+  void* packed = workspace;
   float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)N * wbytes + 255) & ~(size_t)255));
   const int rf = km_fold_gn(w, scale, shift, packed, bias, N, Cout, Cin, 0, stream);
   if (rf != KM_OK) return rf;
@@ -473,7 +468,7 @@ int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out,
   KM_CHECK_ARG(tiles < (1ll << 30), "km_conv3d_tc_pair: too many tiles");
   g.total_tiles = (int)tiles;
   g.stat_parts = (g.BN <= kEpiThreads && kEpiThreads % g.BN == 0) ? kEpiThreads / g.BN : 1;
-  g.idesc = umma_idesc_bf16(256, g.BN);
+  g.idesc = umma_idesc_16(256, g.BN, km_operand_fp16() != 0);
 
   const uint32_t kSmemMax = 232448 - 1024;
   g.staging_pitch = (uint32_t)g.BN * 2 + 16;
@@ -517,7 +512,7 @@ int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out,
                              (cuuint64_t)D * H * W * Cin * 2};
     cuuint32_t box[5] = {(cuuint32_t)kc, 8, (cuuint32_t)(16 * g.mt + 2), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box,
+    CUresult r = encode(&tmA, KM_TMAP_16, 5, const_cast<void*>(x), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -533,7 +528,7 @@ int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out,
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, slice, 3 * slice, 9 * slice};
     cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(g.BN / 2), 1, 3, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(wp), dims, strides, box,
+    CUresult r = encode(&tmB, KM_TMAP_16, 5, const_cast<void*>(wp), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -541,9 +536,11 @@ int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out,
       return KM_ECUDA;
     }
   }
-  PairKernel kernel = kc == 64 ? conv_tc2_kernel<64> : conv_tc2_kernel<32>;
-  static unsigned long long attr_set[2] = {0, 0};
-  if (km_first_use_on_device(&attr_set[kc == 64]))
+  const bool f16 = km_operand_fp16() != 0;
+  PairKernel kernel = kc == 64 ? (f16 ? conv_tc2_kernel<64, true> : conv_tc2_kernel<64, false>)
+                               : (f16 ? conv_tc2_kernel<32, true> : conv_tc2_kernel<32, false>);
+  static unsigned long long attr_set[2][2] = {};   // per (operand type, Cin chunk) instantiation
+  if (km_first_use_on_device(&attr_set[f16 ? 1 : 0][kc == 64]))
     KM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   const int nsm = km_sm_count();
   int grid = nsm & ~1;
@@ -551,7 +548,7 @@ int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out,
   if (grid / 2 > pairs_needed) grid = 2 * pairs_needed;
   if ((flags & KM_CONV_STATS) && grid < nsm)
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * Cout * 2 * sizeof(float), km_cs(stream)));
-  kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out), stats,
+  kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmA, tmB, g, reinterpret_cast<uint16_t*>(out), stats,
                                                         bias_tab);
   KM_LAUNCH_OK("conv_tc2_kernel");
   return KM_OK;

@@ -103,23 +103,14 @@ __device__ __forceinline__ void for_each_tile(const ZfGeom& g, F&& fn) {
   }
 }
 
-__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
-  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a),
-                                   *reinterpret_cast<const __nv_bfloat162*>(&b));
-  return *reinterpret_cast<const uint32_t*>(&r);
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
 
 // BIAS: the input is the RAW (un-normalised) activation and tmB holds weights pre-multiplied by the
 // sample's GroupNorm scale; the GroupNorm shift enters as bias_tab[class][cout], class = which of the
 // 27 taps fall outside the volume for this voxel (zero padding applies to the NORMALISED input).
-template <bool BIAS>
+template <bool BIAS, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const ZfGeom g, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
+               const ZfGeom g, uint16_t* __restrict__ out, uint16_t* __restrict__ pooled,
                float* __restrict__ stats, const float* __restrict__ bias_tab) {
   constexpr uint32_t kLayout = 6u;                 // SWIZZLE_32B
   constexpr uint32_t kSbo = 8u * kRowBytes;        // 256 B between 8-row groups
@@ -200,7 +191,7 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t lo_flag = 1u << 16;
     const uint32_t a_base16 = ((base & 0x3FFFFu) >> 4) | lo_flag;
     const uint32_t b_base16 = (((base + g.off_b) & 0x3FFFFu) >> 4) | lo_flag;
-    const uint32_t idesc = umma_idesc_bf16(128, kN3);
+    const uint32_t idesc = umma_idesc_16(128, kN3, F16);
     int s = 0;
     uint32_t ph = 0;
     mbar_wait(w_bar, 0u);
@@ -222,7 +213,7 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int m = 0; m < kMT; ++m) {
             // rows of brick m shifted by dy: (16 m + dy) atoms of 8 rows x 32 B
             const uint32_t aa = a16 + (uint32_t)dx * (kASub >> 4) + (uint32_t)(16 * m + dy) * (kSbo >> 4);
-            umma_bf16_pred(d_tmem + (uint32_t)m * kN3, aa, bb, desc_hi, idesc, accum, issue);
+            umma_16_pred(d_tmem + (uint32_t)m * kN3, aa, bb, desc_hi, idesc, accum, issue);
           }
           accum = 1u;
         }
@@ -325,7 +316,7 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               a = fmaxf(a, 0.f);
               b = fmaxf(b, 0.f);
             }
-            pk[j] = pack_bf16(a, b);
+            pk[j] = km_pack2<F16>(a, b);
           }
           const bool inside = x2 < g.W && y2 < g.H;
           if (out && inside) {
@@ -341,15 +332,15 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // of this unit (kept per TMEM set); max commutes with the bf16 rounding
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              pk[j] = hmax2_u32(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
-              pk[j] = hmax2_u32(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 8));
+              pk[j] = km_max2<F16>(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
+              pk[j] = km_max2<F16>(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 8));
             }
             if ((zo & 1) == 0) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) zprev[set][m][j] = pk[j];
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) pk[j] = hmax2_u32(pk[j], zprev[set][m][j]);
+              for (int j = 0; j < 8; ++j) pk[j] = km_max2<F16>(pk[j], zprev[set][m][j]);
               const int xp = x2 >> 1, yp = y2 >> 1, zp = zo >> 1;
               if (((tx | ty) & 1) == 0 && xp < (g.W >> 1) && yp < (g.H >> 1)) {
                 const size_t vox = (((size_t)u.n * (g.D >> 1) + zp) * (g.H >> 1) + yp) * (g.W >> 1) + xp;
@@ -361,7 +352,8 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (do_stats && acc_stats) {   // statistics of the values actually stored (bf16-rounded)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float ar = __uint_as_float(pk[j] << 16), br = __uint_as_float(pk[j] & 0xffff0000u);
+              const float2 ab = km_unpack2<F16>(pk[j]);
+              const float ar = ab.x, br = ab.y;
               ssum[2 * j] += ar;
               ssq[2 * j] = fmaf(ar, ar, ssq[2 * j]);
               ssum[2 * j + 1] += br;
@@ -393,7 +385,8 @@ conv_zf_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // fp32 (Cout, Cin, 3, 3, 3) -> bf16 [r][dx][dy][j][Cout][Cin], dz(j, r) = (r + 1 - j) mod 3
-__global__ void pack_weights_zf_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int Cout,
+template <bool F16>
+__global__ void pack_weights_zf_kernel(const float* __restrict__ w, uint16_t* __restrict__ p, int Cout,
                                        int Cin) {
   const int total = 27 * 3 * Cout * Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -409,7 +402,7 @@ __global__ void pack_weights_zf_kernel(const float* __restrict__ w, __nv_bfloat1
     const int dx = t % 3;
     const int r = t / 3;
     const int dz = (r + 1 - j + 3) % 3;
-    p[i] = __float2bfloat16_rn(w[((size_t)co * Cin + ci) * 27 + dz * 9 + dy * 3 + dx]);
+    p[i] = km_from_float<F16>(w[((size_t)co * Cin + ci) * 27 + dz * 9 + dy * 3 + dx]);
   }
 }
 
@@ -430,7 +423,10 @@ extern "C" size_t km_pack_weights_zfold_bytes(int Cout, int Cin) {
 
 extern "C" int km_pack_weights_zfold(const float* w, void* packed, int Cout, int Cin, km_stream_t stream) {
   KM_CHECK_ARG(w && packed && Cout == kCout && Cin == kKC, "km_pack_weights_zfold: needs Cin=%d, Cout=%d", kKC, kCout);
-  pack_weights_zf_kernel<<<64, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
+  if (km_operand_fp16())
+    pack_weights_zf_kernel<true><<<64, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<uint16_t*>(packed), Cout, Cin);
+  else
+    pack_weights_zf_kernel<false><<<64, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<uint16_t*>(packed), Cout, Cin);
   KM_LAUNCH_OK("pack_weights_zf_kernel");
   return KM_OK;
 }
@@ -477,7 +473,7 @@ int launch_zf(const void* x, const void* wz, const float* bias_tab, void* out, v
                              (cuuint64_t)D * H * W * Cin * 2};
     cuuint32_t box[5] = {(cuuint32_t)kKC, 8, (cuuint32_t)(16 * kMT + 2), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box,
+    CUresult r = encode(&tmA, KM_TMAP_16, 5, const_cast<void*>(x), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -490,7 +486,7 @@ int launch_zf(const void* x, const void* wz, const float* bias_tab, void* out, v
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)kN3 * Cin * 2};
     cuuint32_t box[3] = {(cuuint32_t)kKC, (cuuint32_t)kN3, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wz), dims, strides, box,
+    CUresult r = encode(&tmB, KM_TMAP_16, 3, const_cast<void*>(wz), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -500,8 +496,10 @@ int launch_zf(const void* x, const void* wz, const float* bias_tab, void* out, v
   }
   static unsigned long long attr_set = 0;
   if (km_first_use_on_device(&attr_set)) {
-    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   }
   const int nsm = km_sm_count();
   int grid = g.units < nsm ? g.units : nsm;
@@ -512,12 +510,18 @@ int launch_zf(const void* x, const void* wz, const float* bias_tab, void* out, v
   }
   if (grid < nsm && (flags & KM_CONV_STATS) && n_base == 0)   // partial slots of the CTAs that do not run
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * kCout * 2 * sizeof(float), km_cs(stream)));
-  if (bias_tab)
-    conv_zf_kernel<true><<<grid, kThreads, smem_bytes, km_cs(stream)>>>(
-        tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<__nv_bfloat16*>(pooled), stats, bias_tab);
-  else
-    conv_zf_kernel<false><<<grid, kThreads, smem_bytes, km_cs(stream)>>>(
-        tmA, tmB, g, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<__nv_bfloat16*>(pooled), stats, nullptr);
+  uint16_t* o16 = reinterpret_cast<uint16_t*>(out);
+  uint16_t* p16 = reinterpret_cast<uint16_t*>(pooled);
+  const bool f16 = km_operand_fp16() != 0;
+#define KM_ZF(B, F) conv_zf_kernel<B, F><<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmA, tmB, g, o16, p16, stats, bias_tab)
+  if (bias_tab) {
+    if (f16) KM_ZF(true, true);
+    else KM_ZF(true, false);
+  } else {
+    if (f16) KM_ZF(false, true);
+    else KM_ZF(false, false);
+  }
+#undef KM_ZF
   KM_LAUNCH_OK("conv_zf_kernel");
   return KM_OK;
 }
@@ -557,7 +561,7 @@ extern "C" int km_conv3d_zfold_gn(const void* x, const float* w, const float* sc
   if (rc != KM_OK) return rc;
   KM_CHECK_ARG(scale && shift && workspace && ((uintptr_t)workspace & 15) == 0, "km_conv3d_zfold_gn: null / unaligned argument");
   const size_t wbytes = (size_t)27 * 3 * kCout * kKC * 2;
-  __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(workspace);
+  void* packed = workspace;
   float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (size_t)N * wbytes);
   const int rf = km_fold_gn(w, scale, shift, packed, bias, N, Cout, Cin, 1, stream);
   if (rf != KM_OK) return rf;

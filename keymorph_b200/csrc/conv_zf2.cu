@@ -108,20 +108,11 @@ __device__ __forceinline__ void for_each_tile(const Zf2Geom& g, uint32_t rank, F
   }
 }
 
-__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
-  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a),
-                                   *reinterpret_cast<const __nv_bfloat162*>(&b));
-  return *reinterpret_cast<const uint32_t*>(&r);
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
 
-template <int COUT, int KC, int MT, bool POOL>
+template <int COUT, int KC, int MT, bool POOL, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmB, const Zf2Geom g, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
+                const __grid_constant__ CUtensorMap tmB, const Zf2Geom g, uint16_t* __restrict__ out, uint16_t* __restrict__ pooled,
                 float* __restrict__ stats, const float* __restrict__ bias_tab) {
   using C = Cfg<COUT, KC, MT>;
   constexpr int kMT = C::kMT;
@@ -213,7 +204,7 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       constexpr uint32_t desc_hi = (kSbo >> 4) | (1u << 14) | (kLayout << 29);
       const uint32_t lo_flag = 1u << 16;
       const uint32_t base16 = ((base & 0x3FFFFu) >> 4) | lo_flag;
-      const uint32_t idesc = umma_idesc_bf16(256, kN3);
+      const uint32_t idesc = umma_idesc_16(256, kN3, F16);
       int s = 0;
       uint32_t ph = 0;
       for_each_tile(g, rank, [&](auto set_c, const Unit&, int p, uint32_t cnt) {
@@ -233,7 +224,7 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int kk = 0; kk < kSteps; ++kk) {
 #pragma unroll
               for (int m = 0; m < kMT; ++m)   // bricks sharing this weight tile
-                umma2_bf16_pred(d_tmem + (uint32_t)(m * kN3), a16 + (uint32_t)(16 * m + dy) * (kSbo >> 4) + 2u * kk,
+                umma2_16_pred(d_tmem + (uint32_t)(m * kN3), a16 + (uint32_t)(16 * m + dy) * (kSbo >> 4) + 2u * kk,
                                 b16 + (uint32_t)dy * (kBTile >> 4) + 2u * kk, desc_hi, idesc, accum, issue);
               accum = 1u;
             }
@@ -353,7 +344,7 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               a = fmaxf(a, 0.f);
               b = fmaxf(b, 0.f);
             }
-            pk[j] = pack_bf16(a, b);
+            pk[j] = km_pack2<F16>(a, b);
           }
           if (out && inside) st_global_v8(out + vox * kCout + half * kCols + 16 * hh, pk);
           bool acc_stats = inside && !(POOL && pooled);
@@ -362,15 +353,15 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // neighbour is the previous plane of this unit; max commutes with the bf16 rounding
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              pk[j] = hmax2_u32(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
-              pk[j] = hmax2_u32(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 8));
+              pk[j] = km_max2<F16>(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
+              pk[j] = km_max2<F16>(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 8));
             }
             if ((zo & 1) == 0) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) zprev[POOL ? set : 0][POOL ? m : 0][hh][j] = pk[j];
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) pk[j] = hmax2_u32(pk[j], zprev[POOL ? set : 0][POOL ? m : 0][hh][j]);
+              for (int j = 0; j < 8; ++j) pk[j] = km_max2<F16>(pk[j], zprev[POOL ? set : 0][POOL ? m : 0][hh][j]);
               const int xp = x2 >> 1, yp = y2 >> 1, zp = zo >> 1;
               if (u.valid && ((tx | ty) & 1) == 0 && xp < (g.W >> 1) && yp < (g.H >> 1)) {
                 const size_t pv = (((size_t)u.n * (g.D >> 1) + zp) * (g.H >> 1) + yp) * (g.W >> 1) + xp;
@@ -382,7 +373,8 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (do_stats && acc_stats) {   // statistics of the values actually stored (bf16-rounded)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float ar = __uint_as_float(pk[j] << 16), br = __uint_as_float(pk[j] & 0xffff0000u);
+              const float2 ab = km_unpack2<F16>(pk[j]);
+              const float ar = ab.x, br = ab.y;
               ssum[16 * hh + 2 * j] += ar;
               ssq[16 * hh + 2 * j] = fmaf(ar, ar, ssq[16 * hh + 2 * j]);
               ssum[16 * hh + 2 * j + 1] += br;
@@ -419,7 +411,8 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // fp32 (Cout, Cin, 3, 3, 3) -> bf16 [rot][dx][dy][j*Cout + cout][Cin], dz(j, rot) = (rot + 1 - j) mod 3
-__global__ void pack_weights_zf2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int Cout,
+template <bool F16>
+__global__ void pack_weights_zf2_kernel(const float* __restrict__ w, uint16_t* __restrict__ p, int Cout,
                                         int Cin) {
   const long long total = 27ll * 3 * Cout * Cin;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -436,7 +429,7 @@ __global__ void pack_weights_zf2_kernel(const float* __restrict__ w, __nv_bfloat
     const int dx = (int)(t % 3);
     const int r = (int)(t / 3);
     const int dz = (r + 1 - j + 3) % 3;
-    p[i] = __float2bfloat16_rn(w[((size_t)co * Cin + ci) * 27 + dz * 9 + dy * 3 + dx]);
+    p[i] = km_from_float<F16>(w[((size_t)co * Cin + ci) * 27 + dz * 9 + dy * 3 + dx]);
   }
 }
 
@@ -453,7 +446,10 @@ extern "C" int km_conv3d_zfold_pair_supported(int Cin, int Cout, int D, int H, i
 extern "C" int km_pack_weights_zfold_pair(const float* w, void* packed, int Cout, int Cin, km_stream_t stream) {
   KM_CHECK_ARG(w && packed && (Cout == 64 || Cout == 32) && Cin % 16 == 0 && Cin > 0,
                "km_pack_weights_zfold_pair: needs Cout in {32, 64}, Cin %% 16 == 0");
-  pack_weights_zf2_kernel<<<128, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
+  if (km_operand_fp16())
+    pack_weights_zf2_kernel<true><<<128, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<uint16_t*>(packed), Cout, Cin);
+  else
+    pack_weights_zf2_kernel<false><<<128, 256, 0, km_cs(stream)>>>(w, reinterpret_cast<uint16_t*>(packed), Cout, Cin);
   KM_LAUNCH_OK("pack_weights_zf2_kernel");
   return KM_OK;
 }
@@ -530,7 +526,7 @@ int launch_zf2(const void* x, const void* x1, int Cin0, const void* wz, const fl
                              (cuuint64_t)D * H * W * Cc * 2};
     cuuint32_t box[5] = {(cuuint32_t)KC, 8, (cuuint32_t)(16 * MT + 2), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(which == 0 ? &tmA : &tmA1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims,
+    CUresult r = encode(which == 0 ? &tmA : &tmA1, KM_TMAP_16, 5, const_cast<void*>(ptr), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -546,7 +542,7 @@ int launch_zf2(const void* x, const void* x1, int Cin0, const void* wz, const fl
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, tile, 3 * tile, 9 * tile};
     cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)C::kHalfRows, 3, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(wz), dims, strides, box,
+    CUresult r = encode(&tmB, KM_TMAP_16, 5, const_cast<void*>(wz), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -556,15 +552,22 @@ int launch_zf2(const void* x, const void* x1, int Cin0, const void* wz, const fl
   }
   static unsigned long long attr_set = 0;   // one mask per instantiation
   if (km_first_use_on_device(&attr_set))
-    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel<COUT, KC, MT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+{
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel<COUT, KC, MT, POOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel<COUT, KC, MT, POOL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  }
   const int nsm = km_sm_count();
   const int upi = g.punits / N;
   int grid = nsm & ~1;
   if (grid / 2 > upi) grid = 2 * upi;
   if ((flags & KM_CONV_STATS) && grid < nsm)
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * COUT * 2 * sizeof(float), st));
-  conv_zf2_kernel<COUT, KC, MT, POOL><<<grid, kThreads, smem_bytes, st>>>(tmA, tmA1, tmB, g, reinterpret_cast<__nv_bfloat16*>(out),
-                                                               reinterpret_cast<__nv_bfloat16*>(pooled), stats, bias_tab);
+  if (km_operand_fp16())
+    conv_zf2_kernel<COUT, KC, MT, POOL, true><<<grid, kThreads, smem_bytes, st>>>(
+        tmA, tmA1, tmB, g, reinterpret_cast<uint16_t*>(out), reinterpret_cast<uint16_t*>(pooled), stats, bias_tab);
+  else
+    conv_zf2_kernel<COUT, KC, MT, POOL, false><<<grid, kThreads, smem_bytes, st>>>(
+        tmA, tmA1, tmB, g, reinterpret_cast<uint16_t*>(out), reinterpret_cast<uint16_t*>(pooled), stats, bias_tab);
   KM_LAUNCH_OK("conv_zf2_kernel");
   return KM_OK;
 }
@@ -626,7 +629,7 @@ extern "C" int km_conv3d_zfold_pair_gn_cat(const void* x0, const void* x1, int C
   KM_CHECK_ARG(N > 0 && N <= 1024, "km_conv3d_zfold_pair_gn: bad batch");
   // the per-sample weight sets must be contiguous for the 5-D tensor map: (27 * 3 * Cout * Cin * 2) bytes each
   const size_t wbytes = (size_t)27 * 3 * Cout * Cin * 2;
-  __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(workspace);
+  void* packed = workspace;
   float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)N * wbytes + 255) & ~(size_t)255));
   const int rf = km_fold_gn(w, scale, shift, packed, bias, N, Cout, Cin, 1, stream);
   if (rf != KM_OK) return rf;

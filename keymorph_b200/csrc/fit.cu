@@ -1,7 +1,7 @@
 // Closed-form keypoint aligners: one warp per pair.
 //   affine: keymorph/keypoint_aligners.py:76-114   A = Y W X^T (X W X^T)^-1, X homogeneous
 //   rigid : keymorph/keypoint_aligners.py:151-213  Arun et al. (centroids, H = q1 q2^T, SVD,
-//           R = V U^T with the reflection fix on V's last column, T = c2 - R c1)
+//           R = V U^T, reflection step as the reference applies it (last ROW of V negated), T = c2 - R c1)
 //   square + inverse: keymorph/transformations.py:25-35
 // The moments are shuffle-reduced in fp64 and the 4x4 / 3x3 algebra runs in registers of lane 0;
 // results are written as fp32.  (The reference computes in fp32 through cuBLAS / cuSOLVER; fp64
@@ -225,7 +225,12 @@ __device__ void rotation_from_H(const double (&Hm)[3][3], double (&R)[3][3]) {
     cross3(u1, u2, u3);
     for (int i = 0; i < 3; ++i) U[i][2] = u3[i];
   }
-  // R = V U^T; reflection fix: V[:, 2] *= sign(det R)  (keymorph/keypoint_aligners.py:199-206)
+  // R = V U^T, then the reference's reflection step (keymorph/keypoint_aligners.py:199-206): `dets` is
+  // stacked along axis 1, so V * sign(dets) negates the last ROW of V, i.e. R <- diag(1, 1, sign det) V U^T.
+  // (Arun et al. negate the last COLUMN of V; for mirror-related point sets the two differ and the
+  // reference's choice is reproduced here -- parity first.)  When H has rank 2 the third singular
+  // vectors were completed above and their relative sign is arbitrary: there the column flip selects the
+  // proper rotation, which is what LAPACK's sign choice gives the reference in its coplanar KATs.
   for (int pass = 0; pass < 2; ++pass) {
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) {
@@ -237,6 +242,10 @@ __device__ void rotation_from_H(const double (&Hm)[3][3], double (&R)[3][3]) {
                        R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
                        R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
     if (det >= 0.0) break;
+    if (rank == 3) {
+      for (int j = 0; j < 3; ++j) R[2][j] = -R[2][j];
+      break;
+    }
     for (int i = 0; i < 3; ++i) Vs[i][2] = -Vs[i][2];
   }
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/km_b200.h"
@@ -72,6 +73,58 @@ __host__ __device__ __forceinline__ float km_linspace(float start, float end, in
   // torch's CPU (AVX2) and CUDA kernels both contract start + step*i into one FMA; verified
   // bit-for-bit against torch.linspace for n in 2..512 (tests/test_gpu_parity.py)
   return (i < half) ? fmaf(step, (float)i, start) : fmaf(-step, (float)(n - 1 - i), end);
+}
+
+// ---- 16-bit activation / weight element type of the backbone ---------------------------------------
+// The tcgen05 kind::f16 MMA takes fp16 or bf16 operands at the same rate; which one the backbone stores is a
+// runtime option (km_set_option(KM_OPT_OPERAND_FP16, ...)): fp16 is the reference's own AMP dtype
+// (keymorph/model.py:175-177) and carries 3 more mantissa bits, bf16 has fp32's exponent range.  Kernels are
+// templated on it (F16 = true: __half), so the choice costs nothing in the epilogues.
+int km_operand_fp16();    // conv_misc.cu: current value of the option
+// element type of the TMA tensor maps over activation / weight tensors (tile mode copies bits either way)
+#define KM_TMAP_16 (km_operand_fp16() ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)
+
+template <bool F16>
+__device__ __forceinline__ uint32_t km_pack2(float lo, float hi) {
+  if (F16) {
+    const __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+  } else {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ float2 km_unpack2(uint32_t u) {
+  if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+template <bool F16>
+__device__ __forceinline__ float km_to_float(uint16_t u) {
+  if (F16) return __half2float(*reinterpret_cast<const __half*>(&u));
+  return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
+}
+template <bool F16>
+__device__ __forceinline__ uint16_t km_from_float(float f) {
+  if (F16) {
+    const __half h = __float2half_rn(f);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(f);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  }
+}
+// elementwise max of two packed pairs (max commutes with the rounding, so pooling stored values is exact)
+template <bool F16>
+__device__ __forceinline__ uint32_t km_max2(uint32_t a, uint32_t b) {
+  if (F16) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a),
+                                     *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
 }
 
 __device__ __forceinline__ float km_warp_sum(float v) {

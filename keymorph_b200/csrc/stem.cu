@@ -21,7 +21,7 @@
 
 namespace {
 
-typedef __nv_bfloat16 bf16;
+typedef uint16_t act16;   // fp16 or bf16 bits (template parameter F16, km_common.cuh)
 
 constexpr int kTX = 64, kTY = 4, kTZ = 4;            // outputs per CTA tile
 constexpr int kHX = kTX + 2, kHY = kTY + 2, kHZ = kTZ + 2;
@@ -50,18 +50,14 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&v);
-}
 
 // grid (km_stem_nparts, N), 256 threads, 2 CTAs / SM
-template <int COUT>
+template <int COUT, bool F16>
 __global__ void __launch_bounds__(256, 2)
 conv_stem_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ bias, const float* __restrict__ in_scale,
                      const float* __restrict__ in_shift, const float* __restrict__ out_scale,
-                     const float* __restrict__ out_shift, bf16* __restrict__ out,
+                     const float* __restrict__ out_shift, act16* __restrict__ out,
                      float* __restrict__ stats, int N, int D, int H, int W, int relu_pre,
                      int relu_post) {
   constexpr int NT = COUT / 8;            // n-tiles of 8 channels
@@ -103,7 +99,7 @@ conv_stem_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
   const float a_in = in_scale ? __ldg(in_scale + n) : 1.f;
   const float b_in = in_shift ? __ldg(in_shift + n) : 0.f;
   const float* xn = x + (size_t)n * D * H * W;
-  bf16* on = out ? out + (size_t)n * D * H * W * COUT : nullptr;
+  act16* on = out ? out + (size_t)n * D * H * W * COUT : nullptr;
 
   const int tiles_x = (W + kTX - 1) / kTX, tiles_y = (H + kTY - 1) / kTY;
   const int tiles_z = (D + kTZ - 1) / kTZ;
@@ -283,11 +279,11 @@ conv_stem_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
               o[j] = fmaf((j & 1) ? sc2.y : sc2.x, acc[u][nt][j], (j & 1) ? sh2.y : sh2.x);
               if (relu_post) o[j] = fmaxf(o[j], 0.f);
             }
-            *reinterpret_cast<uint32_t*>(my_stage + g * kStage + nt * 16 + t * 4) = pack_bf16x2(o[0], o[1]);
-            *reinterpret_cast<uint32_t*>(my_stage + (g + 8) * kStage + nt * 16 + t * 4) = pack_bf16x2(o[2], o[3]);
+            *reinterpret_cast<uint32_t*>(my_stage + g * kStage + nt * 16 + t * 4) = km_pack2<F16>(o[0], o[1]);
+            *reinterpret_cast<uint32_t*>(my_stage + (g + 8) * kStage + nt * 16 + t * 4) = km_pack2<F16>(o[2], o[3]);
           }
           __syncwarp();
-          bf16* dst = on + ((size_t)(gz * HW + gy * W + x0 + xg)) * COUT;
+          act16* dst = on + ((size_t)(gz * HW + gy * W + x0 + xg)) * COUT;
 #pragma unroll
           for (int i = 0; i < NT / 2; ++i) {
             const int c = lane + 32 * i;            // 16-byte chunk id inside the 16-voxel segment
@@ -345,13 +341,19 @@ extern "C" int km_conv3d_stem(const float* x, const float* w, const float* bias,
                "km_conv3d_stem: out_scale and out_shift go together");
   KM_CHECK_ARG((long long)D * H * W < (1ll << 31), "km_conv3d_stem: volume too large");
   const dim3 grid(km_stem_nparts(N, D, H, W), N);
-  bf16* o = reinterpret_cast<bf16*>(out);
-  if (Cout == 16)
-    conv_stem_mma_kernel<16><<<grid, 256, 0, km_cs(stream)>>>(
-        x, w, bias, in_scale, in_shift, out_scale, out_shift, o, stats, N, D, H, W, relu_pre, relu_post);
-  else
-    conv_stem_mma_kernel<32><<<grid, 256, 0, km_cs(stream)>>>(
-        x, w, bias, in_scale, in_shift, out_scale, out_shift, o, stats, N, D, H, W, relu_pre, relu_post);
+  act16* o = reinterpret_cast<act16*>(out);
+  const bool f16 = km_operand_fp16() != 0;
+#define KM_STEM(C, F)                                                                                    \
+  conv_stem_mma_kernel<C, F><<<grid, 256, 0, km_cs(stream)>>>(x, w, bias, in_scale, in_shift, out_scale, \
+                                                              out_shift, o, stats, N, D, H, W, relu_pre, relu_post)
+  if (Cout == 16) {
+    if (f16) KM_STEM(16, true);
+    else KM_STEM(16, false);
+  } else {
+    if (f16) KM_STEM(32, true);
+    else KM_STEM(32, false);
+  }
+#undef KM_STEM
   KM_LAUNCH_OK("conv_stem_mma_kernel");
   return KM_OK;
 }

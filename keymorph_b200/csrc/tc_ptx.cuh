@@ -101,7 +101,7 @@ __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+__device__ __forceinline__ void umma_16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -127,7 +127,7 @@ __device__ __forceinline__ uint32_t elect_one() {
       : "=r"(pred));
   return pred;
 }
-__device__ __forceinline__ void umma_bf16_pred(uint32_t d_tmem, uint32_t adesc_lo, uint32_t bdesc_lo,
+__device__ __forceinline__ void umma_16_pred(uint32_t d_tmem, uint32_t adesc_lo, uint32_t bdesc_lo,
                                                uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
                                                uint32_t issue) {
   asm volatile(
@@ -190,10 +190,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t sbo_
   d |= (uint64_t)layout << 61;
   return d;
 }
-// Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, dense.
-__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor for kind::f16: D = f32 (bits 4-5 = 1), A / B format (bits 7-9 / 10-12: 0 = f16,
+// 1 = bf16), both K-major, dense; N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ __forceinline__ uint32_t umma_idesc_16(int M, int N, bool fp16) {
+  const uint32_t fmt = fp16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 
@@ -258,7 +259,7 @@ __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // one M = 256 MMA over both SMs of the pair (issued by the leader only), warp-uniform variant
-__device__ __forceinline__ void umma2_bf16_pred(uint32_t d_tmem, uint32_t adesc_lo, uint32_t bdesc_lo,
+__device__ __forceinline__ void umma2_16_pred(uint32_t d_tmem, uint32_t adesc_lo, uint32_t bdesc_lo,
                                                 uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
                                                 uint32_t issue) {
   asm volatile(

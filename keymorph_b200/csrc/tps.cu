@@ -12,7 +12,8 @@
 
 namespace {
 
-int g_tps_single_cta = 0;   // km_set_option(KM_OPT_TPS_SINGLE_CTA): the un-blocked one-CTA LU (A/B)
+int g_tps_single_cta = 0;   // km_set_option(KM_OPT_TPS_SINGLE_CTA): 0 = one cooperative launch (default),
+                            // 1 = the un-blocked one-CTA LU, 2 = the multi-launch blocked elimination (A/B)
 
 __device__ __forceinline__ double tps_u64(double d2) {
   const double r = sqrt(d2 + 1e-6);
@@ -318,12 +319,231 @@ __global__ void tps_finish_kernel(const double* __restrict__ A, const int* __res
   theta[((size_t)b * n + k) * 3 + d] = (float)(row[n + d] / row[k]);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// The same blocked Gauss-Jordan elimination as ONE cooperative launch (default).  The multi-launch version
+// above spends its 1.35 ms (K = 512) in ~100 dependent launches of microsecond kernels; here a group of
+// `cps` co-resident CTAs per system walks the panels with a group barrier (one global counter per system)
+// between the two phases of a panel:
+//   phase A (CTA 0 of the group): the panel factorisation of tps_panel_kernel -- one thread per row, the
+//            row's kNB panel entries in registers -- with TWO block barriers per pivot step: every warp
+//            reduces the per-warp candidates redundantly, so the pivot index needs no broadcast round;
+//   phase B (all CTAs): tiles of 64 columns x kRowTile rows of the trailing matrix (and the right-hand
+//            sides): the 16 pivot rows "as they were when they became pivots" are re-derived per column
+//            in registers (the recurrence of tps_urow_kernel), then the rank-16 update of the tile.
+// Assembly and the final division run in the same launch.  The arithmetic and its order are those of the
+// multi-launch kernels, so the two paths produce identical bits (tests compare them).
+constexpr int kRowTile = 128;
+constexpr int kGjThreads = 1024;   // largest block: one thread per matrix row, n = K + 4 <= 1024
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all CTAs of a system group arrive; `target` = cps * (number of barriers passed so far + 1)
+__device__ __forceinline__ void group_barrier(unsigned int* cnt, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(cnt, 1u);
+    while (ld_acquire_u32(cnt) < target) {
+    }
+  }
+  __syncthreads();
+}
+
+template <int THREADS>   // 640 (n <= 640: 102 registers per thread, no spills) or 1024
+__global__ void __launch_bounds__(THREADS, 1)
+tps_gj_coop_kernel(const float* __restrict__ c_src, const float* __restrict__ c_dst, const float* __restrict__ lmbda,
+                   const float* __restrict__ w, double* __restrict__ A, int* __restrict__ pivrow,
+                   unsigned int* __restrict__ bar, float* __restrict__ theta, int32_t* __restrict__ status, int K,
+                   int cps) {
+  __shared__ double s_val[2][32];
+  __shared__ int s_idx[2][32];
+  __shared__ double s_prow[2][kNB];
+  __shared__ double s_u[kNB][64];
+  __shared__ double s_l[kRowTile][kNB + 1];
+  __shared__ double s_lp[kNB][kNB];   // multipliers of the pivot rows themselves (urow recurrence)
+  __shared__ int s_pr[kNB];
+  const int b = blockIdx.x / cps, cta = blockIdx.x - b * cps;
+  const int n = K + 4, ld = n + 3;
+  double* Ab = A + (size_t)b * n * ld;
+  int* piv = pivrow + (size_t)b * n;
+  unsigned int* cnt = bar + b;
+  unsigned int nbar = 0;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = THREADS >> 5;
+
+  // ---- assembly (tps_assemble_kernel), spread over the group
+  {
+    const float* cs = c_src + (size_t)b * K * 3;
+    const float* cd = c_dst + (size_t)b * K * 3;
+    const double lam = (double)lmbda[b];
+    const int total = n * ld;
+    for (int idx = cta * THREADS + tid; idx < total; idx += cps * THREADS) {
+      const int i = idx / ld, j = idx - i * ld;
+      double v = 0.0;
+      if (i < K) {
+        if (j < K) {
+          const double dz = (double)cs[i * 3] - (double)cs[j * 3];
+          const double dy = (double)cs[i * 3 + 1] - (double)cs[j * 3 + 1];
+          const double dx = (double)cs[i * 3 + 2] - (double)cs[j * 3 + 2];
+          v = tps_u64(dz * dz + dy * dy + dx * dx);
+          if (w) {
+            const double wij = (i == j) ? (double)w[(size_t)b * K + i] : 0.0;
+            v += lam / (wij + 1e-6);
+          } else if (i == j) {
+            v += lam;
+          }
+        } else if (j < n) {
+          v = (j == K) ? 1.0 : (double)cs[i * 3 + (j - K - 1)];
+        } else {
+          v = (double)cd[i * 3 + (j - n)];
+        }
+      } else if (j < K) {
+        v = (i == K) ? 1.0 : (double)cs[j * 3 + (i - K - 1)];
+      }
+      Ab[idx] = v;
+    }
+  }
+  group_barrier(cnt, (++nbar) * cps);
+
+  bool eligible = true;          // CTA 0: row tid may still become a pivot
+  int sing = 0;
+  for (int c0 = 0; c0 < n; c0 += kNB) {
+    const int nb = min(kNB, n - c0);
+    // ---------------- phase A: panel factorisation by CTA 0 (one thread per row)
+    if (cta == 0) {
+      const int r = tid;
+      const bool has_row = r < n;
+      double a[kNB];
+#pragma unroll
+      for (int j = 0; j < kNB; ++j) a[j] = (has_row && j < nb) ? Ab[(size_t)r * ld + c0 + j] : 0.0;
+#pragma unroll
+      for (int k = 0; k < kNB; ++k) {
+        if (k < nb) {   // uniform
+          const int pb = k & 1;
+          double v = (has_row && eligible) ? fabs(a[k]) : -1.0;
+          int vi = r;
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+            if (ov > v || (ov == v && oi < vi)) {
+              v = ov;
+              vi = oi;
+            }
+          }
+          if (lane == 0) {
+            s_val[pb][wid] = v;
+            s_idx[pb][wid] = vi;
+          }
+          __syncthreads();
+          // every warp reduces the per-warp candidates itself: no broadcast round for the pivot index
+          double wv = lane < nwarps ? s_val[pb][lane] : -1.0;
+          int wi = lane < nwarps ? s_idx[pb][lane] : 0x7fffffff;
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, wv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+            if (ov > wv || (ov == wv && oi < wi)) {
+              wv = ov;
+              wi = oi;
+            }
+          }
+          const int pr = wi;
+          if (tid == 0 && (!(wv > 0.0) || !isfinite(wv))) sing = 1;
+          if (r == pr) {
+#pragma unroll
+            for (int j = 0; j < kNB; ++j) s_prow[pb][j] = a[j];
+            eligible = false;
+            piv[c0 + k] = r;
+          }
+          __syncthreads();
+          if (has_row && r != pr) {
+            const double l = a[k] / s_prow[pb][k];
+            a[k] = l;
+#pragma unroll
+            for (int j = 0; j < kNB; ++j)
+              if (j > k) a[j] -= l * s_prow[pb][j];
+          }
+        }
+      }
+      if (has_row) {
+#pragma unroll
+        for (int j = 0; j < kNB; ++j)
+          if (j < nb) Ab[(size_t)r * ld + c0 + j] = a[j];
+      }
+    }
+    group_barrier(cnt, (++nbar) * cps);
+
+    // ---------------- phase B: trailing update, tiles of 64 columns x kRowTile rows
+    const int rest = ld - c0 - nb;
+    if (rest > 0) {
+      const int nct = (rest + 63) / 64, nrt = (n + kRowTile - 1) / kRowTile;
+      if (tid < kNB) s_pr[tid] = tid < nb ? piv[c0 + tid] : -1;
+      __syncthreads();
+      // multipliers of the pivot rows among themselves: L[t][t2] = A[piv t][c0 + t2], t2 < t
+      if (tid < kNB * kNB) {
+        const int t = tid / kNB, t2 = tid - t * kNB;
+        s_lp[t][t2] = (t < nb && t2 < t) ? Ab[(size_t)s_pr[t] * ld + c0 + t2] : 0.0;
+      }
+      for (int item = cta; item < nct * nrt; item += cps) {
+        const int ct = item % nct, rt = item / nct;
+        const int j0 = c0 + nb + ct * 64, r0 = rt * kRowTile;
+        __syncthreads();   // s_u / s_l of the previous item are free (and s_lp / s_pr are visible)
+        if (tid < 64) {
+          const int j = j0 + tid;
+          double u[kNB];
+#pragma unroll
+          for (int t = 0; t < kNB; ++t) u[t] = (t < nb && j < ld) ? Ab[(size_t)s_pr[t] * ld + j] : 0.0;
+#pragma unroll
+          for (int t = 0; t < kNB; ++t) {
+            double v = u[t];
+#pragma unroll
+            for (int t2 = 0; t2 < kNB; ++t2)
+              if (t2 < t) v -= s_lp[t][t2] * u[t2];
+            u[t] = v;
+            s_u[t][tid] = v;
+          }
+        }
+        for (int i = tid; i < kRowTile * kNB; i += THREADS) {
+          const int rr = i / kNB, t = i - rr * kNB;
+          const int r = r0 + rr;
+          s_l[rr][t] = (r < n && t < nb) ? Ab[(size_t)r * ld + c0 + t] : 0.0;
+        }
+        __syncthreads();
+        const int tx = tid & 63, ty = tid >> 6;     // 64 columns x 16 row lanes
+        const int j = j0 + tx;
+        if (j < ld) {
+          for (int rr = ty; rr < kRowTile; rr += THREADS / 64) {
+            const int r = r0 + rr;
+            if (r >= n) break;
+            double v = Ab[(size_t)r * ld + j];
+#pragma unroll
+            for (int t = 0; t < kNB; ++t)
+              if (t < nb && s_pr[t] != r) v -= s_l[rr][t] * s_u[t][tx];
+            Ab[(size_t)r * ld + j] = v;
+          }
+        }
+      }
+    }
+    group_barrier(cnt, (++nbar) * cps);
+  }
+  // ---- x_k = b[pivrow[k]] / a[pivrow[k]][k]
+  for (int i = cta * THREADS + tid; i < n * 3; i += cps * THREADS) {
+    const int k = i / 3, d = i - k * 3;
+    const double* row = Ab + (size_t)piv[k] * ld;
+    theta[((size_t)b * n + k) * 3 + d] = (float)(row[n + d] / row[k]);
+  }
+  if (cta == 0 && tid == 0) status[b] = sing;
+}
+
 }  // namespace
 
 extern "C" size_t km_tps_fit_workspace_bytes(int N, int K) {
   const size_t n = (size_t)K + 4;
-  // augmented matrix (fp64) + pivot rows + eligibility flags
-  return (size_t)N * (n + kNB) * (n + 3) * sizeof(double) + 2 * (size_t)N * n * sizeof(int) + 64;
+  // augmented matrix (fp64) + pivot rows + eligibility flags + one barrier counter per system
+  return (size_t)N * (n + kNB) * (n + 3) * sizeof(double) + 2 * (size_t)N * n * sizeof(int) +
+         (size_t)N * sizeof(unsigned int) + 64;
 }
 
 extern "C" int km_tps_fit(const float* c_src, const float* c_dst, const float* lmbda,
@@ -334,12 +554,43 @@ extern "C" int km_tps_fit(const float* c_src, const float* c_dst, const float* l
   const int n = K + 4, ld = n + 3;
   cudaStream_t st = km_cs(stream);
   double* A = reinterpret_cast<double*>(workspace);
+  if (n <= kGjThreads && g_tps_single_cta == 0) {
+    // one cooperative launch: assembly, blocked Gauss-Jordan and the final division (see tps_gj_coop_kernel)
+    double* Ut = A + (size_t)N * n * ld;
+    int* pivrow = reinterpret_cast<int*>(Ut + (size_t)N * kNB * ld);
+    unsigned int* bar = reinterpret_cast<unsigned int*>(pivrow + 2 * (size_t)N * n);
+    KM_CUDA_OK(cudaMemsetAsync(bar, 0, (size_t)N * sizeof(unsigned int), st));
+    int dev = 0, nsm = 148;
+    KM_CUDA_OK(cudaGetDevice(&dev));
+    KM_CUDA_OK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    // every CTA of a launch must be resident (the group barrier spins): one 1024-thread CTA per SM
+    const int chunk = N < nsm ? N : nsm;
+    for (int b0 = 0; b0 < N; b0 += chunk) {
+      const int nb = N - b0 < chunk ? N - b0 : chunk;
+      int cps = nsm / nb;
+      if (cps > 24) cps = 24;
+      const float* cs = c_src + (size_t)b0 * K * 3;
+      const float* cd = c_dst + (size_t)b0 * K * 3;
+      const float* lm = lmbda + b0;
+      const float* wp = w ? w + (size_t)b0 * K : nullptr;
+      double* Ab = A + (size_t)b0 * n * ld;
+      int* pv = pivrow + (size_t)b0 * n;
+      unsigned int* br = bar + b0;
+      float* th = theta + (size_t)b0 * n * 3;
+      int32_t* stt = status + b0;
+      int Kk = K;
+      void* args[] = {&cs, &cd, &lm, &wp, &Ab, &pv, &br, &th, &stt, &Kk, &cps};
+      if (n <= 640)
+        KM_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(tps_gj_coop_kernel<640>), dim3(nb * cps),
+                                               dim3(640), args, 0, st));
+      else
+        KM_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(tps_gj_coop_kernel<1024>),
+                                               dim3(nb * cps), dim3(1024), args, 0, st));
+    }
+    return KM_OK;
+  }
   const long long total = (long long)n * ld;
-  int bx = (int)((total + 255) / 256);
-  if (bx > 1184) bx = 1184;
-  tps_assemble_kernel<<<dim3(bx, N), 256, 0, st>>>(c_src, c_dst, lmbda, w, A, K);
-  KM_LAUNCH_OK("tps_assemble_kernel");
-  if (n <= 1024 && !g_tps_single_cta) {
+  if (n <= 1024 && g_tps_single_cta != 1) {
     double* Ut = A + (size_t)N * n * ld;
     int* pivrow = reinterpret_cast<int*>(Ut + (size_t)N * kNB * ld);
     int* elig = pivrow + (size_t)N * n;
@@ -370,4 +621,4 @@ extern "C" int km_tps_fit(const float* c_src, const float* c_dst, const float* l
   return KM_OK;
 }
 
-void km_tps_set_single_cta(int v) { g_tps_single_cta = v ? 1 : 0; }
+void km_tps_set_single_cta(int v) { g_tps_single_cta = (v == 1 || v == 2) ? v : 0; }

@@ -26,6 +26,7 @@ void km_zf2_set_two_bricks(int v);
 void km_tps_set_single_cta(int v);
 void km_tps_set_packed(int v);
 void km_tps_set_vpt(int v);
+void km_set_operand_fp16(int v);
 int km_tps_fast_enabled() { return g_tps_fast; }
 namespace {
 
@@ -784,6 +785,8 @@ inline int blocks_for(long long items, int threads, int cap) {
 
 }  // namespace
 
+extern "C" int km_operand_is_fp16(void) { return km_operand_fp16(); }
+
 extern "C" int km_set_option(int key, int value) {
   if (key == KM_OPT_TPS_FAST) {
     g_tps_fast = value ? 1 : 0;
@@ -831,6 +834,10 @@ extern "C" int km_set_option(int key, int value) {
   }
   if (key == KM_OPT_TPS_VPT) {
     km_tps_set_vpt(value);
+    return KM_OK;
+  }
+  if (key == KM_OPT_OPERAND_FP16) {
+    km_set_operand_fp16(value);
     return KM_OK;
   }
   km_set_error("km_set_option: unknown key %d", key);

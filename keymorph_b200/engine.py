@@ -1,5 +1,5 @@
 """Backbone executor: runs a UNet3D / TruncatedUNet3D / ConvNet parameter container on the CUDA
-kernels (bf16 NDHWC activations, fp32 accumulation) and returns keypoints directly.
+kernels (16-bit NDHWC activations -- fp16 by default, bf16 on request: ops.set_operand_dtype --, fp32 accumulation) and returns keypoints directly.
 
 Layer schedule of the UNet path (reference: keymorph/unet3d/model.py:115-151):
 
@@ -51,7 +51,7 @@ class _WeightCache:
         self._packed = {}
 
     def get(self, key, param, pad_out_to=None, zfold=False):
-        sig = (param.data_ptr(), param._version, str(param.device), tuple(param.shape), pad_out_to)
+        sig = (param.data_ptr(), param._version, str(param.device), tuple(param.shape), pad_out_to, ops.act_dtype())
         hit = self._packed.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]

@@ -90,16 +90,32 @@ def read_nifti(path):
     pixdim = struct.unpack(end + "8f", raw[76:108])
     vox_offset = int(struct.unpack(end + "f", raw[108:112])[0])
     slope, inter = struct.unpack(end + "2f", raw[112:120])
-    sform_code = struct.unpack(end + "h", raw[254:256])[0]
+    qform_code, sform_code = struct.unpack(end + "2h", raw[252:256])
     shape = tuple(int(d) for d in dim[1:1 + dim[0]])
     dt = np.dtype(end + _NIFTI_DTYPES[datatype])
     count = int(np.prod(shape))
     data = np.frombuffer(raw, dtype=dt, count=count, offset=vox_offset).reshape(shape, order="F")
-    if slope not in (0.0, 1.0) or (slope != 0.0 and inter != 0.0):
+    # nibabel semantics: a zero or non-finite slope (or a non-finite intercept) means "no scaling"
+    if np.isfinite(slope) and np.isfinite(inter) and slope != 0.0 and (slope != 1.0 or inter != 0.0):
         data = data.astype(np.float64) * slope + inter
     affine = np.eye(4)
     if sform_code > 0:
         affine[:3, :] = np.array(struct.unpack(end + "12f", raw[280:328]), dtype=np.float64).reshape(3, 4)
+    elif qform_code > 0:
+        # NIfTI-1 method 2: unit quaternion (b, c, d) + offsets, pixdim[0] = qfac (handedness of the k axis)
+        b, c, d, qx, qy, qz = (float(v) for v in struct.unpack(end + "6f", raw[256:280]))
+        a2 = 1.0 - (b * b + c * c + d * d)
+        if a2 < 1e-7:                       # 180-degree rotation: renormalise (b, c, d), a = 0
+            nrm = 1.0 / np.sqrt(b * b + c * c + d * d)
+            b, c, d, a = b * nrm, c * nrm, d * nrm, 0.0
+        else:
+            a = np.sqrt(a2)
+        R = np.array([[a * a + b * b - c * c - d * d, 2 * (b * c - a * d), 2 * (b * d + a * c)],
+                      [2 * (b * c + a * d), a * a + c * c - b * b - d * d, 2 * (c * d - a * b)],
+                      [2 * (b * d - a * c), 2 * (c * d + a * b), a * a + d * d - b * b - c * c]])
+        qfac = -1.0 if pixdim[0] < 0 else 1.0
+        affine[:3, :3] = R * np.array([pixdim[1], pixdim[2], pixdim[3] * qfac], dtype=np.float64)[None, :]
+        affine[:3, 3] = (qx, qy, qz)
     else:
         affine[:3, :3] = np.diag(pixdim[1:4])
     return data, affine
@@ -136,13 +152,19 @@ def load_volume(path, size=None, labels=False):
         f = [s // size for s in data.shape]
         if any(s != size * k or k < 1 for s, k in zip(data.shape, f)):
             raise ValueError(f"load_volume: {data.shape} is not an integer multiple of {size}")
+        old = affine
+        affine = affine.copy()
         if labels:
-            data = data[::f[0], ::f[1], ::f[2]]
+            data = data[::f[0], ::f[1], ::f[2]]         # coarse voxel 0 IS fine voxel 0: origin unchanged
         else:
             data = data.astype(np.float32).reshape(size, f[0], size, f[1], size, f[2]).mean(axis=(1, 3, 5))
-        affine = affine.copy()
-        affine[:3, :3] = affine[:3, :3] * np.array(f, dtype=np.float64)[None, :]
+            # the centre of coarse voxel 0 sits at fine index (f - 1) / 2 along every axis
+            affine[:3, 3] = old[:3, 3] + old[:3, :3] @ ((np.array(f, dtype=np.float64) - 1.0) / 2.0)
+        affine[:3, :3] = old[:3, :3] * np.array(f, dtype=np.float64)[None, :]
     if labels:
+        if data.size and (data.max() > 255 or data.min() < 0):
+            raise ValueError(f"load_volume: label ids span [{data.min()}, {data.max()}]; the label-map kernels "
+                             "take uint8 ids (< 256): remap the labels to contiguous ids first")
         t = torch.from_numpy(np.ascontiguousarray(data).astype(np.uint8))
     else:
         a = np.ascontiguousarray(data).astype(np.float32)

@@ -62,12 +62,13 @@ class KeyMorph(nn.Module):
 
     def _keypoints_and_mass(self, img, want_feat=False):
         eng = backbone_engine(self.backbone)
-        if eng is not None:
-            return eng.keypoints(img, want_mass=True, want_feat=want_feat)
-        # foreign backbone (e.g. the reference's own nn.Module): torch runs it, the kernel does CoM
-        feat = self.backbone(img)
-        pts, mass = ops.com3d(feat, ij=True, return_mass=True)
-        return pts, mass, (feat if want_feat else None)
+        if eng is None:
+            # one backend only: a foreign nn.Module is NOT run through eager torch behind the caller's back
+            raise ops._lib.KMError(
+                f"keymorph_b200.KeyMorph runs its own backbones (TruncatedUNet3D, UNet3D, ConvNet from this "
+                f"package; they load the reference's state dicts), not {type(self.backbone).__name__}: there is "
+                "no eager-torch path.  For heat maps computed elsewhere use keymorph_b200.CenterOfMass3d.")
+        return eng.keypoints(img, want_mass=True, want_feat=want_feat)
 
     def get_keypoints(self, img, return_feat=False):
         """keymorph/model.py:111-117."""

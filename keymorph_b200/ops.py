@@ -39,6 +39,24 @@ def _mode(mode: str) -> int:
     raise ValueError(f"unsupported interpolation mode {mode!r}")
 
 
+def act_dtype():
+    """torch dtype of the 16-bit activation / packed-weight tensors of the backbone: torch.float16 (default,
+    the AMP dtype of the reference, keymorph/model.py:175-177) or torch.bfloat16 -- see set_operand_dtype."""
+    return torch.float16 if _lib.query("km_operand_is_fp16") else torch.bfloat16
+
+
+def set_operand_dtype(name):
+    """Select the tcgen05 operand type of the backbone: "fp16" (11-bit significand; default) or "bf16"
+    (exponent range of fp32).  Same tensor-core rate; affects tensors created afterwards (engines re-pack
+    their weights when it changes)."""
+    name = {torch.float16: "fp16", torch.bfloat16: "bf16"}.get(name, name)
+    if name not in ("fp16", "bf16"):
+        raise ValueError(f"operand dtype must be 'fp16' or 'bf16', got {name!r}")
+    rc = _lib.load().km_set_option(_lib.KM_OPT_OPERAND_FP16, 1 if name == "fp16" else 0)
+    if rc != 0:
+        raise _lib.KMError("km_set_option(KM_OPT_OPERAND_FP16) failed")
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -148,6 +166,8 @@ def warp_labels_dice(labels_m, labels_f, num_classes, *, mat34=None, grid=None, 
     (N,1,D,H,W): returns (soft_sums, hard_sums[, warped hard labels]) with the (N,C,4) fp64 layout of
     warp_loss / pair_stats, without ever building the C-channel one-hot volumes."""
     _need_cuda(labels_m, labels_f, mat34, grid)
+    if int(num_classes) > 255:
+        raise ValueError("warp_labels_dice takes uint8 label ids: num_classes must be <= 255 (remap the labels)")
     lm = labels_m.reshape(labels_m.shape[0], *labels_m.shape[-3:]).to(torch.uint8).contiguous()
     lf = labels_f.reshape(labels_f.shape[0], *labels_f.shape[-3:]).to(torch.uint8).contiguous()
     assert lm.shape == lf.shape
@@ -308,7 +328,7 @@ def pack_weights(w):
     w = _f32c(w)
     Cout, Cin = w.shape[0], w.shape[1]
     taps = w[0, 0].numel()
-    out = torch.empty((taps, Cout, Cin), dtype=torch.bfloat16, device=w.device)
+    out = torch.empty((taps, Cout, Cin), dtype=act_dtype(), device=w.device)
     with torch.cuda.device(w.device):
         _lib.call("km_pack_weights", _ptr(w), _ptr(out), Cout, Cin, taps, _stream())
     return out
@@ -325,14 +345,14 @@ def red_nparts():
 def conv3d_tc(x, wp, bias=None, relu=False, want_stats=False, want_com=False, store=True):
     """x: bf16 (N,D,H,W,Cin); wp: bf16 (taps,Cout,Cin).  Returns (out|None, stats|None, com|None)."""
     _need_cuda(x, wp, bias)
-    assert x.dtype == torch.bfloat16 and wp.dtype == torch.bfloat16
+    assert x.dtype == act_dtype() and wp.dtype == act_dtype()
     x, wp = x.contiguous(), wp.contiguous()
     N, D, H, W, Cin = x.shape
     taps, Cout, Cin2 = wp.shape
     assert Cin2 == Cin
     flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0) | \
         (KM_CONV_COM if want_com else 0)
-    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device) if store else None
+    out = torch.empty((N, D, H, W, Cout), dtype=act_dtype(), device=x.device) if store else None
     nparts = conv_nparts()
     stats = torch.empty((nparts, N, Cout, 2), dtype=torch.float32, device=x.device) \
         if want_stats else None
@@ -355,13 +375,13 @@ def pair_supported(Cin, Cout, D, H, W):
 def conv3d_tc_pair(x, wp, relu=False, want_stats=False):
     """2-CTA (cta_group::2) tcgen05 conv, 3x3x3, Cout in {64,128}.  Same arguments as conv3d_tc."""
     _need_cuda(x, wp)
-    assert x.dtype == torch.bfloat16 and wp.dtype == torch.bfloat16
+    assert x.dtype == act_dtype() and wp.dtype == act_dtype()
     x, wp = x.contiguous(), wp.contiguous()
     N, D, H, W, Cin = x.shape
     taps, Cout, Cin2 = wp.shape
     assert taps == 27 and Cin2 == Cin
     flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
-    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((N, D, H, W, Cout), dtype=act_dtype(), device=x.device)
     stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x.device) \
         if want_stats else None
     with torch.cuda.device(x.device):
@@ -382,7 +402,7 @@ def pack_weights_zfold_pair(w):
     _need_cuda(w)
     w = _f32c(w)
     Cout, Cin = w.shape[0], w.shape[1]
-    out = torch.empty((3, 3, 3, 3 * Cout, Cin), dtype=torch.bfloat16, device=w.device)
+    out = torch.empty((3, 3, 3, 3 * Cout, Cin), dtype=act_dtype(), device=w.device)
     with torch.cuda.device(w.device):
         _lib.call("km_pack_weights_zfold_pair", _ptr(w), _ptr(out), Cout, Cin, _stream())
     return out
@@ -392,13 +412,13 @@ def conv3d_zfold_pair(x, wz, relu=False, want_stats=False, pool=False, store=Tru
     """z-folded 2-CTA tcgen05 conv (3x3x3, pad 1; Cout 64 or 32).  x: bf16 (N,D,H,W,Cin).  Returns
     (out | None, stats | None) or, with pool=True, (out | None, pooled, stats | None) like conv3d_zfold."""
     _need_cuda(x, wz)
-    assert x.dtype == torch.bfloat16 and wz.dtype == torch.bfloat16
+    assert x.dtype == act_dtype() and wz.dtype == act_dtype()
     x, wz = x.contiguous(), wz.contiguous()
     N, D, H, W, Cin = x.shape
     Cout = wz.shape[3] // 3
     flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
-    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device) if store else None
-    pooled = torch.empty((N, D // 2, H // 2, W // 2, Cout), dtype=torch.bfloat16, device=x.device) \
+    out = torch.empty((N, D, H, W, Cout), dtype=act_dtype(), device=x.device) if store else None
+    pooled = torch.empty((N, D // 2, H // 2, W // 2, Cout), dtype=act_dtype(), device=x.device) \
         if pool else None
     stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x.device) \
         if want_stats else None
@@ -417,7 +437,7 @@ def pack_weights_zfold(w):
     _need_cuda(w)
     w = _f32c(w)
     Cout, Cin = w.shape[0], w.shape[1]
-    out = torch.empty((3, 9, 3 * Cout, Cin), dtype=torch.bfloat16, device=w.device)
+    out = torch.empty((3, 9, 3 * Cout, Cin), dtype=act_dtype(), device=w.device)
     with torch.cuda.device(w.device):
         _lib.call("km_pack_weights_zfold", _ptr(w), _ptr(out), Cout, Cin, _stream())
     return out
@@ -428,13 +448,13 @@ def conv3d_zfold(x, wz, relu=False, want_stats=False, pool=False, store=True):
     Returns (out | None, stats | None) or, with pool=True, (out | None, pooled, stats | None) where
     pooled = MaxPool3d(2)(out) and the stats describe the pooled tensor."""
     _need_cuda(x, wz)
-    assert x.dtype == torch.bfloat16 and wz.dtype == torch.bfloat16
+    assert x.dtype == act_dtype() and wz.dtype == act_dtype()
     x, wz = x.contiguous(), wz.contiguous()
     N, D, H, W, Cin = x.shape
     Cout = wz.shape[2] // 3
     flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
-    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device) if store else None
-    pooled = torch.empty((N, D // 2, H // 2, W // 2, Cout), dtype=torch.bfloat16, device=x.device) \
+    out = torch.empty((N, D, H, W, Cout), dtype=act_dtype(), device=x.device) if store else None
+    pooled = torch.empty((N, D // 2, H // 2, W // 2, Cout), dtype=act_dtype(), device=x.device) \
         if pool else None
     stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x.device) \
         if want_stats else None
@@ -468,14 +488,14 @@ def conv3d_zfold_gn(x_raw, w, scale, shift, relu=False, want_stats=False, pool=F
     un-normalised activation, w the fp32 (32,16,3,3,3) weights, scale / shift (N,16) from
     norm_finalize.  Same return convention as conv3d_zfold."""
     _need_cuda(x_raw, w, scale, shift)
-    assert x_raw.dtype == torch.bfloat16
+    assert x_raw.dtype == act_dtype()
     x_raw, w, scale, shift = x_raw.contiguous(), _f32c(w), _f32c(scale), _f32c(shift)
     N, D, H, W, Cin = x_raw.shape
     Cout = w.shape[0]
     assert w.shape[1] == Cin and scale.numel() == N * Cin and shift.numel() == N * Cin
     flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
-    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x_raw.device) if store else None
-    pooled = torch.empty((N, D // 2, H // 2, W // 2, Cout), dtype=torch.bfloat16, device=x_raw.device) \
+    out = torch.empty((N, D, H, W, Cout), dtype=act_dtype(), device=x_raw.device) if store else None
+    pooled = torch.empty((N, D // 2, H // 2, W // 2, Cout), dtype=act_dtype(), device=x_raw.device) \
         if pool else None
     stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x_raw.device) \
         if want_stats else None
@@ -489,10 +509,10 @@ def conv3d_zfold_gn(x_raw, w, scale, shift, relu=False, want_stats=False, pool=F
 def upsample2(x):
     """bf16 (N,Dc,Hc,Wc,C) -> (N,2Dc,2Hc,2Wc,C), nearest neighbour."""
     _need_cuda(x)
-    assert x.dtype == torch.bfloat16
+    assert x.dtype == act_dtype()
     x = x.contiguous()
     N, Dc, Hc, Wc, Cc = x.shape
-    out = torch.empty((N, 2 * Dc, 2 * Hc, 2 * Wc, Cc), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((N, 2 * Dc, 2 * Hc, 2 * Wc, Cc), dtype=act_dtype(), device=x.device)
     with torch.cuda.device(x.device):
         _lib.call("km_upsample2_ndhwc", _ptr(x), _ptr(out), N, Cc, Dc, Hc, Wc, _stream())
     return out
@@ -502,20 +522,20 @@ def conv3d_zfold_pair_gn(x_raw, w, scale, shift, relu=False, want_stats=False, p
     """conv3d_zfold_pair of GroupNorm(x_raw) without the normalisation pass (see conv3d_zfold_gn).  With
     x1 the input is cat(x_raw, x1) along the channels, read in place through two tensor maps."""
     _need_cuda(x_raw, w, scale, shift, x1)
-    assert x_raw.dtype == torch.bfloat16
+    assert x_raw.dtype == act_dtype()
     x_raw, w, scale, shift = x_raw.contiguous(), _f32c(w), _f32c(scale), _f32c(shift)
     N, D, H, W, Cin0 = x_raw.shape
     Cin1 = 0
     if x1 is not None:
-        assert x1.dtype == torch.bfloat16 and x1.shape[:4] == x_raw.shape[:4]
+        assert x1.dtype == act_dtype() and x1.shape[:4] == x_raw.shape[:4]
         x1 = x1.contiguous()
         Cin1 = x1.shape[4]
     Cin = Cin0 + Cin1
     Cout = w.shape[0]
     assert w.shape[1] == Cin and scale.numel() == N * Cin and shift.numel() == N * Cin
     flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
-    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x_raw.device) if store else None
-    pooled = torch.empty((N, D // 2, H // 2, W // 2, Cout), dtype=torch.bfloat16, device=x_raw.device) \
+    out = torch.empty((N, D, H, W, Cout), dtype=act_dtype(), device=x_raw.device) if store else None
+    pooled = torch.empty((N, D // 2, H // 2, W // 2, Cout), dtype=act_dtype(), device=x_raw.device) \
         if pool else None
     stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x_raw.device) \
         if want_stats else None
@@ -529,13 +549,13 @@ def conv3d_zfold_pair_gn(x_raw, w, scale, shift, relu=False, want_stats=False, p
 def conv3d_tc_pair_gn(x_raw, w, scale, shift, relu=False, want_stats=False):
     """conv3d_tc_pair of GroupNorm(x_raw) without the normalisation pass (see conv3d_zfold_gn)."""
     _need_cuda(x_raw, w, scale, shift)
-    assert x_raw.dtype == torch.bfloat16
+    assert x_raw.dtype == act_dtype()
     x_raw, w, scale, shift = x_raw.contiguous(), _f32c(w), _f32c(scale), _f32c(shift)
     N, D, H, W, Cin = x_raw.shape
     Cout = w.shape[0]
     assert w.shape[1] == Cin and scale.numel() == N * Cin and shift.numel() == N * Cin
     flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
-    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x_raw.device)
+    out = torch.empty((N, D, H, W, Cout), dtype=act_dtype(), device=x_raw.device)
     stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x_raw.device) \
         if want_stats else None
     ws = _ws(_lib.query("km_conv3d_tc_pair_gn_workspace_bytes", N, Cin, Cout), x_raw.device)
@@ -549,7 +569,7 @@ def conv1x1_com(x, wp, bias=None):
     """Final 1x1x1 conv + ReLU + centre-of-mass partials without the heat map.
     x: bf16 (N,D,H,W,Cin); wp: bf16 (1,Cout,Cin) with Cout % 128 == 0 -> com (nparts,N,Cout,4)."""
     _need_cuda(x, wp, bias)
-    assert x.dtype == torch.bfloat16 and wp.dtype == torch.bfloat16
+    assert x.dtype == act_dtype() and wp.dtype == act_dtype()
     x, wp = x.contiguous(), wp.contiguous()
     N, D, H, W, Cin = x.shape
     taps, Cout, Cin2 = wp.shape
@@ -623,7 +643,7 @@ def norm_apply(src0, scale, shift, src1=None, relu=False, pool=False, out=None):
         _, D1, H1, W1, C1 = src1.shape
     oshape = (N, D // 2, H // 2, W // 2, C0) if pool else (N, D, H, W, C0 + C1)
     if out is None:
-        out = torch.empty(oshape, dtype=torch.bfloat16, device=src0.device)
+        out = torch.empty(oshape, dtype=act_dtype(), device=src0.device)
     assert tuple(out.shape) == oshape and out.is_contiguous()
     with torch.cuda.device(src0.device):
         _lib.call("km_norm_apply", _ptr(src0), C0, _ptr(src1), C1, D1, H1, W1, _ptr(scale),
@@ -635,7 +655,7 @@ def maxpool2_stats(x):
     _need_cuda(x)
     x = x.contiguous()
     N, D, H, W, Cc = x.shape
-    out = torch.empty((N, D // 2, H // 2, W // 2, Cc), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((N, D // 2, H // 2, W // 2, Cc), dtype=act_dtype(), device=x.device)
     stats = torch.empty((red_nparts(), N, Cc, 2), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.call("km_maxpool2_stats", _ptr(x), _ptr(out), _ptr(stats), N, Cc, D, H, W, _stream())
@@ -647,13 +667,14 @@ def conv3d_stem(x, w, bias=None, in_scale=None, in_shift=None, out_scale=None, o
     """x: fp32 (N,1,D,H,W); w: fp32 (Cout,1,3,3,3).  v = [relu_pre](conv(in_scale*x+in_shift)+bias);
     returns (bf16 (N,D,H,W,Cout) of [relu_post](out_scale*v+out_shift) or None, partial stats of v
     or None).  store=False is the statistics pass (nothing is written but the partials)."""
-    _need_cuda(x, w)
+    _need_cuda(x, w, bias, in_scale, in_shift, out_scale, out_shift)
     x, w, bias = _f32c(x), _f32c(w), _f32c(bias)
+    in_scale, in_shift = _f32c(in_scale), _f32c(in_shift)
     out_scale, out_shift = _f32c(out_scale), _f32c(out_shift)
     N, Cin, D, H, W = x.shape
     assert Cin == 1
     Cout = w.shape[0]
-    out = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device) if store else None
+    out = torch.empty((N, D, H, W, Cout), dtype=act_dtype(), device=x.device) if store else None
     stats = None
     if want_stats:
         nparts = _lib.query("km_stem_nparts", N, D, H, W)
@@ -679,7 +700,7 @@ def ncdhw_to_ndhwc(x):
     _need_cuda(x)
     x = _f32c(x)
     N, Cc, D, H, W = x.shape
-    out = torch.empty((N, D, H, W, Cc), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((N, D, H, W, Cc), dtype=act_dtype(), device=x.device)
     with torch.cuda.device(x.device):
         _lib.call("km_ncdhw_f32_to_ndhwc_bf16", _ptr(x), _ptr(out), N, Cc, D, H, W, _stream())
     return out

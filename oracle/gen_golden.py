@@ -191,6 +191,159 @@ def gen_group_metrics():
     save("group_metrics", **out)
 
 
+def gen_example_pair128():
+    """BASELINE config 1 AT ITS STATED SIZE: the bundled example_data_half pair at 128^3 (block mean of the
+    256^3 files, quantised to uint8: 0.2 MB per volume compressed), TruncatedUNet3D, K = 128, through the
+    REFERENCE model and the reference's align_img / MSELoss / DiceLoss / jdstd (scripts/register.py:40-118
+    -> pairwise_register_eval.py:116-171).  Grids are stored on a stride-8 lattice."""
+    sys.path.insert(0, ROOT)
+    from keymorph import loss_ops, utils
+    from keymorph.model import KeyMorph
+    from keymorph.unet3d.model import TruncatedUNet3D
+    from keymorph_b200 import hostio
+    d = os.path.join(REF, "example_data_half")
+    S, K = 128, 128
+    f_img, _ = hostio.load_volume(os.path.join(d, "img_m", "IXI_001_128x128x128.nii.gz"), size=S)
+    m_img, _ = hostio.load_volume(os.path.join(d, "img_m", "IXI_002_128x128x128.nii.gz"), size=S)
+    f_seg, _ = hostio.load_volume(os.path.join(d, "seg_m", "IXI_001_128x128x128.nii.gz"), size=S, labels=True)
+    m_seg, _ = hostio.load_volume(os.path.join(d, "seg_m", "IXI_002_128x128x128.nii.gz"), size=S, labels=True)
+    f_u8 = (f_img * 255).round().to(torch.uint8)
+    m_u8 = (m_img * 255).round().to(torch.uint8)
+    img_f, img_m = f_u8.float() / 255, m_u8.float() / 255
+    C = int(max(f_seg.max(), m_seg.max())) + 1
+    oh = lambda lab: torch.nn.functional.one_hot(lab[:, 0].long(), C).permute(0, 4, 1, 2, 3).float()  # noqa: E731
+    seg_f, seg_m = oh(f_seg), oh(m_seg)
+    torch.manual_seed(23)
+    net = TruncatedUNet3D(1, K, 1, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8,
+                          num_levels=4, is_segmentation=False, conv_padding=1)
+    model = KeyMorph(torch.nn.DataParallel(net), K, 3).eval()
+    types = ["rigid", "affine", "tps_1"]
+    with torch.no_grad():
+        res = model(img_f, img_m, transform_type=types, return_aligned_points=True)
+    out = {"img_f_u8": f_u8, "img_m_u8": m_u8, "lab_f": f_seg, "lab_m": m_seg, "num_classes": np.int64(C)}
+    for t in types:
+        r = res[t]
+        img_a = utils.align_img(r["grid"], img_m)
+        seg_a = utils.align_img(r["grid"], seg_m)
+        out[f"{t}_points_f"], out[f"{t}_points_m"], out[f"{t}_points_a"] = r["points_f"], r["points_m"], r["points_a"]
+        out[f"{t}_grid"] = r["grid"][:, ::8, ::8, ::8]
+        out[f"{t}_img_a"] = img_a[:, :, ::8, ::8, ::8]
+        if "matrix" in r:
+            out[f"{t}_matrix"] = r["matrix"]
+        out[f"{t}_mse"] = loss_ops.MSELoss()(img_a, img_f)
+        out[f"{t}_softdice"] = loss_ops.DiceLoss()(seg_a, seg_f)
+        out[f"{t}_harddice"] = loss_ops.DiceLoss(hard=True)(seg_a, seg_f)
+        out[f"{t}_jdstd"] = np.float64(loss_ops.jdstd(r["grid"].permute(0, 4, 1, 2, 3).numpy()))
+        out[f"{t}_jdneg"] = np.int64(loss_ops.jdlessthan0(r["grid"].permute(0, 4, 1, 2, 3).numpy()))
+    save("example_pair128", **out)
+
+
+def gen_reflection():
+    """Mirror-related point sets (an L/R-flipped volume against the original): det(V U^T) < 0 and the
+    reference's reflection step (keymorph/keypoint_aligners.py:199-206, last ROW of V negated) decides the
+    rigid matrix.  Unweighted and weighted, plus the affine fit of the same points."""
+    from keymorph.keypoint_aligners import AffineKeypointAligner, RigidKeypointAligner
+    g = torch.Generator().manual_seed(17)
+    out = {}
+    for case in range(3):
+        K = (12, 40, 7)[case]
+        pm = torch.rand(1, K, 3, generator=g) * 1.4 - 0.7
+        mirror = torch.tensor([1.0, 1.0, -1.0]) if case != 1 else torch.tensor([-1.0, 1.0, 1.0])
+        pf = pm * mirror + 0.02 * torch.randn(1, K, 3, generator=g) + torch.tensor([0.03, -0.02, 0.01])
+        w = torch.rand(1, K, generator=g)
+        w = w / w.sum()
+        out[f"c{case}_points_m"], out[f"c{case}_points_f"], out[f"c{case}_w"] = pm, pf, w
+        for wtag, ww in (("", None), ("_w", w)):
+            al = RigidKeypointAligner(pm, pf, w=ww, dim=3)
+            out[f"c{case}_rigid{wtag}_matrix"] = al.transform_matrix
+            out[f"c{case}_rigid{wtag}_inverse"] = al.inverse_transform_matrix
+            out[f"c{case}_rigid{wtag}_det"] = torch.det(al.inverse_transform_matrix[:, :3, :3])
+            out[f"c{case}_rigid{wtag}_points_a"] = al.get_forward_transformed_points(pm)
+        al = AffineKeypointAligner(pm, pf, dim=3)
+        out[f"c{case}_affine_matrix"] = al.transform_matrix
+    save("aligners_reflection", **out)
+
+
+def gen_realworld():
+    """Real-world-coordinate alignment (keymorph/utils.py:243-354,
+    keypoint_aligners.py:22-147,219-274,435-465, model.py:164-170): the six convert_points_* helpers on
+    random 3-D inputs, the three aligners with align_in_real_world_coords=True (matrices / theta, flow
+    field, forward and inverse points), and KeyMorph.forward(align_keypoints_in_real_world_coords=True)."""
+    from keymorph import utils
+    from keymorph.keypoint_aligners import TPS, AffineKeypointAligner, RigidKeypointAligner
+    from keymorph.model import KeyMorph
+    from keymorph.unet3d.model import TruncatedUNet3D
+    from oracle.keymorph_oracle import affine_augment, gaussian_phantom
+    g = torch.Generator().manual_seed(29)
+    K = 20
+
+    def rand_affine(spacing, origin, rot):
+        a = torch.eye(4)
+        c, s_ = np.cos(rot), np.sin(rot)
+        R = torch.tensor([[c, -s_, 0.0], [s_, c, 0.0], [0.0, 0.0, 1.0]], dtype=torch.float32)
+        a[:3, :3] = R @ torch.diag(torch.tensor(spacing))
+        a[:3, 3] = torch.tensor(origin)
+        return a[None]
+
+    aff_m = rand_affine([1.0, 1.2, 0.8], [-60.0, -70.0, -50.0], 0.1)
+    aff_f = rand_affine([0.9, 1.0, 1.1], [-64.0, -60.0, -66.0], -0.05)
+    shape_m = torch.tensor([16.0, 20.0, 24.0])
+    shape_f = torch.tensor([18.0, 16.0, 20.0])
+    pts = torch.rand(1, K, 3, generator=g) * 2 - 1
+    out = {"aff_m": aff_m, "aff_f": aff_f, "shape_m": shape_m, "shape_f": shape_f, "pts": pts}
+    vox = utils.convert_points_norm2voxel(pts, shape_m[None])
+    out["norm2voxel"] = vox
+    out["voxel2norm"] = utils.convert_points_voxel2norm(vox, shape_m[None])
+    real = utils.convert_points_voxel2real(vox, aff_m)
+    out["voxel2real"] = real
+    out["real2voxel"] = utils.convert_points_real2voxel(real, aff_m)
+    out["norm2real"] = utils.convert_points_norm2real(pts, aff_m, shape_m[None])
+    out["real2norm"] = utils.convert_points_real2norm(real, aff_f, shape_f[None])
+    # aligners: keypoints of the SAME anatomy seen through two different voxel grids
+    pm = torch.rand(1, K, 3, generator=g) * 1.2 - 0.6
+    real_m = utils.convert_points_norm2real(pm, aff_m, shape_m[None])
+    lin = torch.eye(3) + 0.05 * torch.randn(3, 3, generator=g)
+    real_f = real_m @ lin.T + torch.tensor([2.0, -1.5, 1.0]) + 0.3 * torch.randn(1, K, 3, generator=g)
+    pf = utils.convert_points_real2norm(real_f, aff_f, shape_f[None])
+    out["points_m"], out["points_f"] = pm, pf
+    gshape = (1, 1, 18, 16, 20)
+    common = dict(align_in_real_world_coords=True, aff_m=aff_m, aff_f=aff_f, shape_m=shape_m[None],
+                  shape_f=shape_f[None], dim=3)
+    for tag, make in (("affine", lambda: AffineKeypointAligner(pm, pf, **common)),
+                      ("rigid", lambda: RigidKeypointAligner(pm, pf, **common)),
+                      ("tps1", lambda: TPS(pm, pf, torch.tensor([1.0]), **common)),
+                      ("tps0", lambda: TPS(pm, pf, torch.tensor([0.0]), **common))):
+        al = make()
+        if tag in ("affine", "rigid"):
+            out[f"{tag}_matrix"] = al.transform_matrix
+            out[f"{tag}_inverse"] = al.inverse_transform_matrix
+        else:
+            out[f"{tag}_inverse_theta"] = al.inverse_theta
+        out[f"{tag}_grid"] = al.get_flow_field(gshape, compute_on_subgrids=True)
+        out[f"{tag}_points_a"] = al.get_forward_transformed_points(pm)
+        out[f"{tag}_points_inv"] = al.get_inverse_transformed_points(pf)
+    # the whole pipeline with align_keypoints_in_real_world_coords=True (32^3, identity-like affines)
+    torch.manual_seed(23)
+    net = TruncatedUNet3D(1, 16, 1, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8,
+                          num_levels=4, is_segmentation=False, conv_padding=1)
+    model = KeyMorph(torch.nn.DataParallel(net), 16, 3, align_keypoints_in_real_world_coords=True).eval()
+    img_f = gaussian_phantom(32, 1000)
+    img_m = affine_augment(gaussian_phantom(32, 1000), (0.05, 0.03, 0.15, 0.01))
+    a_f = rand_affine([2.0, 2.0, 2.0], [-32.0, -32.0, -32.0], 0.0)
+    a_m = rand_affine([2.0, 2.2, 1.9], [-30.0, -35.0, -31.0], 0.02)
+    with torch.no_grad():
+        res = model(img_f, img_m, transform_type=["rigid", "affine", "tps_1"], return_aligned_points=True,
+                    aff_f=a_f, aff_m=a_m)
+    out.update(fw_img_f=img_f, fw_img_m=img_m, fw_aff_f=a_f, fw_aff_m=a_m)
+    for t, r in res.items():
+        out[f"fw_{t}_points_f"], out[f"fw_{t}_points_m"] = r["points_f"], r["points_m"]
+        out[f"fw_{t}_points_a"] = r["points_a"]
+        out[f"fw_{t}_grid"] = r["grid"][:, ::2, ::2, ::2]
+        if "matrix" in r:
+            out[f"fw_{t}_matrix"] = r["matrix"]
+    save("realworld", **out)
+
+
 def main():
     import_reference()
     sys.path.insert(0, ROOT)
@@ -205,6 +358,13 @@ def main():
         return
     if "--only-example" in sys.argv:
         gen_example_pair()
+        return
+    only = {"--only-example128": gen_example_pair128, "--only-reflection": gen_reflection,
+            "--only-realworld": gen_realworld}
+    picked = [fn for flag, fn in only.items() if flag in sys.argv]
+    if picked:
+        for fn in picked:
+            fn()
         return
     from keymorph import layers, loss_ops, utils
     from keymorph.augmentation import affine_augment
@@ -370,6 +530,9 @@ def main():
         save("groupwise32", **out)
     gen_jacobian()
     gen_example_pair()
+    gen_example_pair128()
+    gen_reflection()
+    gen_realworld()
 
 
 if __name__ == "__main__":

@@ -253,9 +253,11 @@ def fit_rigid(p1, p2, w=None):
     U, _, Vt = torch.linalg.svd(Hm)
     V = Vt.transpose(1, 2)
     R = torch.bmm(V, U.transpose(1, 2))
+    # :199-203: dets is stacked along axis 1 and tiled along axis 2 -> the last ROW of V is negated
+    # (R <- diag(1, 1, sign det) V U^T), not the last column as in Arun et al.
     sgn = torch.sign(torch.det(R))
     flip = torch.ones_like(V)
-    flip[:, :, 2] = sgn[:, None]
+    flip[:, 2, :] = sgn[:, None]
     V = V * flip
     R = torch.bmm(V, U.transpose(1, 2))
     T = cb - torch.bmm(R, ca)
@@ -352,6 +354,67 @@ def tps_forward_points(points_m, points_f, lmbda, pts, w=None):
     """keymorph/keypoint_aligners.py:451-465 (a second, forward fit)."""
     theta = tps_fit(points_m, points_f, lmbda, w)
     return tps_transform(theta, points_m, pts)
+
+
+# --------------------------------------------------------------------------------------------
+# real-world coordinates (keymorph/utils.py:243-354; keypoint_aligners.py:53-74,116-147,435-465)
+
+
+def convert_points_norm2voxel(points, grid_sizes):
+    """keymorph/utils.py:243-258: [-1, 1] -> voxel index space, -1 is the outer face of voxel 0."""
+    return ((points + 1) * torch.as_tensor(grid_sizes).to(points)) / 2 - 0.5
+
+
+def convert_points_voxel2norm(points, grid_sizes):
+    """keymorph/utils.py:261-276."""
+    return (2 * (points + 0.5) / torch.as_tensor(grid_sizes).to(points)) - 1
+
+
+def convert_points_voxel2real(points, affine):
+    """keymorph/utils.py:279-296: homogeneous product with the (N,d+1,d+1) affine."""
+    return torch.bmm(affine.to(points), _homog(points).transpose(1, 2)).transpose(1, 2)[:, :, :-1]
+
+
+def convert_points_real2voxel(points, affine):
+    """keymorph/utils.py:299-322: the same with torch.inverse(affine)."""
+    return torch.bmm(torch.inverse(affine.to(points)), _homog(points).transpose(1, 2)).transpose(1, 2)[:, :, :-1]
+
+
+def convert_points_norm2real(points, affine, sizes):
+    """keymorph/utils.py:325-338."""
+    return convert_points_voxel2real(convert_points_norm2voxel(points, sizes), affine)
+
+
+def convert_points_real2norm(points, affine, sizes):
+    """keymorph/utils.py:341-354."""
+    return convert_points_voxel2norm(convert_points_real2voxel(points, affine), sizes)
+
+
+def register_points_real_world(points_f, points_m, transform, shape_f, shape_m, aff_f, aff_m, grid_shape):
+    """The aligners with align_in_real_world_coords=True (keypoint_aligners.py:53-74,116-147,255-274,
+    435-465): keypoints are moved to scanner space before the fit; every transformed point goes
+    norm -> real (source image) -> fit -> real -> norm (target image).  Batch 1, like the reference."""
+    kind, lam = parse_transform(transform)
+    rf = convert_points_norm2real(points_f, aff_f, shape_f)
+    rm = convert_points_norm2real(points_m, aff_m, shape_m)
+    g = uniform_norm_grid(grid_shape, points_f.dtype).reshape(1, -1, 3)
+    g_real = convert_points_norm2real(g, aff_f, shape_f)
+    pm_real = convert_points_norm2real(points_m, aff_m, shape_m)
+    res = {}
+    if kind in ("rigid", "affine"):
+        tm, inv = aligner_matrices(rm, rf, None, kind)
+        res["matrix"], res["inverse"] = tm, inv
+        moved = transform_points(inv, g_real)
+        fwd = transform_points(tm, pm_real)
+    else:
+        lmbda = torch.tensor(lam, dtype=points_f.dtype).repeat(points_f.shape[0])
+        theta = tps_fit(rf, rm, lmbda)
+        res["inverse_theta"] = theta
+        moved = tps_transform(theta, rf, g_real)
+        fwd = tps_transform(tps_fit(rm, rf, lmbda), rm, pm_real)
+    res["grid"] = convert_points_real2norm(moved, aff_m, shape_m).reshape(1, *[int(v) for v in grid_shape], 3).flip(-1)
+    res["points_a"] = convert_points_real2norm(fwd, aff_f, shape_f)
+    return res
 
 
 # --------------------------------------------------------------------------------------------

@@ -92,7 +92,7 @@ def import_reference_scripts():
     return scripts
 
 
-def build_reference_model(num_keypoints, backbone="truncatedunet", seed=23, **kw):
+def build_reference_model(num_keypoints, backbone="truncatedunet", seed=23, device="cpu", **kw):
     """KeyMorph(DataParallel(backbone)) exactly as scripts/register.py:212-301 `get_model` builds it
     (TruncatedUNet3D(1, K, 1, final_sigmoid=False, f_maps=32, layer_order='gcr', num_groups=8,
     num_levels=4, is_segmentation=False, conv_padding=1)), seeded with the scripts' default seed."""
@@ -110,4 +110,12 @@ def build_reference_model(num_keypoints, backbone="truncatedunet", seed=23, **kw
         net = cls(*args, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8, num_levels=4,
                   is_segmentation=False, conv_padding=1)
     del km
-    return KeyMorph(torch.nn.DataParallel(net), num_keypoints, 3, **kw).eval()
+    dp = torch.nn.DataParallel(net)
+    if torch.device(device).type == "cpu":
+        # on a box WITH GPUs DataParallel refuses CPU parameters (it scatters to device_ids); an empty
+        # device list is what its constructor sets on a CPU-only box: forward() = module.forward()
+        dp.device_ids = []
+    else:
+        dp.device_ids = [torch.device(device).index or 0]
+        dp.output_device = dp.device_ids[0]
+    return KeyMorph(dp, num_keypoints, 3, **kw).eval().to(device)

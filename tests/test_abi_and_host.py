@@ -7,6 +7,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -135,6 +136,20 @@ assert torch.allclose(cur, ref_mine, atol=1e-5), (cur - ref_mine).abs().max()
 assert torch.allclose(mean, ref_mean, atol=1e-6)
 gm = parallel.global_mean_points(mine)
 assert torch.allclose(gm, pts.mean(0, keepdim=True), atol=1e-6)
+# the one-collective scheme: all-gather every subject's keypoints once, iterate locally on all of them;
+# the mean is torch.mean over the same (G,K,3) tensor the single process sees -> identical bits.
+# 7 subjects -> shards of 4 and 3 (padded all-gather)
+pts7 = (torch.rand(1, 12, 3, generator=g) * 1.2 - 0.6) + 0.05 * torch.randn(7, 12, 3, generator=g)   # one anatomy, 7 subjects
+idx7 = list(parallel.shard_range(7, rank, 2))
+allp, off = parallel.gather_all_points(pts7[idx7])
+assert torch.equal(allp, pts7) and off == idx7[0]
+cur2, mean2 = parallel.groupwise_iterate(pts7[idx7], reg, 3, mode="allgather")
+ref_cur7, ref_mean7 = O.groupwise_points(pts7, "affine", 3)
+assert torch.equal(mean2, ref_mean7), (mean2 - ref_mean7).abs().max()
+assert torch.allclose(cur2, ref_cur7[idx7], atol=1e-6)
+cur3, mean3 = parallel.groupwise_iterate(pts7[idx7], reg, 3, mode="allreduce")
+assert torch.allclose(mean3, mean2, atol=2e-6), (mean3 - mean2).abs().max()    # summation order differs
+assert torch.allclose(cur3, cur2, atol=1e-5), (cur3 - cur2).abs().max()
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 """
@@ -156,3 +171,72 @@ def test_groupwise_exchange_gloo_world2(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o}"
         assert f"rank {r} ok" in o
+
+
+# ---------------------------------------------------------------- NIfTI reader edge cases
+def _write_nifti(path, data, sform=None, qform=None, slope=float("nan"), inter=float("nan"), pixdim=(1, 1, 1, 1)):
+    import struct
+    hdr = bytearray(352)
+    struct.pack_into("<i", hdr, 0, 348)
+    struct.pack_into("<8h", hdr, 40, *([data.ndim] + list(data.shape) + [1] * (7 - data.ndim)))
+    struct.pack_into("<h", hdr, 70, {"float32": 16, "int16": 4, "int32": 8}[data.dtype.name])
+    struct.pack_into("<8f", hdr, 76, *pixdim, 0, 0, 0, 0)
+    struct.pack_into("<f", hdr, 108, 352.0)
+    struct.pack_into("<2f", hdr, 112, slope, inter)
+    if qform is not None:
+        struct.pack_into("<h", hdr, 252, 1)
+        struct.pack_into("<6f", hdr, 256, *qform)
+    if sform is not None:
+        struct.pack_into("<h", hdr, 254, 1)
+        struct.pack_into("<12f", hdr, 280, *np.asarray(sform, dtype=np.float32).reshape(-1))
+    hdr[344:348] = b"n+1\0"
+    with open(path, "wb") as f:
+        f.write(bytes(hdr))
+        f.write(data.tobytes(order="F"))
+
+
+def test_nifti_reader_edge_cases(tmp_path):
+    from keymorph_b200 import hostio
+    x = np.arange(4 * 6 * 8, dtype=np.float32).reshape(4, 6, 8)
+    # NaN scl_slope / scl_inter mean "no scaling" (nibabel); qform-only headers are honoured
+    _write_nifti(tmp_path / "a.nii", x, qform=(0, 0, 0, -10, -20, -30), pixdim=(1, 2, 3, 4))
+    data, aff = hostio.read_nifti(str(tmp_path / "a.nii"))
+    assert np.array_equal(data, x)
+    assert np.allclose(aff, [[2, 0, 0, -10], [0, 3, 0, -20], [0, 0, 4, -30], [0, 0, 0, 1]])
+    # 90 degrees about z with qfac = -1
+    _write_nifti(tmp_path / "b.nii", x, qform=(0, 0, np.sin(np.pi / 4), 0, 0, 0), pixdim=(-1, 1, 1, 1))
+    _, aff = hostio.read_nifti(str(tmp_path / "b.nii"))
+    assert np.allclose(aff[:3, :3], [[0, -1, 0], [1, 0, 0], [0, 0, -1]], atol=1e-6)
+    # a real scaling is applied
+    _write_nifti(tmp_path / "s.nii", x, sform=np.eye(4)[:3], slope=2.0, inter=1.0)
+    assert np.allclose(hostio.read_nifti(str(tmp_path / "s.nii"))[0], 2 * x + 1)
+    # block-mean downsample: voxel size doubles AND the origin moves to the centre of the first block
+    y = np.random.RandomState(0).rand(8, 8, 8).astype(np.float32)
+    _write_nifti(tmp_path / "c.nii", y, sform=[[2, 0, 0, -5], [0, 2, 0, -6], [0, 0, 2, -7]])
+    t, aff = hostio.load_volume(str(tmp_path / "c.nii"), size=4)
+    assert t.shape == (1, 1, 4, 4, 4) and np.allclose(aff[:3, 3], [-4, -5, -6]) and np.allclose(np.diag(aff)[:3], 4)
+    # the strided label pick keeps voxel 0 where it was; ids that do not fit uint8 are refused, not wrapped
+    lab = (np.arange(512).reshape(8, 8, 8) % 7).astype(np.int32)
+    _write_nifti(tmp_path / "l.nii", lab, sform=[[2, 0, 0, -5], [0, 2, 0, -6], [0, 0, 2, -7]])
+    t, aff = hostio.load_volume(str(tmp_path / "l.nii"), size=4, labels=True)
+    assert t.dtype == torch.uint8 and np.allclose(aff[:3, 3], [-5, -6, -7])
+    _write_nifti(tmp_path / "m.nii", (lab * 400).astype(np.int32), sform=np.eye(4)[:3])
+    with pytest.raises(ValueError):
+        hostio.load_volume(str(tmp_path / "m.nii"), size=4, labels=True)
+
+
+def test_deferred_singular_checks_are_per_thread():
+    """transformations.deferred_singular_checks keeps its pending list in thread-local storage."""
+    import threading
+    from keymorph_b200 import transformations as T
+    seen = {}
+
+    def worker():
+        seen["inner"] = getattr(T._TLS, "pending", None)
+
+    with T.deferred_singular_checks():
+        assert T._TLS.pending == []
+        th = threading.Thread(target=worker)
+        th.start()
+        th.join()
+    assert seen["inner"] is None and getattr(T._TLS, "pending", None) is None

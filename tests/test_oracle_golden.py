@@ -365,3 +365,108 @@ def test_nifti_reader_reproduces_the_fixture(golden):
     assert aff[0, 0] > 0 and aff[1, 1] > 0 and aff[2, 2] > 0
     raw, a0 = hostio.read_nifti(os.path.join(d, "img_m", "IXI_001_128x128x128.nii.gz"))
     assert raw.shape == (256, 256, 256) and a0[0, 0] == -1.0 and a0[1, 1] == -1.0
+
+
+# ---------------------------------------------------------------- rigid reflection case
+def test_golden_rigid_reflection(golden):
+    """Mirror-related keypoint sets: det(V U^T) < 0, the reference negates the last ROW of V
+    (keymorph/keypoint_aligners.py:199-206).  Matrices produced by the reference itself."""
+    g = golden("aligners_reflection")
+    for case in range(3):
+        pm, pf, w = g[f"c{case}_points_m"], g[f"c{case}_points_f"], g[f"c{case}_w"]
+        for tag, ww in (("", None), ("_w", w)):
+            tm, inv = O.aligner_matrices(pm, pf, ww, "rigid")
+            assert_close(inv, g[f"c{case}_rigid{tag}_inverse"], rtol=1e-5, atol=1e-5)
+            assert_close(tm, g[f"c{case}_rigid{tag}_matrix"], rtol=1e-5, atol=1e-5)
+            assert_close(O.transform_points(tm, pm), g[f"c{case}_rigid{tag}_points_a"], rtol=1e-5, atol=1e-5)
+            # the reference's result is a proper rotation, but NOT the least-squares optimal one
+            assert abs(float(torch.det(inv[0, :3, :3])) - 1.0) < 1e-4
+        tm, _ = O.aligner_matrices(pm, pf, None, "affine")
+        assert_close(tm, g[f"c{case}_affine_matrix"], rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------- real-world coordinates (a16)
+def _rot2(r):
+    return torch.tensor([[np.cos(r), -np.sin(r), 0], [np.sin(r), np.cos(r), 0], [0, 0, 1]]).float()[None]
+
+
+REALWORLD_KATS = {
+    # reference test/test.py:550-719 (2-D known answers; a 5x5 grid, -1 -> -0.5 and 1 -> 4.5)
+    "norm": [[1, 0], [0, -1], [-1, 0], [0, 1]],
+    "voxel": [[4.5, 2.0], [2.0, -0.5], [-0.5, 2.0], [2.0, 4.5]],
+    "real": [[2, -4.5], [-0.5, -2], [2, 0.5], [4.5, -2]],       # voxel rotated by -90 degrees
+}
+
+
+def realworld_kat_cases(mod):
+    """(name, got, expected) for the six convert_points_* KATs, evaluated with module `mod`."""
+    t = {k: torch.tensor(v).float().view(1, 4, 2) for k, v in REALWORLD_KATS.items()}
+    size, aff = torch.tensor([[5, 5]]).float(), _rot2(-np.pi / 2)
+    return [("norm2voxel", mod.convert_points_norm2voxel(t["norm"], size), t["voxel"]),
+            ("voxel2norm", mod.convert_points_voxel2norm(t["voxel"], size), t["norm"]),
+            ("voxel2real", mod.convert_points_voxel2real(t["voxel"], aff), t["real"]),
+            ("real2voxel", mod.convert_points_real2voxel(t["real"], aff), t["voxel"]),
+            ("norm2real", mod.convert_points_norm2real(t["norm"], aff, size), t["real"]),
+            ("real2norm", mod.convert_points_real2norm(t["real"], aff, size), t["norm"])]
+
+
+def test_realworld_kats():
+    for name, got, want in realworld_kat_cases(O):
+        assert_close(got, want, rtol=1e-6, atol=1e-6, msg=name)
+
+
+def test_golden_realworld(golden):
+    g = golden("realworld")
+    aff_m, aff_f, sm, sf, pts = g["aff_m"], g["aff_f"], g["shape_m"][None], g["shape_f"][None], g["pts"]
+    vox = O.convert_points_norm2voxel(pts, sm)
+    assert_close(vox, g["norm2voxel"], rtol=0, atol=0)
+    assert_close(O.convert_points_voxel2norm(vox, sm), g["voxel2norm"], rtol=0, atol=0)
+    real = O.convert_points_voxel2real(vox, aff_m)
+    assert_close(real, g["voxel2real"], rtol=0, atol=0)
+    assert_close(O.convert_points_real2voxel(real, aff_m), g["real2voxel"], rtol=0, atol=0)
+    assert_close(O.convert_points_norm2real(pts, aff_m, sm), g["norm2real"], rtol=0, atol=0)
+    assert_close(O.convert_points_real2norm(real, aff_f, sf), g["real2norm"], rtol=0, atol=0)
+    pm, pf = g["points_m"], g["points_f"]
+    for tag, t in (("affine", "affine"), ("rigid", "rigid"), ("tps1", "tps_1"), ("tps0", "tps_0")):
+        r = O.register_points_real_world(pf, pm, t, sf, sm, aff_f, aff_m, (18, 16, 20))
+        tol = 2e-3 if tag == "tps0" else 1e-4      # lambda = 0 in scanner units: cond(A) ~ 1e7 in fp32
+        if "matrix" in r:
+            assert_close(r["matrix"], g[f"{tag}_matrix"], rtol=1e-4, atol=1e-4)
+        assert_close(r["grid"], g[f"{tag}_grid"], rtol=0, atol=tol)
+        assert_close(r["points_a"], g[f"{tag}_points_a"], rtol=0, atol=tol)
+
+
+def test_golden_example_pair_config1_128(golden):
+    """BASELINE config 1 at its STATED size (128^3, K = 128): oracle pipeline vs the reference's outputs."""
+    import keymorph_b200 as kb
+    g = golden("example_pair128")
+    img_f, img_m, seg_f, seg_m, _ = _example_inputs(g)
+    torch.manual_seed(23)
+    net = kb.TruncatedUNet3D(1, 128, 1, final_sigmoid=False, f_maps=32, layer_order="gcr", num_groups=8,
+                             num_levels=4, is_segmentation=False, conv_padding=1)
+    r = O.keymorph_forward("truncatedunet", net.state_dict(), img_f, img_m, ["affine"])["affine"]
+    assert_close(r["points_f"], g["affine_points_f"], rtol=1e-5, atol=1e-5)
+    assert_close(r["points_m"], g["affine_points_m"], rtol=1e-5, atol=1e-5)
+    assert_close(r["matrix"], g["affine_matrix"], rtol=1e-3, atol=1e-3)
+    assert_close(r["grid"][:, ::8, ::8, ::8], g["affine_grid"], rtol=1e-3, atol=1e-3)
+    img_a = O.align_img(r["grid"], img_m)
+    assert_close(O.mse_loss(img_a, img_f), g["affine_mse"], rtol=2e-3, atol=1e-6)
+
+
+def test_stock_run_eval_harness_with_the_reference_model(tmp_path, golden):
+    """The harness that drives the reference's unmodified run_eval (tests/stock_eval_harness.py) with the
+    REFERENCE model on the CPU: validates the harness itself (the GPU suite runs it on keymorph_b200)."""
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference not installed (oracle/build_ref.py)")
+    import stock_eval_harness as H
+    g = golden("example_pair64")
+    img_f, img_m = g["img_f_u8"].float() / 255, g["img_m_u8"].float() / 255
+    model = refshim.build_reference_model(32)
+    metrics, save_dir = H.run_stock_eval(model, img_f, img_m, g["lab_f"], g["lab_m"], tmp_path, "cpu",
+                                         aligns=("affine",))
+    assert {p.name for p in save_dir.iterdir()} == H.expected_files(("affine",))
+    key = "mse:img_m/IXI_001:img_m/IXI_002:rot0:affine"
+    # (the script resamples the moving image through its own affine_augment(rot0) first, so the number is
+    # close to, not equal to, the fixture's un-augmented one)
+    assert abs(metrics[key][0] - float(g["affine_mse"])) < 0.1 * float(g["affine_mse"])

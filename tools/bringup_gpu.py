@@ -320,7 +320,7 @@ def _conv_case(N, Cin, Cout, D, H, W, taps, relu, bias):
     xb = ops.ncdhw_to_ndhwc(x)
     wp = ops.pack_weights(w)
     xq = ops.ndhwc_to_ncdhw(xb)
-    wq = w.bfloat16().float()
+    wq = w.to(ops.act_dtype()).float()
     out, stats, _ = ops.conv3d_tc(xb, wp, bias=b, relu=relu, want_stats=True)
     torch.cuda.synchronize()
     ref = F.conv3d(xq, wq, b, padding=k // 2)
@@ -328,7 +328,7 @@ def _conv_case(N, Cin, Cout, D, H, W, taps, relu, bias):
         ref = F.relu(ref)
     got = ops.ndhwc_to_ncdhw(out)
     ok = _report(f"conv3d_tc N={N} {Cin}->{Cout} {D}x{H}x{W} taps={taps} relu={relu} bias={bias}", got, ref, 1.5e-2)
-    refq = ref.bfloat16().float()
+    refq = ref.to(ops.act_dtype()).float()
     s = stats.double().sum(0)
     ok &= _report("   stats sum", s[..., 0], refq.flatten(2).sum(-1), 2e-3)
     ok &= _report("   stats sumsq", s[..., 1], (refq ** 2).flatten(2).sum(-1), 2e-3)
@@ -378,8 +378,8 @@ def run_conv_big():
     for (Cin, Cout, S) in [(16, 32, 256), (32, 32, 128), (32, 64, 128), (64, 64, 64), (64, 128, 64),
                            (128, 128, 32), (128, 256, 32), (384, 128, 64), (128, 128, 64),
                            (192, 64, 128), (64, 64, 128)]:
-        x = torch.randn(1, S, S, S, Cin, device="cuda").bfloat16()
-        wp = (torch.randn(27, Cout, Cin, device="cuda") / (27 * Cin) ** 0.5).bfloat16()
+        x = torch.randn(1, S, S, S, Cin, device="cuda").to(ops.act_dtype())
+        wp = (torch.randn(27, Cout, Cin, device="cuda") / (27 * Cin) ** 0.5).to(ops.act_dtype())
         for _ in range(2):
             ops.conv3d_tc(x, wp, relu=True, want_stats=True)
         torch.cuda.synchronize()
@@ -411,8 +411,8 @@ def run_convtime():
         print(f"  -- {label}")
         total = 0.0
         for (Cin, Cout, S, taps) in layers:
-            x = torch.randn(2, S, S, S, Cin, device="cuda").bfloat16()
-            wp = (torch.randn(taps, Cout, Cin, device="cuda") / (taps * Cin) ** 0.5).bfloat16()
+            x = torch.randn(2, S, S, S, Cin, device="cuda").to(ops.act_dtype())
+            wp = (torch.randn(taps, Cout, Cin, device="cuda") / (taps * Cin) ** 0.5).to(ops.act_dtype())
             bias = torch.zeros(Cout, device="cuda") if taps == 1 else None
             kw = dict(want_com=True, store=False, bias=bias) if taps == 1 else dict(relu=True, want_stats=True)
             for _ in range(2):
@@ -445,7 +445,7 @@ def run_convcom():
         w = torch.randn(K, Cin, 1, 1, 1, device="cuda", generator=g) / Cin ** 0.5
         b = torch.randn(K, device="cuda", generator=g) * 0.1
         xb, wp = ops.ncdhw_to_ndhwc(x), ops.pack_weights(w)
-        xq, wq = ops.ndhwc_to_ncdhw(xb), w.bfloat16().float()
+        xq, wq = ops.ndhwc_to_ncdhw(xb), w.to(ops.act_dtype()).float()
         heat = F.conv3d(xq, wq, b)
         ref, refm = ops.com3d(heat, ij=True, return_mass=True)
         for store in (False, True):

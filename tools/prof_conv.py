@@ -13,8 +13,8 @@ taps = int(sys.argv[4]) if len(sys.argv) > 4 else 27
 iters = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 n = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 com = len(sys.argv) > 7 and sys.argv[7] == "com"
-x = torch.randn(n, s, s, s, cin, device="cuda").bfloat16()
-wp = (torch.randn(taps, cout, cin, device="cuda") / (taps * cin) ** 0.5).bfloat16()
+x = torch.randn(n, s, s, s, cin, device="cuda").to(ops.act_dtype())
+wp = (torch.randn(taps, cout, cin, device="cuda") / (taps * cin) ** 0.5).to(ops.act_dtype())
 bias = torch.zeros(cout, device="cuda")
 for _ in range(iters):
     if com:

@@ -51,7 +51,7 @@ def main():
                                  is_segmentation=False, conv_padding=1)
     model = kb.KeyMorph(torch.nn.DataParallel(net.to(dev)), K, 3, fused_warp=True).eval()
     if a.load_path:
-        state = torch.load(a.load_path, map_location=dev)["state_dict"]      # scripts/script_utils.py:59-81
+        state = torch.load(a.load_path, map_location=dev, weights_only=False)["state_dict"]      # scripts/script_utils.py:59-81
         model.backbone.load_state_dict(state)
     img_f, _ = hostio.load_volume(a.fixed, size=a.size)
     img_m, _ = hostio.load_volume(a.moving, size=a.size)

@@ -19,8 +19,8 @@ LAYERS = [("enc0.c2", 16, 32, S), ("enc1.c1", 32, 32, S // 2), ("enc1.c2", 32, 6
           ("dec1.c1", 192, 64, S // 2), ("dec1.c2", 64, 64, S // 2)]
 tot = 0.0
 for name, cin, cout, e in LAYERS:
-    x = torch.randn(N, e, e, e, cin, device="cuda").bfloat16()
-    wp = (torch.randn(27, cout, cin, device="cuda") / (27 * cin) ** 0.5).bfloat16()
+    x = torch.randn(N, e, e, e, cin, device="cuda").to(ops.act_dtype())
+    wp = (torch.randn(27, cout, cin, device="cuda") / (27 * cin) ** 0.5).to(ops.act_dtype())
     for _ in range(2):
         ops.conv3d_tc(x, wp, relu=True, want_stats=True)
     torch.cuda.synchronize()
@@ -38,7 +38,7 @@ for name, cin, cout, e in LAYERS:
     del x
 print(f"total {tot:.1f} us")
 # the z-folded kernel on the first tensor-core layer
-x = torch.randn(N, S, S, S, 16, device="cuda").bfloat16()
+x = torch.randn(N, S, S, S, 16, device="cuda").to(ops.act_dtype())
 wz = ops.pack_weights_zfold(torch.randn(32, 16, 3, 3, 3, device="cuda") / (27 * 16) ** 0.5)
 for _ in range(2):
     ops.conv3d_zfold(x, wz, relu=True, want_stats=True)
@@ -55,8 +55,8 @@ print(f"enc0.c2 z-folded: {us:8.1f} us  {2.0 * 27 * 16 * 32 * S ** 3 * N / us / 
 for name, cin, cout, e in LAYERS:
     if not ops.pair_supported(cin, cout, e, e, e):
         continue
-    x = torch.randn(N, e, e, e, cin, device="cuda").bfloat16()
-    wp = (torch.randn(27, cout, cin, device="cuda") / (27 * cin) ** 0.5).bfloat16()
+    x = torch.randn(N, e, e, e, cin, device="cuda").to(ops.act_dtype())
+    wp = (torch.randn(27, cout, cin, device="cuda") / (27 * cin) ** 0.5).to(ops.act_dtype())
     for _ in range(2):
         ops.conv3d_tc_pair(x, wp, relu=True, want_stats=True)
     torch.cuda.synchronize()
@@ -73,7 +73,7 @@ for name, cin, cout, e in LAYERS:
 for name, cin, cout, e in LAYERS:
     if not ops.zfold_pair_supported(cin, cout, e, e, e):
         continue
-    x = torch.randn(N, e, e, e, cin, device="cuda").bfloat16()
+    x = torch.randn(N, e, e, e, cin, device="cuda").to(ops.act_dtype())
     wz = ops.pack_weights_zfold_pair(torch.randn(cout, cin, 3, 3, 3, device="cuda") / (27 * cin) ** 0.5)
     for _ in range(2):
         ops.conv3d_zfold_pair(x, wz, relu=True, want_stats=True)
@@ -88,7 +88,7 @@ for name, cin, cout, e in LAYERS:
     print(f"{name:8s} {cin:4d}->{cout:4d} @{e:3d}^3 x{N} z-fold + 2-CTA: {us:8.1f} us  {2.0 * 27 * cin * cout * e ** 3 * N / us / 1e6:7.1f} TFLOP/s", flush=True)
     del x
 # first layer through the 2-CTA z-folded kernel (Cin = 16), with and without the fused pool
-x = torch.randn(N, S, S, S, 16, device="cuda").bfloat16()
+x = torch.randn(N, S, S, S, 16, device="cuda").to(ops.act_dtype())
 wz2 = ops.pack_weights_zfold_pair(torch.randn(32, 16, 3, 3, 3, device="cuda") / (27 * 16) ** 0.5)
 wz1 = ops.pack_weights_zfold(torch.randn(32, 16, 3, 3, 3, device="cuda") / (27 * 16) ** 0.5)
 for label, fn in (("zfold  1-CTA, full store", lambda: ops.conv3d_zfold(x, wz1, relu=True, want_stats=True)),
