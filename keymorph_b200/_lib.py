@@ -99,6 +99,8 @@ KM_OPT_ZF2_TWO_BRICKS = 10
 KM_OPT_TPS_PACKED = 11
 KM_OPT_TPS_VPT = 12
 KM_OPT_OPERAND_FP16 = 13
+KM_OPT_WARP_TILE = 14
+KM_OPT_WARP_OCC = 15
 
 _lib = None
 

@@ -321,20 +321,24 @@ __global__ void tps_finish_kernel(const double* __restrict__ A, const int* __res
 
 
 // ------------------------------------------------------------------------------------------
-// The same blocked Gauss-Jordan elimination as ONE cooperative launch (default).  The multi-launch version
-// above spends its 1.35 ms (K = 512) in ~100 dependent launches of microsecond kernels; here a group of
-// `cps` co-resident CTAs per system walks the panels with a group barrier (one global counter per system)
-// between the two phases of a panel:
-//   phase A (CTA 0 of the group): the panel factorisation of tps_panel_kernel -- one thread per row, the
-//            row's kNB panel entries in registers -- with TWO block barriers per pivot step: every warp
-//            reduces the per-warp candidates redundantly, so the pivot index needs no broadcast round;
-//   phase B (all CTAs): tiles of 64 columns x kRowTile rows of the trailing matrix (and the right-hand
-//            sides): the 16 pivot rows "as they were when they became pivots" are re-derived per column
-//            in registers (the recurrence of tps_urow_kernel), then the rank-16 update of the tile.
-// Assembly and the final division run in the same launch.  The arithmetic and its order are those of the
-// multi-launch kernels, so the two paths produce identical bits (tests compare them).
-constexpr int kRowTile = 128;
-constexpr int kGjThreads = 1024;   // largest block: one thread per matrix row, n = K + 4 <= 1024
+// The blocked Gauss-Jordan elimination as ONE cooperative launch (default).  The multi-launch version above
+// spends its 1.35 ms (K = 512) in ~100 dependent launches of microsecond kernels whose critical path is the
+// 516 sequential pivot steps, each a block-wide arg-max over 17 warps with three block barriers.  Here a
+// group of `cps` co-resident 256-thread CTAs per system walks the panels with a group barrier (one global
+// counter per system) between the two phases of a panel:
+//   phase A (PT = 128 or 256 threads of CTA 0): panel factorisation with RPT rows per thread, the rows'
+//            kNB panel entries in registers.  Pivot search = thread-local maximum, then ONE warp redux on
+//            the high word of |a| (a pivot within 2^-20 of the largest candidate is as good as the largest;
+//            ties go to the lowest row), then the 4..8 per-warp candidates through shared memory: two
+//            named barriers per pivot step among PT threads instead of three among 544;
+//   phase B (all CTAs): column tiles of the trailing matrix (and the right-hand sides), each owned by one
+//            CTA for all rows: the 16 pivot rows "as they were when they became pivots" are re-derived per
+//            column in registers (the recurrence of tps_urow_kernel) BEFORE the owner overwrites them,
+//            then the rank-16 update of the tile, 64 rows at a time.
+// Assembly and the final division run in the same launch.
+constexpr int kGjThreads = 256;
+constexpr int kGjColTile = 8;      // columns of the trailing matrix owned by one CTA per panel (65 tiles at K = 512)
+constexpr int kGjMaxRows = 1024;   // n = K + 4 <= PT * RPT
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
@@ -352,19 +356,23 @@ __device__ __forceinline__ void group_barrier(unsigned int* cnt, unsigned int ta
   }
   __syncthreads();
 }
+template <int PT>
+__device__ __forceinline__ void panel_barrier() {   // named barrier 1 among the PT panel threads
+  asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
+}
 
-template <int THREADS>   // 640 (n <= 640: 102 registers per thread, no spills) or 1024
-__global__ void __launch_bounds__(THREADS, 1)
+template <int PT, int RPT>
+__global__ void __launch_bounds__(kGjThreads, 1)
 tps_gj_coop_kernel(const float* __restrict__ c_src, const float* __restrict__ c_dst, const float* __restrict__ lmbda,
                    const float* __restrict__ w, double* __restrict__ A, int* __restrict__ pivrow,
                    unsigned int* __restrict__ bar, float* __restrict__ theta, int32_t* __restrict__ status, int K,
-                   int cps) {
-  __shared__ double s_val[2][32];
-  __shared__ int s_idx[2][32];
+                   int cps, int dbg) {
+  __shared__ unsigned int s_key[2][PT / 32];
+  __shared__ int s_idx[2][PT / 32];
   __shared__ double s_prow[2][kNB];
-  __shared__ double s_u[kNB][64];
-  __shared__ double s_l[kRowTile][kNB + 1];
-  __shared__ double s_lp[kNB][kNB];   // multipliers of the pivot rows themselves (urow recurrence)
+  __shared__ double s_pinv[2];
+  __shared__ double s_u[kNB][kGjColTile];
+  __shared__ double s_lp[kNB][kNB];   // multipliers of the pivot rows among themselves (urow recurrence)
   __shared__ int s_pr[kNB];
   const int b = blockIdx.x / cps, cta = blockIdx.x - b * cps;
   const int n = K + 4, ld = n + 3;
@@ -372,7 +380,8 @@ tps_gj_coop_kernel(const float* __restrict__ c_src, const float* __restrict__ c_
   int* piv = pivrow + (size_t)b * n;
   unsigned int* cnt = bar + b;
   unsigned int nbar = 0;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = THREADS >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  extern __shared__ double s_mul[];   // [n][kNB + 1]: multipliers of every row for the current panel
 
   // ---- assembly (tps_assemble_kernel), spread over the group
   {
@@ -380,7 +389,7 @@ tps_gj_coop_kernel(const float* __restrict__ c_src, const float* __restrict__ c_
     const float* cd = c_dst + (size_t)b * K * 3;
     const double lam = (double)lmbda[b];
     const int total = n * ld;
-    for (int idx = cta * THREADS + tid; idx < total; idx += cps * THREADS) {
+    for (int idx = cta * kGjThreads + tid; idx < total; idx += cps * kGjThreads) {
       const int i = idx / ld, j = idx - i * ld;
       double v = 0.0;
       if (i < K) {
@@ -408,128 +417,188 @@ tps_gj_coop_kernel(const float* __restrict__ c_src, const float* __restrict__ c_
   }
   group_barrier(cnt, (++nbar) * cps);
 
-  bool eligible = true;          // CTA 0: row tid may still become a pivot
+  unsigned int elig = (1u << RPT) - 1u;   // panel threads of CTA 0: bit i = row tid + i * PT may still be a pivot
   int sing = 0;
+  long long t_a = 0, t_b = 0, t_bar = 0, t_mark = clock64();   // dbg: cycles of CTA 0 per phase
   for (int c0 = 0; c0 < n; c0 += kNB) {
     const int nb = min(kNB, n - c0);
-    // ---------------- phase A: panel factorisation by CTA 0 (one thread per row)
-    if (cta == 0) {
-      const int r = tid;
-      const bool has_row = r < n;
-      double a[kNB];
+    // ---------------- phase A: panel factorisation by PT threads of CTA 0, RPT rows per thread
+    if (cta == 0 && tid < PT) {
+      double a[RPT][kNB];
 #pragma unroll
-      for (int j = 0; j < kNB; ++j) a[j] = (has_row && j < nb) ? Ab[(size_t)r * ld + c0 + j] : 0.0;
+      for (int i = 0; i < RPT; ++i) {
+        const int r = tid + i * PT;
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) a[i][j] = (r < n && j < nb) ? Ab[(size_t)r * ld + c0 + j] : 0.0;
+      }
 #pragma unroll
       for (int k = 0; k < kNB; ++k) {
         if (k < nb) {   // uniform
           const int pb = k & 1;
-          double v = (has_row && eligible) ? fabs(a[k]) : -1.0;
-          int vi = r;
-          for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
-            if (ov > v || (ov == v && oi < vi)) {
-              v = ov;
-              vi = oi;
+          // candidates are compared on the high word of |a| (sign cleared): FP64 issue is the scarce resource
+          // of this chip (measured ~16 cycles per warp instruction), integer compares are free next to it
+          unsigned int key = 0u;
+          int bi = 0x7fffffff;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int r = tid + i * PT;
+            unsigned int ki = (unsigned int)__double2hiint(a[i][k]) & 0x7fffffffu;
+            if (ki == 0u && __double2loint(a[i][k]) != 0) ki = 1u;        // tiny but non-zero stays eligible
+            if (ki >= 0x7ff00000u) ki = 0x7ff00000u;                       // Inf / NaN: surfaces as "singular"
+            if (r < n && ((elig >> i) & 1u) && ki > key) {
+              key = ki;
+              bi = r;
             }
           }
+          const unsigned int wkey = __reduce_max_sync(0xffffffffu, key);
+          const int widx = __reduce_min_sync(0xffffffffu, (key == wkey && key != 0u) ? bi : 0x7fffffff);
           if (lane == 0) {
-            s_val[pb][wid] = v;
-            s_idx[pb][wid] = vi;
+            s_key[pb][wid] = wkey;
+            s_idx[pb][wid] = widx;
           }
-          __syncthreads();
-          // every warp reduces the per-warp candidates itself: no broadcast round for the pivot index
-          double wv = lane < nwarps ? s_val[pb][lane] : -1.0;
-          int wi = lane < nwarps ? s_idx[pb][lane] : 0x7fffffff;
-          for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, wv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-            if (ov > wv || (ov == wv && oi < wi)) {
-              wv = ov;
-              wi = oi;
+          panel_barrier<PT>();
+          unsigned int gk = 0u;
+          int pr = 0x7fffffff;
+#pragma unroll
+          for (int q = 0; q < PT / 32; ++q) {
+            const unsigned int kq = s_key[pb][q];
+            const int iq = s_idx[pb][q];
+            if (kq > gk || (kq == gk && iq < pr)) {
+              gk = kq;
+              pr = iq;
             }
           }
-          const int pr = wi;
-          if (tid == 0 && (!(wv > 0.0) || !isfinite(wv))) sing = 1;
-          if (r == pr) {
+          // a vanishing or non-finite pivot marks the system singular
+          if (tid == 0 && (gk == 0u || gk >= 0x7ff00000u || pr == 0x7fffffff)) sing = 1;
+          if (pr == 0x7fffffff) pr = 0;   // nothing eligible (cannot happen for k < n): keep going, flagged
 #pragma unroll
-            for (int j = 0; j < kNB; ++j) s_prow[pb][j] = a[j];
-            eligible = false;
-            piv[c0 + k] = r;
+          for (int i = 0; i < RPT; ++i) {
+            if (tid + i * PT == pr) {
+#pragma unroll
+              for (int j = 0; j < kNB; ++j) s_prow[pb][j] = a[i][j];
+              // one reciprocal per step, by the owner of the pivot row: fp32 seed + two Newton steps in fp64
+              // (4 dependent FP64 instructions instead of the ~10 of a correctly rounded division; the
+              // multipliers l = a * pinv are within 1e-16 relative of a / pivot)
+              {
+                const double p = a[i][k];
+                double rcp = (double)(1.0f / (float)p);
+                rcp = rcp * (2.0 - p * rcp);
+                rcp = rcp * (2.0 - p * rcp);
+                s_pinv[pb] = (fabs(p) > 1e-30 && fabs(p) < 1e30) ? rcp : 1.0 / p;   // outside the fp32 range: divide
+              }
+              elig &= ~(1u << i);
+              piv[c0 + k] = pr;
+            }
           }
-          __syncthreads();
-          if (has_row && r != pr) {
-            const double l = a[k] / s_prow[pb][k];
-            a[k] = l;
+          panel_barrier<PT>();
+          const double pinv = s_pinv[pb];
 #pragma unroll
-            for (int j = 0; j < kNB; ++j)
-              if (j > k) a[j] -= l * s_prow[pb][j];
+          for (int i = 0; i < RPT; ++i) {
+            const int r = tid + i * PT;
+            if (r < n && r != pr) {
+              const double l = a[i][k] * pinv;
+              a[i][k] = l;
+#pragma unroll
+              for (int j = 0; j < kNB; ++j)
+                if (j > k) a[i][j] -= l * s_prow[pb][j];
+            }
           }
         }
       }
-      if (has_row) {
 #pragma unroll
-        for (int j = 0; j < kNB; ++j)
-          if (j < nb) Ab[(size_t)r * ld + c0 + j] = a[j];
+      for (int i = 0; i < RPT; ++i) {
+        const int r = tid + i * PT;
+        if (r < n) {
+#pragma unroll
+          for (int j = 0; j < kNB; ++j)
+            if (j < nb) Ab[(size_t)r * ld + c0 + j] = a[i][j];
+        }
       }
     }
+    if (dbg) { const long long t = clock64(); t_a += t - t_mark; t_mark = t; }
     group_barrier(cnt, (++nbar) * cps);
+    if (dbg) { const long long t = clock64(); t_bar += t - t_mark; t_mark = t; }
 
-    // ---------------- phase B: trailing update, tiles of 64 columns x kRowTile rows
+    // ---------------- phase B: trailing update.  A column tile (kGjColTile columns, all rows) belongs to ONE
+    // CTA: the pivot rows "as they were" (u) are derived from the tile's own columns before that CTA
+    // overwrites them, and no other CTA touches these columns -- no side buffer, no extra barrier.
     const int rest = ld - c0 - nb;
     if (rest > 0) {
-      const int nct = (rest + 63) / 64, nrt = (n + kRowTile - 1) / kRowTile;
+      const int nct = (rest + kGjColTile - 1) / kGjColTile;
       if (tid < kNB) s_pr[tid] = tid < nb ? piv[c0 + tid] : -1;
       __syncthreads();
       // multipliers of the pivot rows among themselves: L[t][t2] = A[piv t][c0 + t2], t2 < t
-      if (tid < kNB * kNB) {
-        const int t = tid / kNB, t2 = tid - t * kNB;
+      {
+        const int t = tid / kNB, t2 = tid - t * kNB;    // 256 threads = kNB x kNB
         s_lp[t][t2] = (t < nb && t2 < t) ? Ab[(size_t)s_pr[t] * ld + c0 + t2] : 0.0;
       }
-      for (int item = cta; item < nct * nrt; item += cps) {
-        const int ct = item % nct, rt = item / nct;
-        const int j0 = c0 + nb + ct * 64, r0 = rt * kRowTile;
-        __syncthreads();   // s_u / s_l of the previous item are free (and s_lp / s_pr are visible)
-        if (tid < 64) {
+      // multipliers of every row for this panel: n x kNB doubles, staged once (each thread's loads are
+      // independent: one L2 round trip), pitch kNB + 1 against bank conflicts
+      const bool mine = cta < nct;
+      if (mine) {
+        for (int i = tid; i < n * kNB; i += kGjThreads) {
+          const int r = i / kNB, t = i - r * kNB;
+          s_mul[r * (kNB + 1) + t] = t < nb ? Ab[(size_t)r * ld + c0 + t] : 0.0;
+        }
+      }
+      for (int ct = cta; ct < nct; ct += cps) {
+        const int j0 = c0 + nb + ct * kGjColTile;
+        __syncthreads();   // s_u of the previous tile is free (and s_lp / s_pr / s_mul are visible)
+        if (tid < kGjColTile) {
           const int j = j0 + tid;
           double u[kNB];
 #pragma unroll
           for (int t = 0; t < kNB; ++t) u[t] = (t < nb && j < ld) ? Ab[(size_t)s_pr[t] * ld + j] : 0.0;
+          // forward substitution in axpy form: the critical path is kNB dependent FMAs, not kNB^2 / 2
 #pragma unroll
           for (int t = 0; t < kNB; ++t) {
-            double v = u[t];
 #pragma unroll
-            for (int t2 = 0; t2 < kNB; ++t2)
-              if (t2 < t) v -= s_lp[t][t2] * u[t2];
-            u[t] = v;
-            s_u[t][tid] = v;
+            for (int t3 = 0; t3 < kNB; ++t3)
+              if (t3 > t) u[t3] -= s_lp[t3][t] * u[t];
+            s_u[t][tid] = u[t];
           }
         }
-        for (int i = tid; i < kRowTile * kNB; i += THREADS) {
-          const int rr = i / kNB, t = i - rr * kNB;
-          const int r = r0 + rr;
-          s_l[rr][t] = (r < n && t < nb) ? Ab[(size_t)r * ld + c0 + t] : 0.0;
-        }
-        __syncthreads();
-        const int tx = tid & 63, ty = tid >> 6;     // 64 columns x 16 row lanes
+        __syncthreads();   // s_u is visible
+        // rank-16 update of all rows of the tile: a thread owns column tx of the rows ty, ty + 32, ...
+        const int tx = tid % kGjColTile, ty = tid / kGjColTile;
         const int j = j0 + tx;
         if (j < ld) {
-          for (int rr = ty; rr < kRowTile; rr += THREADS / 64) {
-            const int r = r0 + rr;
-            if (r >= n) break;
-            double v = Ab[(size_t)r * ld + j];
+          double uc[kNB];
 #pragma unroll
-            for (int t = 0; t < kNB; ++t)
-              if (t < nb && s_pr[t] != r) v -= s_l[rr][t] * s_u[t][tx];
-            Ab[(size_t)r * ld + j] = v;
+          for (int t = 0; t < kNB; ++t) uc[t] = s_u[t][tx];
+          constexpr int kLanes = kGjThreads / kGjColTile;
+          constexpr int kBatch = 6;               // rows in flight per thread: independent L2 loads
+          for (int rb = ty; rb < n; rb += kLanes * kBatch) {
+            double v[kBatch];
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+              const int r = rb + q * kLanes;
+              v[q] = r < n ? Ab[(size_t)r * ld + j] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+              const int r = rb + q * kLanes;
+              if (r < n) {
+                const double* l = s_mul + r * (kNB + 1);
+                double acc = v[q];
+#pragma unroll
+                for (int t = 0; t < kNB; ++t)
+                  if (s_pr[t] != r) acc -= l[t] * uc[t];      // l[t] = 0 for t >= nb
+                Ab[(size_t)r * ld + j] = acc;
+              }
+            }
           }
         }
       }
     }
+    if (dbg) { const long long t = clock64(); t_b += t - t_mark; t_mark = t; }
     group_barrier(cnt, (++nbar) * cps);
+    if (dbg) { const long long t = clock64(); t_bar += t - t_mark; t_mark = t; }
   }
+  if (dbg && blockIdx.x == 0 && tid == 0)
+    printf("tps_gj_coop: n=%d cps=%d cycles of CTA 0: panel %lld, update %lld, barriers %lld\n", n, cps, t_a, t_b, t_bar);
   // ---- x_k = b[pivrow[k]] / a[pivrow[k]][k]
-  for (int i = cta * THREADS + tid; i < n * 3; i += cps * THREADS) {
+  for (int i = cta * kGjThreads + tid; i < n * 3; i += cps * kGjThreads) {
     const int k = i / 3, d = i - k * 3;
     const double* row = Ab + (size_t)piv[k] * ld;
     theta[((size_t)b * n + k) * 3 + d] = (float)(row[n + d] / row[k]);
@@ -554,7 +623,7 @@ extern "C" int km_tps_fit(const float* c_src, const float* c_dst, const float* l
   const int n = K + 4, ld = n + 3;
   cudaStream_t st = km_cs(stream);
   double* A = reinterpret_cast<double*>(workspace);
-  if (n <= kGjThreads && g_tps_single_cta == 0) {
+  if (n <= kGjMaxRows && (g_tps_single_cta == 0 || g_tps_single_cta == 3)) {
     // one cooperative launch: assembly, blocked Gauss-Jordan and the final division (see tps_gj_coop_kernel)
     double* Ut = A + (size_t)N * n * ld;
     int* pivrow = reinterpret_cast<int*>(Ut + (size_t)N * kNB * ld);
@@ -563,12 +632,14 @@ extern "C" int km_tps_fit(const float* c_src, const float* c_dst, const float* l
     int dev = 0, nsm = 148;
     KM_CUDA_OK(cudaGetDevice(&dev));
     KM_CUDA_OK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    // every CTA of a launch must be resident (the group barrier spins): one 1024-thread CTA per SM
+    // every CTA of a launch must be resident (the group barrier spins): at most one CTA per SM
     const int chunk = N < nsm ? N : nsm;
     for (int b0 = 0; b0 < N; b0 += chunk) {
-      const int nb = N - b0 < chunk ? N - b0 : chunk;
-      int cps = nsm / nb;
-      if (cps > 24) cps = 24;
+      const int nbs = N - b0 < chunk ? N - b0 : chunk;
+      int cps = nsm / nbs;
+      const int max_tiles = (ld - kNB + kGjColTile - 1) / kGjColTile;   // tiles of the first (widest) panel
+      if (cps > max_tiles) cps = max_tiles;
+      if (cps < 1) cps = 1;
       const float* cs = c_src + (size_t)b0 * K * 3;
       const float* cd = c_dst + (size_t)b0 * K * 3;
       const float* lm = lmbda + b0;
@@ -578,18 +649,25 @@ extern "C" int km_tps_fit(const float* c_src, const float* c_dst, const float* l
       unsigned int* br = bar + b0;
       float* th = theta + (size_t)b0 * n * 3;
       int32_t* stt = status + b0;
-      int Kk = K;
-      void* args[] = {&cs, &cd, &lm, &wp, &Ab, &pv, &br, &th, &stt, &Kk, &cps};
-      if (n <= 640)
-        KM_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(tps_gj_coop_kernel<640>), dim3(nb * cps),
-                                               dim3(640), args, 0, st));
-      else
-        KM_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(tps_gj_coop_kernel<1024>),
-                                               dim3(nb * cps), dim3(1024), args, 0, st));
+      int Kk = K, dbg = g_tps_single_cta == 3;
+      void* args[] = {&cs, &cd, &lm, &wp, &Ab, &pv, &br, &th, &stt, &Kk, &cps, &dbg};
+      const void* fn = n <= 640 ? reinterpret_cast<const void*>(tps_gj_coop_kernel<128, 5>)
+                                : reinterpret_cast<const void*>(tps_gj_coop_kernel<256, 4>);
+      const size_t smem = (size_t)n * (kNB + 1) * sizeof(double);     // <= 139 KB at n = 1024
+      static unsigned long long attr_set = 0;
+      if (km_first_use_on_device(&attr_set)) {
+        KM_CUDA_OK(cudaFuncSetAttribute(tps_gj_coop_kernel<128, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        KM_CUDA_OK(cudaFuncSetAttribute(tps_gj_coop_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      }
+      KM_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(nbs * cps), dim3(kGjThreads), args, smem, st));
     }
     return KM_OK;
   }
   const long long total = (long long)n * ld;
+  int bx = (int)((total + 255) / 256);
+  if (bx > 1184) bx = 1184;
+  tps_assemble_kernel<<<dim3(bx, N), 256, 0, st>>>(c_src, c_dst, lmbda, w, A, K);
+  KM_LAUNCH_OK("tps_assemble_kernel");
   if (n <= 1024 && g_tps_single_cta != 1) {
     double* Ut = A + (size_t)N * n * ld;
     int* pivrow = reinterpret_cast<int*>(Ut + (size_t)N * kNB * ld);
@@ -621,4 +699,4 @@ extern "C" int km_tps_fit(const float* c_src, const float* c_dst, const float* l
   return KM_OK;
 }
 
-void km_tps_set_single_cta(int v) { g_tps_single_cta = (v == 1 || v == 2) ? v : 0; }
+void km_tps_set_single_cta(int v) { g_tps_single_cta = (v >= 1 && v <= 3) ? v : 0; }   // 3: 0 + phase timing printed

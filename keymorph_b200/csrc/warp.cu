@@ -14,6 +14,7 @@
 namespace {
 
 int g_tps_fast = 1;
+int g_warp_occ = 4;   // km_set_option(KM_OPT_WARP_OCC): occupancy target of the single-channel fused warp kernels
 }  // namespace
 void km_conv_set_force_generic(int v);
 void km_conv_set_no_resident(int v);
@@ -27,6 +28,11 @@ void km_tps_set_single_cta(int v);
 void km_tps_set_packed(int v);
 void km_tps_set_vpt(int v);
 void km_set_operand_fp16(int v);
+void km_warp_set_tile(int v);
+bool km_warp_tile_eligible(const float* moving, int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo);
+int km_warp_tile_launch(int coord, bool exact, const float* mat, const float* grid, const float* moving,
+                        const float* fixed, float* out, float* grid_out, float* partials, int N, int C, int Di,
+                        int Hi, int Wi, int Do, int Ho, int Wo, cudaStream_t st);
 int km_tps_fast_enabled() { return g_tps_fast; }
 namespace {
 
@@ -282,8 +288,8 @@ grid_sample_kernel(const float* __restrict__ x, const float* __restrict__ grid,
 // field: they are moved with three 16-byte accesses per lane and transposed through a per-warp
 // shared-memory buffer (stride-3 word access is bank-conflict free), instead of 12-byte-strided
 // scalar accesses whose L1 wavefronts bound the kernel.
-template <int COORD, int CCH, bool FAST>
-__global__ void __launch_bounds__(256)
+template <int COORD, int CCH, bool FAST, int MINB>   // MINB: resident CTAs / SM asked of the compiler (A/B: 4, 5, 6)
+__global__ void __launch_bounds__(256, MINB)
 warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict__ theta, int K,
                  const float* __restrict__ grid, const float* __restrict__ moving,
                  const float* __restrict__ fixed, float* __restrict__ out,
@@ -840,6 +846,14 @@ extern "C" int km_set_option(int key, int value) {
     km_set_operand_fp16(value);
     return KM_OK;
   }
+  if (key == KM_OPT_WARP_TILE) {
+    km_warp_set_tile(value);
+    return KM_OK;
+  }
+  if (key == KM_OPT_WARP_OCC) {
+    g_warp_occ = (value == 5 || value == 6) ? value : 4;
+    return KM_OK;
+  }
   km_set_error("km_set_option: unknown key %d", key);
   return KM_EINVAL;
 }
@@ -852,6 +866,12 @@ extern "C" int km_grid_sample3d(const float* x, const float* grid, float* out, i
                "km_grid_sample3d: bad shape");
   KM_CHECK_ARG(mode == KM_INTERP_BILINEAR || mode == KM_INTERP_NEAREST, "km_grid_sample3d: bad mode");
   const long long nvo = (long long)Do * Ho * Wo;
+  if (mode == KM_INTERP_BILINEAR && km_warp_tile_eligible(x, C, Di, Hi, Wi, Do, Ho, Wo))
+    // TMA-staged tiles, ATen's un-fused arithmetic: same bits as grid_sample_kernel (C = 14: 5.3 -> 2.0 ms;
+    // the fused warp + loss kernels below stay on the direct gather: measured faster for one channel, and
+    // their per-CTA summation order is what makes the label-map Dice path bit-identical to them)
+    return km_warp_tile_launch(KM_COORD_GRID, true, nullptr, grid, x, nullptr, out, nullptr, nullptr, N, C, Di, Hi, Wi,
+                               Do, Ho, Wo, km_cs(stream));
   const dim3 g(blocks_for((nvo + 3) / 4, 256, 148 * 8), N);
   grid_sample_kernel<<<g, 256, 0, km_cs(stream)>>>(x, grid, out, C, Di, Hi, Wi, nvo, mode);
   KM_LAUNCH_OK("grid_sample_kernel");
@@ -897,17 +917,30 @@ extern "C" size_t km_pair_stats_workspace_bytes(int N, int C, long long M, int h
   return pair_partials_bytes(N, C) + (hard ? (size_t)N * (size_t)M * sizeof(int32_t) : 0);
 }
 
+template <int COORD, int CCH, int MINB>
+static void launch_warp_loss_occ(bool fast, dim3 grid, size_t smem, cudaStream_t st, const float* a,
+                                 const float* theta, int K, const float* g, const float* mov,
+                                 const float* fix, float* out, float* gout, float* part, int N, int C,
+                                 int D, int H, int W, int mode) {
+  if (fast)
+    warp_loss_kernel<COORD, CCH, true, MINB><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, gout,
+                                                                      part, N, C, D, H, W, mode);
+  else
+    warp_loss_kernel<COORD, CCH, false, MINB><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, gout,
+                                                                       part, N, C, D, H, W, mode);
+}
+
 template <int COORD, int CCH>
 static void launch_warp_loss(bool fast, dim3 grid, size_t smem, cudaStream_t st, const float* a,
                              const float* theta, int K, const float* g, const float* mov,
                              const float* fix, float* out, float* gout, float* part, int N, int C,
                              int D, int H, int W, int mode) {
-  if (fast)
-    warp_loss_kernel<COORD, CCH, true><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, gout,
-                                                                part, N, C, D, H, W, mode);
+  if (CCH == 1 && COORD != KM_COORD_TPS && g_warp_occ == 5)
+    launch_warp_loss_occ<COORD, CCH, (CCH == 1 && COORD != KM_COORD_TPS) ? 5 : 4>(fast, grid, smem, st, a, theta, K, g, mov, fix, out, gout, part, N, C, D, H, W, mode);
+  else if (CCH == 1 && COORD != KM_COORD_TPS && g_warp_occ == 6)
+    launch_warp_loss_occ<COORD, CCH, (CCH == 1 && COORD != KM_COORD_TPS) ? 6 : 4>(fast, grid, smem, st, a, theta, K, g, mov, fix, out, gout, part, N, C, D, H, W, mode);
   else
-    warp_loss_kernel<COORD, CCH, false><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, gout,
-                                                                 part, N, C, D, H, W, mode);
+    launch_warp_loss_occ<COORD, CCH, 4>(fast, grid, smem, st, a, theta, K, g, mov, fix, out, gout, part, N, C, D, H, W, mode);
 }
 
 extern "C" int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const float* theta, int K,
