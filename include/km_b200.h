@@ -85,9 +85,6 @@ int km_sm_count(void);
  * mode gather from TMA-staged shared-memory tiles (warp_tile.cu) instead of issuing 8 global loads per voxel
  * (0 = the direct-gather kernels, A/B; identical results). */
 #define KM_OPT_WARP_TILE 14
-/* key KM_OPT_WARP_OCC (default 4): resident CTAs per SM the single-channel fused warp kernels are compiled
- * for (4 = 64 registers, 5 = 48, 6 = 40; A/B: the gather is latency-bound at 50 % occupancy). */
-#define KM_OPT_WARP_OCC 15
 int km_set_option(int key, int value);
 /* 1 when the 16-bit tensors of the backbone are fp16, 0 when they are bf16 (KM_OPT_OPERAND_FP16) */
 int km_operand_is_fp16(void);

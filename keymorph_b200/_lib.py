@@ -100,7 +100,6 @@ KM_OPT_TPS_PACKED = 11
 KM_OPT_TPS_VPT = 12
 KM_OPT_OPERAND_FP16 = 13
 KM_OPT_WARP_TILE = 14
-KM_OPT_WARP_OCC = 15
 
 _lib = None
 

@@ -14,7 +14,6 @@
 namespace {
 
 int g_tps_fast = 1;
-int g_warp_occ = 4;   // km_set_option(KM_OPT_WARP_OCC): occupancy target of the single-channel fused warp kernels
 }  // namespace
 void km_conv_set_force_generic(int v);
 void km_conv_set_no_resident(int v);
@@ -288,8 +287,10 @@ grid_sample_kernel(const float* __restrict__ x, const float* __restrict__ grid,
 // field: they are moved with three 16-byte accesses per lane and transposed through a per-warp
 // shared-memory buffer (stride-3 word access is bank-conflict free), instead of 12-byte-strided
 // scalar accesses whose L1 wavefronts bound the kernel.
-template <int COORD, int CCH, bool FAST, int MINB>   // MINB: resident CTAs / SM asked of the compiler (A/B: 4, 5, 6)
-__global__ void __launch_bounds__(256, MINB)
+// (Occupancy was A/B-tested: compiled for 5 / 6 resident CTAs per SM (48 / 40 registers) the affine kernel takes
+// 211 / 222 us instead of 208 us at 256^3 -- the gather is bound by L1 wavefronts, not by latency hiding.)
+template <int COORD, int CCH, bool FAST>
+__global__ void __launch_bounds__(256)
 warp_loss_kernel(const float* __restrict__ mat_or_ctrl, const float* __restrict__ theta, int K,
                  const float* __restrict__ grid, const float* __restrict__ moving,
                  const float* __restrict__ fixed, float* __restrict__ out,
@@ -850,10 +851,7 @@ extern "C" int km_set_option(int key, int value) {
     km_warp_set_tile(value);
     return KM_OK;
   }
-  if (key == KM_OPT_WARP_OCC) {
-    g_warp_occ = (value == 5 || value == 6) ? value : 4;
-    return KM_OK;
-  }
+
   km_set_error("km_set_option: unknown key %d", key);
   return KM_EINVAL;
 }
@@ -917,30 +915,17 @@ extern "C" size_t km_pair_stats_workspace_bytes(int N, int C, long long M, int h
   return pair_partials_bytes(N, C) + (hard ? (size_t)N * (size_t)M * sizeof(int32_t) : 0);
 }
 
-template <int COORD, int CCH, int MINB>
-static void launch_warp_loss_occ(bool fast, dim3 grid, size_t smem, cudaStream_t st, const float* a,
-                                 const float* theta, int K, const float* g, const float* mov,
-                                 const float* fix, float* out, float* gout, float* part, int N, int C,
-                                 int D, int H, int W, int mode) {
-  if (fast)
-    warp_loss_kernel<COORD, CCH, true, MINB><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, gout,
-                                                                      part, N, C, D, H, W, mode);
-  else
-    warp_loss_kernel<COORD, CCH, false, MINB><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, gout,
-                                                                       part, N, C, D, H, W, mode);
-}
-
 template <int COORD, int CCH>
 static void launch_warp_loss(bool fast, dim3 grid, size_t smem, cudaStream_t st, const float* a,
                              const float* theta, int K, const float* g, const float* mov,
                              const float* fix, float* out, float* gout, float* part, int N, int C,
                              int D, int H, int W, int mode) {
-  if (CCH == 1 && COORD != KM_COORD_TPS && g_warp_occ == 5)
-    launch_warp_loss_occ<COORD, CCH, (CCH == 1 && COORD != KM_COORD_TPS) ? 5 : 4>(fast, grid, smem, st, a, theta, K, g, mov, fix, out, gout, part, N, C, D, H, W, mode);
-  else if (CCH == 1 && COORD != KM_COORD_TPS && g_warp_occ == 6)
-    launch_warp_loss_occ<COORD, CCH, (CCH == 1 && COORD != KM_COORD_TPS) ? 6 : 4>(fast, grid, smem, st, a, theta, K, g, mov, fix, out, gout, part, N, C, D, H, W, mode);
+  if (fast)
+    warp_loss_kernel<COORD, CCH, true><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, gout,
+                                                                part, N, C, D, H, W, mode);
   else
-    launch_warp_loss_occ<COORD, CCH, 4>(fast, grid, smem, st, a, theta, K, g, mov, fix, out, gout, part, N, C, D, H, W, mode);
+    warp_loss_kernel<COORD, CCH, false><<<grid, 256, smem, st>>>(a, theta, K, g, mov, fix, out, gout,
+                                                                 part, N, C, D, H, W, mode);
 }
 
 extern "C" int km_warp_loss(int coord_mode, const float* mat_or_ctrl, const float* theta, int K,
