@@ -476,16 +476,9 @@ tps_gj_coop_kernel(const float* __restrict__ c_src, const float* __restrict__ c_
             if (tid + i * PT == pr) {
 #pragma unroll
               for (int j = 0; j < kNB; ++j) s_prow[pb][j] = a[i][j];
-              // one reciprocal per step, by the owner of the pivot row: fp32 seed + two Newton steps in fp64
-              // (4 dependent FP64 instructions instead of the ~10 of a correctly rounded division; the
-              // multipliers l = a * pinv are within 1e-16 relative of a / pivot)
-              {
-                const double p = a[i][k];
-                double rcp = (double)(1.0f / (float)p);
-                rcp = rcp * (2.0 - p * rcp);
-                rcp = rcp * (2.0 - p * rcp);
-                s_pinv[pb] = (fabs(p) > 1e-30 && fabs(p) < 1e30) ? rcp : 1.0 / p;   // outside the fp32 range: divide
-              }
+              // one division per step, by the owner of the pivot row (an fp32-seeded Newton reciprocal was
+              // measured SLOWER: +0.4 ms over the 516 steps, profiles/r02_tps_fit_cooperative_phases.log)
+              s_pinv[pb] = 1.0 / a[i][k];
               elig &= ~(1u << i);
               piv[c0 + k] = pr;
             }

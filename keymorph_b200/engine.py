@@ -161,7 +161,7 @@ class UNetEngine(_EngineBase):
         g1 = sc1.groupnorm
         w1 = sc1.conv.weight
         zf = ops.zfold_supported(w0.shape[0], w1.shape[0], D, H, W)
-        fold = ops.USE_GN_FOLD and ops.USE_GN_FOLD_STEM and zf and self.debug is None
+        fold = ops.USE_GN_FOLD and ops.gn_fold_stem_enabled() and zf and self.debug is None
         if fold:
             # ONE stem pass stores the raw ReLU'd map and its statistics; the next GroupNorm is folded into
             # the z-folded conv (per-sample scaled weights + border-class bias), so the map is never normalised

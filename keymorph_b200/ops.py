@@ -465,17 +465,20 @@ def conv3d_zfold(x, wz, relu=False, want_stats=False, pool=False, store=True):
 
 
 USE_GN_FOLD = True
-# The stem -> conv_zf pair can be folded too (the stem then runs once: +5 % registrations/s), but there the
-# fold REPLACES an fp32 normalisation before the single bf16 rounding by a rounding of the un-centred
-# activation, and a flat background then carries one coherent rounding offset under every centre of mass: at
-# 256^3 the keypoint error vs the fp32 oracle goes from max 1.36e-2 / mean 1.15e-3 (below torch's own
-# bf16-autocast drift, 1.41e-2 / 1.53e-3) to 2.78e-2 / 1.59e-3 (tools/accuracy_256.py).  Measured remedies:
-# storing v - c with the EXACT channel mean c restores 1.30e-2 / 1.29e-3 but needs the statistics pass the
-# fold was meant to save; c estimated from 1/8 of the planes (15-35 % off) does not help (2.92e-2);
-# position-hashed stochastic rounding gives 1.72e-2 / 1.82e-3 and costs 0.2 ms in the stem.  Everywhere else
-# the fold removes a rounding (the activation was already stored raw in bf16 and re-rounded by the norm
-# pass) and IMPROVES accuracy (2.10e-2 / 1.22e-3 -> 1.36e-2 / 1.15e-3).  Off by default: parity first.
-USE_GN_FOLD_STEM = False
+# The stem -> conv_zf pair can be folded too (the stem then runs once instead of twice).  There the fold REPLACES
+# an fp32 normalisation before the single 16-bit rounding by a rounding of the un-centred activation, and a flat
+# background then carries one coherent rounding offset under every centre of mass.  Measured at 256^3, K = 256
+# (tools/accuracy_256.py, profiles/r02_accuracy_256_operand_types_and_folds.log), keypoint error vs the fp32 oracle:
+#   fp16 operands: 3.50e-3 / 1.45e-4 (max / mean) without, 2.83e-3 / 1.63e-4 with the stem fold -- no loss;
+#   bf16 operands: 2.74e-2 / 1.01e-3 without, 3.88e-2 / 1.18e-3 with -- 3 mantissa bits fewer make the offset visible.
+# None = automatic: folded with fp16 operands (the default type), not folded with bf16.  True / False force it.
+USE_GN_FOLD_STEM = None
+
+
+def gn_fold_stem_enabled():
+    if USE_GN_FOLD_STEM is None:
+        return act_dtype() == torch.float16
+    return bool(USE_GN_FOLD_STEM)
 # The fold is also built for the plain CTA-pair kernel (conv3d_tc_pair_gn, parity-tested) but stays off
 # in the engine: its staged epilogue is on the critical path, the bias loads cost more (+0.3 ms over the
 # four layers) than the four in-place normalisation passes they replace (0.2 ms), and at 256^3 the extra

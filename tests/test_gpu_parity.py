@@ -1186,14 +1186,19 @@ def test_full_size_256_backbone_and_registration_vs_oracle():
         # is one worst, weakly localised blob in either run, so it gets 25 % of slack
         assert mean_err < max(1e-3, 1.0 * drift_mean)
         assert err < max(1e-2, 1.25 * drift)
-    # the optional stem fold (ops.USE_GN_FOLD_STEM) trades accuracy for 5 % speed: it has to stay inside 2x
-    ops.USE_GN_FOLD_STEM = True
+    # the stem -> conv_zf GroupNorm fold (automatic: on with fp16 operands, off with bf16): the other setting
+    # has to stay inside the same budget (fp16) / inside 2x of the drift (bf16)
+    ops.USE_GN_FOLD_STEM = not ops.gn_fold_stem_enabled()
     try:
         pts2 = model(f, m, transform_type="affine", return_aligned_points=False)["affine"]["points_f"].cpu()
     finally:
-        ops.USE_GN_FOLD_STEM = False
-    assert (pts2 - ref_pts).abs().mean().item() < max(1e-3, 1.1 * drift_mean)
-    assert (pts2 - ref_pts).abs().max().item() < max(1e-2, 2.0 * drift)
+        ops.USE_GN_FOLD_STEM = None
+    e2, m2 = (pts2 - ref_pts).abs().max().item(), (pts2 - ref_pts).abs().mean().item()
+    print(f"   with the stem fold {'off' if fp16 else 'on'}: max err {e2:.3e} mean {m2:.3e}")
+    if fp16:
+        assert e2 < 5e-3 and m2 < 3e-4
+    else:
+        assert m2 < max(1e-3, 1.1 * drift_mean) and e2 < max(1e-2, 2.0 * drift)
     for t in ("rigid", "affine"):
         ref = O.register_points(r[t]["points_f"].cpu(), r[t]["points_m"].cpu(), t, (S, S, S))
         assert_close(r[t]["matrix"].cpu(), ref["matrix"], rtol=1e-4, atol=1e-4)

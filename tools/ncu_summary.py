@@ -16,6 +16,12 @@ KEYS = [
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
     # pipes
     ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active %"),
+    ("sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "tensor hmma sub-pipe active cycles (avg/SM)"),
+    ("sm__ops_path_tensor_op_hmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed", "tensor ops fp16->fp32 % of peak"),
+    ("sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed", "tensor ops bf16->fp32 % of peak"),
+    ("sm__ops_path_tensor_op_hmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed", "tensor ops tf32->fp32 % of peak"),
+    ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor memory (TMEM) cycles active %"),
+    ("sm__cycles_elapsed.avg", "SM cycles elapsed (avg)"),
     ("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "tensor (tc) pipe inst %"),
     ("sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "tmem pipe inst %"),
     ("sm__inst_executed_pipe_tma.avg.pct_of_peak_sustained_active", "tma pipe inst %"),
@@ -76,8 +82,10 @@ def main():
             print(f"== {path.split('/')[-1]}: {name}")
             got = {}
             for key, label in KEYS:
-                if key in hdr:
-                    i = hdr.index(key)
+                # some metrics carry a section prefix ("TPC.TriageCompute.<metric>"): match on the suffix
+                cand = [h for h in hdr if h == key or h.endswith("." + key)]
+                if cand:
+                    i = hdr.index(cand[0])
                     got[key] = fnum(vals[i])
                     print(f"   {label:32s} {vals[i]:>18s} {units[i]}")
             rq, sc = got.get("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"), got.get(
