@@ -524,8 +524,16 @@ def groupwise_block(model, ctx):
     out["sharded_allreduce_vs_single_process"] = {
         "mean_points_maxabs": ctx["max"](float(e_mean)), "aligned_points_maxabs": ctx["max"](float(e_pts)),
         "flow_field_maxabs_subject0": ctx["max"](float((g_ar - g_ag).abs().max())),
-        "note": "all-gather scheme == single process bit for bit (gloo test); 0 at N = 1"}
-    del g_ar, g_ag
+        "flow_field_maxabs_subject0_interior": ctx["max"](float(
+            (g_ar - g_ag)[:, S // 4:3 * S // 4, S // 4:3 * S // 4, S // 4:3 * S // 4].abs().max())),
+        "note": "all-gather scheme == single process bit for bit (gloo test); 0 at N = 1.  tps_0 interpolates 512 "
+                "CLUSTERED keypoints exactly (random-init weights): its far field amplifies a 5e-5 change of the "
+                "targets by orders of magnitude; the affine field of the same two means is compared beside it"}
+    a_ar = parallel.groupwise_grids(model, pts[:1], results["allreduce"][1], "affine", subjects[:1])
+    a_ag = parallel.groupwise_grids(model, pts[:1], results["allgather"][1], "affine", subjects[:1])
+    out["sharded_allreduce_vs_single_process"]["affine_flow_field_maxabs_subject0"] = ctx["max"](
+        float((a_ar - a_ag).abs().max()))
+    del g_ar, g_ag, a_ar, a_ag
     # latency of the collective itself: (K*3+1) floats, NCCL all-reduce, 200 back-to-back calls
     if world > 1:
         buf = torch.zeros(512 * 3 + 1, device=dev)
