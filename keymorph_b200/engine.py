@@ -317,10 +317,24 @@ class ConvNetEngine(_EngineBase):
                                    out=None if blk.down_sample else raw)
             nxt = blocks[b + 1]
             last = b + 1 == len(blocks) - 1
-            wp = self.weights.get(f"block{b + 2}", nxt.conv.weight, pad_out_to=16 if last else None)
-            bias = nxt.conv.bias.detach()
-            raw, st, _ = ops.conv3d_tc(y, wp, bias=_padded(bias, 16) if last else bias, relu=False,
-                                       want_stats=True)
+            w = nxt.conv.weight
+            Cin, Cout = w.shape[1], w.shape[0]
+            Dn, Hn, Wn = y.shape[1:4]
+            # An InstanceNorm follows the conv: a per-channel constant cancels exactly in (v - mean) / std, so
+            # the conv bias is dropped there and the bias-free CTA-pair kernels of the UNet path take the layer
+            # (z-folded pair for Cout 64 with Cin % 64 == 0 at >= 96^3, plain pair for Cout 64 / 128)
+            no_bias = nxt.norm is not None and not last
+            if no_bias and ops.USE_ZFOLD_PAIR and Dn * Hn * Wn >= 96 ** 3 and Cout == 64 and Cin % 64 == 0 \
+                    and ops.zfold_pair_supported(Cin, Cout, Dn, Hn, Wn):
+                raw, st = ops.conv3d_zfold_pair(y, self.weights.get(f"block{b + 2}.zf2", w, zfold="pair"), relu=False,
+                                                want_stats=True)
+            elif no_bias and ops.USE_PAIR_CONV and Dn * Hn * Wn >= 64 ** 3 and ops.pair_supported(Cin, Cout, Dn, Hn, Wn):
+                raw, st = ops.conv3d_tc_pair(y, self.weights.get(f"block{b + 2}", w), relu=False, want_stats=True)
+            else:
+                wp = self.weights.get(f"block{b + 2}", w, pad_out_to=16 if last else None)
+                bias = nxt.conv.bias.detach()
+                raw, st, _ = ops.conv3d_tc(y, wp, bias=_padded(bias, 16) if last else bias, relu=False,
+                                           want_stats=True)
             del y
         feat = ops.ndhwc_to_ncdhw(heat)[:, :K].contiguous()
         pts, mass = ops.com3d(feat, ij=True, return_mass=True)
