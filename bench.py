@@ -322,7 +322,7 @@ def measure_pairwise(model, name, img_f, img_m, steps, warmup, ctx):
             "mse": float(r["mse"].item()), "points": torch.cat([r["points_f"], r["points_m"]]).cpu()}
 
 
-def measure_e2e(model, name, host_f, host_m, steps, ctx, with_grid=False):
+def measure_e2e(model, name, host_f, host_m, steps, ctx, with_grid=False, clone_outputs=False):
     """The public call fed from pinned HOST buffers.  Every step: H2D of both volumes (prefetched on a side
     stream), D2H of the warped image (+ the flow field with with_grid) and of the MSE into pinned host
     memory on a second side stream; the host reads step i's results after step i+1 has been enqueued."""
@@ -341,6 +341,8 @@ def measure_e2e(model, name, host_f, host_m, steps, ctx, with_grid=False):
         pending, last = None, None
         for i, (f, m) in enumerate(prefetch_to_device([(host_f, host_m)] * n, dev)):
             r = model(f, m, transform_type=t, return_aligned_points=True)[t]
+            if clone_outputs:     # a replayed CUDA graph overwrites its static outputs at the next call
+                r = {k: r[k].clone() for k in (("img_a", "mse", "grid") if with_grid else ("img_a", "mse"))}
             slot = ring[i & 1]
             done = torch.cuda.Event()
             done.record(compute)
@@ -374,6 +376,40 @@ def measure_e2e(model, name, host_f, host_m, steps, ctx, with_grid=False):
                                                    "; the flow field stays on the device (it is a function of the "
                                                    "returned matrix / spline parameters; --e2e-grid copies it too)"),
             "loss": last[0], "img_a_center": last[1]}
+
+
+def graph_block(models, eager, img_f, img_m, host_f, host_m, args, ctx):
+    """The same forward() replayed from one CUDA graph per configuration (KeyMorph(cuda_graph=True)): removes the
+    launch gaps between the ~100 small launches of a step and nearly all host work.  Reported beside the eager
+    headline, not instead of it."""
+    import torch
+
+    import keymorph_b200 as kb
+    out = {}
+    for name, model in models.items():
+        cfg = CONFIGS[name]
+        t = cfg["transform"]
+        gm = kb.KeyMorph(model.backbone, cfg["K"], 3, fused_warp=True, cuda_graph=True).eval()
+        for _ in range(max(args.warmup, 3)):      # call 1 eager, call 2 captures, call 3+ replays
+            r = gm(img_f, img_m, transform_type=t, return_aligned_points=True)[t]
+        state = "; ".join(gm.graph_state().values())
+        ctx["sync"]()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            r = gm(img_f, img_m, transform_type=t, return_aligned_points=True)[t]
+        e1.record()
+        ctx["sync"]()
+        ms = ctx["max"](e0.elapsed_time(e1) / args.steps)
+        e2e = measure_e2e(gm, name, host_f, host_m, args.steps, ctx, with_grid=args.e2e_grid, clone_outputs=True)
+        out[name] = {"state": state, "value": ctx["world"] * 1e3 / ms, "unit": UNIT, "ms_per_step": ms,
+                     "eager_ms_per_step": eager[name], "mse": float(r["mse"].item()),
+                     "e2e": {k: e2e[k] for k in ("value", "unit", "ms_per_step", "loss")}}
+        del gm
+        torch.cuda.empty_cache()
+    out["note"] = ("forward() captured once per (shape, transform list) and replayed: 2 device copies into the static "
+                   "inputs + 1 graph launch per registration; the headline `value` above is the eager path")
+    return out
 
 
 def conv_rooflines(tr, name, steps, ms_step, peaks, timed_s):
@@ -667,6 +703,15 @@ def run_engine(args):
             "roofline_conv": main3, "tps_fit_ms_per_step": fit_ms,
             "backbone_ms_per_step": other3[-1]["kernel_ms_per_step"]}
 
+    if not args.no_graph:
+        try:
+            eager_ms = {"affine": ms_step}
+            if "tps_config3" in line:
+                eager_ms["tps"] = line["tps_config3"]["ms_per_step"]
+            line["cuda_graph"] = graph_block(models, eager_ms, img_f, img_m, img_f_host, img_m_host, args, ctx)
+        except Exception as e:  # noqa: BLE001
+            line["cuda_graph"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---- configs[4]: groupwise, the only collective on the path
     if "tps" in models and not args.no_groupwise:
         try:
@@ -713,6 +758,7 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-GPU reference leg")
     ap.add_argument("--no-tps", action="store_true", help="skip the configs[2] (TPS) block")
     ap.add_argument("--no-groupwise", action="store_true", help="skip the configs[4] (groupwise) block")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay block")
     ap.add_argument("--e2e-grid", action="store_true", help="the e2e loop also copies the flow field to the host")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -19,16 +19,31 @@ from .loss_ops import dice_from_sums
 from .utils import str_or_float
 
 
+# Staging of a graph's static inputs: Tensor.copy_ is a cudaMemcpyAsync, which the driver may hand to a copy
+# engine -- where it queues behind the H2D / D2H transfers of the neighbouring registrations in a pipelined
+# loop.  An elementwise kernel on the SMs (67 MB: 20 us) never waits for PCIe traffic.
+GRAPH_STAGE_WITH_KERNEL = True
+
+
+def _stage(dst, src):
+    if GRAPH_STAGE_WITH_KERNEL:
+        torch.mul(src, 1.0, out=dst)
+    else:
+        dst.copy_(src)
+
+
 class KeyMorph(nn.Module):
     def __init__(self, backbone, num_keypoints, dim, keypoint_layer="com", max_train_keypoints=None,
                  use_amp=False, use_checkpoint=False, weight_keypoints=None,
                  align_keypoints_in_real_world_coords=False, max_rand_tps_lmbda=10,
-                 fused_warp=False):
+                 fused_warp=False, cuda_graph=False):
         """Same arguments as keymorph/model.py:23-35.  `use_amp` / `use_checkpoint` are accepted for
         compatibility (the backbone always runs bf16 operands with fp32 accumulation, and nothing is
         checkpointed at inference).  `fused_warp=True` additionally returns `img_a` (and `seg_a`,
         `mse`, `dice` when segmentations are passed) from forward(); the stock
-        scripts/pairwise_register_eval.py:137-138,156-157 uses them instead of calling align_img."""
+        scripts/pairwise_register_eval.py:137-138,156-157 uses them instead of calling align_img.
+        `cuda_graph=True` captures the whole forward() of a given (shape, transform list) into one CUDA graph
+        on its second call and replays it afterwards: see `_forward_graphed`."""
         super().__init__()
         if dim != 3:
             raise NotImplementedError("keymorph_b200 implements the 3-D path only")
@@ -51,6 +66,9 @@ class KeyMorph(nn.Module):
         self.weight_keypoints = weight_keypoints
         self.align_keypoints_in_real_world_coords = align_keypoints_in_real_world_coords
         self.fused_warp = fused_warp
+        self.cuda_graph = cuda_graph
+        self._graphs = {}           # (shape, device, transforms, ...) -> captured forward
+        self._lmbda_cache = {}      # numeric TPS lambdas resident on the device (no H2D copy per call)
 
     # ------------------------------------------------------------------ keypoints
     def weight_by_power(self, feat1, feat2):
@@ -84,6 +102,17 @@ class KeyMorph(nn.Module):
             return torch.tensor(loguniform.rvs(1e-6, self.max_rand_tps_lmbda, size=num_samples))
         return torch.tensor(tps_lmbda).repeat(num_samples)
 
+    def _tps_lmbda_on(self, num_samples, spec, device):
+        """_convert_tps_lmbda on the device; numeric lambdas are uploaded once (a pageable H2D copy per call
+        stalls the stream and cannot be captured into a CUDA graph)."""
+        if isinstance(spec, str):
+            return self._convert_tps_lmbda(num_samples, spec).to(device)
+        key = (num_samples, float(spec), str(device))
+        hit = self._lmbda_cache.get(key)
+        if hit is None:
+            hit = self._lmbda_cache[key] = self._convert_tps_lmbda(num_samples, spec).to(device)
+        return hit
+
     @staticmethod
     def is_supported_transform_type(s):
         return s in ["affine", "rigid"] or bool(re.match(r"^tps_.*$", s))
@@ -112,6 +141,16 @@ class KeyMorph(nn.Module):
             transform_type = [transform_type]
         assert all(self.is_supported_transform_type(s) for s in transform_type), \
             "Invalid transform_type"
+        if self.cuda_graph:
+            key = self._graph_key(img_f, img_m, transform_type, kwargs)
+            if key is not None:
+                return self._forward_graphed(key, img_f, img_m, list(transform_type), kwargs)
+        return self._forward_eager(img_f, img_m, transform_type, None, kwargs)
+
+    def _forward_eager(self, img_f, img_m, transform_type, status_sink, kwargs, batch=None):
+        """`batch`: img_f and img_m are the two halves of this tensor already (graph replay stages its inputs
+        there), so the concatenation below is skipped."""
+        return_aligned_points = kwargs["return_aligned_points"]
         if self.align_keypoints_in_real_world_coords:
             aff_f, aff_m = kwargs["aff_f"], kwargs["aff_m"]
             shape_m = torch.tensor(img_m.shape[2:]).to(img_m)
@@ -125,7 +164,7 @@ class KeyMorph(nn.Module):
         nb = img_f.shape[0]
         if img_f.shape == img_m.shape and backbone_engine(self.backbone) is not None:
             # both volumes through the backbone as one batch (fills the small pyramid levels)
-            pts, mass, _ = self._keypoints_and_mass(torch.cat([img_f, img_m], 0))
+            pts, mass, _ = self._keypoints_and_mass(torch.cat([img_f, img_m], 0) if batch is None else batch)
             points_f, points_m = pts[:nb], pts[nb:]
             mass_f, mass_m = mass[:nb], mass[nb:]
         else:
@@ -140,10 +179,84 @@ class KeyMorph(nn.Module):
         keypoint_extract_time = time.time() - start_time
 
         result_dict = {}
-        with deferred_singular_checks():   # one read of the status flags, after the last launch
+        with deferred_singular_checks(status_sink):   # one read of the status flags, after the last launch
             self._align_all(result_dict, transform_type, img_f, img_m, points_f, points_m, weights, aff_f,
                             aff_m, shape_f, shape_m, return_aligned_points, keypoint_extract_time, kwargs)
         return result_dict
+
+    # ------------------------------------------------------------------ CUDA-graph replay of forward()
+    def _graph_key(self, img_f, img_m, transform_type, kwargs):
+        """Key of the captured graph this call can replay, or None when the call has to run eagerly: the graph
+        holds one fixed launch sequence over static buffers, so per-call tensors other than the two images
+        (segmentations, label maps, real-world affines), random TPS lambdas and training mode are excluded."""
+        if not (img_f.is_cuda and img_m.is_cuda and img_f.device == img_m.device and img_f.shape == img_m.shape
+                and img_f.dtype == torch.float32 and img_m.dtype == torch.float32
+                and not self.training and not self.align_keypoints_in_real_world_coords):
+            return None
+        for v in kwargs.values():
+            if torch.is_tensor(v) or isinstance(v, np.ndarray):
+                return None
+        for s in transform_type:
+            if s.startswith("tps") and isinstance(str_or_float(s[4:]), str):
+                return None
+        return (tuple(img_f.shape), img_f.device.index, tuple(transform_type),
+                bool(kwargs["return_aligned_points"]))
+
+    def _graph_signature(self):
+        """Everything a captured launch sequence bakes in besides the key: parameter storage / versions (packed
+        weights are rebuilt when they change) and the engine's schedule switches."""
+        params = tuple((p.data_ptr(), p._version) for p in self.backbone.parameters())
+        return (params, str(ops.act_dtype()), ops.USE_GN_FOLD, ops.gn_fold_stem_enabled(), ops.USE_GN_FOLD_TC_PAIR,
+                ops.USE_PAIR_CONV, ops.USE_ZFOLD_PAIR, self.fused_warp, self.weight_keypoints)
+
+    def _forward_graphed(self, key, img_f, img_m, transform_type, kwargs):
+        """First call of a key: eager (packs weights, sets kernel attributes, fills every cache).  Second call:
+        the same launch sequence is captured into a torch.cuda.CUDAGraph over static input buffers.  From then
+        on: two device copies into the static inputs + one graph launch.  The returned tensors are the graph's
+        static outputs: they are overwritten by the next forward() with the same key (clone what must outlive
+        it), and the `time*` entries are those of the capture.  Singular-fit flags cannot be read inside a
+        graph; they are checked after the replay (one small D2H read, as in the eager path)."""
+        sig = self._graph_signature()
+        ent = self._graphs.get(key)
+        if ent is None or ent["sig"] != sig:
+            self._graphs[key] = {"sig": sig, "graph": None}
+            return self._forward_eager(img_f, img_m, transform_type, None, kwargs)
+        if ent["graph"] is None:
+            if ent.get("failed"):
+                return self._forward_eager(img_f, img_m, transform_type, None, kwargs)
+            nb = img_f.shape[0]
+            batch = torch.cat([img_f, img_m], 0)      # static input: the backbone's two-volume batch itself
+            static_f, static_m = batch[:nb], batch[nb:]
+            status = []
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(img_f.device)
+            try:
+                # thread_local: other threads' CUDA calls (NCCL watchdog, prefetch threads) must not abort the capture
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    out = self._forward_eager(static_f, static_m, transform_type, status, kwargs, batch=batch)
+                    flags = torch.stack([st.reshape(-1).any() for st, _ in status]) if status else None
+            except Exception as exc:        # a launch the runtime refuses to capture: stay eager, say why once
+                ent["failed"] = f"{type(exc).__name__}: {exc}"
+                import warnings
+                warnings.warn(f"keymorph_b200: CUDA-graph capture of forward{key} failed ({ent['failed']}); "
+                              "running eagerly")
+                torch.cuda.synchronize(img_f.device)
+                return self._forward_eager(img_f, img_m, transform_type, None, kwargs)
+            ent.update(graph=graph, out=out, static_f=static_f, static_m=static_m, status=status, flags=flags)
+        _stage(ent["static_f"], img_f)
+        _stage(ent["static_m"], img_m)
+        ent["graph"].replay()
+        from . import transformations
+        if ent["flags"] is not None and transformations.CHECK_SINGULAR:
+            for bad, (st, what) in zip(ent["flags"].cpu().tolist(), ent["status"]):
+                if bad:
+                    raise torch.linalg.LinAlgError(f"{what}: the matrix is singular (status={st.tolist()})")
+        return ent["out"]
+
+    def graph_state(self):
+        """{key: "captured" | "eager (<why>)" | "warm-up"} of the CUDA-graph cache (diagnostics, bench.py)."""
+        return {k: ("captured" if e["graph"] is not None else
+                    (f"eager ({e['failed']})" if e.get("failed") else "warm-up")) for k, e in self._graphs.items()}
 
     def _align_all(self, result_dict, transform_type, img_f, img_m, points_f, points_m, weights, aff_f, aff_m,
                    shape_f, shape_m, return_aligned_points, keypoint_extract_time, kwargs):
@@ -151,8 +264,7 @@ class KeyMorph(nn.Module):
             start_time = time.time()
             if align_type_str.startswith("tps"):
                 align_type = "tps"
-                tps_lmbda = self._convert_tps_lmbda(
-                    len(img_f), str_or_float(align_type_str[4:])).to(img_f.device)
+                tps_lmbda = self._tps_lmbda_on(len(img_f), str_or_float(align_type_str[4:]), img_f.device)
             else:
                 align_type, tps_lmbda = align_type_str, None
             aligner = self._make_aligner(align_type, points_m, points_f, weights, tps_lmbda, aff_f,
@@ -266,8 +378,7 @@ class KeyMorph(nn.Module):
             start_time = time.time()
             if align_type_str.startswith("tps"):
                 align_type = "tps"
-                tps_lmbda = self._convert_tps_lmbda(
-                    len(img_m), str_or_float(align_type_str[4:])).to(img_m.device)
+                tps_lmbda = self._tps_lmbda_on(len(img_m), str_or_float(align_type_str[4:]), img_m.device)
             else:
                 align_type, tps_lmbda = align_type_str, None
             curr_points = group_points.clone()

@@ -38,6 +38,11 @@ class deferred_singular_checks:
     synchronisation instead of one per fit (the kernels are safe on singular input; their outputs
     are simply not returned)."""
 
+    def __init__(self, sink=None):
+        # sink: a list that receives the (status, name) pairs instead of being read here -- used while a
+        # CUDA graph is being captured, where a device->host read is not allowed (KeyMorph(cuda_graph=True))
+        self._sink = sink
+
     def __enter__(self):
         self._outer = getattr(_TLS, "pending", None)
         _TLS.pending = []
@@ -45,6 +50,9 @@ class deferred_singular_checks:
 
     def __exit__(self, exc_type, exc, tb):
         pending, _TLS.pending = _TLS.pending, self._outer
+        if self._sink is not None:
+            self._sink.extend(pending)
+            return False
         if exc_type is None and pending:
             flags = torch.stack([st.reshape(-1).any() for st, _ in pending]).cpu()
             for bad, (st, what) in zip(flags.tolist(), pending):

@@ -1484,3 +1484,52 @@ def test_tiled_warp_kernel_equals_the_direct_gather_kernels(shape, C, scale):
     assert_close(t[0].cpu(), ref, rtol=0, atol=2e-6)
     ps = ops.pair_stats(t[0], fix)
     assert_close(t[1], ps, rtol=1e-5, atol=1e-3)
+
+
+def test_cuda_graph_replay_matches_eager():
+    """KeyMorph(cuda_graph=True): call 1 eager, call 2 captures forward() into one CUDA graph, later calls replay
+    it over static input buffers.  Replays on NEW inputs must reproduce the eager path (same kernels, same
+    order: equal up to the atomics' summation order), a tensor kwarg must take the eager path, a parameter
+    update must invalidate the capture, and a singular fit must still raise after a replay."""
+    K, S = 32, 64
+    net = _seeded("trunc", K).to(DEV)
+    eager = kb.KeyMorph(net, K, 3, fused_warp=True).eval()
+    graphed = kb.KeyMorph(net, K, 3, fused_warp=True, cuda_graph=True).eval()
+    t = ["affine", "tps_0.1"]
+    pairs = [(cu(O.gaussian_phantom(S, 10 + i)), cu(O.gaussian_phantom(S, 20 + i))) for i in range(4)]
+    for i, (f, m) in enumerate(pairs):
+        got = graphed(f, m, transform_type=t, return_aligned_points=True)
+        want = eager(f, m, transform_type=t, return_aligned_points=True)
+        for a in t:
+            for k in ("grid", "points_f", "points_m", "points_a", "img_a", "mse"):
+                assert_close(got[a][k], want[a][k], rtol=1e-5, atol=2e-5), (i, a, k)
+            if a == "affine":
+                assert_close(got[a]["matrix"], want[a]["matrix"], rtol=1e-5, atol=1e-5)
+    state = graphed.graph_state()
+    assert list(state.values()) == ["captured"], state
+    # per-call tensors other than the images: eager path, same answer as the plain model
+    lab = cu((torch.rand(1, 1, S, S, S) * 4).floor().to(torch.uint8))
+    f, m = pairs[0]
+    g2 = graphed(f, m, transform_type="affine", return_aligned_points=False, labels_f=lab, labels_m=lab, num_classes=4)
+    e2 = eager(f, m, transform_type="affine", return_aligned_points=False, labels_f=lab, labels_m=lab, num_classes=4)
+    assert_close(g2["affine"]["harddice"], e2["affine"]["harddice"], rtol=1e-5, atol=1e-6)
+    assert len(graphed.graph_state()) == 1
+    # a weight update invalidates the capture (the packed weights are rebuilt): warm-up again, then re-capture
+    with torch.no_grad():
+        net.final_conv.weight.mul_(1.5)
+    for i in range(3):
+        got = graphed(f, m, transform_type=t, return_aligned_points=True)
+        assert list(graphed.graph_state().values()) == [["warm-up", "captured", "captured"][i]]
+    want = eager(f, m, transform_type=t, return_aligned_points=True)
+    assert_close(got["tps_0.1"]["grid"], want["tps_0.1"]["grid"], rtol=1e-5, atol=2e-5)
+    # a singular fit raises from the warm-up call, from the capturing call and from a replay, like the eager path
+    # (constant heat maps: every keypoint is the same point)
+    with torch.no_grad():
+        net.final_conv.weight.zero_()
+        net.final_conv.bias.fill_(1.0)
+    with pytest.raises(torch.linalg.LinAlgError):
+        eager(f, m, transform_type=t, return_aligned_points=True)
+    for i in range(3):
+        with pytest.raises(torch.linalg.LinAlgError):
+            graphed(f, m, transform_type=t, return_aligned_points=True)
+    assert list(graphed.graph_state().values()) == ["captured"]
