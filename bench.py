@@ -69,6 +69,12 @@ def conv_layers(S, K, n_img):
          ("enc3.c1", 128, 128, S // 8, 27), ("enc3.c2", 128, 256, S // 8, 27),
          ("dec0.c1", 384, 128, S // 4, 27), ("dec0.c2", 128, 128, S // 4, 27),
          ("dec1.c1", 192, 64, S // 2, 27), ("dec1.c2", 64, 64, S // 2, 27), ("final", 64, K, S // 2, 1)]
+    from keymorph_b200 import ops
+    if ops.USE_COARSE_UPCONV and ops.USE_GN_FOLD and ops.USE_ZFOLD_PAIR:
+        # EXECUTED flops: the 128 upsampled channels of dec1.c1 run as 8 pre-summed taps per output voxel on the
+        # coarse lattice (conv_up2.cu), the 64 skip channels as the usual 27
+        i = [l[0] for l in L].index("dec1.c1")
+        L[i:i + 1] = [("dec1.c1", 64, 64, S // 2, 27), ("dec1.c1.up", 128, 64, S // 2, 8)]
     return [(n, ci, co, e, t, 2.0 * t * ci * co * e ** 3 * n_img) for (n, ci, co, e, t) in L]
 
 
@@ -291,7 +297,7 @@ class Tracer:
 
 
 CONV_CALLS = ("km_conv3d_tc", "km_conv3d_tc_pair", "km_conv3d_zfold_pair", "km_conv3d_zfold_pair_gn",
-              "km_conv3d_zfold_pair_gn_cat", "km_conv3d_tc_pair_gn")
+              "km_conv3d_zfold_pair_gn_cat", "km_conv3d_tc_pair_gn", "km_conv3d_up2_gn", "km_conv3d_zfold_pair_gn_add")
 ZF_CALLS = ("km_conv3d_zfold", "km_conv3d_zfold_gn")
 TRACED = CONV_CALLS + ZF_CALLS + ("km_conv1x1_com", "km_conv3d_stem", "km_warp_loss", "km_flow_field_tps", "km_tps_fit")
 
@@ -425,9 +431,9 @@ def conv_rooflines(tr, name, steps, ms_step, peaks, timed_s):
     com_flops = layers["final"] if com_ms > 0 else 0.0
     tc_flops = sum(v for k, v in layers.items() if k != "enc0.c1") - zf_flops - com_flops
     traffic = traffic_from_profile() or {}
-    conv_traffic = sum(traffic.get(k, 0.0) for k in ("conv_tc_kernel", "conv_tc2_kernel", "conv_zf2_kernel")) or None
+    conv_traffic = sum(traffic.get(k, 0.0) for k in ("conv_tc_kernel", "conv_tc2_kernel", "conv_zf2_kernel", "conv_up2_kernel")) or None
     ach = tc_flops / (conv_ms * 1e-3) / 1e12
-    main = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel / conv_zf2_kernel (tcgen05 3x3x3 convolutions)",
+    main = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel / conv_zf2_kernel / conv_up2_kernel (tcgen05 3x3x3 convolutions; EXECUTED flops)",
             "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": conv_traffic,
             "flops_per_step": tc_flops, "launches_per_step": tr.count(*CONV_CALLS, per=steps),
             "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / ms_step,

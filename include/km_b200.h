@@ -380,6 +380,24 @@ int km_conv3d_zfold_pair_gn_cat(const void* x0, const void* x1, int Cin0, int Ci
                                 void* workspace, int N, int Cout, int D, int H, int W, int flags,
                                 km_stream_t stream);
 
+/* The same layer split so that the upsampled half is computed on the COARSE lattice and never materialised
+ * (decoder: cat(skip, F.interpolate(x, 2, 'nearest')) -> GN -> conv, keymorph/unet3d/buildingblocks.py:409-445).
+ * Nearest upsampling repeats each coarse voxel on 2x2x2 fine voxels, so per output parity class the 27 taps
+ * collapse to 8 taps over the coarse tensor with pre-summed weights (8/27 of the MMA work):
+ *   km_conv3d_up2_gn            xc (N,Dc,Hc,Wc,Cu) raw 16-bit; w (Cout, Cs+Cu, 3,3,3) fp32; scale (N, Cs+Cu) or NULL;
+ *                               out (N,2Dc,2Hc,2Wc,Cout) 16-bit PARTIAL sums of input channels [Cs, Cs+Cu)
+ *                               (no bias / activation).  Cout = 64, Cu % 64 == 0.
+ *   km_conv3d_zfold_pair_gn_add the skip half (input channels [0, Cs) of x (N,D,H,W,Cs)) with `addend` = the
+ *                               partial sums above added before the folded-norm bias (all Cs+Cu channels' shift
+ *                               terms), ReLU and statistics.  workspace as km_conv3d_zfold_pair_gn(N, Cs, Cout). */
+int km_conv3d_up2_supported(int Cu, int Cout, int Dc, int Hc, int Wc);
+size_t km_conv3d_up2_gn_workspace_bytes(int N, int Cu, int Cout);
+int km_conv3d_up2_gn(const void* xc, const float* w, const float* scale, int Cs, int Cu, void* out, void* workspace,
+                     int N, int Cout, int Dc, int Hc, int Wc, km_stream_t stream);
+int km_conv3d_zfold_pair_gn_add(const void* x, int Cs, int Cu, const float* w, const float* scale, const float* shift,
+                                const void* addend, void* out, float* stats, void* workspace, int N, int Cout, int D,
+                                int H, int W, int flags, km_stream_t stream);
+
 /* Nearest-neighbour x2 upsampling of a bf16 NDHWC tensor (F.interpolate in the decoders,
  * buildingblocks.py:409-445): (N,Dc,Hc,Wc,C) -> (N,2Dc,2Hc,2Wc,C), C % 8 == 0. */
 int km_upsample2_ndhwc(const void* src, void* dst, int N, int C, int Dc, int Hc, int Wc, km_stream_t stream);

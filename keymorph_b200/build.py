@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "_build")
 LIB = os.path.join(CSRC, "libkm_b200.so")
-SOURCES = ["km_api.cu", "warp.cu", "warp_tile.cu", "com.cu", "fit.cu", "tps.cu", "tps_field.cu", "conv_misc.cu", "stem.cu", "com_tc.cu", "conv_zf.cu", "conv_tc.cu", "conv_tc2.cu", "conv_zf2.cu", "hausdorff.cu"]
+SOURCES = ["km_api.cu", "warp.cu", "warp_tile.cu", "com.cu", "fit.cu", "tps.cu", "tps_field.cu", "conv_misc.cu", "stem.cu", "com_tc.cu", "conv_zf.cu", "conv_tc.cu", "conv_tc2.cu", "conv_zf2.cu", "conv_up2.cu", "hausdorff.cu"]
 HEADERS = ["km_common.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "km_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

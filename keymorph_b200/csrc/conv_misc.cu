@@ -468,13 +468,15 @@ template <bool F16>
 __global__ void __launch_bounds__(256)
 fold_gn_kernel(const float* __restrict__ w, const float* __restrict__ scale, const float* __restrict__ shift,
                act16* __restrict__ packed, float* __restrict__ bias, int N, int Cout, int Cin, int layout,
-               int pack_blocks) {
+               int pack_blocks, int c0, int Cp) {
+  // the packed weights cover input channels [c0, c0 + Cp) (Cp = Cin unless the layer is split over two kernels,
+  // conv_up2.cu); the bias tables always sum over all Cin channels
   if ((int)blockIdx.x < pack_blocks) {
-    const long long total = 27ll * (layout ? 3 : 1) * Cout * Cin;
+    const long long total = 27ll * (layout ? 3 : 1) * Cout * Cp;
     for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * pack_blocks) {
       long long t = i;
-      const int ci = (int)(t % Cin);
-      t /= Cin;
+      const int ci = c0 + (int)(t % Cp);
+      t /= Cp;
       const int co = (int)(t % Cout);
       t /= Cout;
       int tap;
@@ -540,16 +542,21 @@ fold_gn_kernel(const float* __restrict__ w, const float* __restrict__ scale, con
   }
 }
 
-int km_fold_gn(const float* w, const float* scale, const float* shift, void* packed, float* bias, int N, int Cout,
-               int Cin, int layout, km_stream_t stream) {
-  const long long total = 27ll * (layout ? 3 : 1) * Cout * Cin;
+int km_fold_gn_part(const float* w, const float* scale, const float* shift, void* packed, float* bias, int N,
+                    int Cout, int Cin, int c0, int Cp, int layout, km_stream_t stream) {
+  const long long total = 27ll * (layout ? 3 : 1) * Cout * Cp;
   long long pb = (total + 1023) / 1024;
   const int pack_blocks = (int)(pb < 1 ? 1 : (pb > 1184 ? 1184 : pb));
   const int bias_blocks = (Cout + 7) / 8;
   KM_LAUNCH_16(fold_gn_kernel, pack_blocks + bias_blocks, 256, 0, km_cs(stream), w, scale, shift, reinterpret_cast<act16*>(packed),
-                                                                       bias, N, Cout, Cin, layout, pack_blocks);
+                                                                       bias, N, Cout, Cin, layout, pack_blocks, c0, Cp);
   KM_LAUNCH_OK("fold_gn_kernel");
   return KM_OK;
+}
+
+int km_fold_gn(const float* w, const float* scale, const float* shift, void* packed, float* bias, int N, int Cout,
+               int Cin, int layout, km_stream_t stream) {
+  return km_fold_gn_part(w, scale, shift, packed, bias, N, Cout, Cin, 0, Cin, layout, stream);
 }
 
 // nearest-neighbour x2 upsampling of a bf16 NDHWC tensor (F.interpolate(scale 2, 'nearest') in the

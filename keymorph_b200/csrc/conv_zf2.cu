@@ -109,11 +109,11 @@ __device__ __forceinline__ void for_each_tile(const Zf2Geom& g, uint32_t rank, F
 }
 
 
-template <int COUT, int KC, int MT, bool POOL, bool F16>
+template <int COUT, int KC, int MT, bool POOL, bool F16, bool ADD = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const Zf2Geom g, uint16_t* __restrict__ out, uint16_t* __restrict__ pooled,
-                float* __restrict__ stats, const float* __restrict__ bias_tab) {
+                float* __restrict__ stats, const float* __restrict__ bias_tab, const uint16_t* __restrict__ addend) {
   using C = Cfg<COUT, KC, MT>;
   constexpr int kMT = C::kMT;
   constexpr uint32_t kSetStride = C::kSetStride;
@@ -305,6 +305,14 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int x2 = u.x0 + tx, y2 = u.y0 + 16 * m + ty;
       if (store) {   // warp-uniform: tcgen05.ld is a warp-collective operation
         uint32_t r[kCols / 16][16];
+        // ADD: partial sums of the same layer computed elsewhere (conv_up2.cu: the upsampled half of a decoder's
+        // concat, on the coarse lattice).  Prefetched into L1 before the TMEM read (no registers held), loaded
+        // 16 channels at a time where they are consumed.
+        const uint16_t* ap = nullptr;
+        if (ADD && u.valid && x2 < g.W && y2 < g.H) {
+          ap = addend + ((((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2) * kCout + half * kCols;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(ap));
+        }
 #pragma unroll
         for (int b = 0; b < kCols / 16; ++b) tmem_ld16(taddr + 16u * b, r[b]);
         tmem_ld_wait();
@@ -317,6 +325,20 @@ conv_zf2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         const bool inside = u.valid && x2 < g.W && y2 < g.H;
         const size_t vox = (((size_t)u.n * g.D + zo) * g.H + y2) * g.W + x2;
+        if (ADD && ap) {
+#pragma unroll
+          for (int b = 0; b < kCols / 16; ++b) {
+            const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(ap) + 2 * b);
+            const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(ap) + 2 * b + 1);
+            const uint32_t a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 ab = km_unpack2<F16>(a8[j]);
+              r[b][2 * j] = __float_as_uint(__uint_as_float(r[b][2 * j]) + ab.x);
+              r[b][2 * j + 1] = __float_as_uint(__uint_as_float(r[b][2 * j + 1]) + ab.y);
+            }
+          }
+        }
         if (bias_tab) {   // GroupNorm shift of the folded norm: bias[sample][border class][cout] (L1-resident)
           const int cls = ((zo == 0 ? 1 : 0) | (zo == g.D - 1 ? 2 : 0)) * 9 +
                           (y2 == 0 ? 1 : (y2 == g.H - 1 ? 2 : 0)) * 3 + (x2 == 0 ? 1 : (x2 == g.W - 1 ? 2 : 0));
@@ -457,8 +479,8 @@ extern "C" int km_pack_weights_zfold_pair(const float* w, void* packed, int Cout
 namespace {
 int g_zf2_mt2 = 0;   // km_set_option(KM_OPT_ZF2_TWO_BRICKS)
 template <int COUT, int KC, int MT, bool POOL>
-int launch_zf2(const void* x, const void* x1, int Cin0, const void* wz, const float* bias_tab, void* out, void* pooled,
-               float* stats, int N, int Cin, int D, int H, int W, int flags, cudaStream_t st) {
+int launch_zf2(const void* x, const void* x1, int Cin0, const void* wz, const float* bias_tab, const void* addend,
+               void* out, void* pooled, float* stats, int N, int Cin, int D, int H, int W, int flags, cudaStream_t st) {
   using C = Cfg<COUT, KC, MT>;
   KM_CHECK_ARG(POOL || !pooled, "km_conv3d_zfold_pair: fused pooling is built for Cout = 32 only");
   Zf2Geom g;
@@ -562,12 +584,29 @@ int launch_zf2(const void* x, const void* x1, int Cin0, const void* wz, const fl
   if (grid / 2 > upi) grid = 2 * upi;
   if ((flags & KM_CONV_STATS) && grid < nsm)
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * COUT * 2 * sizeof(float), st));
+  uint16_t* o16 = reinterpret_cast<uint16_t*>(out);
+  uint16_t* p16 = reinterpret_cast<uint16_t*>(pooled);
+  const uint16_t* a16 = reinterpret_cast<const uint16_t*>(addend);
+  if constexpr (COUT == 64 && KC == 64 && MT == 1 && !POOL) {
+    if (addend) {   // the only shape the split decoder layer uses
+      static unsigned long long attr_add = 0;
+      if (km_first_use_on_device(&attr_add)) {
+        KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel<COUT, KC, MT, POOL, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        KM_CUDA_OK(cudaFuncSetAttribute(conv_zf2_kernel<COUT, KC, MT, POOL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      }
+      if (km_operand_fp16())
+        conv_zf2_kernel<COUT, KC, MT, POOL, true, true><<<grid, kThreads, smem_bytes, st>>>(tmA, tmA1, tmB, g, o16, p16, stats, bias_tab, a16);
+      else
+        conv_zf2_kernel<COUT, KC, MT, POOL, false, true><<<grid, kThreads, smem_bytes, st>>>(tmA, tmA1, tmB, g, o16, p16, stats, bias_tab, a16);
+      KM_LAUNCH_OK("conv_zf2_kernel");
+      return KM_OK;
+    }
+  }
+  KM_CHECK_ARG(!addend, "km_conv3d_zfold_pair: an addend needs Cout = 64 and Cin %% 64 == 0");
   if (km_operand_fp16())
-    conv_zf2_kernel<COUT, KC, MT, POOL, true><<<grid, kThreads, smem_bytes, st>>>(
-        tmA, tmA1, tmB, g, reinterpret_cast<uint16_t*>(out), reinterpret_cast<uint16_t*>(pooled), stats, bias_tab);
+    conv_zf2_kernel<COUT, KC, MT, POOL, true><<<grid, kThreads, smem_bytes, st>>>(tmA, tmA1, tmB, g, o16, p16, stats, bias_tab, a16);
   else
-    conv_zf2_kernel<COUT, KC, MT, POOL, false><<<grid, kThreads, smem_bytes, st>>>(
-        tmA, tmA1, tmB, g, reinterpret_cast<uint16_t*>(out), reinterpret_cast<uint16_t*>(pooled), stats, bias_tab);
+    conv_zf2_kernel<COUT, KC, MT, POOL, false><<<grid, kThreads, smem_bytes, st>>>(tmA, tmA1, tmB, g, o16, p16, stats, bias_tab, a16);
   KM_LAUNCH_OK("conv_zf2_kernel");
   return KM_OK;
 }
@@ -577,8 +616,8 @@ void km_zf2_set_two_bricks(int v) { g_zf2_mt2 = v ? 1 : 0; }
 
 namespace {
 int dispatch_zf2(const char* who, const void* x, const void* x1, int Cin0, const void* wz, const float* bias_tab,
-                 void* out, void* pooled, float* stats, int N, int Cin, int Cout, int D, int H, int W, int flags,
-                 km_stream_t stream) {
+                 const void* addend, void* out, void* pooled, float* stats, int N, int Cin, int Cout, int D, int H,
+                 int W, int flags, km_stream_t stream) {
   KM_CHECK_ARG(x && wz && (out || pooled), "%s: null argument", who);
   KM_CHECK_ARG(km_conv3d_zfold_pair_supported(Cin, Cout, D, H, W), "%s: unsupported shape (Cin=%d Cout=%d H=%d W=%d)",
                who, Cin, Cout, H, W);
@@ -587,29 +626,29 @@ int dispatch_zf2(const char* who, const void* x, const void* x1, int Cin0, const
   KM_CHECK_ARG(!(flags & KM_CONV_STATS) || stats, "%s: KM_CONV_STATS needs stats", who);
   KM_CHECK_ARG(!(flags & KM_CONV_COM), "%s: KM_CONV_COM is not supported", who);
   KM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)x1 & 15) == 0 && ((uintptr_t)wz & 15) == 0 &&
-                   ((uintptr_t)out & 31) == 0 && ((uintptr_t)pooled & 31) == 0,
+                   ((uintptr_t)out & 31) == 0 && ((uintptr_t)pooled & 31) == 0 && ((uintptr_t)addend & 31) == 0,
                "%s: pointers must be 16-byte (outputs: 32-byte) aligned", who);
   cudaStream_t st = km_cs(stream);
-  if (Cin == 16) return launch_zf2<32, 16, 1, true>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  if (Cin == 16) return launch_zf2<32, 16, 1, true>(x, x1, Cin0, wz, bias_tab, addend, out, pooled, stats, N, Cin, D, H, W, flags, st);
   const bool k64 = Cin % 64 == 0 && (!x1 || Cin0 % 64 == 0);
   if (Cout == 64 && k64) {
     // two bricks per unit halve the weight bytes per output (the kernel is bound by L2 -> SM traffic)
     // at the price of a single TMEM set; needs two brick rows
-    if (H >= 32 && g_zf2_mt2)
-      return launch_zf2<64, 64, 2, false>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
-    return launch_zf2<64, 64, 1, false>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
+    if (H >= 32 && g_zf2_mt2 && !addend)
+      return launch_zf2<64, 64, 2, false>(x, x1, Cin0, wz, bias_tab, addend, out, pooled, stats, N, Cin, D, H, W, flags, st);
+    return launch_zf2<64, 64, 1, false>(x, x1, Cin0, wz, bias_tab, addend, out, pooled, stats, N, Cin, D, H, W, flags, st);
   }
-  if (Cout == 64) return launch_zf2<64, 32, 1, false>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
-  return k64 ? launch_zf2<32, 64, 1, true>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st)
-             : launch_zf2<32, 32, 1, true>(x, x1, Cin0, wz, bias_tab, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  if (Cout == 64) return launch_zf2<64, 32, 1, false>(x, x1, Cin0, wz, bias_tab, addend, out, pooled, stats, N, Cin, D, H, W, flags, st);
+  return k64 ? launch_zf2<32, 64, 1, true>(x, x1, Cin0, wz, bias_tab, addend, out, pooled, stats, N, Cin, D, H, W, flags, st)
+             : launch_zf2<32, 32, 1, true>(x, x1, Cin0, wz, bias_tab, addend, out, pooled, stats, N, Cin, D, H, W, flags, st);
 }
 }  // namespace
 
 extern "C" int km_conv3d_zfold_pair(const void* x, const void* wz, void* out, void* pooled, float* stats,
                                     int N, int Cin, int Cout, int D, int H, int W, int flags,
                                     km_stream_t stream) {
-  return dispatch_zf2("km_conv3d_zfold_pair", x, nullptr, Cin, wz, nullptr, out, pooled, stats, N, Cin, Cout, D, H, W,
-                      flags, stream);
+  return dispatch_zf2("km_conv3d_zfold_pair", x, nullptr, Cin, wz, nullptr, nullptr, out, pooled, stats, N, Cin, Cout,
+                      D, H, W, flags, stream);
 }
 
 extern "C" size_t km_conv3d_zfold_pair_gn_workspace_bytes(int N, int Cin, int Cout) {
@@ -633,8 +672,27 @@ extern "C" int km_conv3d_zfold_pair_gn_cat(const void* x0, const void* x1, int C
   float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)N * wbytes + 255) & ~(size_t)255));
   const int rf = km_fold_gn(w, scale, shift, packed, bias, N, Cout, Cin, 1, stream);
   if (rf != KM_OK) return rf;
-  return dispatch_zf2("km_conv3d_zfold_pair_gn", x0, x1, Cin0, workspace, bias, out, pooled, stats, N, Cin, Cout, D, H,
-                      W, flags, stream);
+  return dispatch_zf2("km_conv3d_zfold_pair_gn", x0, x1, Cin0, workspace, bias, nullptr, out, pooled, stats, N, Cin,
+                      Cout, D, H, W, flags, stream);
+}
+
+// The first Cs channels of a (Cs + Cu)-channel folded layer; `addend` holds the other channels' partial sums
+// (km_conv3d_up2_gn).  The border-class bias table covers ALL channels, the packed weights the first Cs.
+extern "C" int km_conv3d_zfold_pair_gn_add(const void* x, int Cs, int Cu, const float* w, const float* scale,
+                                           const float* shift, const void* addend, void* out, float* stats,
+                                           void* workspace, int N, int Cout, int D, int H, int W, int flags,
+                                           km_stream_t stream) {
+  KM_CHECK_ARG(w && scale && shift && addend && workspace && ((uintptr_t)workspace & 255) == 0,
+               "km_conv3d_zfold_pair_gn_add: null / unaligned (256 B) argument");
+  KM_CHECK_ARG(Cs > 0 && Cs % 64 == 0 && Cout == 64 && Cu > 0 && km_conv3d_zfold_pair_supported(Cs, Cout, D, H, W),
+               "km_conv3d_zfold_pair_gn_add: unsupported shape (Cs=%d Cu=%d Cout=%d H=%d W=%d)", Cs, Cu, Cout, H, W);
+  KM_CHECK_ARG(N > 0 && N <= 1024, "km_conv3d_zfold_pair_gn_add: bad batch");
+  const size_t wbytes = (size_t)27 * 3 * Cout * Cs * 2;
+  float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)N * wbytes + 255) & ~(size_t)255));
+  const int rf = km_fold_gn_part(w, scale, shift, workspace, bias, N, Cout, Cs + Cu, 0, Cs, 1, stream);
+  if (rf != KM_OK) return rf;
+  return dispatch_zf2("km_conv3d_zfold_pair_gn_add", x, nullptr, Cs, workspace, bias, addend, out, nullptr, stats, N,
+                      Cs, Cout, D, H, W, flags, stream);
 }
 
 extern "C" int km_conv3d_zfold_pair_gn(const void* x, const float* w, const float* scale, const float* shift,

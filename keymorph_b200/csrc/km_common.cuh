@@ -44,6 +44,9 @@ void km_set_error(const char* fmt, ...);
 // [N][36 border classes][Cout] bias tables of a GroupNorm folded into its consumer conv
 int km_fold_gn(const float* w, const float* scale, const float* shift, void* packed, float* bias, int N, int Cout,
                int Cin, int layout, km_stream_t stream);
+// the same with the packed weights restricted to input channels [c0, c0 + Cp) (the bias tables cover all Cin)
+int km_fold_gn_part(const float* w, const float* scale, const float* shift, void* packed, float* bias, int N,
+                    int Cout, int Cin, int c0, int Cp, int layout, km_stream_t stream);
 
 // cudaFuncSetAttribute (opt-in shared memory) is per device: one bit per device ordinal in a per-kernel mask,
 // so that a process driving several GPUs sets it on each of them once

@@ -237,11 +237,21 @@ class UNetEngine(_EngineBase):
                         and ops.zfold_pair_supported(Cs + Cu, w1.shape[0], *sd):
                     # the concat is never materialised: the skip is read raw through its own tensor map, only
                     # the upsampled half is written (also raw); the joint GroupNorm is folded into the conv
-                    up = ops.upsample2(cur)
-                    c1, st = ops.conv3d_zfold_pair_gn(skip, w1.detach(), scale, shift, relu=True, want_stats=True,
-                                                      x1=up)
+                    if ops.USE_COARSE_UPCONV and ops.up2_supported(Cu, w1.shape[0], *cur.shape[1:4]) \
+                            and ops.zfold_pair_supported(Cs, w1.shape[0], *sd):
+                        # ... and the upsampled half is not even written: its 27 fine taps are 8 pre-summed taps
+                        # on the coarse lattice per output parity class (8/27 of the MMAs); the skip half's
+                        # kernel adds those partial sums before bias / ReLU / statistics
+                        part = ops.conv3d_up2_gn(cur, w1.detach(), scale, Cs)
+                        c1, st = ops.conv3d_zfold_pair_gn_add(skip, w1.detach(), scale, shift, part, relu=True,
+                                                              want_stats=True)
+                        del part
+                    else:
+                        up = ops.upsample2(cur)
+                        c1, st = ops.conv3d_zfold_pair_gn(skip, w1.detach(), scale, shift, relu=True,
+                                                          want_stats=True, x1=up)
+                        del up
                     self._dbg(f"dec{j}.c1", c1)
-                    del up
                     skips[j] = None
                     g = dc.SingleConv2.groupnorm
                     scale, shift = ops.norm_finalize(st, nvox(c1), g.weight, g.bias, g.num_groups, g.eps)

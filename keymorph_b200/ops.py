@@ -549,6 +549,54 @@ def conv3d_zfold_pair_gn(x_raw, w, scale, shift, relu=False, want_stats=False, p
     return (out, pooled, stats) if pool else (out, stats)
 
 
+USE_COARSE_UPCONV = True   # engine switch: upsampled half of a decoder's first conv on the coarse lattice
+
+
+def up2_supported(Cu, Cout, Dc, Hc, Wc):
+    return bool(_lib.query("km_conv3d_up2_supported", Cu, Cout, Dc, Hc, Wc))
+
+
+def conv3d_up2_gn(x_coarse, w, scale, Cs):
+    """Partial sums of conv3d(GN(cat(skip, upsample2(x_coarse)))) over the upsampled channels [Cs, Cs + Cu),
+    computed on the coarse lattice with 8 pre-summed taps per output parity class (the upsampled tensor is never
+    written).  -> (N, 2Dc, 2Hc, 2Wc, Cout) 16-bit, to be passed as `addend` to conv3d_zfold_pair_gn_add."""
+    _need_cuda(x_coarse, w, scale)
+    assert x_coarse.dtype == act_dtype()
+    x_coarse, w = x_coarse.contiguous(), _f32c(w)
+    scale = None if scale is None else _f32c(scale)
+    N, Dc, Hc, Wc, Cu = x_coarse.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == Cs + Cu and (scale is None or scale.numel() == N * (Cs + Cu))
+    out = torch.empty((N, 2 * Dc, 2 * Hc, 2 * Wc, Cout), dtype=act_dtype(), device=x_coarse.device)
+    ws = _ws(_lib.query("km_conv3d_up2_gn_workspace_bytes", N, Cu, Cout), x_coarse.device)
+    with torch.cuda.device(x_coarse.device):
+        _lib.call("km_conv3d_up2_gn", _ptr(x_coarse), _ptr(w), _ptr(scale), Cs, Cu, _ptr(out), _ptr(ws), N, Cout,
+                  Dc, Hc, Wc, _stream())
+    return out
+
+
+def conv3d_zfold_pair_gn_add(x_raw, w, scale, shift, addend, relu=False, want_stats=False):
+    """The skip half of the same layer: input channels [0, Cs) from x_raw, plus `addend` (conv3d_up2_gn), then
+    the folded-norm bias of ALL channels, ReLU and statistics."""
+    _need_cuda(x_raw, w, scale, shift, addend)
+    assert x_raw.dtype == act_dtype() and addend.dtype == act_dtype()
+    x_raw, w, scale, shift, addend = x_raw.contiguous(), _f32c(w), _f32c(scale), _f32c(shift), addend.contiguous()
+    N, D, H, W, Cs = x_raw.shape
+    Cout = w.shape[0]
+    Cu = w.shape[1] - Cs
+    assert Cu > 0 and scale.numel() == N * (Cs + Cu) and shift.numel() == N * (Cs + Cu)
+    assert tuple(addend.shape) == (N, D, H, W, Cout)
+    flags = (KM_CONV_RELU if relu else 0) | (KM_CONV_STATS if want_stats else 0)
+    out = torch.empty((N, D, H, W, Cout), dtype=act_dtype(), device=x_raw.device)
+    stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x_raw.device) \
+        if want_stats else None
+    ws = _ws(_lib.query("km_conv3d_zfold_pair_gn_workspace_bytes", N, Cs, Cout), x_raw.device)
+    with torch.cuda.device(x_raw.device):
+        _lib.call("km_conv3d_zfold_pair_gn_add", _ptr(x_raw), Cs, Cu, _ptr(w), _ptr(scale), _ptr(shift),
+                  _ptr(addend), _ptr(out), _ptr(stats), _ptr(ws), N, Cout, D, H, W, flags, _stream())
+    return out, stats
+
+
 def conv3d_tc_pair_gn(x_raw, w, scale, shift, relu=False, want_stats=False):
     """conv3d_tc_pair of GroupNorm(x_raw) without the normalisation pass (see conv3d_zfold_gn)."""
     _need_cuda(x_raw, w, scale, shift)

@@ -360,6 +360,46 @@ def test_conv3d_zfold_pair_gn_reads_concat_in_place(cfg):
         assert_close(sa.double().sum(0), sb.double().sum(0), rtol=1e-6, atol=1e-4)
 
 
+@pytest.mark.parametrize("cfg", [(2, 64, 128, 6, 32, 24), (1, 64, 64, 3, 16, 16), (2, 128, 64, 1, 20, 12),
+                                 (1, 64, 128, 37, 17, 9), (3, 64, 192, 2, 34, 10)])
+def test_decoder_first_conv_upsampled_half_on_the_coarse_lattice(cfg):
+    """km_conv3d_up2_gn + km_conv3d_zfold_pair_gn_add (the upsampled half of cat(skip, upsample(x)) -> GN -> conv
+    as 8 pre-summed taps per output parity class on the coarse tensor, added in the skip half's epilogue) against
+    the fp64 convolution of the explicitly normalised, materialised concat, and against the in-place concat
+    kernel.  Odd coarse sizes, one plane, several z segments and batches > 1 included."""
+    import torch.nn.functional as F
+    N, Cs, Cu, Dc, Hc, Wc = cfg
+    Cout = 64
+    g = torch.Generator().manual_seed(sum(cfg) + 9)
+    skip = ops.ncdhw_to_ndhwc(cu(F.relu(torch.randn(N, Cs, 2 * Dc, 2 * Hc, 2 * Wc, generator=g))))
+    coarse = ops.ncdhw_to_ndhwc(cu(F.relu(torch.randn(N, Cu, Dc, Hc, Wc, generator=g))))
+    w = cu(torch.randn(Cout, Cs + Cu, 3, 3, 3, generator=g) / (27 * (Cs + Cu)) ** 0.5)
+    scale = cu(torch.rand(N, Cs + Cu, generator=g) + 0.5)
+    shift = cu(torch.randn(N, Cs + Cu, generator=g))
+    assert ops.up2_supported(Cu, Cout, Dc, Hc, Wc)
+    # the partial sums alone: conv of the scaled upsampled channels, no shift, no activation
+    part = ops.conv3d_up2_gn(coarse, w, scale, Cs)
+    up64 = F.interpolate(coarse.float().permute(0, 4, 1, 2, 3), scale_factor=2, mode="nearest").double().cpu()
+    ref_part = F.conv3d(up64 * scale[:, Cs:].double().cpu()[:, :, None, None, None], w[:, Cs:].double().cpu(), padding=1)
+    got_part = part.float().permute(0, 4, 1, 2, 3).cpu()
+    assert_close(got_part, ref_part.float(), rtol=1e-2, atol=2e-2)
+    assert (got_part - ref_part.float()).abs().mean().item() < 3e-3
+    # the whole layer
+    out, st = ops.conv3d_zfold_pair_gn_add(skip, w, scale, shift, part, relu=True, want_stats=True)
+    cat = torch.cat([skip.float().permute(0, 4, 1, 2, 3).double().cpu(), up64], 1)
+    xn = cat * scale.double().cpu()[:, :, None, None, None] + shift.double().cpu()[:, :, None, None, None]
+    ref = F.relu(F.conv3d(xn, w.double().cpu(), padding=1)).float()
+    a = out.float().permute(0, 4, 1, 2, 3).cpu()
+    assert_close(a, ref, rtol=1e-2, atol=2e-2)
+    e_new = (a - ref).abs().mean().item()
+    b, sb = ops.conv3d_zfold_pair_gn(skip, w, scale, shift, relu=True, want_stats=True, x1=ops.upsample2(coarse))
+    e_old = (b.float().permute(0, 4, 1, 2, 3).cpu() - ref).abs().mean().item()
+    print(f"coarse-lattice decoder conv {cfg}: mean |err| {e_new:.2e} (in-place concat kernel {e_old:.2e})")
+    assert e_new < 1.5 * e_old + 1e-4       # one extra 16-bit rounding of the partial sums
+    s_ref = torch.stack([a.double().flatten(2).sum(-1), (a.double() ** 2).flatten(2).sum(-1)], -1)
+    assert_close(st.double().sum(0).cpu(), s_ref, rtol=1e-4, atol=1e-2)
+
+
 @pytest.mark.parametrize("cfg", [(1, 64, 64, 8, 32, 32), (2, 32, 64, 3, 70, 17), (2, 128, 128, 4, 32, 16),
                                  (3, 64, 128, 1, 48, 20), (2, 64, 64, 2, 32, 8)])
 def test_conv3d_tc_pair_groupnorm_folded(cfg):
