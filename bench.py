@@ -71,10 +71,13 @@ def conv_layers(S, K, n_img):
          ("dec1.c1", 192, 64, S // 2, 27), ("dec1.c2", 64, 64, S // 2, 27), ("final", 64, K, S // 2, 1)]
     from keymorph_b200 import ops
     if ops.USE_COARSE_UPCONV and ops.USE_GN_FOLD and ops.USE_ZFOLD_PAIR:
-        # EXECUTED flops: the 128 upsampled channels of dec1.c1 run as 8 pre-summed taps per output voxel on the
-        # coarse lattice (conv_up2.cu), the 64 skip channels as the usual 27
+        # EXECUTED flops: the upsampled channels of the decoders' first convs run as 8 pre-summed taps per output
+        # voxel on the coarse lattice (conv_up2.cu), the skip channels as the usual 27
         i = [l[0] for l in L].index("dec1.c1")
         L[i:i + 1] = [("dec1.c1", 64, 64, S // 2, 27), ("dec1.c1.up", 128, 64, S // 2, 8)]
+        if ops.USE_PAIR_CONV:
+            i = [l[0] for l in L].index("dec0.c1")
+            L[i:i + 1] = [("dec0.c1", 128, 128, S // 4, 27), ("dec0.c1.up", 256, 128, S // 4, 8)]
     return [(n, ci, co, e, t, 2.0 * t * ci * co * e ** 3 * n_img) for (n, ci, co, e, t) in L]
 
 
@@ -297,7 +300,7 @@ class Tracer:
 
 
 CONV_CALLS = ("km_conv3d_tc", "km_conv3d_tc_pair", "km_conv3d_zfold_pair", "km_conv3d_zfold_pair_gn",
-              "km_conv3d_zfold_pair_gn_cat", "km_conv3d_tc_pair_gn", "km_conv3d_up2_gn", "km_conv3d_zfold_pair_gn_add")
+              "km_conv3d_zfold_pair_gn_cat", "km_conv3d_tc_pair_gn", "km_conv3d_up2_gn", "km_conv3d_zfold_pair_gn_add", "km_conv3d_tc_pair_gn_add")
 ZF_CALLS = ("km_conv3d_zfold", "km_conv3d_zfold_gn")
 TRACED = CONV_CALLS + ZF_CALLS + ("km_conv1x1_com", "km_conv3d_stem", "km_warp_loss", "km_flow_field_tps", "km_tps_fit")
 

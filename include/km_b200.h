@@ -386,7 +386,7 @@ int km_conv3d_zfold_pair_gn_cat(const void* x0, const void* x1, int Cin0, int Ci
  * collapse to 8 taps over the coarse tensor with pre-summed weights (8/27 of the MMA work):
  *   km_conv3d_up2_gn            xc (N,Dc,Hc,Wc,Cu) raw 16-bit; w (Cout, Cs+Cu, 3,3,3) fp32; scale (N, Cs+Cu) or NULL;
  *                               out (N,2Dc,2Hc,2Wc,Cout) 16-bit PARTIAL sums of input channels [Cs, Cs+Cu)
- *                               (no bias / activation).  Cout = 64, Cu % 64 == 0.
+ *                               (no bias / activation).  Cout % 64 == 0, Cu % 64 == 0.
  *   km_conv3d_zfold_pair_gn_add the skip half (input channels [0, Cs) of x (N,D,H,W,Cs)) with `addend` = the
  *                               partial sums above added before the folded-norm bias (all Cs+Cu channels' shift
  *                               terms), ReLU and statistics.  workspace as km_conv3d_zfold_pair_gn(N, Cs, Cout). */
@@ -397,6 +397,11 @@ int km_conv3d_up2_gn(const void* xc, const float* w, const float* scale, int Cs,
 int km_conv3d_zfold_pair_gn_add(const void* x, int Cs, int Cu, const float* w, const float* scale, const float* shift,
                                 const void* addend, void* out, float* stats, void* workspace, int N, int Cout, int D,
                                 int H, int W, int flags, km_stream_t stream);
+/* The same on the plain CTA-pair kernel (Cout in {64, 128}, below 96^3 voxels; workspace as
+ * km_conv3d_tc_pair_gn(N, Cs, Cout)). */
+int km_conv3d_tc_pair_gn_add(const void* x, int Cs, int Cu, const float* w, const float* scale, const float* shift,
+                             const void* addend, void* out, float* stats, void* workspace, int N, int Cout, int D,
+                             int H, int W, int flags, km_stream_t stream);
 
 /* Nearest-neighbour x2 upsampling of a bf16 NDHWC tensor (F.interpolate in the decoders,
  * buildingblocks.py:409-445): (N,Dc,Hc,Wc,C) -> (N,2Dc,2Hc,2Wc,C), C % 8 == 0. */

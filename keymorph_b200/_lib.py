@@ -69,6 +69,7 @@ SIGNATURES = {
     "km_conv3d_up2_gn_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "km_conv3d_up2_gn": (_i, [_p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "km_conv3d_zfold_pair_gn_add": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "km_conv3d_tc_pair_gn_add": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "km_upsample2_ndhwc": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "km_hausdorff_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "km_hausdorff": (_i, [_p, _p, C.c_longlong, C.c_longlong, _i, _i, _i, _i, C.c_float, C.c_float, C.c_float, _p, _p, _p]),
@@ -132,7 +133,7 @@ def load() -> C.CDLL:
 
 # kernels launched by one call of each entry point (bench.py's "gpu_launches" claim)
 KERNELS_PER_CALL = {
-    "km_warp_loss": 2, "km_pair_stats": 2, "km_com3d": 2, "km_tps_fit": 1, "km_warp_labels_dice": 3, "km_jacobian_stats": 2, "km_hausdorff": 13, "km_conv3d_zfold_gn": 2, "km_conv3d_zfold_pair_gn": 2, "km_conv3d_zfold_pair_gn_cat": 2, "km_conv3d_tc_pair_gn": 2, "km_conv3d_up2_gn": 2, "km_conv3d_zfold_pair_gn_add": 2,
+    "km_warp_loss": 2, "km_pair_stats": 2, "km_com3d": 2, "km_tps_fit": 1, "km_warp_labels_dice": 3, "km_jacobian_stats": 2, "km_hausdorff": 13, "km_conv3d_zfold_gn": 2, "km_conv3d_zfold_pair_gn": 2, "km_conv3d_zfold_pair_gn_cat": 2, "km_conv3d_tc_pair_gn": 2, "km_conv3d_up2_gn": 2, "km_conv3d_zfold_pair_gn_add": 2, "km_conv3d_tc_pair_gn_add": 2,
 }
 launch_count = 0
 # optional tracer: callable(name, phase) with phase in {"pre", "post"}; bench.py installs one that

@@ -66,11 +66,11 @@ __device__ __forceinline__ TileCoord decode_tile(const PairGeom& g, int t) {
   return c;
 }
 
-template <int KC, bool F16>
+template <int KC, bool F16, bool ADD = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const PairGeom g, uint16_t* __restrict__ out, float* __restrict__ stats,
-                const float* __restrict__ bias_tab) {
+                const float* __restrict__ bias_tab, const uint16_t* __restrict__ addend) {
   constexpr int kRowBytes = KC * 2;
   constexpr int kSteps = KC / 16;
   constexpr uint32_t kLayout = kRowBytes == 128 ? 2u : (kRowBytes == 64 ? 4u : 6u);
@@ -291,6 +291,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                               (y2 == 0 ? 1 : (y2 == g.H - 1 ? 2 : 0)) * 3 + (x2 == 0 ? 1 : (x2 == g.W - 1 ? 2 : 0));
               brow = reinterpret_cast<const float4*>(bias_tab + ((size_t)tc0.n * kBiasClasses + cls) * g.Cout);
             }
+            // ADD: partial sums of the same layer from conv_up2.cu (the upsampled half of a decoder's concat)
+            const uint4* arow = nullptr;
+            if (ADD && vrow) {
+              const int x2 = tc0.x0 + tx, y2 = y0 + 16 * mb + ty;
+              arow = reinterpret_cast<const uint4*>(
+                  addend + ((((size_t)tc0.n * g.D + tc0.z0) * g.H + y2) * g.W + x2) * g.Cout);
+            }
             for (int blk = b_lo; blk < b_hi; ++blk) {
               const int c0 = blk * 16;
               uint32_t r[16];
@@ -300,7 +307,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) bv[j4] = __ldg(brow + blk * 4 + j4);
               }
+              uint4 a0 = make_uint4(0u, 0u, 0u, 0u), a1 = a0;
+              if (ADD && arow) {
+                a0 = __ldg(arow + 2 * blk);
+                a1 = __ldg(arow + 2 * blk + 1);
+              }
               tmem_ld_wait();
+              if (ADD && arow) {
+                const uint32_t a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 ab = km_unpack2<F16>(a8[j]);
+                  r[2 * j] = __float_as_uint(__uint_as_float(r[2 * j]) + ab.x);
+                  r[2 * j + 1] = __float_as_uint(__uint_as_float(r[2 * j + 1]) + ab.y);
+                }
+              }
               if (brow) {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -391,7 +412,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 inline uint32_t pair_round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 typedef void (*PairKernel)(const CUtensorMap, const CUtensorMap, const PairGeom, uint16_t*, float*,
-                           const float*);
+                           const float*, const uint16_t*);
 
 
 }  // namespace
@@ -404,13 +425,13 @@ extern "C" int km_conv3d_tc_pair_supported(int Cin, int Cout, int D, int H, int 
 }
 
 namespace {
-int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out, float* stats, int N, int Cin,
-                int Cout, int D, int H, int W, int flags, km_stream_t stream);
+int launch_pair(const void* x, const void* wp, const float* bias_tab, const void* addend, void* out, float* stats,
+                int N, int Cin, int Cout, int D, int H, int W, int flags, km_stream_t stream);
 }
 
 extern "C" int km_conv3d_tc_pair(const void* x, const void* wp, void* out, float* stats, int N, int Cin,
                                  int Cout, int D, int H, int W, int flags, km_stream_t stream) {
-  return launch_pair(x, wp, nullptr, out, stats, N, Cin, Cout, D, H, W, flags, stream);
+  return launch_pair(x, wp, nullptr, nullptr, out, stats, N, Cin, Cout, D, H, W, flags, stream);
 }
 
 extern "C" size_t km_conv3d_tc_pair_gn_workspace_bytes(int N, int Cin, int Cout) {
@@ -430,12 +451,31 @@ extern "C" int km_conv3d_tc_pair_gn(const void* x, const float* w, const float* 
   float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)N * wbytes + 255) & ~(size_t)255));
   const int rf = km_fold_gn(w, scale, shift, packed, bias, N, Cout, Cin, 0, stream);
   if (rf != KM_OK) return rf;
-  return launch_pair(x, workspace, bias, out, stats, N, Cin, Cout, D, H, W, flags, stream);
+  return launch_pair(x, workspace, bias, nullptr, out, stats, N, Cin, Cout, D, H, W, flags, stream);
+}
+
+// The first Cs channels of a (Cs + Cu)-channel folded layer; `addend` holds the other channels' partial sums
+// (km_conv3d_up2_gn).  The border-class bias table covers ALL channels, the packed weights the first Cs.
+extern "C" int km_conv3d_tc_pair_gn_add(const void* x, int Cs, int Cu, const float* w, const float* scale,
+                                        const float* shift, const void* addend, void* out, float* stats,
+                                        void* workspace, int N, int Cout, int D, int H, int W, int flags,
+                                        km_stream_t stream) {
+  KM_CHECK_ARG(w && scale && shift && addend && workspace && ((uintptr_t)workspace & 255) == 0 &&
+                   ((uintptr_t)addend & 15) == 0,
+               "km_conv3d_tc_pair_gn_add: null / unaligned argument");
+  KM_CHECK_ARG(Cs > 0 && Cu > 0 && km_conv3d_tc_pair_supported(Cs, Cout, D, H, W),
+               "km_conv3d_tc_pair_gn_add: unsupported shape (Cs=%d Cu=%d Cout=%d H=%d W=%d)", Cs, Cu, Cout, H, W);
+  KM_CHECK_ARG(N > 0 && N <= 1024, "km_conv3d_tc_pair_gn_add: bad batch");
+  const size_t wbytes = (size_t)27 * Cout * Cs * 2;
+  float* bias = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)N * wbytes + 255) & ~(size_t)255));
+  const int rf = km_fold_gn_part(w, scale, shift, workspace, bias, N, Cout, Cs + Cu, 0, Cs, 0, stream);
+  if (rf != KM_OK) return rf;
+  return launch_pair(x, workspace, bias, addend, out, stats, N, Cs, Cout, D, H, W, flags, stream);
 }
 
 namespace {
-int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out, float* stats, int N, int Cin,
-                int Cout, int D, int H, int W, int flags, km_stream_t stream) {
+int launch_pair(const void* x, const void* wp, const float* bias_tab, const void* addend, void* out, float* stats,
+                int N, int Cin, int Cout, int D, int H, int W, int flags, km_stream_t stream) {
   KM_CHECK_ARG(x && wp && out, "km_conv3d_tc_pair: null argument");
   KM_CHECK_ARG(km_conv3d_tc_pair_supported(Cin, Cout, D, H, W),
                "km_conv3d_tc_pair: unsupported shape (Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
@@ -537,10 +577,12 @@ int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out,
     }
   }
   const bool f16 = km_operand_fp16() != 0;
-  PairKernel kernel = kc == 64 ? (f16 ? conv_tc2_kernel<64, true> : conv_tc2_kernel<64, false>)
-                               : (f16 ? conv_tc2_kernel<32, true> : conv_tc2_kernel<32, false>);
-  static unsigned long long attr_set[2][2] = {};   // per (operand type, Cin chunk) instantiation
-  if (km_first_use_on_device(&attr_set[f16 ? 1 : 0][kc == 64]))
+  KM_CHECK_ARG(!addend || kc == 64, "km_conv3d_tc_pair: an addend needs Cin %% 64 == 0");
+  PairKernel kernel = addend ? (f16 ? conv_tc2_kernel<64, true, true> : conv_tc2_kernel<64, false, true>)
+                      : kc == 64 ? (f16 ? conv_tc2_kernel<64, true> : conv_tc2_kernel<64, false>)
+                                 : (f16 ? conv_tc2_kernel<32, true> : conv_tc2_kernel<32, false>);
+  static unsigned long long attr_set[2][3] = {};   // per (operand type, Cin chunk | addend) instantiation
+  if (km_first_use_on_device(&attr_set[f16 ? 1 : 0][addend ? 2 : (kc == 64)]))
     KM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   const int nsm = km_sm_count();
   int grid = nsm & ~1;
@@ -549,7 +591,7 @@ int launch_pair(const void* x, const void* wp, const float* bias_tab, void* out,
   if ((flags & KM_CONV_STATS) && grid < nsm)
     KM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nsm * N * Cout * 2 * sizeof(float), km_cs(stream)));
   kernel<<<grid, kThreads, smem_bytes, km_cs(stream)>>>(tmA, tmB, g, reinterpret_cast<uint16_t*>(out), stats,
-                                                        bias_tab);
+                                                        bias_tab, reinterpret_cast<const uint16_t*>(addend));
   KM_LAUNCH_OK("conv_tc2_kernel");
   return KM_OK;
 }

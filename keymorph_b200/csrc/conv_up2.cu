@@ -41,13 +41,14 @@ constexpr uint32_t kSbo = 8u * kRowBytes;
 
 struct Up2Geom {
   int N, Dc, Hc, Wc, chunks;
-  int xpairs, tiles_y, zsegs, lz, units;   // units = N * zsegs * 4 classes * tiles_y * xpairs (unit pairs)
+  int cblocks, cout_total;                 // output channels in blocks of 64 (one unit computes one block)
+  int xpairs, tiles_y, zsegs, lz, units;   // units = N * zsegs * cblocks * 4 classes * tiles_y * xpairs (unit pairs)
   uint32_t off_bars;
   int stages;
 };
 
 struct Unit {
-  int n, x0, y0, zs, planes, px, py;
+  int n, x0, y0, zs, planes, px, py, cb;
   bool valid;
 };
 
@@ -61,6 +62,8 @@ __device__ __forceinline__ Unit decode_unit(const Up2Geom& g, int u, uint32_t ra
   r.px = u & 1;
   r.py = (u >> 1) & 1;
   u >>= 2;
+  r.cb = u % g.cblocks;
+  u /= g.cblocks;
   r.zs = (u % g.zsegs) * g.lz;
   r.n = u / g.zsegs;
   r.planes = min(g.lz, g.Dc - r.zs) + 2;   // coarse input planes zs-1 .. zs+lz
@@ -139,7 +142,7 @@ conv_up2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t ph = 0;
       for_each_tile(g, rank, [&](auto, const Unit& u, int p, uint32_t) {
         const int j = u.zs - 1 + p;   // coarse input plane; outside [0, Dc) -> TMA zero fill
-        const int wsel = ((u.n * 4 + u.py * 2 + u.px) << 1) | (j & 1);
+        const int wsel = ((((u.n * g.cblocks + u.cb) * 4 + u.py * 2 + u.px)) << 1) | (j & 1);
         for (int dx = 0; dx < 2; ++dx) {
           for (int ch = 0; ch < g.chunks; ++ch) {
             mbar_wait(empty_bar(s), ph ^ 1u);
@@ -244,7 +247,7 @@ conv_up2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             pk[i] = km_pack2<F16>(__uint_as_float(r[k][hh][2 * i]), __uint_as_float(r[k][hh][2 * i + 1]));
-          st_global_v8(out + vox * kCout + half * kCols + 16 * hh, pk);
+          st_global_v8(out + vox * g.cout_total + u.cb * kCout + half * kCols + 16 * hh, pk);
         }
       }
     });
@@ -259,26 +262,27 @@ conv_up2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-// fp32 (Cout, Cs + Cu, 3, 3, 3) and scale (N, Cs + Cu) -> 16-bit [n][class py px][rot][dx'][dy'][slot * 64 + cout][Cu]:
+// fp32 (Cout, Cs + Cu, 3, 3, 3) and scale (N, Cs + Cu) -> 16-bit [n][cout block][class py px][rot][dx'][dy'][slot * 64 + cout][Cu]:
 // the taps a coarse neighbour stands for, summed, times the GroupNorm scale of the channel.
 //   x: fine taps dx in {px - 1 + 2 dx', px + 2 dx'} & [0, 2]  (same for y);
 //   z: the slot holds fine plane 2j + d, d = ((slot - 2 rot + 1) & 3) - 1, fine taps dz in {1 - d, 2 - d} & [0, 2]
 template <bool F16>
 __global__ void __launch_bounds__(256)
 pack_up2_kernel(const float* __restrict__ w, const float* __restrict__ scale, uint16_t* __restrict__ packed, int N,
-                int Cs, int Cu) {
+                int Cs, int Cu, int cblocks) {
   const int Cin = Cs + Cu;
-  const long long per = 32ll * kN * Cu;
+  const long long per = 32ll * kN * Cu * cblocks;   // [cout block][class][rot][dx'][dy'][slot][64][Cu]
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < per; i += 256ll * gridDim.x) {
     long long t = i;
     const int ci = (int)(t % Cu);
     t /= Cu;
-    const int co = (int)(t % kCout);
+    int co = (int)(t % kCout);
     t /= kCout;
     const int slot = (int)(t & 3);
     t >>= 2;
     const int dyp = (int)(t & 1), dxp = (int)((t >> 1) & 1), rot = (int)((t >> 2) & 1), px = (int)((t >> 3) & 1),
               py = (int)((t >> 4) & 1);
+    co += (int)(t >> 5) * kCout;
     const int d = ((slot - 2 * rot + 1) & 3) - 1;
     const float* wk = w + ((size_t)co * Cin + Cs + ci) * 27;
     float acc = 0.f;
@@ -305,12 +309,12 @@ pack_up2_kernel(const float* __restrict__ w, const float* __restrict__ scale, ui
 extern "C" int km_sm_count(void);
 
 extern "C" int km_conv3d_up2_supported(int Cu, int Cout, int Dc, int Hc, int Wc) {
-  return (Cout == kCout && Cu % kKC == 0 && Cu >= kKC && Cu <= 512 && Wc >= 8 && Hc >= 16 && Dc >= 1) ? 1 : 0;
+  return (Cout % kCout == 0 && Cout >= kCout && Cout <= 256 && Cu % kKC == 0 && Cu >= kKC && Cu <= 512 && Wc >= 8 &&
+          Hc >= 16 && Dc >= 1) ? 1 : 0;
 }
 
 extern "C" size_t km_conv3d_up2_gn_workspace_bytes(int N, int Cu, int Cout) {
-  (void)Cout;
-  return (size_t)N * 32 * kN * Cu * 2;
+  return (size_t)N * 32 * kN * Cu * 2 * (size_t)((Cout + kCout - 1) / kCout);
 }
 
 extern "C" int km_conv3d_up2_gn(const void* xc, const float* w, const float* scale, int Cs, int Cu, void* out,
@@ -322,16 +326,19 @@ extern "C" int km_conv3d_up2_gn(const void* xc, const float* w, const float* sca
   KM_CHECK_ARG(((uintptr_t)xc & 15) == 0 && ((uintptr_t)out & 31) == 0 && ((uintptr_t)workspace & 255) == 0,
                "km_conv3d_up2_gn: pointers must be 16-byte (output 32, workspace 256) aligned");
   cudaStream_t st = km_cs(stream);
+  const int cblocks = Cout / kCout;
   if (km_operand_fp16())
-    pack_up2_kernel<true><<<256, 256, 0, st>>>(w, scale, reinterpret_cast<uint16_t*>(workspace), N, Cs, Cu);
+    pack_up2_kernel<true><<<256 * cblocks, 256, 0, st>>>(w, scale, reinterpret_cast<uint16_t*>(workspace), N, Cs, Cu, cblocks);
   else
-    pack_up2_kernel<false><<<256, 256, 0, st>>>(w, scale, reinterpret_cast<uint16_t*>(workspace), N, Cs, Cu);
+    pack_up2_kernel<false><<<256 * cblocks, 256, 0, st>>>(w, scale, reinterpret_cast<uint16_t*>(workspace), N, Cs, Cu, cblocks);
   KM_LAUNCH_OK("pack_up2_kernel");
 
   Up2Geom g;
   memset(&g, 0, sizeof(g));
   g.N = N; g.Dc = Dc; g.Hc = Hc; g.Wc = Wc;
   g.chunks = Cu / kKC;
+  g.cblocks = cblocks;
+  g.cout_total = Cout;
   const int tiles_x = (Wc + 7) / 8;
   g.xpairs = (tiles_x + 1) / 2;
   g.tiles_y = (Hc + 15) / 16;
@@ -341,7 +348,7 @@ extern "C" int km_conv3d_up2_gn(const void* xc, const float* w, const float* sca
   double best = 1e30;
   for (int lz = 64; lz >= 8; lz /= 2) {
     const long long zs = (Dc + lz - 1) / lz;
-    const long long units = (long long)N * zs * 4 * g.tiles_y * g.xpairs;
+    const long long units = (long long)N * zs * cblocks * 4 * g.tiles_y * g.xpairs;
     const long long rounds = (units + npairs_hw - 1) / npairs_hw;
     const double cost = (double)rounds * (double)(std::min(lz, Dc) + 2);   // planes walked by the busiest pair
     if (cost < best) {
@@ -350,7 +357,7 @@ extern "C" int km_conv3d_up2_gn(const void* xc, const float* w, const float* sca
     }
   }
   g.zsegs = (Dc + g.lz - 1) / g.lz;
-  const long long units = (long long)N * g.zsegs * 4 * g.tiles_y * g.xpairs;
+  const long long units = (long long)N * g.zsegs * cblocks * 4 * g.tiles_y * g.xpairs;
   KM_CHECK_ARG(units < (1ll << 30), "km_conv3d_up2_gn: too many units");
   g.units = (int)units;
   g.stages = kStagesMax;
@@ -379,9 +386,9 @@ extern "C" int km_conv3d_up2_gn(const void* xc, const float* w, const float* sca
     }
   }
   {
-    // packed weights [n, class, rot][dx'][dy'][256 rows][Cu] viewed as (Cu, rows, dy', dx', n class rot)
+    // packed weights [n, cout block, class, rot][dx'][dy'][256 rows][Cu] viewed as (Cu, rows, dy', dx', the rest)
     const cuuint64_t tile = (cuuint64_t)kN * Cu * 2;
-    cuuint64_t dims[5] = {(cuuint64_t)Cu, (cuuint64_t)kN, 2, 2, (cuuint64_t)(8 * N)};
+    cuuint64_t dims[5] = {(cuuint64_t)Cu, (cuuint64_t)kN, 2, 2, (cuuint64_t)(8 * N * cblocks)};
     cuuint64_t strides[4] = {(cuuint64_t)Cu * 2, tile, 2 * tile, 4 * tile};
     cuuint32_t box[5] = {(cuuint32_t)kKC, (cuuint32_t)kHalfRows, 2, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};

@@ -232,19 +232,27 @@ class UNetEngine(_EngineBase):
                 w1 = dc.SingleConv1.conv.weight
                 Cs, Cu = skip.shape[-1], cur.shape[-1]
                 sd = skip.shape[1:4]
-                if ops.USE_GN_FOLD and ops.USE_ZFOLD_PAIR and sd[0] * sd[1] * sd[2] >= 96 ** 3 \
-                        and (w1.shape[0] == 32 or (Cs % 64 == 0 and Cu % 64 == 0)) and Cs % 32 == 0 and Cu % 32 == 0 \
-                        and ops.zfold_pair_supported(Cs + Cu, w1.shape[0], *sd):
-                    # the concat is never materialised: the skip is read raw through its own tensor map, only
-                    # the upsampled half is written (also raw); the joint GroupNorm is folded into the conv
-                    if ops.USE_COARSE_UPCONV and ops.up2_supported(Cu, w1.shape[0], *cur.shape[1:4]) \
-                            and ops.zfold_pair_supported(Cs, w1.shape[0], *sd):
-                        # ... and the upsampled half is not even written: its 27 fine taps are 8 pre-summed taps
-                        # on the coarse lattice per output parity class (8/27 of the MMAs); the skip half's
-                        # kernel adds those partial sums before bias / ReLU / statistics
+                Cout, vox = w1.shape[0], sd[0] * sd[1] * sd[2]
+                # (1) the upsampled half on the COARSE lattice: its 27 fine taps are 8 pre-summed taps per output
+                # parity class (8/27 of the MMAs, conv_up2.cu) and the upsampled tensor is never written; the skip
+                # half's kernel reads the skip raw (joint GroupNorm folded into both) and adds those partial sums
+                # before bias / ReLU / statistics
+                split = None
+                if ops.USE_GN_FOLD and ops.USE_COARSE_UPCONV and Cs % 64 == 0 \
+                        and ops.up2_supported(Cu, Cout, *cur.shape[1:4]):
+                    if ops.USE_ZFOLD_PAIR and vox >= 96 ** 3 and Cout == 64 and ops.zfold_pair_supported(Cs, Cout, *sd):
+                        split = "zfold_pair"
+                    elif ops.USE_PAIR_CONV and vox >= 64 ** 3 and ops.pair_supported(Cs, Cout, *sd):
+                        split = "tc_pair"
+                # (2) the concat read in place through two tensor maps: only the upsampled half is written (raw)
+                cat_in_place = ops.USE_GN_FOLD and ops.USE_ZFOLD_PAIR and vox >= 96 ** 3 \
+                    and (Cout == 32 or (Cs % 64 == 0 and Cu % 64 == 0)) and Cs % 32 == 0 and Cu % 32 == 0 \
+                    and ops.zfold_pair_supported(Cs + Cu, Cout, *sd)
+                if split or cat_in_place:
+                    if split:
                         part = ops.conv3d_up2_gn(cur, w1.detach(), scale, Cs)
                         c1, st = ops.conv3d_zfold_pair_gn_add(skip, w1.detach(), scale, shift, part, relu=True,
-                                                              want_stats=True)
+                                                              want_stats=True, kernel=split)
                         del part
                     else:
                         up = ops.upsample2(cur)

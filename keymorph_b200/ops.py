@@ -575,9 +575,10 @@ def conv3d_up2_gn(x_coarse, w, scale, Cs):
     return out
 
 
-def conv3d_zfold_pair_gn_add(x_raw, w, scale, shift, addend, relu=False, want_stats=False):
+def conv3d_zfold_pair_gn_add(x_raw, w, scale, shift, addend, relu=False, want_stats=False, kernel="zfold_pair"):
     """The skip half of the same layer: input channels [0, Cs) from x_raw, plus `addend` (conv3d_up2_gn), then
-    the folded-norm bias of ALL channels, ReLU and statistics."""
+    the folded-norm bias of ALL channels, ReLU and statistics.  kernel: "zfold_pair" (Cout 64, large volumes) or
+    "tc_pair" (Cout 64 / 128)."""
     _need_cuda(x_raw, w, scale, shift, addend)
     assert x_raw.dtype == act_dtype() and addend.dtype == act_dtype()
     x_raw, w, scale, shift, addend = x_raw.contiguous(), _f32c(w), _f32c(scale), _f32c(shift), addend.contiguous()
@@ -590,9 +591,9 @@ def conv3d_zfold_pair_gn_add(x_raw, w, scale, shift, addend, relu=False, want_st
     out = torch.empty((N, D, H, W, Cout), dtype=act_dtype(), device=x_raw.device)
     stats = torch.empty((conv_nparts(), N, Cout, 2), dtype=torch.float32, device=x_raw.device) \
         if want_stats else None
-    ws = _ws(_lib.query("km_conv3d_zfold_pair_gn_workspace_bytes", N, Cs, Cout), x_raw.device)
+    ws = _ws(_lib.query(f"km_conv3d_{kernel}_gn_workspace_bytes", N, Cs, Cout), x_raw.device)
     with torch.cuda.device(x_raw.device):
-        _lib.call("km_conv3d_zfold_pair_gn_add", _ptr(x_raw), Cs, Cu, _ptr(w), _ptr(scale), _ptr(shift),
+        _lib.call(f"km_conv3d_{kernel}_gn_add", _ptr(x_raw), Cs, Cu, _ptr(w), _ptr(scale), _ptr(shift),
                   _ptr(addend), _ptr(out), _ptr(stats), _ptr(ws), N, Cout, D, H, W, flags, _stream())
     return out, stats
 

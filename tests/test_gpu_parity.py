@@ -360,17 +360,18 @@ def test_conv3d_zfold_pair_gn_reads_concat_in_place(cfg):
         assert_close(sa.double().sum(0), sb.double().sum(0), rtol=1e-6, atol=1e-4)
 
 
-@pytest.mark.parametrize("cfg", [(2, 64, 128, 6, 32, 24), (1, 64, 64, 3, 16, 16), (2, 128, 64, 1, 20, 12),
-                                 (1, 64, 128, 37, 17, 9), (3, 64, 192, 2, 34, 10)])
+@pytest.mark.parametrize("cfg", [(2, 64, 128, 6, 32, 24, 64, "zfold_pair"), (1, 64, 64, 3, 16, 16, 64, "zfold_pair"),
+                                 (2, 128, 64, 1, 20, 12, 64, "zfold_pair"), (1, 64, 128, 37, 17, 9, 64, "zfold_pair"),
+                                 (3, 64, 192, 2, 34, 10, 64, "zfold_pair"), (2, 128, 256, 5, 16, 16, 128, "tc_pair"),
+                                 (1, 64, 128, 3, 20, 9, 64, "tc_pair"), (2, 64, 64, 2, 17, 12, 128, "tc_pair")])
 def test_decoder_first_conv_upsampled_half_on_the_coarse_lattice(cfg):
     """km_conv3d_up2_gn + km_conv3d_zfold_pair_gn_add (the upsampled half of cat(skip, upsample(x)) -> GN -> conv
     as 8 pre-summed taps per output parity class on the coarse tensor, added in the skip half's epilogue) against
     the fp64 convolution of the explicitly normalised, materialised concat, and against the in-place concat
     kernel.  Odd coarse sizes, one plane, several z segments and batches > 1 included."""
     import torch.nn.functional as F
-    N, Cs, Cu, Dc, Hc, Wc = cfg
-    Cout = 64
-    g = torch.Generator().manual_seed(sum(cfg) + 9)
+    N, Cs, Cu, Dc, Hc, Wc, Cout, kernel = cfg
+    g = torch.Generator().manual_seed(sum(cfg[:7]) + 9)
     skip = ops.ncdhw_to_ndhwc(cu(F.relu(torch.randn(N, Cs, 2 * Dc, 2 * Hc, 2 * Wc, generator=g))))
     coarse = ops.ncdhw_to_ndhwc(cu(F.relu(torch.randn(N, Cu, Dc, Hc, Wc, generator=g))))
     w = cu(torch.randn(Cout, Cs + Cu, 3, 3, 3, generator=g) / (27 * (Cs + Cu)) ** 0.5)
@@ -385,14 +386,18 @@ def test_decoder_first_conv_upsampled_half_on_the_coarse_lattice(cfg):
     assert_close(got_part, ref_part.float(), rtol=1e-2, atol=2e-2)
     assert (got_part - ref_part.float()).abs().mean().item() < 3e-3
     # the whole layer
-    out, st = ops.conv3d_zfold_pair_gn_add(skip, w, scale, shift, part, relu=True, want_stats=True)
+    out, st = ops.conv3d_zfold_pair_gn_add(skip, w, scale, shift, part, relu=True, want_stats=True, kernel=kernel)
     cat = torch.cat([skip.float().permute(0, 4, 1, 2, 3).double().cpu(), up64], 1)
     xn = cat * scale.double().cpu()[:, :, None, None, None] + shift.double().cpu()[:, :, None, None, None]
     ref = F.relu(F.conv3d(xn, w.double().cpu(), padding=1)).float()
     a = out.float().permute(0, 4, 1, 2, 3).cpu()
     assert_close(a, ref, rtol=1e-2, atol=2e-2)
     e_new = (a - ref).abs().mean().item()
-    b, sb = ops.conv3d_zfold_pair_gn(skip, w, scale, shift, relu=True, want_stats=True, x1=ops.upsample2(coarse))
+    if kernel == "zfold_pair":
+        b, sb = ops.conv3d_zfold_pair_gn(skip, w, scale, shift, relu=True, want_stats=True, x1=ops.upsample2(coarse))
+    else:
+        b, sb = ops.conv3d_tc_pair_gn(torch.cat([skip, ops.upsample2(coarse)], -1), w, scale, shift, relu=True,
+                                      want_stats=True)
     e_old = (b.float().permute(0, 4, 1, 2, 3).cpu() - ref).abs().mean().item()
     print(f"coarse-lattice decoder conv {cfg}: mean |err| {e_new:.2e} (in-place concat kernel {e_old:.2e})")
     assert e_new < 1.5 * e_old + 1e-4       # one extra 16-bit rounding of the partial sums
