@@ -61,7 +61,7 @@ def config_dict(world):
             "l2": "per-step working set (>5 GB of activations) exceeds the 126 MB L2"}
 
 
-def conv_layers(S, K, n_img):
+def conv_layers(S, K, n_img, executed=True):
     """(name, Cin, Cout, edge, taps, FLOPs) of every conv on the path, keymorph/unet3d/buildingblocks.py
     :171-181 channel rule; FLOPs = 2*taps*Cin*Cout*edge^3 per image."""
     L = [("enc0.c1", 1, 16, S, 27), ("enc0.c2", 16, 32, S, 27), ("enc1.c1", 32, 32, S // 2, 27),
@@ -70,7 +70,7 @@ def conv_layers(S, K, n_img):
          ("dec0.c1", 384, 128, S // 4, 27), ("dec0.c2", 128, 128, S // 4, 27),
          ("dec1.c1", 192, 64, S // 2, 27), ("dec1.c2", 64, 64, S // 2, 27), ("final", 64, K, S // 2, 1)]
     from keymorph_b200 import ops
-    if ops.USE_COARSE_UPCONV and ops.USE_GN_FOLD and ops.USE_ZFOLD_PAIR:
+    if executed and ops.USE_COARSE_UPCONV and ops.USE_GN_FOLD and ops.USE_ZFOLD_PAIR:
         # EXECUTED flops: the upsampled channels of the decoders' first convs run as 8 pre-summed taps per output
         # voxel on the coarse lattice (conv_up2.cu), the skip channels as the usual 27
         i = [l[0] for l in L].index("dec1.c1")
@@ -269,7 +269,7 @@ def run_reference(args):
                                              "reference's K x M x 3 temporaries fit in host RAM (BASELINE.md 4.3)"}
         except Exception as e:  # noqa: BLE001
             line["tps_config3"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -387,38 +387,24 @@ def measure_e2e(model, name, host_f, host_m, steps, ctx, with_grid=False, clone_
             "loss": last[0], "img_a_center": last[1]}
 
 
-def graph_block(models, eager, img_f, img_m, host_f, host_m, args, ctx):
-    """The same forward() replayed from one CUDA graph per configuration (KeyMorph(cuda_graph=True)): removes the
-    launch gaps between the ~100 small launches of a step and nearly all host work.  Reported beside the eager
-    headline, not instead of it."""
+def measure_graph(gm, name, img_f, img_m, steps, warmup, ctx):
+    """Device-resident timing of forward() replayed from its CUDA graph (KeyMorph(cuda_graph=True): call 1 eager,
+    call 2 captures, every later call = 2 staging copies + 1 graph launch)."""
     import torch
-
-    import keymorph_b200 as kb
-    out = {}
-    for name, model in models.items():
-        cfg = CONFIGS[name]
-        t = cfg["transform"]
-        gm = kb.KeyMorph(model.backbone, cfg["K"], 3, fused_warp=True, cuda_graph=True).eval()
-        for _ in range(max(args.warmup, 3)):      # call 1 eager, call 2 captures, call 3+ replays
-            r = gm(img_f, img_m, transform_type=t, return_aligned_points=True)[t]
-        state = "; ".join(gm.graph_state().values())
-        ctx["sync"]()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            r = gm(img_f, img_m, transform_type=t, return_aligned_points=True)[t]
-        e1.record()
-        ctx["sync"]()
-        ms = ctx["max"](e0.elapsed_time(e1) / args.steps)
-        e2e = measure_e2e(gm, name, host_f, host_m, args.steps, ctx, with_grid=args.e2e_grid, clone_outputs=True)
-        out[name] = {"state": state, "value": ctx["world"] * 1e3 / ms, "unit": UNIT, "ms_per_step": ms,
-                     "eager_ms_per_step": eager[name], "mse": float(r["mse"].item()),
-                     "e2e": {k: e2e[k] for k in ("value", "unit", "ms_per_step", "loss")}}
-        del gm
-        torch.cuda.empty_cache()
-    out["note"] = ("forward() captured once per (shape, transform list) and replayed: 2 device copies into the static "
-                   "inputs + 1 graph launch per registration; the headline `value` above is the eager path")
-    return out
+    t = CONFIGS[name]["transform"]
+    for _ in range(max(warmup, 3)):
+        r = gm(img_f, img_m, transform_type=t, return_aligned_points=True)[t]
+    state = "; ".join(gm.graph_state().values())
+    ctx["sync"]()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = gm(img_f, img_m, transform_type=t, return_aligned_points=True)[t]
+    e1.record()
+    ctx["sync"]()
+    captured = ctx["max"](0.0 if state == "captured" else 1.0) == 0.0      # on every rank
+    return {"ms_step": ctx["max"](e0.elapsed_time(e1) / steps), "state": state, "captured": captured,
+            "mse": float(r["mse"].item())}
 
 
 def conv_rooflines(tr, name, steps, ms_step, peaks, timed_s):
@@ -428,6 +414,8 @@ def conv_rooflines(tr, name, steps, ms_step, peaks, timed_s):
     tc_peak = peaks["tc_burst"] if burst else peaks["tc_sustained"]
     which = "burst" if burst else "sustained"
     layers = {l[0]: l[5] for l in conv_layers(S, K, 2)}
+    alg = {l[0]: l[5] for l in conv_layers(S, K, 2, executed=False)}
+    alg_flops = sum(v for k, v in alg.items() if k not in ("enc0.c1", "enc0.c2", "final"))
     conv_ms, zf_ms = tr.ms(*CONV_CALLS, per=steps), tr.ms(*ZF_CALLS, per=steps)
     com_ms, stem_ms = tr.ms("km_conv1x1_com", per=steps), tr.ms("km_conv3d_stem", per=steps)
     zf_flops = layers["enc0.c2"] if zf_ms > 0 else 0.0
@@ -438,7 +426,10 @@ def conv_rooflines(tr, name, steps, ms_step, peaks, timed_s):
     ach = tc_flops / (conv_ms * 1e-3) / 1e12
     main = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel / conv_zf2_kernel / conv_up2_kernel (tcgen05 3x3x3 convolutions; EXECUTED flops)",
             "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": conv_traffic,
-            "flops_per_step": tc_flops, "launches_per_step": tr.count(*CONV_CALLS, per=steps),
+            "flops_per_step": tc_flops, "algorithmic_flops_per_step": alg_flops,
+            "algorithmic_tflops": alg_flops / (conv_ms * 1e-3) / 1e12,
+            "flops_note": "achieved / frac count the MMAs EXECUTED; the reference's 27-tap arithmetic on the upsampled "
+                          "decoder channels (algorithmic_flops) is done with 8 pre-summed taps on the coarse lattice", "launches_per_step": tr.count(*CONV_CALLS, per=steps),
             "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / ms_step,
             "peak_source": f"{peaks['src']}: {which} bf16 figure (timed region {timed_s:.2f} s)",
             "frac_of_sustained": ach / peaks["tc_sustained"], "frac_of_burst": ach / peaks["tc_burst"],
@@ -646,11 +637,20 @@ def run_engine(args):
     clocks = ClockSampler(local)
     clocks.start()
     # ---- headline: configs[1]
+    # eager pass with per-call CUDA events (kernel times for the rooflines, launch count), then the same forward()
+    # replayed from its CUDA graph: the public API's cuda_graph=True mode is the headline (no launch gaps, no
+    # dependence on how fast the host enqueues ~100 launches); --eager keeps the eager number as the headline
     res = measure_pairwise(models["affine"], "affine", img_f, img_m, args.steps, args.warmup, ctx)
-    ms_step = res["ms_step"]
+    eager_ms = res["ms_step"]
+    timed_s = eager_ms * args.steps * 1e-3
+    roofline, roofline_other = conv_rooflines(res["tr"], "affine", args.steps, eager_ms, peaks, timed_s)
+    gmodels = {}
+    for name, m in models.items():
+        gmodels[name] = kb.KeyMorph(m.backbone, CONFIGS[name]["K"], 3, fused_warp=True, cuda_graph=True).eval()
+    gres = None if args.eager else measure_graph(gmodels["affine"], "affine", img_f, img_m, args.steps, args.warmup, ctx)
+    use_graph = gres is not None and gres["captured"]
+    ms_step = gres["ms_step"] if use_graph else eager_ms
     value = world * 1e3 / ms_step
-    timed_s = ms_step * args.steps * 1e-3
-    roofline, roofline_other = conv_rooflines(res["tr"], "affine", args.steps, ms_step, peaks, timed_s)
     warp_ms = res["tr"].ms("km_warp_loss", per=args.steps)
     warp_bytes = 24.0 * S ** 3     # grid written 12 + moving 4 + fixed 4 + warped written 4
     traffic = traffic_from_profile() or {}
@@ -658,7 +658,8 @@ def run_engine(args):
                      "peak": peaks["hbm"], "unit": "GB/s", "frac": warp_bytes / (warp_ms * 1e-3) / 1e9 / peaks["hbm"],
                      "traffic": traffic.get("warp_tile_kernel") or traffic.get("warp_loss_kernel"),
                      "bytes_per_launch": warp_bytes, "kernel_ms_per_step": warp_ms}
-    e2e = measure_e2e(models["affine"], "affine", img_f_host, img_m_host, args.steps, ctx, with_grid=args.e2e_grid)
+    e2e = measure_e2e(gmodels["affine"] if use_graph else models["affine"], "affine", img_f_host, img_m_host, args.steps,
+                      ctx, with_grid=args.e2e_grid, clone_outputs=use_graph)
     clk = clocks.stop()
     dtype_name = "fp16" if kb.act_dtype() == torch.float16 else "bf16"
     engine_points = {"affine": {dtype_name: res["points"]}}
@@ -667,7 +668,10 @@ def run_engine(args):
     kb.set_operand_dtype(other)
     try:
         rb = measure_pairwise(models["affine"], "affine", img_f, img_m, args.steps, args.warmup, ctx)
-        other_block = {"value": world * 1e3 / rb["ms_step"], "unit": UNIT, "ms_per_step": rb["ms_step"], "mse": rb["mse"],
+        rbg = measure_graph(gmodels["affine"], "affine", img_f, img_m, args.steps, args.warmup, ctx) if use_graph else None
+        ob_ms = rbg["ms_step"] if rbg and rbg["captured"] else rb["ms_step"]
+        other_block = {"value": world * 1e3 / ob_ms, "unit": UNIT, "ms_per_step": ob_ms, "mse": rb["mse"],
+                       "eager_ms_per_step": rb["ms_step"],
                        "note": f"identical kernels and schedule with {other} activations / weights"}
         engine_points["affine"][other] = rb["points"]
     finally:
@@ -678,28 +682,42 @@ def run_engine(args):
             "vs_baseline": None, "dtype": dtype_name, "data": "synthetic", "config": config_dict(world),
             "clocks": clk, "e2e": e2e, "gpu_launches": res["launches"], "roofline": roofline,
             "roofline_warp": roofline_warp, "roofline_other": roofline_other, "mse": res["mse"],
-            f"{other}_operands": other_block}
+            f"{other}_operands": other_block,
+            "execution": {"mode": "cuda_graph_replay" if use_graph else "eager",
+                          "api": "keymorph_b200.KeyMorph(..., fused_warp=True, cuda_graph=%s).forward" % use_graph,
+                          "eager_value": world * 1e3 / eager_ms, "eager_ms_per_step": eager_ms,
+                          "graph_state": gres["state"] if gres else "not requested (--eager)",
+                          "graph_mse": gres["mse"] if gres else None,
+                          "note": "value / e2e: forward() captured once per (shape, transform list) into one CUDA graph and "
+                                  "replayed (2 staging copies + 1 graph launch per registration, identical kernels); the "
+                                  "rooflines and gpu_launches come from the eager pass of the same model, timed with "
+                                  "CUDA events around every C-ABI call"}}
 
     # ---- configs[2], the north-star target: TPS lambda = 0, 512 keypoints
     if "tps" in models:
         c2 = ClockSampler(local)
         c2.start()
         r3 = measure_pairwise(models["tps"], "tps", img_f, img_m, args.steps, args.warmup, ctx)
+        g3 = measure_graph(gmodels["tps"], "tps", img_f, img_m, args.steps, args.warmup, ctx) if use_graph else None
+        graph3 = g3 is not None and g3["captured"]
+        ms3 = g3["ms_step"] if graph3 else r3["ms_step"]
         engine_points["tps"] = {dtype_name: r3["points"]}
         tr = r3["tr"]
         flow_ms, fit_ms = tr.ms("km_flow_field_tps", per=args.steps), tr.ms("km_tps_fit", per=args.steps)
         wl_ms = tr.ms("km_warp_loss", per=args.steps)
         terms = 512.0 * S ** 3
         clk3 = None
-        e2e3 = measure_e2e(models["tps"], "tps", img_f_host, img_m_host, args.steps, ctx, with_grid=args.e2e_grid)
+        e2e3 = measure_e2e(gmodels["tps"] if graph3 else models["tps"], "tps", img_f_host, img_m_host, args.steps, ctx,
+                           with_grid=args.e2e_grid, clone_outputs=graph3)
         clk3 = c2.stop()
         f_sm = (clk3.get("sm_mhz") or peaks["sm_max_mhz"]) * 1e6
         # one MUFU (lg2) per radial-basis term, 16 MUFU lanes / clk / SM (XU pipe), 148 SMs
         xu_peak = 16 * 148 * f_sm / 1e9
         main3, other3 = conv_rooflines(tr, "tps", args.steps, r3["ms_step"], peaks, r3["ms_step"] * args.steps * 1e-3)
         line["tps_config3"] = {
-            "workload": CONFIGS["tps"]["workload"], "value": world * 1e3 / r3["ms_step"], "unit": UNIT,
-            "ms_per_step": r3["ms_step"], "e2e": e2e3, "gpu_launches": r3["launches"], "mse": r3["mse"], "clocks": clk3,
+            "workload": CONFIGS["tps"]["workload"], "value": world * 1e3 / ms3, "unit": UNIT,
+            "ms_per_step": ms3, "execution": "cuda_graph_replay" if graph3 else "eager",
+            "eager_value": world * 1e3 / r3["ms_step"], "eager_ms_per_step": r3["ms_step"], "e2e": e2e3, "gpu_launches": r3["launches"], "mse": r3["mse"], "clocks": clk3,
             "roofline": {"bound": "issue/XU (MUFU)", "kernel": "flow_tps_rows_kernel (dense TPS field, K radial-basis terms per voxel)",
                          "achieved": terms / (flow_ms * 1e-3) / 1e9, "peak": xu_peak, "unit": "G terms/s",
                          "frac": terms / (flow_ms * 1e-3) / 1e9 / xu_peak, "kernel_ms_per_step": flow_ms,
@@ -712,15 +730,6 @@ def run_engine(args):
             "roofline_conv": main3, "tps_fit_ms_per_step": fit_ms,
             "backbone_ms_per_step": other3[-1]["kernel_ms_per_step"]}
 
-    if not args.no_graph:
-        try:
-            eager_ms = {"affine": ms_step}
-            if "tps_config3" in line:
-                eager_ms["tps"] = line["tps_config3"]["ms_per_step"]
-            line["cuda_graph"] = graph_block(models, eager_ms, img_f, img_m, img_f_host, img_m_host, args, ctx)
-        except Exception as e:  # noqa: BLE001
-            line["cuda_graph"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-
     # ---- configs[4]: groupwise, the only collective on the path
     if "tps" in models and not args.no_groupwise:
         try:
@@ -729,7 +738,7 @@ def run_engine(args):
             line["groupwise"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
-        del models
+        del models, gmodels
         torch.cuda.empty_cache()
         line["gpu_baseline"] = gpu_baseline(dev, img_f, img_m, engine_points=engine_points)
         gb = line["gpu_baseline"]
@@ -752,12 +761,26 @@ def run_engine(args):
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line, on the process's ORIGINAL stdout."""
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
+
+
 def main():
+    # libraries chat on stdout (NCCL prints its version banner there at the first communicator): keep fd 1 for
+    # the JSON line only and send everything else to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -767,7 +790,7 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-GPU reference leg")
     ap.add_argument("--no-tps", action="store_true", help="skip the configs[2] (TPS) block")
     ap.add_argument("--no-groupwise", action="store_true", help="skip the configs[4] (groupwise) block")
-    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay block")
+    ap.add_argument("--eager", action="store_true", help="headline from the eager path (no CUDA-graph replay)")
     ap.add_argument("--e2e-grid", action="store_true", help="the e2e loop also copies the flow field to the host")
     args = ap.parse_args()
     if args.impl == "reference":

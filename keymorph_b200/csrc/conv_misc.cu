@@ -462,8 +462,9 @@ extern "C" int km_maxpool2_stats(const void* src, void* out, float* stats, int N
 //               (layout 0: [tap][Cout][Cin]; layout 1, z-folded: [rot][dx][dy][j][Cout][Cin], dz = (rot+1-j) mod 3)
 //   bias[n][class][cout], class = zcode * 9 + ycode * 3 + xcode; code bit 0 = voxel on the low border of that
 //               axis (tap offset -1 outside), bit 1 = on the high border (tap offset +1 outside)
-// Blocks [0, pack_blocks) pack; the others build the tables, one warp per output channel with the lanes
-// over the input channels: the 36 class sums of a 3x3x3 kernel come from three separable reductions.
+// Blocks [0, pack_blocks) pack (one thread per (cout, cin) pair); the others build the tables, one block per
+// (cout, sample) with the threads over the input channels: the 36 class sums of a 3x3x3 kernel come from three
+// separable reductions.
 template <bool F16>
 __global__ void __launch_bounds__(256)
 fold_gn_kernel(const float* __restrict__ w, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -472,38 +473,48 @@ fold_gn_kernel(const float* __restrict__ w, const float* __restrict__ scale, con
   // the packed weights cover input channels [c0, c0 + Cp) (Cp = Cin unless the layer is split over two kernels,
   // conv_up2.cu); the bias tables always sum over all Cin channels
   if ((int)blockIdx.x < pack_blocks) {
-    const long long total = 27ll * (layout ? 3 : 1) * Cout * Cp;
-    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * pack_blocks) {
-      long long t = i;
-      const int ci = c0 + (int)(t % Cp);
-      t /= Cp;
-      const int co = (int)(t % Cout);
-      t /= Cout;
-      int tap;
+    // one thread per (cout, cin): its 27 taps are contiguous in w (a warp reads one contiguous span), and every
+    // packed position is written by consecutive threads to consecutive elements
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= Cout * Cp) return;
+    const int co = t / Cp, cl = t % Cp, ci = c0 + cl;
+    float wk[27];
+    const float* src = w + ((size_t)co * Cin + ci) * 27;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) wk[k] = src[k];
+    const size_t plane = (size_t)Cout * Cp;
+    const size_t total = (size_t)27 * (layout ? 3 : 1) * plane;
+    for (int n = 0; n < N; ++n) {
+      const float sc = scale[n * Cin + ci];
+      act16* dst = packed + (size_t)n * total + (size_t)co * Cp + cl;
       if (layout) {
-        const int j = (int)(t % 3);
-        t /= 3;
-        const int dy = (int)(t % 3);
-        t /= 3;
-        const int dx = (int)(t % 3);
-        const int r = (int)(t / 3);
-        tap = ((r + 1 - j + 3) % 3) * 9 + dy * 3 + dx;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                dst[(size_t)(((r * 3 + dx) * 3 + dy) * 3 + j) * plane] =
+                    km_from_float<F16>(wk[((r + 1 - j + 3) % 3) * 9 + dy * 3 + dx] * sc);
       } else {
-        tap = (int)t;
+#pragma unroll
+        for (int k = 0; k < 27; ++k) dst[(size_t)k * plane] = km_from_float<F16>(wk[k] * sc);
       }
-      const float wv = w[((size_t)co * Cin + ci) * 27 + tap];
-      for (int n = 0; n < N; ++n) packed[(size_t)n * total + i] = km_from_float<F16>(wv * scale[n * Cin + ci]);
     }
     return;
   }
-  const int lane = threadIdx.x & 31;
-  const int co = ((int)blockIdx.x - pack_blocks) * 8 + (threadIdx.x >> 5);
-  if (co >= Cout) return;
-  for (int n = 0; n < N; ++n) {
+  // bias tables: one block per (cout, sample), the warps split the input channels
+  __shared__ float s_part[8][36];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int bb = (int)blockIdx.x - pack_blocks;
+  const int co = bb % Cout, n = bb / Cout;
+  {
     float acc[36];
 #pragma unroll
     for (int c = 0; c < 36; ++c) acc[c] = 0.f;
-    for (int ci = lane; ci < Cin; ci += 32) {
+    for (int ci = threadIdx.x; ci < Cin; ci += 256) {
       const float* wk = w + ((size_t)co * Cin + ci) * 27;
       const float sh = shift[n * Cin + ci];
       float xs[3][3][3];   // [dz][dy][x code]: mid = all three dx, low border = dx 1..2, high border = dx 0..1
@@ -537,17 +548,22 @@ fold_gn_kernel(const float* __restrict__ w, const float* __restrict__ scale, con
 #pragma unroll
     for (int c = 0; c < 36; ++c) {
       const float v = km_warp_sum(acc[c]);
-      if (lane == 0) bias[((size_t)n * 36 + c) * Cout + co] = v;
+      if (lane == 0) s_part[wid][c] = v;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 36) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += s_part[k][threadIdx.x];
+    bias[((size_t)n * 36 + threadIdx.x) * Cout + co] = v;
   }
 }
 
 int km_fold_gn_part(const float* w, const float* scale, const float* shift, void* packed, float* bias, int N,
                     int Cout, int Cin, int c0, int Cp, int layout, km_stream_t stream) {
-  const long long total = 27ll * (layout ? 3 : 1) * Cout * Cp;
-  long long pb = (total + 1023) / 1024;
-  const int pack_blocks = (int)(pb < 1 ? 1 : (pb > 1184 ? 1184 : pb));
-  const int bias_blocks = (Cout + 7) / 8;
+  const int pack_blocks = (Cout * Cp + 255) / 256;
+  const int bias_blocks = Cout * N;
   KM_LAUNCH_16(fold_gn_kernel, pack_blocks + bias_blocks, 256, 0, km_cs(stream), w, scale, shift, reinterpret_cast<act16*>(packed),
                                                                        bias, N, Cout, Cin, layout, pack_blocks, c0, Cp);
   KM_LAUNCH_OK("fold_gn_kernel");

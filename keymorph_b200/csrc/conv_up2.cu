@@ -270,37 +270,65 @@ template <bool F16>
 __global__ void __launch_bounds__(256)
 pack_up2_kernel(const float* __restrict__ w, const float* __restrict__ scale, uint16_t* __restrict__ packed, int N,
                 int Cs, int Cu, int cblocks) {
+  // one thread per (cout, upsampled cin): its 27 taps are contiguous; the 2 x 2 x 2 tap sets per axis are the four
+  // selectors {0}, {1,2}, {0,1}, {2} (index p * 2 + tap'), reduced separably into 64 sums
   const int Cin = Cs + Cu;
-  const long long per = 32ll * kN * Cu * cblocks;   // [cout block][class][rot][dx'][dy'][slot][64][Cu]
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < per; i += 256ll * gridDim.x) {
-    long long t = i;
-    const int ci = (int)(t % Cu);
-    t /= Cu;
-    int co = (int)(t % kCout);
-    t /= kCout;
-    const int slot = (int)(t & 3);
-    t >>= 2;
-    const int dyp = (int)(t & 1), dxp = (int)((t >> 1) & 1), rot = (int)((t >> 2) & 1), px = (int)((t >> 3) & 1),
-              py = (int)((t >> 4) & 1);
-    co += (int)(t >> 5) * kCout;
-    const int d = ((slot - 2 * rot + 1) & 3) - 1;
-    const float* wk = w + ((size_t)co * Cin + Cs + ci) * 27;
-    float acc = 0.f;
-    for (int a = 0; a < 2; ++a) {
-      const int dz = 1 - d + a;
-      if (dz < 0 || dz > 2) continue;
-      for (int b = 0; b < 2; ++b) {
-        const int dy = py - 1 + 2 * dyp + b;
-        if (dy < 0 || dy > 2) continue;
-        for (int c = 0; c < 2; ++c) {
-          const int dx = px - 1 + 2 * dxp + c;
-          if (dx < 0 || dx > 2) continue;
-          acc += wk[dz * 9 + dy * 3 + dx];
-        }
-      }
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= cblocks * kCout * Cu) return;
+  const int co = t / Cu, ci = t % Cu;
+  const float* src = w + ((size_t)co * Cin + Cs + ci) * 27;
+  float wk[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) wk[k] = src[k];
+  float sx[3][3][4], sy[3][4][4], sz[4][4][4];
+#pragma unroll
+  for (int d = 0; d < 9; ++d) {
+    const float w0 = wk[d * 3], w1 = wk[d * 3 + 1], w2 = wk[d * 3 + 2];
+    sx[d / 3][d % 3][0] = w0;
+    sx[d / 3][d % 3][1] = w1 + w2;
+    sx[d / 3][d % 3][2] = w0 + w1;
+    sx[d / 3][d % 3][3] = w2;
+  }
+#pragma unroll
+  for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const float a0 = sx[dz][0][x], a1 = sx[dz][1][x], a2 = sx[dz][2][x];
+      sy[dz][0][x] = a0;
+      sy[dz][1][x] = a1 + a2;
+      sy[dz][2][x] = a0 + a1;
+      sy[dz][3][x] = a2;
     }
-    for (int n = 0; n < N; ++n)
-      packed[(size_t)n * per + i] = km_from_float<F16>(acc * (scale ? scale[(size_t)n * Cin + Cs + ci] : 1.f));
+#pragma unroll
+  for (int y = 0; y < 4; ++y)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const float a0 = sy[0][y][x], a1 = sy[1][y][x], a2 = sy[2][y][x];
+      sz[0][y][x] = a0;
+      sz[1][y][x] = a1 + a2;
+      sz[2][y][x] = a0 + a1;
+      sz[3][y][x] = a2;
+    }
+  const int cb = co / kCout, co64 = co % kCout;
+  const size_t per = (size_t)32 * kN * Cu * cblocks;   // [cout block][class][rot][dx'][dy'][slot][64][Cu]
+  for (int n = 0; n < N; ++n) {
+    const float sc = scale ? scale[(size_t)n * Cin + Cs + ci] : 1.f;
+    uint16_t* dst = packed + (size_t)n * per + (size_t)cb * 32 * kN * Cu + (size_t)co64 * Cu + ci;
+#pragma unroll
+    for (int cls = 0; cls < 4; ++cls)
+#pragma unroll
+      for (int rot = 0; rot < 2; ++rot)
+#pragma unroll
+        for (int dxp = 0; dxp < 2; ++dxp)
+#pragma unroll
+          for (int dyp = 0; dyp < 2; ++dyp)
+#pragma unroll
+            for (int slot = 0; slot < 4; ++slot) {
+              const int d = ((slot - 2 * rot + 1) & 3) - 1;              // fine plane 2j + d lives in this slot
+              const int zsel = d == -1 ? 3 : (d == 0 ? 1 : (d == 1 ? 2 : 0));
+              const float v = sz[zsel][(cls >> 1) * 2 + dyp][(cls & 1) * 2 + dxp] * sc;
+              dst[(size_t)((((cls * 2 + rot) * 2 + dxp) * 2 + dyp) * 4 + slot) * kCout * Cu] = km_from_float<F16>(v);
+            }
   }
 }
 
@@ -328,9 +356,9 @@ extern "C" int km_conv3d_up2_gn(const void* xc, const float* w, const float* sca
   cudaStream_t st = km_cs(stream);
   const int cblocks = Cout / kCout;
   if (km_operand_fp16())
-    pack_up2_kernel<true><<<256 * cblocks, 256, 0, st>>>(w, scale, reinterpret_cast<uint16_t*>(workspace), N, Cs, Cu, cblocks);
+    pack_up2_kernel<true><<<(Cout * Cu + 255) / 256, 256, 0, st>>>(w, scale, reinterpret_cast<uint16_t*>(workspace), N, Cs, Cu, cblocks);
   else
-    pack_up2_kernel<false><<<256 * cblocks, 256, 0, st>>>(w, scale, reinterpret_cast<uint16_t*>(workspace), N, Cs, Cu, cblocks);
+    pack_up2_kernel<false><<<(Cout * Cu + 255) / 256, 256, 0, st>>>(w, scale, reinterpret_cast<uint16_t*>(workspace), N, Cs, Cu, cblocks);
   KM_LAUNCH_OK("pack_up2_kernel");
 
   Up2Geom g;
