@@ -391,6 +391,7 @@ def conv3d_tc_pair(x, wp, relu=False, want_stats=False):
 
 
 USE_ZFOLD_PAIR = True     # engine switch: z-folded 2-CTA kernel for the Cout = 64 layers (A/B testing)
+USE_ZFOLD_PAIR_CIN32 = False   # ... also for 32 -> 64 (enc1.c2): N = 192 per activation read instead of 64
 
 
 def zfold_pair_supported(Cin, Cout, D, H, W):
