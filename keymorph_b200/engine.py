@@ -110,7 +110,7 @@ class UNetEngine(_EngineBase):
         w = sc_mod.conv.weight
         _, D, H, W, Cin = x.shape
         use_zf2 = ops.USE_ZFOLD_PAIR and D * H * W >= 96 ** 3 \
-            and (w.shape[0] == 32 or Cin % 64 == 0 or (ops.USE_ZFOLD_PAIR_CIN32 and Cin % 32 == 0)) \
+            and (w.shape[0] == 32 or Cin % 64 == 0 or (scale is not None and ops.USE_GN_FOLD and ops.zfold_pair_cin32_enabled() and Cin % 32 == 0)) \
             and ops.zfold_pair_supported(Cin, w.shape[0], D, H, W) \
             and not ops.zfold_supported(Cin, w.shape[0], D, H, W)
         use_pair = not use_zf2 and not ops.zfold_supported(Cin, w.shape[0], D, H, W) and ops.USE_PAIR_CONV \

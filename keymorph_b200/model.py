@@ -207,7 +207,8 @@ class KeyMorph(nn.Module):
         weights are rebuilt when they change) and the engine's schedule switches."""
         params = tuple((p.data_ptr(), p._version) for p in self.backbone.parameters())
         return (params, str(ops.act_dtype()), ops.USE_GN_FOLD, ops.gn_fold_stem_enabled(), ops.USE_GN_FOLD_TC_PAIR,
-                ops.USE_PAIR_CONV, ops.USE_ZFOLD_PAIR, self.fused_warp, self.weight_keypoints)
+                ops.USE_PAIR_CONV, ops.USE_ZFOLD_PAIR, ops.zfold_pair_cin32_enabled(), ops.USE_COARSE_UPCONV,
+                self.fused_warp, self.weight_keypoints)
 
     def _forward_graphed(self, key, img_f, img_m, transform_type, kwargs):
         """First call of a key: eager (packs weights, sets kernel attributes, fills every cache).  Second call:

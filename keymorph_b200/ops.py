@@ -391,7 +391,17 @@ def conv3d_tc_pair(x, wp, relu=False, want_stats=False):
 
 
 USE_ZFOLD_PAIR = True     # engine switch: z-folded 2-CTA kernel for the Cout = 64 layers (A/B testing)
-USE_ZFOLD_PAIR_CIN32 = False   # ... also for 32 -> 64 (enc1.c2): N = 192 per activation read instead of 64
+# ... also for 32 -> 64 (enc1.c2) with its GroupNorm folded in: N = 192 per MMA instead of 64 (571 -> 412 us for
+# two 128^3 volumes, tools/time_enc1c2.py).  The fold stores that layer's input un-normalised: fine with fp16
+# operands (256^3 keypoint error 2.07e-3 -> 2.21e-3 max), not with bf16 (round 1: fails the 256^3 criterion).
+# None = automatic (fp16 only); True / False force it.
+USE_ZFOLD_PAIR_CIN32 = None
+
+
+def zfold_pair_cin32_enabled():
+    if USE_ZFOLD_PAIR_CIN32 is None:
+        return act_dtype() == torch.float16
+    return bool(USE_ZFOLD_PAIR_CIN32)
 
 
 def zfold_pair_supported(Cin, Cout, D, H, W):

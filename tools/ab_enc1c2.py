@@ -23,7 +23,7 @@ f = f_cpu.cuda()
 pair = torch.cat([f, g_cpu.cuda()])
 torch.set_num_threads(os.cpu_count() or 1)
 ref = O.center_of_mass3d(O.unet3d_forward(sd, f_cpu, 4, 1))
-for flag in (False, True, False, True):
+for flag in (False, True, False, True, None):
     ops.USE_ZFOLD_PAIR_CIN32 = flag
     pts = model.get_keypoints(f)
     e = (pts.cpu() - ref).abs()
