@@ -1,4 +1,4 @@
-"""enc1.c2 of the bench network (32 -> 64 at 128^3, two volumes): normalisation pass + plain CTA-pair kernel (N = 64
+"""enc1.c2 of the bench network (32 -> 64 at 128^3, two volumes; or [Cin Cout edge] from the command line): normalisation pass + plain CTA-pair kernel (N = 64
 per MMA) vs the z-folded pair kernel with the GroupNorm folded in (N = 192).  python tools/time_enc1c2.py"""
 import os
 import sys
@@ -9,6 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from keymorph_b200 import ops  # noqa: E402
 
 N, Cin, Cout, E = 2, 32, 64, 128
+if len(sys.argv) > 3:
+    Cin, Cout, E = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 g = torch.Generator().manual_seed(3)
 x = torch.relu(torch.randn(N, E, E, E, Cin, generator=g)).to("cuda", ops.act_dtype())
 w = (torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5).cuda()
@@ -39,5 +41,5 @@ fl = 2.0 * 27 * Cin * Cout * E ** 3 * N
 a = timed(unfolded)
 b = timed(lambda: ops.conv3d_zfold_pair_gn(x, w, scale, shift, relu=True, want_stats=True))
 c = timed(lambda: ops.conv3d_tc_pair(x, wp, relu=True, want_stats=True))
-print(f"norm_apply + conv_tc2 (N = 64 per MMA): {a:7.1f} us ({fl / a / 1e6:6.1f} TFLOP/s); the conv alone {c:7.1f} us")
-print(f"conv_zf2 with the folded GroupNorm (N = 192): {b:7.1f} us ({fl / b / 1e6:6.1f} TFLOP/s)")
+print(f"{Cin} -> {Cout} @ {E}^3: norm_apply + conv_tc2 (N = Cout per MMA): {a:7.1f} us ({fl / a / 1e6:6.1f} TFLOP/s); the conv alone {c:7.1f} us")
+print(f"{Cin} -> {Cout} @ {E}^3: conv_zf2 with the folded GroupNorm (N = 3 Cout): {b:7.1f} us ({fl / b / 1e6:6.1f} TFLOP/s)")
