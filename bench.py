@@ -601,6 +601,11 @@ def run_engine(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None
+    if world > 1 and not args.no_numa:
+        # one process per GPU: keep it, and the pinned buffers it allocates from here on, on the GPU's NUMA node
+        from keymorph_b200.parallel import bind_cpu_to_gpu
+        numa_cpus = bind_cpu_to_gpu(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
@@ -683,6 +688,8 @@ def run_engine(args):
             "clocks": clk, "e2e": e2e, "gpu_launches": res["launches"], "roofline": roofline,
             "roofline_warp": roofline_warp, "roofline_other": roofline_other, "mse": res["mse"],
             f"{other}_operands": other_block,
+            "cpu_affinity": ({"cpus_rank0": len(numa_cpus), "source": "NVML cpu affinity of the rank's GPU"}
+                             if numa_cpus else None),
             "execution": {"mode": "cuda_graph_replay" if use_graph else "eager",
                           "api": "keymorph_b200.KeyMorph(..., fused_warp=True, cuda_graph=%s).forward" % use_graph,
                           "eager_value": world * 1e3 / eager_ms, "eager_ms_per_step": eager_ms,
@@ -790,6 +797,7 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-GPU reference leg")
     ap.add_argument("--no-tps", action="store_true", help="skip the configs[2] (TPS) block")
     ap.add_argument("--no-groupwise", action="store_true", help="skip the configs[4] (groupwise) block")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind each rank to its GPU's NUMA node (N > 1)")
     ap.add_argument("--eager", action="store_true", help="headline from the eager path (no CUDA-graph replay)")
     ap.add_argument("--e2e-grid", action="store_true", help="the e2e loop also copies the flow field to the host")
     args = ap.parse_args()

@@ -19,6 +19,35 @@ def world():
     return 0, 1
 
 
+def bind_cpu_to_gpu(device_index: int):
+    """Pin this process to the CPU cores NVML reports as local to GPU `device_index` (its NUMA node).  One process
+    per GPU feeds its board from pinned host buffers: allocated after this call they land on the local node
+    (first touch), so H2D / D2H copies do not cross the socket interconnect.  Returns the CPU list, or None when
+    NVML / sched_setaffinity is unavailable or reports nothing usable (never raises)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = device_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                idx = int(ids[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus or len(cpus) >= len(allowed):
+            return None          # nothing to narrow (single node, or the mask is empty)
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001 -- an optimisation, never a requirement
+        return None
+
+
 def shard_range(n_items: int, rank: int, world_size: int) -> range:
     """Contiguous, balanced block of item indices for `rank` (first n % world ranks get one more)."""
     base, rem = divmod(n_items, world_size)

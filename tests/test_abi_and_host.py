@@ -240,3 +240,21 @@ def test_deferred_singular_checks_are_per_thread():
         th.start()
         th.join()
     assert seen["inner"] is None and getattr(T._TLS, "pending", None) is None
+
+
+def test_bind_cpu_to_gpu_is_best_effort():
+    """parallel.bind_cpu_to_gpu narrows the CPU affinity to the GPU's NUMA node when NVML knows it and is a no-op
+    (None, no exception, affinity untouched) otherwise -- e.g. in this container, which has no GPU."""
+    import os
+
+    from keymorph_b200.parallel import bind_cpu_to_gpu
+    before = os.sched_getaffinity(0)
+    got = bind_cpu_to_gpu(0)
+    after = os.sched_getaffinity(0)
+    if got is None:
+        assert after == before
+    else:
+        assert set(got) == after and after < before
+        os.sched_setaffinity(0, before)
+    assert bind_cpu_to_gpu(10 ** 6) is None       # no such device: still no exception
+    assert os.sched_getaffinity(0) == before
