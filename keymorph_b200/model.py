@@ -67,7 +67,8 @@ class KeyMorph(nn.Module):
         self.align_keypoints_in_real_world_coords = align_keypoints_in_real_world_coords
         self.fused_warp = fused_warp
         self.cuda_graph = cuda_graph
-        self._graphs = {}           # (shape, device, transforms, ...) -> captured forward
+        self._graphs = {}           # (shape, device, transforms, ...) -> captured forward (insertion order = age)
+        self.max_graphs = 4         # captured graphs kept alive (each pins its activations: ~6 GB for a 256^3 pair)
         self._lmbda_cache = {}      # numeric TPS lambdas resident on the device (no H2D copy per call)
 
     # ------------------------------------------------------------------ keypoints
@@ -220,6 +221,9 @@ class KeyMorph(nn.Module):
         sig = self._graph_signature()
         ent = self._graphs.get(key)
         if ent is None or ent["sig"] != sig:
+            self._graphs.pop(key, None)
+            while len(self._graphs) >= max(1, self.max_graphs):      # evict the oldest capture (frees its pool)
+                self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = {"sig": sig, "graph": None}
             return self._forward_eager(img_f, img_m, transform_type, None, kwargs)
         if ent["graph"] is None:

@@ -1567,6 +1567,13 @@ def test_cuda_graph_replay_matches_eager():
         assert list(graphed.graph_state().values()) == [["warm-up", "captured", "captured"][i]]
     want = eager(f, m, transform_type=t, return_aligned_points=True)
     assert_close(got["tps_0.1"]["grid"], want["tps_0.1"]["grid"], rtol=1e-5, atol=2e-5)
+    # at most max_graphs captures stay alive: a third key evicts the oldest
+    graphed.max_graphs = 2
+    for tt in ("rigid", "affine"):
+        for _ in range(2):
+            graphed(f, m, transform_type=tt, return_aligned_points=False)
+    assert len(graphed.graph_state()) == 2 and list(graphed.graph_state().values()) == ["captured", "captured"]
+    graphed.max_graphs = 4
     # a singular fit raises from the warm-up call, from the capturing call and from a replay, like the eager path
     # (constant heat maps: every keypoint is the same point)
     with torch.no_grad():
@@ -1577,4 +1584,4 @@ def test_cuda_graph_replay_matches_eager():
     for i in range(3):
         with pytest.raises(torch.linalg.LinAlgError):
             graphed(f, m, transform_type=t, return_aligned_points=True)
-    assert list(graphed.graph_state().values()) == ["captured"]
+    assert graphed.graph_state()[next(k for k in graphed.graph_state() if k[2] == tuple(t))] == "captured"
