@@ -7,11 +7,15 @@
 Headline workload = BASELINE configs[1]: synthetic 256^3 pair, affine, 256 keypoints, TruncatedUNet3D, bf16.
 One step = one pairwise registration: two 256^3 fp32 volumes -> backbone on both -> centre-of-mass keypoints
 -> fit -> flow field -> warped moving image + MSE.
-  value        registrations/s, volumes resident in HBM (CUDA events around the K steps, max over ranks)
+  value        registrations/s, volumes resident in HBM (CUDA events around the K steps, max over ranks), through
+               KeyMorph(..., fused_warp=True, cuda_graph=True).forward: the call replays the CUDA graph it captured
+               on its second invocation (identical kernels; `execution` reports the eager number beside it, and
+               --eager or a failed capture makes the eager path the headline)
   e2e          the same call fed from pinned HOST memory: H2D of both volumes and D2H of the warped image
                + MSE of every step inside the timed region
-  roofline     the tcgen05 convolution kernels (tensor bound), timed live with CUDA events; peak = the burst
-               figure of MEASURED_PEAKS.json when the timed region is shorter than 1 s, else the sustained one
+  roofline     the tcgen05 convolution kernels (tensor bound), timed live with CUDA events around every C-ABI call
+               of an EAGER pass of the same model; flops = the MMAs executed; peak = the burst figure of
+               MEASURED_PEAKS.json when the timed region is shorter than 1 s, else the sustained one
   tps_config3  BASELINE configs[2] (the north-star target: 256^3 pair, TPS lambda=0, 512 keypoints): value,
                e2e and the roofline of the dense TPS field kernel (issue / MUFU bound) and of the fused warp
   gpu_baseline the UNMODIFIED reference (oracle/_ref, stock torch CUDA ops: cuDNN conv3d, ATen grid_sampler_3d,
