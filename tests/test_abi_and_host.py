@@ -258,3 +258,26 @@ def test_bind_cpu_to_gpu_is_best_effort():
         os.sched_setaffinity(0, before)
     assert bind_cpu_to_gpu(10 ** 6) is None       # no such device: still no exception
     assert os.sched_getaffinity(0) == before
+
+
+def test_bench_flop_model_and_traffic_profile():
+    """bench.py's roofline inputs: the executed-flop model counts the decoders' upsampled channels with 8 taps
+    instead of 27 (conv_up2.cu) and stays below the reference's 27-tap arithmetic by exactly that difference; the
+    committed ncu launch list parses into per-kernel DRAM bytes for every tcgen05 conv kernel it names."""
+    import bench
+    ex = {l[0]: l for l in bench.conv_layers(256, 256, 2)}
+    al = {l[0]: l for l in bench.conv_layers(256, 256, 2, executed=False)}
+    assert set(al) == {"enc0.c1", "enc0.c2", "enc1.c1", "enc1.c2", "enc2.c1", "enc2.c2", "enc3.c1", "enc3.c2",
+                       "dec0.c1", "dec0.c2", "dec1.c1", "dec1.c2", "final"}
+    assert al["dec1.c1"][1:5] == (192, 64, 128, 27) and al["dec0.c1"][1:5] == (384, 128, 64, 27)
+    assert ex["dec1.c1"][1:5] == (64, 64, 128, 27) and ex["dec1.c1.up"][1:5] == (128, 64, 128, 8)
+    assert ex["dec0.c1"][1:5] == (128, 128, 64, 27) and ex["dec0.c1.up"][1:5] == (256, 128, 64, 8)
+    f_ex, f_al = sum(l[5] for l in ex.values()), sum(l[5] for l in al.values())
+    saved = 2.0 * 19 * (128 * 64 * 128 ** 3 + 256 * 128 * 64 ** 3) * 2       # 19 of 27 taps of the upsampled channels
+    assert abs((f_al - f_ex) - saved) < 1e-6 * f_al
+    assert abs(al["enc1.c1"][5] - 2.0 * 27 * 32 * 32 * 128 ** 3 * 2) < 1.0
+    tr = bench.traffic_from_profile()
+    assert tr is not None
+    for k in ("conv_zf_kernel", "conv_zf2_kernel", "conv_up2_kernel", "conv_tc2_kernel", "conv_stem_mma_kernel"):
+        assert tr.get(k, 0.0) > 1e8, k          # hundreds of MB per step each
+    assert 0.5e9 < tr["conv_up2_kernel"] < 1.2e9     # reads the coarse tensors, writes the 16-bit partial sums
